@@ -1,0 +1,158 @@
+/*
+ * r2f_b200.h -- C ABI of the B200-native raw2film render path (libr2f_b200.so).
+ *
+ * This is the drop-in boundary for the reference's per-pixel film-emulation path
+ * (JanLohse/raw2film, src/raw2film/cpu_processor.py:363-407 == the body of
+ * CpuProcessor.process after the LUTs are loaded, and the equivalent WebGPU
+ * pipeline src/raw2film/gpu_processor.py:1695-1890).  Plain pointers and sizes only;
+ * no torch / numpy types.  All image pointers passed to the *_dev entry points are
+ * CUDA device pointers on the context's device; `stream` is a cudaStream_t (NULL =
+ * legacy default stream).  Table setters take HOST pointers and copy synchronously.
+ *
+ * Every function returns R2F_OK (0) or an error code; r2f_last_error() returns a
+ * thread-local message (the reference raises plain Python exceptions; the Python shim
+ * raw2film_b200/_cabi.py turns non-zero codes into RuntimeError).
+ *
+ * There is NO CPU fallback behind this interface.
+ */
+#ifndef R2F_B200_H
+#define R2F_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define R2F_ABI_VERSION 1
+
+/* status codes */
+#define R2F_OK 0
+#define R2F_ERR_INVALID 1 /* bad argument / table not set */
+#define R2F_ERR_CUDA 2    /* CUDA runtime error (message has the cudaError string) */
+#define R2F_ERR_NOMEM 3   /* workspace too small */
+
+/* stage gates: mirror the `if` chain of cpu_processor.py:368-403 */
+#define R2F_HALATION 0x01u /* cpu_processor.py:368  `if halation`                         */
+#define R2F_MTF 0x02u      /* cpu_processor.py:382  `if sharpness and stock.mtf`           */
+#define R2F_GRAIN 0x04u    /* cpu_processor.py:387  `if grain and stock.rms_density`       */
+#define R2F_GRAIN_BW 0x08u /* cpu_processor.py:394  bw_grain = (grain == 1)               */
+#define R2F_BURN 0x10u     /* cpu_processor.py:399  `if highlight_burn and (...)`          */
+
+/* float working-space taps for parity tests (r2f_render_tap) */
+#define R2F_TAP_EXPOSURE 1 /* after apply_2d_lut          cpu_processor.py:364 */
+#define R2F_TAP_HALATION 2 /* after effects.halation      cpu_processor.py:369 */
+#define R2F_TAP_DENSITY 3  /* after multi_channel_interp  cpu_processor.py:380 */
+#define R2F_TAP_MTF 4      /* after effects.film_sharpness cpu_processor.py:383 */
+#define R2F_TAP_GRAIN 5    /* after apply_grain + clip    cpu_processor.py:397 */
+#define R2F_TAP_BURN 6     /* after effects.burn          cpu_processor.py:403 */
+#define R2F_TAP_RGB 7      /* after apply_lut_tetrahedral cpu_processor.py:405 */
+
+typedef struct r2f_ctx r2f_ctx;
+
+int r2f_abi_version(void);
+const char *r2f_last_error(void);
+
+/* Replaces CpuProcessor.__init__ / GpuProcessor.__init__ device acquisition
+ * (cpu_processor.py:27-29, gpu_processor.py:176-190): one context per GPU. */
+int r2f_create(int device, r2f_ctx **out);
+int r2f_destroy(r2f_ctx *ctx);
+
+/* ---- table setters: the device-side half of the reference's load_* caches ------------- */
+
+/* 2-D chromaticity input LUT, (n, n, 3) float32, index order lut[x_idx][y_idx]
+ * (load_input_lut cpu_processor.py:142-164; _ensure_lut_2d gpu_processor.py:349-376). */
+int r2f_set_lut2d(r2f_ctx *ctx, const float *lut, int n);
+
+/* H-D curve, (4, N) float32: row 0 = log10-exposure abscissa (uniform), rows 1..3 = R,G,B
+ * density (load_density_curve cpu_processor.py:166-188; _ensure_lut_1d gpu_processor.py:307-347).
+ * log_eps is the lower clip of log_clip (cpu_processor.py:378; shaders/lut_1d.wgsl:24). */
+int r2f_set_curve1d(r2f_ctx *ctx, const float *curve, int N, float log_eps);
+
+/* Output 3-D LUT, (n, n, n, 3) float32 indexed lut[r][g][b], sampled at density * scale
+ * (load_output_lut cpu_processor.py:190-267; apply_lut_tetrahedral utils.py:247-380;
+ *  call site cpu_processor.py:405 passes scale = 0.25). */
+int r2f_set_lut3d(r2f_ctx *ctx, const float *lut, int n, double scale);
+
+/* Halation kernel, (k, k, 3) float32, k odd, as built by compute_halation_kernel
+ * (effects.py:239-263).  A channel whose kernel is an exact centre delta is passed through. */
+int r2f_set_halation_kernel(r2f_ctx *ctx, const float *kernel, int k);
+
+/* MTF kernel, (k, k, 3) float32, k odd, as built by mtf_kernel (effects.py:165-185). */
+int r2f_set_mtf_kernel(r2f_ctx *ctx, const float *kernel, int k);
+
+/* Grain: amplitude curve (4, N) over density (get_grain_curve, gpu_processor.py:913;
+ * shaders/grain.wgsl:77-86), smoothing kernel (k, k) float32 or NULL for a 1x1 kernel
+ * (grain_kernel, gpu_processor.py:927-934), and the seed of the on-device Philox stream
+ * (the reference draws a fresh seed per frame, gpu_processor.py:586-592). */
+int r2f_set_grain(r2f_ctx *ctx, const float *curve, int N, const float *kernel, int k, uint64_t seed);
+
+/* Re-seed the on-device noise stream only (no table upload, no synchronisation). */
+int r2f_set_grain_seed(r2f_ctx *ctx, uint64_t seed);
+
+/* Highlight burn parameters (effects.burn effects.py:392-418): d_ref of the green layer,
+ * strength, and burn_scale (down-sampling divisor, effects.py:365). */
+int r2f_set_burn(r2f_ctx *ctx, float d_ref, float highlight_burn, float burn_scale);
+
+/* ---- the render call -------------------------------------------------------------------- */
+
+/* Bytes of device scratch r2f_render needs for an H x W frame with these stage flags. */
+size_t r2f_workspace_bytes(int H, int W, unsigned flags);
+
+/* Replaces the body of CpuProcessor.process after the loaders (cpu_processor.py:363-407):
+ *   in_dev   float32 H x W x in_channels (3 = XYZ, 4 = XYZ + alpha as in the GPU payload,
+ *            gpu_processor.py:765), C-contiguous
+ *   out_dev  uint8 H x W x 3
+ *   noise_dev  optional injected white N(0,1) field, float32 H x W x noise_channels
+ *            (3, or 1 with R2F_GRAIN_BW); NULL = generate on device from the seed
+ *   workspace_dev / workspace_bytes  caller-owned scratch (>= r2f_workspace_bytes) */
+int r2f_render(r2f_ctx *ctx, const float *in_dev, int H, int W, int in_channels, uint8_t *out_dev,
+               unsigned flags, const float *noise_dev, int noise_channels, void *workspace_dev,
+               size_t workspace_bytes, void *stream);
+
+/* Same pipeline, stopped after `tap_stage`; writes the float32 H x W x 3 working image. */
+int r2f_render_tap(r2f_ctx *ctx, const float *in_dev, int H, int W, int in_channels, unsigned flags,
+                   const float *noise_dev, int noise_channels, void *workspace_dev, size_t workspace_bytes,
+                   int tap_stage, float *tap_dev, void *stream);
+
+/* Host-buffer variant for non-torch callers (what a cgo/JNI/ctypes binding of
+ * GpuProcessor.process_preloaded, gpu_processor.py:1643-1693, would call): copies in,
+ * renders, copies out and synchronises; staging and scratch are owned by the context. */
+int r2f_render_host(r2f_ctx *ctx, const float *in_host, int H, int W, int in_channels, uint8_t *out_host,
+                    unsigned flags, const float *noise_host, int noise_channels);
+
+/* ---- stage entry points (same kernels, exposed for stage-level parity tests) ------------- */
+
+/* convolve_2d (effects.py:146-156): per-channel correlation, centre anchor, BORDER_REFLECT_101.
+ * in/out: float32 H x W x 3 interleaved device images; kernel: HOST (k, k, 3). */
+int r2f_convolve2d(r2f_ctx *ctx, const float *in_dev, float *out_dev, int H, int W, const float *kernel, int k,
+                   void *workspace_dev, size_t workspace_bytes, void *stream);
+
+/* White N(0,1) field from the context's Philox stream: float32 H x W x channels (1 or 3). */
+int r2f_generate_noise(r2f_ctx *ctx, float *out_dev, int H, int W, int channels, uint64_t seed, void *stream);
+
+/* Number of kernel launches issued by this context since creation (bench.py gpu_launches). */
+uint64_t r2f_launch_count(const r2f_ctx *ctx);
+
+/* Per-kernel device timing (bench.py roofline): when enabled, every launch of the render
+ * pipeline is bracketed by CUDA events on the launching stream.  r2f_profile_read waits for the
+ * recorded events, ACCUMULATES milliseconds and launch counts per kernel id into the caller's
+ * arrays (length R2F_PROF_COUNT) and clears the recorded events. */
+#define R2F_PROF_POINTWISE 0 /* k_pointwise (fused a2+a4+a5+a9+a10)        */
+#define R2F_PROF_EXPOSE 1    /* k_expose (a2)                              */
+#define R2F_PROF_HALATION 2  /* k_conv2d halation + density epilogue (a3-5) */
+#define R2F_PROF_DENSITY 3   /* pointwise density pass when halation is off */
+#define R2F_PROF_MTF 4       /* k_conv2d MTF (a6)                           */
+#define R2F_PROF_NOISE 5     /* k_noise / noise upload shuffle (a7)        */
+#define R2F_PROF_GRAIN 6     /* k_conv2d grain + apply epilogue (a7)       */
+#define R2F_PROF_BURN 7      /* burn mask kernels (a8)                     */
+#define R2F_PROF_FINISH 8    /* k_finish (a8 apply + a9 + a10)             */
+#define R2F_PROF_COUNT 9
+int r2f_profile_enable(r2f_ctx *ctx, int on);
+int r2f_profile_read(r2f_ctx *ctx, double *ms_accum, uint64_t *count_accum);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* R2F_B200_H */

@@ -1,0 +1,172 @@
+// Per-pixel device functions of the raw2film render path (sm_100a).
+//
+// Everything here is compiled with -fmad=false: each float operation is a separately
+// rounded IEEE-754 operation in the order written, which is what makes the pointwise
+// chain bit-exact against oracle/pointwise_oracle.c.  Where a fused multiply-add is
+// wanted (the convolutions) the code calls fmaf() explicitly.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace r2f {
+
+struct Lut2D {
+    const float *tab;  // (n, n, 3) lut[x_idx][y_idx]
+    int n;
+};
+
+struct Curve1D {
+    const float *rows;  // rows R,G,B of the (4, N) table, contiguous (3*N floats)
+    int N;
+    float x0;         // first abscissa
+    float inv_range;  // float32(1 / (x_last - x_first))
+};
+
+struct Lut3D {
+    const float4 *tab;  // (n, n, n) vertices padded to float4
+    int n;
+    double s;  // scale * (n - 1)
+};
+
+// ---- a2: chromaticity-indexed input LUT (reference shaders/lut_2d.wgsl:18-108) ---------
+__device__ __forceinline__ int clamp_floor_idx(float fl, int hi) {
+    if (!(fl >= 0.0f)) return 0;
+    if (fl > (float)hi) return hi;
+    return (int)fl;
+}
+
+__device__ __forceinline__ void lut2d_eval(const Lut2D &L, float X, float Y, float Z, float &e0, float &e1,
+                                           float &e2) {
+    const float S = (X + Y) + Z;
+    if (S < 1e-12f) {
+        e0 = e1 = e2 = 0.0f;
+        return;
+    }
+    const int n = L.n;
+    const float inv_sum = __fdiv_rn((float)(n - 1), S);
+    const float r = X * inv_sum, g = Y * inv_sum;
+    const float rfl = floorf(r), gfl = floorf(g);
+    const int ri = clamp_floor_idx(rfl, n - 2), gi = clamp_floor_idx(gfl, n - 2);
+    const float rf = r - rfl, gf = g - gfl;
+    const float fs = rf + gf;
+    const float *a = L.tab + ((ri + 1) * n + gi) * 3;
+    const float *b = L.tab + (ri * n + gi + 1) * 3;
+    const float *c;
+    float wa, wb, wc;
+    if (fs <= 1.0f) {
+        c = L.tab + (ri * n + gi) * 3;
+        wa = rf;
+        wb = gf;
+        wc = 1.0f - fs;
+    } else {
+        c = L.tab + ((ri + 1) * n + gi + 1) * 3;
+        wa = 1.0f - gf;
+        wb = 1.0f - rf;
+        wc = fs - 1.0f;
+    }
+    e0 = ((a[0] * wa + b[0] * wb) + c[0] * wc) * S;
+    e1 = ((a[1] * wa + b[1] * wb) + c[1] * wc) * S;
+    e2 = ((a[2] * wa + b[2] * wb) + c[2] * wc) * S;
+}
+
+// ---- a4: log10 with lower clip (shaders/lut_1d.wgsl:23-26) -------------------------------
+// binary64 log10 rounded once to binary32 (see oracle/pointwise_oracle.c log10_clip1).
+__device__ __forceinline__ float log10_clip(float v, float eps) {
+    const float c = v > eps ? v : eps;
+    return (float)log10((double)c);
+}
+
+// ---- a5: per-channel curve, uniform abscissa, clamped ends (lut_1d.wgsl:43-47) -----------
+__device__ __forceinline__ float curve_eval(const Curve1D &C, int ch, float v) {
+    float t = (v - C.x0) * C.inv_range;
+    t = t < 0.0f ? 0.0f : (t > 1.0f ? 1.0f : t);
+    if (!(t == t)) t = 0.0f;
+    const float p = t * (float)(C.N - 1);
+    int i = (int)p;
+    if (i > C.N - 2) i = C.N - 2;
+    const float f = p - (float)i;
+    const float *row = C.rows + ch * C.N;
+    const float lo = row[i], hi = row[i + 1];
+    return lo + f * (hi - lo);
+}
+
+__device__ __forceinline__ float density_eval(const Curve1D &C, int ch, float exposure, float eps) {
+    return curve_eval(C, ch, log10_clip(exposure, eps));
+}
+
+// ---- a9: tetrahedral 3-D LUT (reference utils.py:247-380) -----------------------------------
+// binary64 coordinates and accumulation, binary32 vertex differences (numba's typing of the
+// reference for a float64 `scale`; bit-exact against it, tests/golden/tetra.npz).
+__device__ __forceinline__ int wrap_idx(int i, int n) {
+    if (i < 0) {
+        i += n;
+        if (i < 0) i = 0;
+    }
+    return i;
+}
+
+__device__ __forceinline__ void tetra_eval(const Lut3D &L, float dr_in, float dg_in, float db_in, float &o0,
+                                           float &o1, float &o2) {
+    const int n = L.n;
+    double d[3];
+    int i0[3];
+    const float in[3] = {dr_in, dg_in, db_in};
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const double v = (double)in[k] * L.s;
+        double vt = v;
+        if (!(vt == vt)) vt = 0.0;
+        vt = fmin(fmax(vt, -2.0e9), 2.0e9);
+        int i = (int)vt;
+        if (i >= n - 1) {
+            i = n - 2;
+            d[k] = 1.0;
+        } else {
+            d[k] = v - (double)i;
+        }
+        i0[k] = i;
+    }
+    const int r0 = wrap_idx(i0[0], n), g0 = wrap_idx(i0[1], n), b0 = wrap_idx(i0[2], n);
+    const int r1 = wrap_idx(i0[0] + 1, n), g1 = wrap_idx(i0[1] + 1, n), b1 = wrap_idx(i0[2] + 1, n);
+    const double dr = d[0], dg = d[1], db = d[2];
+    // vertex 1 and 2 of the chosen tetrahedron as (r,g,b) corner selectors, and ordered fractions
+    int m1r, m1g, m1b, m2r, m2g, m2b;
+    double d1, d2, d3;
+    if (dr >= dg) {
+        if (dg >= db) { m1r = r1; m1g = g0; m1b = b0; m2r = r1; m2g = g1; m2b = b0; d1 = dr; d2 = dg; d3 = db; }
+        else if (dr >= db) { m1r = r1; m1g = g0; m1b = b0; m2r = r1; m2g = g0; m2b = b1; d1 = dr; d2 = db; d3 = dg; }
+        else { m1r = r0; m1g = g0; m1b = b1; m2r = r1; m2g = g0; m2b = b1; d1 = db; d2 = dr; d3 = dg; }
+    } else {
+        if (db >= dg) { m1r = r0; m1g = g0; m1b = b1; m2r = r0; m2g = g1; m2b = b1; d1 = db; d2 = dg; d3 = dr; }
+        else if (db >= dr) { m1r = r0; m1g = g1; m1b = b0; m2r = r0; m2g = g1; m2b = b1; d1 = dg; d2 = db; d3 = dr; }
+        else { m1r = r0; m1g = g1; m1b = b0; m2r = r1; m2g = g1; m2b = b0; d1 = dg; d2 = dr; d3 = db; }
+    }
+    const float4 c000 = __ldg(L.tab + (r0 * n + g0) * n + b0);
+    const float4 cm1 = __ldg(L.tab + (m1r * n + m1g) * n + m1b);
+    const float4 cm2 = __ldg(L.tab + (m2r * n + m2g) * n + m2b);
+    const float4 c111 = __ldg(L.tab + (r1 * n + g1) * n + b1);
+#define R2F_TETRA_CH(f)                                                                                       \
+    (float)((((double)c000.f + d1 * (double)(cm1.f - c000.f)) + d2 * (double)(cm2.f - cm1.f)) +               \
+            d3 * (double)(c111.f - cm2.f))
+    o0 = R2F_TETRA_CH(x);
+    o1 = R2F_TETRA_CH(y);
+    o2 = R2F_TETRA_CH(z);
+#undef R2F_TETRA_CH
+}
+
+// ---- a10: quantise (reference cpu_processor.py:407): float32 * 255, truncate ----------------
+__device__ __forceinline__ uint32_t quantise_u8(float v) {
+    const float q = v * 255.0f;
+    if (!(q > 0.0f)) return 0u;
+    if (q >= 255.0f) return 255u;
+    return (uint32_t)(int)q;
+}
+
+// ---- BORDER_REFLECT_101 index (cv2.filter2D default, reference effects.py:146-156) -----------
+__device__ __forceinline__ int reflect101(int p, int len) {
+    if (len == 1) return 0;
+    while ((unsigned)p >= (unsigned)len) p = p < 0 ? -p : 2 * len - 2 - p;
+    return p;
+}
+
+}  // namespace r2f

@@ -1,0 +1,627 @@
+// C ABI of libr2f_b200.so (see include/r2f_b200.h for the contract and reference citations).
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/r2f_b200.h"
+#include "r2f_kernels.h"
+
+using namespace r2f;
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const std::string &msg) {
+    g_err = msg;
+    return code;
+}
+
+int fail_cuda(cudaError_t e, const char *what) {
+    g_err = std::string(what) + ": " + cudaGetErrorString(e);
+    return R2F_ERR_CUDA;
+}
+
+#define CU(x)                                           \
+    do {                                                \
+        cudaError_t _e = (x);                           \
+        if (_e != cudaSuccess) return fail_cuda(_e, #x); \
+    } while (0)
+
+struct DevBuf {
+    void *p = nullptr;
+    size_t bytes = 0;
+    cudaError_t ensure(size_t need) {
+        if (need <= bytes) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr;
+        bytes = 0;
+        cudaError_t e = cudaMalloc(&p, need);
+        if (e == cudaSuccess) bytes = need;
+        return e;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        bytes = 0;
+    }
+};
+
+// one spatial kernel (k x k x 3), stored per channel transposed + padded on the device
+struct KernelSet {
+    DevBuf buf;
+    int k = 0, kp = 0;
+    int mode[3] = {0, 0, 0};
+    const float *chan[3] = {nullptr, nullptr, nullptr};
+    bool set = false;
+};
+
+}  // namespace
+
+struct r2f_ctx {
+    int device = 0;
+    int num_sms = 148;
+    uint64_t launches = 0;
+
+    DevBuf lut2d;
+    int n2 = 0;
+    DevBuf curve;
+    int n1 = 0;
+    float x0 = 0.f, inv_range = 0.f, eps = 1e-6f;
+    DevBuf lut3d;
+    int n3 = 0;
+    double s3 = 0.0;
+
+    KernelSet hal, mtf, grain;
+    DevBuf gcurve;
+    int ng = 0;
+    float gx0 = 0.f, ginv = 0.f;
+    uint64_t seed = 0;
+
+    bool burn_set = false;
+    float d_ref = 0.f, burn_strength = 0.f, burn_scale = 50.f;
+    DevBuf burn_buf;
+
+    // r2f_render_host staging
+    DevBuf h_in, h_out, h_ws, h_noise;
+    cudaStream_t host_stream = nullptr;
+
+    // per-kernel profiling (r2f_profile_*)
+    bool profiling = false;
+    struct ProfRec {
+        int id;
+        cudaEvent_t a, b;
+    };
+    std::vector<ProfRec> prof;
+};
+
+namespace {
+
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int dev) {
+        cudaGetDevice(&prev);
+        if (prev != dev) cudaSetDevice(dev);
+        else prev = -1;
+    }
+    ~DeviceGuard() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
+int upload(DevBuf &b, const void *host, size_t bytes) {
+    CU(b.ensure(bytes));
+    CU(cudaMemcpy(b.p, host, bytes, cudaMemcpyHostToDevice));
+    return R2F_OK;
+}
+
+float inv_range_of(float first, float last) {
+    const double d = (double)last - (double)first;
+    return d != 0.0 ? (float)(1.0 / d) : 0.0f;
+}
+
+// channels == 3: (k,k,3) interleaved; channels == 1: (k,k)
+int upload_kernel(KernelSet &ks, const float *kernel, int k, int channels) {
+    if (kernel == nullptr || k < 1 || (k & 1) == 0) return fail(R2F_ERR_INVALID, "kernel must be non-null with odd size");
+    const int kp = (k + 3) / 4 * 4;
+    const size_t per = (size_t)k * kp;
+    std::vector<float> host(per * channels, 0.0f);
+    int mode[3] = {1, 1, 1};
+    for (int c = 0; c < channels; ++c) {
+        bool delta = true;
+        for (int i = 0; i < k; ++i)
+            for (int j = 0; j < k; ++j) {
+                const float v = kernel[((size_t)i * k + j) * channels + c];
+                host[per * c + (size_t)j * kp + i] = v;
+                const bool centre = (i == k / 2 && j == k / 2);
+                if (centre ? (v != 1.0f) : (v != 0.0f)) delta = false;
+            }
+        mode[c] = delta ? 0 : 1;
+    }
+    int rc = upload(ks.buf, host.data(), host.size() * sizeof(float));
+    if (rc != R2F_OK) return rc;
+    ks.k = k;
+    ks.kp = kp;
+    for (int c = 0; c < 3; ++c) {
+        const int src = channels == 3 ? c : 0;
+        ks.mode[c] = mode[src];
+        ks.chan[c] = static_cast<const float *>(ks.buf.p) + per * src;
+    }
+    ks.set = true;
+    return R2F_OK;
+}
+
+Lut2D lut2d_of(const r2f_ctx *c) { return Lut2D{static_cast<const float *>(c->lut2d.p), c->n2}; }
+Curve1D curve_of(const r2f_ctx *c) {
+    return Curve1D{static_cast<const float *>(c->curve.p), c->n1, c->x0, c->inv_range};
+}
+Curve1D gcurve_of(const r2f_ctx *c) {
+    return Curve1D{static_cast<const float *>(c->gcurve.p), c->ng, c->gx0, c->ginv};
+}
+Lut3D lut3d_of(const r2f_ctx *c) { return Lut3D{static_cast<const float4 *>(c->lut3d.p), c->n3, c->s3}; }
+
+ConvArgs conv_args(const KernelSet &ks, const float *in, float *out, size_t ps, int H, int W) {
+    ConvArgs a{};
+    a.in = in;
+    a.out = out;
+    a.aux = nullptr;
+    a.plane_stride = ps;
+    a.H = H;
+    a.W = W;
+    a.k = ks.k;
+    a.kp = ks.kp;
+    for (int c = 0; c < 3; ++c) {
+        a.kern[c] = ks.chan[c];
+        a.mode[c] = ks.mode[c];
+        a.in_plane[c] = c;
+    }
+    a.epi = EPI_NONE;
+    a.eps = 0.f;
+    return a;
+}
+
+ConvArgs identity_args(const float *in, float *out, size_t ps, int H, int W) {
+    ConvArgs a{};
+    a.in = in;
+    a.out = out;
+    a.plane_stride = ps;
+    a.H = H;
+    a.W = W;
+    a.k = 1;
+    a.kp = 4;
+    for (int c = 0; c < 3; ++c) {
+        a.kern[c] = nullptr;
+        a.mode[c] = 0;
+        a.in_plane[c] = c;
+    }
+    return a;
+}
+
+// Brackets the launches issued while it is alive with a pair of events on `st`.
+struct ProfScope {
+    r2f_ctx *c;
+    cudaStream_t st;
+    int id;
+    cudaEvent_t a = nullptr, b = nullptr;
+    ProfScope(r2f_ctx *ctx, cudaStream_t s, int kid) : c(ctx), st(s), id(kid) {
+        if (!c->profiling) return;
+        if (cudaEventCreate(&a) != cudaSuccess || cudaEventCreate(&b) != cudaSuccess) {
+            a = b = nullptr;
+            return;
+        }
+        cudaEventRecord(a, st);
+    }
+    ~ProfScope() {
+        if (!a) return;
+        cudaEventRecord(b, st);
+        c->prof.push_back({id, a, b});
+    }
+};
+
+struct BurnDims {
+    int lh, lw, zh, zw;
+};
+
+BurnDims burn_dims(int H, int W, float burn_scale) {
+    const int step = (int)std::ceil((double)std::min(H, W) / (double)burn_scale);  // effects.py:365
+    BurnDims d;
+    d.lw = W / step;                                                                // effects.py:372
+    d.lh = H / step;
+    d.zh = (int)std::lrint((double)d.lh * step);                                    // scipy zoom output shape
+    d.zw = (int)std::lrint((double)d.lw * step);
+    return d;
+}
+
+int check_tables(const r2f_ctx *c, unsigned flags) {
+    if (!c->lut2d.p) return fail(R2F_ERR_INVALID, "2D input LUT not set (r2f_set_lut2d)");
+    if (!c->curve.p) return fail(R2F_ERR_INVALID, "density curve not set (r2f_set_curve1d)");
+    if (!c->lut3d.p) return fail(R2F_ERR_INVALID, "3D output LUT not set (r2f_set_lut3d)");
+    if ((flags & R2F_HALATION) && !c->hal.set) return fail(R2F_ERR_INVALID, "halation kernel not set");
+    if ((flags & R2F_MTF) && !c->mtf.set) return fail(R2F_ERR_INVALID, "MTF kernel not set");
+    if ((flags & R2F_GRAIN) && (!c->grain.set || !c->gcurve.p)) return fail(R2F_ERR_INVALID, "grain tables not set");
+    if ((flags & R2F_BURN) && !c->burn_set) return fail(R2F_ERR_INVALID, "burn parameters not set");
+    return R2F_OK;
+}
+
+// The whole pipeline.  tap_stage == 0: normal render to out_u8.
+int render_impl(r2f_ctx *c, const float *in, int H, int W, int cin, uint8_t *out_u8, unsigned flags,
+                const float *noise, int noise_ch, void *ws, size_t ws_bytes, int tap_stage, float *tap,
+                cudaStream_t st) {
+    if (!c) return fail(R2F_ERR_INVALID, "null context");
+    if (!in || H < 1 || W < 1 || (cin != 3 && cin != 4)) return fail(R2F_ERR_INVALID, "bad input image arguments");
+    if (tap_stage == 0 && !out_u8) return fail(R2F_ERR_INVALID, "null output");
+    if (tap_stage != 0 && (!tap || tap_stage < R2F_TAP_EXPOSURE || tap_stage > R2F_TAP_RGB))
+        return fail(R2F_ERR_INVALID, "bad tap arguments");
+    if ((reinterpret_cast<uintptr_t>(in) & 15) != 0) return fail(R2F_ERR_INVALID, "input must be 16-byte aligned");
+    if (out_u8 && (reinterpret_cast<uintptr_t>(out_u8) & 3) != 0)
+        return fail(R2F_ERR_INVALID, "output must be 4-byte aligned");
+    int rc = check_tables(c, flags);
+    if (rc != R2F_OK) return rc;
+    DeviceGuard guard(c->device);
+
+    const size_t npix = (size_t)H * W;
+    const unsigned spatial = flags & (R2F_HALATION | R2F_MTF | R2F_GRAIN | R2F_BURN);
+    const Lut2D l2 = lut2d_of(c);
+    const Curve1D cv = curve_of(c);
+    const Lut3D l3 = lut3d_of(c);
+
+    if (tap_stage == 0 && spatial == 0) {  // configs C1 / C5: one fused pass
+        ProfScope ps_(c, st, R2F_PROF_POINTWISE);
+        CU(launch_pointwise(in, cin, out_u8, npix, l2, cv, c->eps, l3, c->num_sms, st));
+        c->launches += 1;
+        return R2F_OK;
+    }
+
+    const size_t need = r2f_workspace_bytes(H, W, flags);
+    if (!ws || ws_bytes < need) return fail(R2F_ERR_NOMEM, "workspace too small (see r2f_workspace_bytes)");
+    if ((reinterpret_cast<uintptr_t>(ws) & 255) != 0) return fail(R2F_ERR_INVALID, "workspace must be 256-byte aligned");
+    const size_t ps = plane_stride_for(H, W);
+    Planes P[3];
+    for (int i = 0; i < 3; ++i) P[i] = Planes{static_cast<float *>(ws) + (size_t)i * 3 * ps, ps};
+    auto export_tap = [&](Planes p) -> int {
+        CU(launch_planar_to_interleaved(p, tap, npix, c->num_sms, st));
+        c->launches += 1;
+        return R2F_OK;
+    };
+
+    // a2: exposure
+    {
+        ProfScope ps_(c, st, R2F_PROF_EXPOSE);
+        CU(launch_expose(in, cin, P[0], npix, l2, c->num_sms, st));
+    }
+    c->launches += 1;
+    if (tap_stage == R2F_TAP_EXPOSURE) return export_tap(P[0]);
+
+    // a3 (+ a4 + a5 fused in the epilogue)
+    if (flags & R2F_HALATION) {
+        ConvArgs a = conv_args(c->hal, P[0].base, P[1].base, ps, H, W);
+        if (tap_stage == R2F_TAP_HALATION) {
+            CU(launch_conv2d(a, st));
+            c->launches += 1;
+            return export_tap(P[1]);
+        }
+        a.epi = EPI_DENSITY;
+        a.curve = cv;
+        a.eps = c->eps;
+        ProfScope ps_(c, st, R2F_PROF_HALATION);
+        CU(launch_conv2d(a, st));
+    } else {
+        if (tap_stage == R2F_TAP_HALATION) return fail(R2F_ERR_INVALID, "halation tap requested but stage is off");
+        ConvArgs a = identity_args(P[0].base, P[1].base, ps, H, W);
+        a.epi = EPI_DENSITY;
+        a.curve = cv;
+        a.eps = c->eps;
+        ProfScope ps_(c, st, R2F_PROF_DENSITY);
+        CU(launch_conv2d(a, st));
+    }
+    c->launches += 1;
+    int cur = 1;
+    if (tap_stage == R2F_TAP_DENSITY) return export_tap(P[cur]);
+
+    // a6: MTF
+    if (flags & R2F_MTF) {
+        ConvArgs a = conv_args(c->mtf, P[cur].base, P[1 - cur].base, ps, H, W);
+        ProfScope ps_(c, st, R2F_PROF_MTF);
+        CU(launch_conv2d(a, st));
+        c->launches += 1;
+        cur = 1 - cur;
+    }
+    if (tap_stage == R2F_TAP_MTF) return export_tap(P[cur]);
+
+    // a7: grain (noise -> grain-kernel correlation -> amplitude from density -> add -> clip >= 0)
+    if (flags & R2F_GRAIN) {
+        const int nch = (flags & R2F_GRAIN_BW) ? 1 : 3;
+        if (noise) {
+            if (noise_ch != nch) return fail(R2F_ERR_INVALID, "injected noise has the wrong channel count");
+            ProfScope ps_(c, st, R2F_PROF_NOISE);
+            CU(launch_interleaved_to_planar(noise, nch, nch, P[2], npix, c->num_sms, st));
+        } else {
+            ProfScope ps_(c, st, R2F_PROF_NOISE);
+            CU(launch_noise(P[2], nch, npix, c->seed, c->num_sms, st));
+        }
+        ConvArgs a = conv_args(c->grain, P[2].base, P[1 - cur].base, ps, H, W);
+        for (int ch = 0; ch < 3; ++ch) a.in_plane[ch] = nch == 1 ? 0 : ch;
+        a.aux = P[cur].base;
+        a.epi = EPI_GRAIN;
+        a.curve = gcurve_of(c);
+        ProfScope ps_(c, st, R2F_PROF_GRAIN);
+        CU(launch_conv2d(a, st));
+        c->launches += 2;
+        cur = 1 - cur;
+    }
+    if (tap_stage == R2F_TAP_GRAIN) return export_tap(P[cur]);
+
+    // a8: burn mask
+    BurnArgs burn{};
+    if (flags & R2F_BURN) {
+        const BurnDims bd = burn_dims(H, W, c->burn_scale);
+        if (bd.lh < 1 || bd.lw < 1) return fail(R2F_ERR_INVALID, "burn_scale too small for this frame");
+        const size_t n = (size_t)bd.lh * bd.lw;
+        CU(c->burn_buf.ensure(2 * n * sizeof(float)));
+        float *map = static_cast<float *>(c->burn_buf.p), *tmp = map + n;
+        ProfScope ps_(c, st, R2F_PROF_BURN);
+        CU(launch_burn_mask(P[cur].base + ps, H, W, bd.lh, bd.lw, c->d_ref, tmp, map, st));
+        c->launches += 3;
+        burn.map = map;
+        burn.lh = bd.lh;
+        burn.lw = bd.lw;
+        burn.zh = bd.zh;
+        burn.zw = bd.zw;
+        burn.strength = c->burn_strength;
+    }
+    if (tap_stage == R2F_TAP_BURN) {
+        CU(launch_finish(P[cur], npix, H, W, l3, burn, nullptr, tap, 0, c->num_sms, st));
+        c->launches += 1;
+        return R2F_OK;
+    }
+
+    // a9 + a10
+    ProfScope ps_(c, st, R2F_PROF_FINISH);
+    if (tap_stage == R2F_TAP_RGB)
+        CU(launch_finish(P[cur], npix, H, W, l3, burn, nullptr, tap, 1, c->num_sms, st));
+    else
+        CU(launch_finish(P[cur], npix, H, W, l3, burn, out_u8, nullptr, 1, c->num_sms, st));
+    c->launches += 1;
+    return R2F_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int r2f_abi_version(void) { return R2F_ABI_VERSION; }
+
+const char *r2f_last_error(void) { return g_err.c_str(); }
+
+int r2f_create(int device, r2f_ctx **out) {
+    if (!out) return fail(R2F_ERR_INVALID, "null out pointer");
+    int count = 0;
+    CU(cudaGetDeviceCount(&count));
+    if (device < 0 || device >= count) return fail(R2F_ERR_INVALID, "no such CUDA device");
+    DeviceGuard guard(device);
+    cudaDeviceProp prop{};
+    CU(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) return fail(R2F_ERR_INVALID, "libr2f_b200 is built for sm_100a (B200) only");
+    r2f_ctx *c = new (std::nothrow) r2f_ctx();
+    if (!c) return fail(R2F_ERR_NOMEM, "out of host memory");
+    c->device = device;
+    c->num_sms = prop.multiProcessorCount;
+    *out = c;
+    return R2F_OK;
+}
+
+int r2f_destroy(r2f_ctx *c) {
+    if (!c) return R2F_OK;
+    DeviceGuard guard(c->device);
+    for (DevBuf *b : {&c->lut2d, &c->curve, &c->lut3d, &c->hal.buf, &c->mtf.buf, &c->grain.buf, &c->gcurve,
+                      &c->burn_buf, &c->h_in, &c->h_out, &c->h_ws, &c->h_noise})
+        b->release();
+    if (c->host_stream) cudaStreamDestroy(c->host_stream);
+    delete c;
+    return R2F_OK;
+}
+
+int r2f_set_lut2d(r2f_ctx *c, const float *lut, int n) {
+    if (!c || !lut || n < 2) return fail(R2F_ERR_INVALID, "r2f_set_lut2d: bad arguments");
+    DeviceGuard guard(c->device);
+    int rc = upload(c->lut2d, lut, (size_t)n * n * 3 * sizeof(float));
+    if (rc == R2F_OK) c->n2 = n;
+    return rc;
+}
+
+int r2f_set_curve1d(r2f_ctx *c, const float *curve, int N, float log_eps) {
+    if (!c || !curve || N < 2) return fail(R2F_ERR_INVALID, "r2f_set_curve1d: bad arguments");
+    DeviceGuard guard(c->device);
+    int rc = upload(c->curve, curve + N, (size_t)3 * N * sizeof(float));
+    if (rc != R2F_OK) return rc;
+    c->n1 = N;
+    c->x0 = curve[0];
+    c->inv_range = inv_range_of(curve[0], curve[N - 1]);
+    c->eps = log_eps;
+    return R2F_OK;
+}
+
+int r2f_set_lut3d(r2f_ctx *c, const float *lut, int n, double scale) {
+    if (!c || !lut || n < 2) return fail(R2F_ERR_INVALID, "r2f_set_lut3d: bad arguments");
+    DeviceGuard guard(c->device);
+    const size_t verts = (size_t)n * n * n;
+    std::vector<float> padded(verts * 4);
+    for (size_t v = 0; v < verts; ++v) {
+        padded[4 * v + 0] = lut[3 * v + 0];
+        padded[4 * v + 1] = lut[3 * v + 1];
+        padded[4 * v + 2] = lut[3 * v + 2];
+        padded[4 * v + 3] = 0.0f;
+    }
+    int rc = upload(c->lut3d, padded.data(), padded.size() * sizeof(float));
+    if (rc != R2F_OK) return rc;
+    c->n3 = n;
+    c->s3 = scale * (double)(n - 1);  // utils.py:258
+    return R2F_OK;
+}
+
+int r2f_set_halation_kernel(r2f_ctx *c, const float *kernel, int k) {
+    if (!c) return fail(R2F_ERR_INVALID, "null context");
+    DeviceGuard guard(c->device);
+    return upload_kernel(c->hal, kernel, k, 3);
+}
+
+int r2f_set_mtf_kernel(r2f_ctx *c, const float *kernel, int k) {
+    if (!c) return fail(R2F_ERR_INVALID, "null context");
+    DeviceGuard guard(c->device);
+    return upload_kernel(c->mtf, kernel, k, 3);
+}
+
+int r2f_set_grain(r2f_ctx *c, const float *curve, int N, const float *kernel, int k, uint64_t seed) {
+    if (!c || !curve || N < 2) return fail(R2F_ERR_INVALID, "r2f_set_grain: bad arguments");
+    DeviceGuard guard(c->device);
+    int rc = upload(c->gcurve, curve + N, (size_t)3 * N * sizeof(float));
+    if (rc != R2F_OK) return rc;
+    c->ng = N;
+    c->gx0 = curve[0];
+    c->ginv = inv_range_of(curve[0], curve[N - 1]);
+    const float one = 1.0f;  // gpu_processor.py:931-932: missing kernel -> 1x1 ones
+    rc = kernel ? upload_kernel(c->grain, kernel, k, 1) : upload_kernel(c->grain, &one, 1, 1);
+    if (rc != R2F_OK) return rc;
+    c->seed = seed;
+    return R2F_OK;
+}
+
+int r2f_set_grain_seed(r2f_ctx *c, uint64_t seed) {
+    if (!c) return fail(R2F_ERR_INVALID, "null context");
+    c->seed = seed;
+    return R2F_OK;
+}
+
+int r2f_set_burn(r2f_ctx *c, float d_ref, float highlight_burn, float burn_scale) {
+    if (!c || !(burn_scale > 0.f)) return fail(R2F_ERR_INVALID, "r2f_set_burn: bad arguments");
+    c->d_ref = d_ref;
+    c->burn_strength = highlight_burn;
+    c->burn_scale = burn_scale;
+    c->burn_set = true;
+    return R2F_OK;
+}
+
+size_t r2f_workspace_bytes(int H, int W, unsigned flags) {
+    (void)flags;  // three planar float32 working images cover every stage combination (and the taps)
+    if (H < 1 || W < 1) return 0;
+    return plane_stride_for(H, W) * 3 * 3 * sizeof(float);
+}
+
+int r2f_render(r2f_ctx *c, const float *in_dev, int H, int W, int in_channels, uint8_t *out_dev, unsigned flags,
+               const float *noise_dev, int noise_channels, void *workspace_dev, size_t workspace_bytes, void *stream) {
+    return render_impl(c, in_dev, H, W, in_channels, out_dev, flags, noise_dev, noise_channels, workspace_dev,
+                       workspace_bytes, 0, nullptr, static_cast<cudaStream_t>(stream));
+}
+
+int r2f_render_tap(r2f_ctx *c, const float *in_dev, int H, int W, int in_channels, unsigned flags,
+                   const float *noise_dev, int noise_channels, void *workspace_dev, size_t workspace_bytes,
+                   int tap_stage, float *tap_dev, void *stream) {
+    if (tap_stage == 0) return fail(R2F_ERR_INVALID, "tap_stage must be one of R2F_TAP_*");
+    return render_impl(c, in_dev, H, W, in_channels, nullptr, flags, noise_dev, noise_channels, workspace_dev,
+                       workspace_bytes, tap_stage, tap_dev, static_cast<cudaStream_t>(stream));
+}
+
+int r2f_render_host(r2f_ctx *c, const float *in_host, int H, int W, int in_channels, uint8_t *out_host, unsigned flags,
+                    const float *noise_host, int noise_channels) {
+    if (!c || !in_host || !out_host || H < 1 || W < 1) return fail(R2F_ERR_INVALID, "r2f_render_host: bad arguments");
+    if (in_channels != 3 && in_channels != 4) return fail(R2F_ERR_INVALID, "in_channels must be 3 or 4");
+    DeviceGuard guard(c->device);
+    if (!c->host_stream) CU(cudaStreamCreateWithFlags(&c->host_stream, cudaStreamNonBlocking));
+    const size_t npix = (size_t)H * W;
+    const size_t in_bytes = npix * in_channels * sizeof(float), out_bytes = npix * 3;
+    CU(c->h_in.ensure(in_bytes));
+    CU(c->h_out.ensure(out_bytes));
+    const size_t ws_bytes = r2f_workspace_bytes(H, W, flags);
+    if (flags & (R2F_HALATION | R2F_MTF | R2F_GRAIN | R2F_BURN)) CU(c->h_ws.ensure(ws_bytes));
+    CU(cudaMemcpyAsync(c->h_in.p, in_host, in_bytes, cudaMemcpyHostToDevice, c->host_stream));
+    const float *noise_dev = nullptr;
+    if (noise_host && (flags & R2F_GRAIN)) {
+        const size_t nb = npix * noise_channels * sizeof(float);
+        CU(c->h_noise.ensure(nb));
+        CU(cudaMemcpyAsync(c->h_noise.p, noise_host, nb, cudaMemcpyHostToDevice, c->host_stream));
+        noise_dev = static_cast<const float *>(c->h_noise.p);
+    }
+    int rc = render_impl(c, static_cast<const float *>(c->h_in.p), H, W, in_channels,
+                         static_cast<uint8_t *>(c->h_out.p), flags, noise_dev, noise_channels, c->h_ws.p,
+                         c->h_ws.bytes, 0, nullptr, c->host_stream);
+    if (rc != R2F_OK) return rc;
+    CU(cudaMemcpyAsync(out_host, c->h_out.p, out_bytes, cudaMemcpyDeviceToHost, c->host_stream));
+    CU(cudaStreamSynchronize(c->host_stream));
+    return R2F_OK;
+}
+
+int r2f_convolve2d(r2f_ctx *c, const float *in_dev, float *out_dev, int H, int W, const float *kernel, int k,
+                   void *workspace_dev, size_t workspace_bytes, void *stream) {
+    if (!c || !in_dev || !out_dev || H < 1 || W < 1) return fail(R2F_ERR_INVALID, "r2f_convolve2d: bad arguments");
+    DeviceGuard guard(c->device);
+    const size_t ps = plane_stride_for(H, W);
+    if (!workspace_dev || workspace_bytes < ps * 6 * sizeof(float))
+        return fail(R2F_ERR_NOMEM, "workspace too small (see r2f_workspace_bytes)");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    KernelSet ks;
+    CU(cudaStreamSynchronize(st));
+    int rc = upload_kernel(ks, kernel, k, 3);
+    if (rc != R2F_OK) return rc;
+    Planes a{static_cast<float *>(workspace_dev), ps}, b{static_cast<float *>(workspace_dev) + 3 * ps, ps};
+    const size_t npix = (size_t)H * W;
+    cudaError_t e = launch_interleaved_to_planar(in_dev, 3, 3, a, npix, c->num_sms, st);
+    if (e == cudaSuccess) e = launch_conv2d(conv_args(ks, a.base, b.base, ps, H, W), st);
+    if (e == cudaSuccess) e = launch_planar_to_interleaved(b, out_dev, npix, c->num_sms, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    ks.buf.release();
+    if (e != cudaSuccess) return fail_cuda(e, "r2f_convolve2d");
+    c->launches += 3;
+    return R2F_OK;
+}
+
+int r2f_generate_noise(r2f_ctx *c, float *out_dev, int H, int W, int channels, uint64_t seed, void *stream) {
+    if (!c || !out_dev || H < 1 || W < 1 || (channels != 1 && channels != 3))
+        return fail(R2F_ERR_INVALID, "r2f_generate_noise: bad arguments");
+    DeviceGuard guard(c->device);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const size_t ps = plane_stride_for(H, W), npix = (size_t)H * W;
+    CU(c->h_noise.ensure(ps * 3 * sizeof(float)));
+    Planes p{static_cast<float *>(c->h_noise.p), ps};
+    CU(launch_noise(p, channels, npix, seed, c->num_sms, st));
+    if (channels == 3) {
+        CU(launch_planar_to_interleaved(p, out_dev, npix, c->num_sms, st));
+    } else {
+        CU(cudaMemcpyAsync(out_dev, p.base, npix * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    }
+    c->launches += 2;
+    return R2F_OK;
+}
+
+uint64_t r2f_launch_count(const r2f_ctx *c) { return c ? c->launches : 0; }
+
+int r2f_profile_enable(r2f_ctx *c, int on) {
+    if (!c) return fail(R2F_ERR_INVALID, "null context");
+    c->profiling = on != 0;
+    return R2F_OK;
+}
+
+int r2f_profile_read(r2f_ctx *c, double *ms_accum, uint64_t *count_accum) {
+    if (!c || !ms_accum || !count_accum) return fail(R2F_ERR_INVALID, "r2f_profile_read: bad arguments");
+    DeviceGuard guard(c->device);
+    int rc = R2F_OK;
+    for (auto &r : c->prof) {
+        float ms = 0.f;
+        cudaError_t e = cudaEventSynchronize(r.b);
+        if (e == cudaSuccess) e = cudaEventElapsedTime(&ms, r.a, r.b);
+        if (e == cudaSuccess && r.id >= 0 && r.id < R2F_PROF_COUNT) {
+            ms_accum[r.id] += (double)ms;
+            count_accum[r.id] += 1;
+        } else if (e != cudaSuccess) {
+            rc = fail_cuda(e, "r2f_profile_read");
+        }
+        cudaEventDestroy(r.a);
+        cudaEventDestroy(r.b);
+    }
+    c->prof.clear();
+    return rc;
+}
+
+}  // extern "C"

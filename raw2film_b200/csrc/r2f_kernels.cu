@@ -1,0 +1,569 @@
+// sm_100a kernels of the raw2film render path.  Compile with -fmad=false (see device_math.cuh).
+//
+// Stage map (reference src/raw2film/cpu_processor.py:363-407):
+//   k_pointwise   a2+a4+a5+a9+a10 fused (configs without spatial stages)
+//   k_expose      a2            XYZ -> planar film exposure
+//   k_conv2d      a3 / a6 / a7  direct 2-D correlation (cv2.filter2D semantics) with fused
+//                               epilogues: log10+H-D curve (a4+a5) or grain apply + clip (a7)
+//   k_noise       a7            white N(0,1) field (Philox4x32-10 + Box-Muller)
+//   k_burn_*      a8            low-res highlight mask
+//   k_finish      a8+a9+a10     burn apply, tetrahedral LUT, quantise
+#include "r2f_kernels.h"
+
+namespace r2f {
+
+constexpr int kThreads = 256;
+
+__device__ __forceinline__ float4 ld_stream(const float4 *p) { return __ldcs(p); }
+
+// ------------------------------------------------------------------------------------------
+// quad (4-pixel) loads of interleaved input
+// ------------------------------------------------------------------------------------------
+template <int CIN>
+__device__ __forceinline__ void load_quad(const float *__restrict__ in, size_t q, float (&px)[4][3]) {
+    if (CIN == 3) {
+        const float4 *p = reinterpret_cast<const float4 *>(in) + 3 * q;
+        const float4 a = ld_stream(p), b = ld_stream(p + 1), c = ld_stream(p + 2);
+        px[0][0] = a.x; px[0][1] = a.y; px[0][2] = a.z;
+        px[1][0] = a.w; px[1][1] = b.x; px[1][2] = b.y;
+        px[2][0] = b.z; px[2][1] = b.w; px[2][2] = c.x;
+        px[3][0] = c.y; px[3][1] = c.z; px[3][2] = c.w;
+    } else {
+        const float4 *p = reinterpret_cast<const float4 *>(in) + 4 * q;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const float4 a = ld_stream(p + i);
+            px[i][0] = a.x; px[i][1] = a.y; px[i][2] = a.z;
+        }
+    }
+}
+
+__device__ __forceinline__ void store_quad_u8(uint8_t *__restrict__ out, size_t q, const uint32_t (&b)[12]) {
+    uint32_t *o = reinterpret_cast<uint32_t *>(out) + 3 * q;
+    __stcs(o + 0, b[0] | (b[1] << 8) | (b[2] << 16) | (b[3] << 24));
+    __stcs(o + 1, b[4] | (b[5] << 8) | (b[6] << 16) | (b[7] << 24));
+    __stcs(o + 2, b[8] | (b[9] << 8) | (b[10] << 16) | (b[11] << 24));
+}
+
+// stage the small tables (2-D LUT, curve rows) in shared memory
+__device__ __forceinline__ void stage_tables(float *smem, Lut2D &l2, Curve1D &cv, bool want2d, bool want1d) {
+    float *p = smem;
+    if (want2d) {
+        const int n = l2.n * l2.n * 3;
+        for (int i = threadIdx.x; i < n; i += blockDim.x) p[i] = l2.tab[i];
+        l2.tab = p;
+        p += (n + 3) / 4 * 4;
+    }
+    if (want1d) {
+        const int n = cv.N * 3;
+        for (int i = threadIdx.x; i < n; i += blockDim.x) p[i] = cv.rows[i];
+        cv.rows = p;
+    }
+    __syncthreads();
+}
+
+__device__ __forceinline__ void pixel_chain(const float (&xyz)[3], const Lut2D &l2, const Curve1D &cv, float eps,
+                                            const Lut3D &l3, uint32_t &r, uint32_t &g, uint32_t &b) {
+    float e0, e1, e2;
+    lut2d_eval(l2, xyz[0], xyz[1], xyz[2], e0, e1, e2);
+    const float d0 = density_eval(cv, 0, e0, eps);
+    const float d1 = density_eval(cv, 1, e1, eps);
+    const float d2 = density_eval(cv, 2, e2, eps);
+    float o0, o1, o2;
+    tetra_eval(l3, d0, d1, d2, o0, o1, o2);
+    r = quantise_u8(o0);
+    g = quantise_u8(o1);
+    b = quantise_u8(o2);
+}
+
+// ------------------------------------------------------------------------------------------
+// K1: fused pointwise chain
+// ------------------------------------------------------------------------------------------
+template <int CIN, bool SMEM_TABLES>
+__global__ void __launch_bounds__(kThreads)
+k_pointwise(const float *__restrict__ in, uint8_t *__restrict__ out, size_t npix, Lut2D l2, Curve1D cv, float eps,
+            Lut3D l3) {
+    extern __shared__ __align__(16) float smem[];
+    if (SMEM_TABLES) stage_tables(smem, l2, cv, true, true);
+    const size_t nquad = npix / 4;
+    const size_t stride = (size_t)gridDim.x * kThreads;
+    for (size_t q = (size_t)blockIdx.x * kThreads + threadIdx.x; q < nquad; q += stride) {
+        float px[4][3];
+        load_quad<CIN>(in, q, px);
+        uint32_t b[12];
+#pragma unroll
+        for (int p = 0; p < 4; ++p) pixel_chain(px[p], l2, cv, eps, l3, b[3 * p], b[3 * p + 1], b[3 * p + 2]);
+        store_quad_u8(out, q, b);
+    }
+    if (blockIdx.x == 0 && threadIdx.x < (npix & 3)) {
+        const size_t p = nquad * 4 + threadIdx.x;
+        const float xyz[3] = {in[p * CIN], in[p * CIN + 1], in[p * CIN + 2]};
+        uint32_t r, g, b;
+        pixel_chain(xyz, l2, cv, eps, l3, r, g, b);
+        out[p * 3] = (uint8_t)r;
+        out[p * 3 + 1] = (uint8_t)g;
+        out[p * 3 + 2] = (uint8_t)b;
+    }
+}
+
+static int grid_for(size_t work_items, int num_sms, int ctas_per_sm) {
+    size_t want = (work_items + kThreads - 1) / kThreads;
+    size_t cap = (size_t)num_sms * ctas_per_sm;
+    if (want < 1) want = 1;
+    return (int)(want < cap ? want : cap);
+}
+
+static size_t table_smem_bytes(const Lut2D &l2, const Curve1D &cv, bool want2d, bool want1d) {
+    size_t f = 0;
+    if (want2d) f += ((size_t)l2.n * l2.n * 3 + 3) / 4 * 4;
+    if (want1d) f += (size_t)cv.N * 3;
+    return f * sizeof(float);
+}
+
+constexpr size_t kMaxTableSmem = 96 * 1024;  // keep >= 2 CTAs/SM resident
+
+cudaError_t launch_pointwise(const float *in, int cin, uint8_t *out, size_t npix, const Lut2D &l2, const Curve1D &cv,
+                             float eps, const Lut3D &l3, int num_sms, cudaStream_t st) {
+    const size_t sm = table_smem_bytes(l2, cv, true, true);
+    const bool use_smem = sm <= kMaxTableSmem;
+    const int grid = grid_for(npix / 4 + 1, num_sms, 8);
+#define R2F_LAUNCH_PW(C, S)                                                                                \
+    do {                                                                                                   \
+        auto kfn = k_pointwise<C, S>;                                                                      \
+        if (S) {                                                                                           \
+            cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm); \
+            if (e != cudaSuccess) return e;                                                                \
+        }                                                                                                  \
+        kfn<<<grid, kThreads, S ? sm : 0, st>>>(in, out, npix, l2, cv, eps, l3);                           \
+    } while (0)
+    if (cin == 3) {
+        if (use_smem) R2F_LAUNCH_PW(3, true); else R2F_LAUNCH_PW(3, false);
+    } else {
+        if (use_smem) R2F_LAUNCH_PW(4, true); else R2F_LAUNCH_PW(4, false);
+    }
+#undef R2F_LAUNCH_PW
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------
+// a2: XYZ -> planar exposure
+// ------------------------------------------------------------------------------------------
+template <int CIN, bool SMEM_TABLES>
+__global__ void __launch_bounds__(kThreads)
+k_expose(const float *__restrict__ in, float *__restrict__ out, size_t plane_stride, size_t npix, Lut2D l2) {
+    extern __shared__ __align__(16) float smem[];
+    Curve1D none{};
+    if (SMEM_TABLES) stage_tables(smem, l2, none, true, false);
+    const size_t nquad = npix / 4;
+    const size_t stride = (size_t)gridDim.x * kThreads;
+    for (size_t q = (size_t)blockIdx.x * kThreads + threadIdx.x; q < nquad; q += stride) {
+        float px[4][3];
+        load_quad<CIN>(in, q, px);
+        float e[3][4];
+#pragma unroll
+        for (int p = 0; p < 4; ++p) lut2d_eval(l2, px[p][0], px[p][1], px[p][2], e[0][p], e[1][p], e[2][p]);
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+            reinterpret_cast<float4 *>(out + c * plane_stride)[q] = make_float4(e[c][0], e[c][1], e[c][2], e[c][3]);
+    }
+    if (blockIdx.x == 0 && threadIdx.x < (npix & 3)) {
+        const size_t p = nquad * 4 + threadIdx.x;
+        float e0, e1, e2;
+        lut2d_eval(l2, in[p * CIN], in[p * CIN + 1], in[p * CIN + 2], e0, e1, e2);
+        out[p] = e0;
+        out[plane_stride + p] = e1;
+        out[2 * plane_stride + p] = e2;
+    }
+}
+
+cudaError_t launch_expose(const float *in, int cin, Planes out, size_t npix, const Lut2D &l2, int num_sms,
+                          cudaStream_t st) {
+    Curve1D none{};
+    const size_t sm = table_smem_bytes(l2, none, true, false);
+    const bool use_smem = sm <= kMaxTableSmem;
+    const int grid = grid_for(npix / 4 + 1, num_sms, 8);
+#define R2F_LAUNCH_EX(C, S)                                                                                \
+    do {                                                                                                   \
+        auto kfn = k_expose<C, S>;                                                                         \
+        if (S) {                                                                                           \
+            cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm); \
+            if (e != cudaSuccess) return e;                                                                \
+        }                                                                                                  \
+        kfn<<<grid, kThreads, S ? sm : 0, st>>>(in, out.base, out.plane_stride, npix, l2);                 \
+    } while (0)
+    if (cin == 3) {
+        if (use_smem) R2F_LAUNCH_EX(3, true); else R2F_LAUNCH_EX(3, false);
+    } else {
+        if (use_smem) R2F_LAUNCH_EX(4, true); else R2F_LAUNCH_EX(4, false);
+    }
+#undef R2F_LAUNCH_EX
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------
+// a3/a6/a7: direct 2-D correlation, BORDER_REFLECT_101, fused epilogue
+//
+// CTA tile TW x TH outputs of one channel.  The input tile (+ (k-1) halo) and the kernel
+// weights (transposed, so the weights a thread walks are contiguous) live in shared memory.
+// Each thread owns a vertical strip of 16 outputs in one column; adjacent lanes own adjacent
+// columns, so every shared-memory read is conflict-free and every weight read is a broadcast.
+// For kernel column j the thread slides a 16-row register window down the tile column:
+// one new LDS per 16 FMAs.
+// ------------------------------------------------------------------------------------------
+template <int TW, int TH, bool W_SMEM>
+__global__ void __launch_bounds__((TW / 32) * (TH / 16) * 32)
+k_conv2d(ConvArgs a) {
+    constexpr int NWX = TW / 32;
+    constexpr int NT = (TW / 32) * (TH / 16) * 32;
+    extern __shared__ __align__(16) float smem[];
+    const int c = blockIdx.z;
+    const int tx0 = blockIdx.x * TW, ty0 = blockIdx.y * TH;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int lx = (warp % NWX) * 32 + lane;
+    const int ly0 = (warp / NWX) * 16;
+    const int gx = tx0 + lx;
+    const int H = a.H, W = a.W;
+    const float *__restrict__ src = a.in + (size_t)a.in_plane[c] * a.plane_stride;
+    float acc[16];
+
+    if (a.mode[c] == 0) {
+#pragma unroll
+        for (int o = 0; o < 16; ++o) {
+            const int gy = ty0 + ly0 + o;
+            acc[o] = (gx < W && gy < H) ? src[(size_t)gy * W + gx] : 0.0f;
+        }
+    } else {
+        const int k = a.k, kp = a.kp, rad = k / 2;
+        const int cols = TW + k - 1, rows = TH + k - 1;
+        float *tile = smem;
+        float *wsm = smem + ((rows * cols + 3) / 4) * 4;
+        for (int idx = threadIdx.x; idx < rows * cols; idx += NT) {
+            const int ty = idx / cols, tx = idx - ty * cols;
+            const int gy = reflect101(ty0 - rad + ty, H);
+            const int gxx = reflect101(tx0 - rad + tx, W);
+            tile[idx] = __ldg(src + (size_t)gy * W + gxx);
+        }
+        const float *__restrict__ wbase = a.kern[c];
+        if (W_SMEM) {
+            for (int idx = threadIdx.x; idx < k * kp; idx += NT) wsm[idx] = __ldg(wbase + idx);
+            wbase = wsm;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int o = 0; o < 16; ++o) acc[o] = 0.0f;
+        for (int j = 0; j < k; ++j) {
+            const float *col = tile + ly0 * cols + lx + j;
+            float v[16];
+#pragma unroll
+            for (int u = 0; u < 16; ++u) v[u] = col[u * cols];
+            const float *wj = wbase + j * kp;
+            for (int i0 = 0; i0 < k; i0 += 16) {
+                float4 w4 = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                for (int u = 0; u < 16; ++u) {
+                    const int i = i0 + u;
+                    if (i < k) {
+                        if ((u & 3) == 0) w4 = *reinterpret_cast<const float4 *>(wj + i);
+                        const float w = (u & 3) == 0 ? w4.x : (u & 3) == 1 ? w4.y : (u & 3) == 2 ? w4.z : w4.w;
+#pragma unroll
+                        for (int o = 0; o < 16; ++o) acc[o] = fmaf(w, v[(o + u) & 15], acc[o]);
+                        if (i + 1 < k) v[u] = col[(16 + i) * cols];
+                    }
+                }
+            }
+        }
+    }
+
+    const size_t ps = a.plane_stride;
+#pragma unroll
+    for (int o = 0; o < 16; ++o) {
+        const int gy = ty0 + ly0 + o;
+        if (gx < W && gy < H) {
+            const size_t idx = (size_t)gy * W + gx;
+            float val = acc[o];
+            if (a.epi == EPI_DENSITY) {
+                val = density_eval(a.curve, c, val, a.eps);
+            } else if (a.epi == EPI_GRAIN) {
+                const float d = a.aux[c * ps + idx];
+                const float g = val * curve_eval(a.curve, c, d);
+                val = d + g;
+                val = val > 0.0f ? val : 0.0f;
+            }
+            a.out[c * ps + idx] = val;
+        }
+    }
+}
+
+template <int TW, int TH, bool W_SMEM>
+static cudaError_t launch_conv_cfg(const ConvArgs &a, size_t smem_bytes, cudaStream_t st) {
+    auto kfn = k_conv2d<TW, TH, W_SMEM>;
+    cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+    if (e != cudaSuccess) return e;
+    dim3 grid((a.W + TW - 1) / TW, (a.H + TH - 1) / TH, 3);
+    kfn<<<grid, (TW / 32) * (TH / 16) * 32, smem_bytes, st>>>(a);
+    return cudaGetLastError();
+}
+
+constexpr size_t kMaxDynSmem = 227 * 1024;
+
+static size_t conv_smem_bytes(int tw, int th, int k, int kp, bool w_smem) {
+    size_t tile = ((size_t)(tw + k - 1) * (th + k - 1) + 3) / 4 * 4;
+    return (tile + (w_smem ? (size_t)k * kp : 0)) * sizeof(float);
+}
+
+cudaError_t launch_conv2d(const ConvArgs &a, cudaStream_t st) {
+    const bool any_conv = a.mode[0] || a.mode[1] || a.mode[2];
+    if (!any_conv) return launch_conv_cfg<64, 64, true>(a, 16, st);
+    size_t s = conv_smem_bytes(64, 64, a.k, a.kp, true);
+    if (s <= kMaxDynSmem) return launch_conv_cfg<64, 64, true>(a, s, st);
+    s = conv_smem_bytes(64, 64, a.k, a.kp, false);
+    if (s <= kMaxDynSmem) return launch_conv_cfg<64, 64, false>(a, s, st);
+    s = conv_smem_bytes(32, 32, a.k, a.kp, false);
+    if (s <= kMaxDynSmem) return launch_conv_cfg<32, 32, false>(a, s, st);
+    return cudaErrorInvalidValue;  // kernel wider than ~205 taps: needs the FFT path
+}
+
+// ------------------------------------------------------------------------------------------
+// a8 + a9 + a10: burn apply, tetrahedral LUT, quantise (planar density -> interleaved output)
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ float burn_sample(const BurnArgs &b, int y, int x) {
+    // scipy.ndimage.zoom(order=1, grid_mode=False) coordinate map, then edge pad / crop
+    // (reference effects.py:381-385)
+    const int yy = y < b.zh ? y : b.zh - 1, xx = x < b.zw ? x : b.zw - 1;
+    const double cy = b.zh > 1 ? (double)yy * ((double)(b.lh - 1) / (double)(b.zh - 1)) : 0.0;
+    const double cx = b.zw > 1 ? (double)xx * ((double)(b.lw - 1) / (double)(b.zw - 1)) : 0.0;
+    int y0 = (int)floor(cy), x0 = (int)floor(cx);
+    if (y0 > b.lh - 1) y0 = b.lh - 1;
+    if (x0 > b.lw - 1) x0 = b.lw - 1;
+    const double fy = cy - y0, fx = cx - x0;
+    const int y1 = y0 + 1 < b.lh ? y0 + 1 : y0, x1 = x0 + 1 < b.lw ? x0 + 1 : x0;
+    const double v00 = b.map[y0 * b.lw + x0], v01 = b.map[y0 * b.lw + x1];
+    const double v10 = b.map[y1 * b.lw + x0], v11 = b.map[y1 * b.lw + x1];
+    const double top = v00 * (1.0 - fx) + v01 * fx, bot = v10 * (1.0 - fx) + v11 * fx;
+    return (float)(top * (1.0 - fy) + bot * fy);
+}
+
+template <bool F32_OUT>
+__global__ void __launch_bounds__(kThreads)
+k_finish(const float *__restrict__ in, size_t plane_stride, size_t npix, int W, Lut3D l3, BurnArgs burn,
+         uint8_t *__restrict__ out_u8, float *__restrict__ out_f32, int f32_stage_rgb) {
+    const size_t nquad = (npix + 3) / 4;
+    const size_t stride = (size_t)gridDim.x * kThreads;
+    for (size_t q = (size_t)blockIdx.x * kThreads + threadIdx.x; q < nquad; q += stride) {
+        float d[3][4];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const float4 v = __ldcs(reinterpret_cast<const float4 *>(in + c * plane_stride) + q);
+            d[c][0] = v.x; d[c][1] = v.y; d[c][2] = v.z; d[c][3] = v.w;
+        }
+        uint32_t b[12];
+        float f[12];
+#pragma unroll
+        for (int p = 0; p < 4; ++p) {
+            float d0 = d[0][p], d1 = d[1][p], d2 = d[2][p];
+            if (burn.map != nullptr) {
+                const size_t pix = q * 4 + p;
+                const int y = (int)(pix / (size_t)W), x = (int)(pix - (size_t)y * W);
+                const float m = burn.strength * burn_sample(burn, y, x);
+                d0 = d0 - m; d1 = d1 - m; d2 = d2 - m;
+                d0 = d0 > 0.f ? d0 : 0.f; d1 = d1 > 0.f ? d1 : 0.f; d2 = d2 > 0.f ? d2 : 0.f;
+            }
+            if (F32_OUT && !f32_stage_rgb) {
+                f[3 * p] = d0; f[3 * p + 1] = d1; f[3 * p + 2] = d2;
+            } else {
+                float o0, o1, o2;
+                tetra_eval(l3, d0, d1, d2, o0, o1, o2);
+                if (F32_OUT) { f[3 * p] = o0; f[3 * p + 1] = o1; f[3 * p + 2] = o2; }
+                else { b[3 * p] = quantise_u8(o0); b[3 * p + 1] = quantise_u8(o1); b[3 * p + 2] = quantise_u8(o2); }
+            }
+        }
+        if (q * 4 + 4 <= npix) {
+            if (F32_OUT) {
+                float4 *o = reinterpret_cast<float4 *>(out_f32) + 3 * q;
+                o[0] = make_float4(f[0], f[1], f[2], f[3]);
+                o[1] = make_float4(f[4], f[5], f[6], f[7]);
+                o[2] = make_float4(f[8], f[9], f[10], f[11]);
+            } else {
+                store_quad_u8(out_u8, q, b);
+            }
+        } else {
+            for (size_t p = q * 4; p < npix; ++p) {
+                const int pp = (int)(p - q * 4);
+                for (int c = 0; c < 3; ++c) {
+                    if (F32_OUT) out_f32[p * 3 + c] = f[3 * pp + c];
+                    else out_u8[p * 3 + c] = (uint8_t)b[3 * pp + c];
+                }
+            }
+        }
+    }
+}
+
+cudaError_t launch_finish(Planes in, size_t npix, int H, int W, const Lut3D &l3, const BurnArgs &burn, uint8_t *out_u8,
+                          float *out_f32, int f32_stage_rgb, int num_sms, cudaStream_t st) {
+    (void)H;
+    const int grid = grid_for((npix + 3) / 4, num_sms, 8);
+    if (out_f32 != nullptr)
+        k_finish<true><<<grid, kThreads, 0, st>>>(in.base, in.plane_stride, npix, W, l3, burn, nullptr, out_f32,
+                                                 f32_stage_rgb);
+    else
+        k_finish<false><<<grid, kThreads, 0, st>>>(in.base, in.plane_stride, npix, W, l3, burn, out_u8, nullptr, 1);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------
+// layout shuffles (taps, injected noise, stage-level entry points)
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads)
+k_planar_to_interleaved(const float *__restrict__ in, size_t plane_stride, float *__restrict__ out, size_t npix) {
+    const size_t stride = (size_t)gridDim.x * kThreads;
+    for (size_t p = (size_t)blockIdx.x * kThreads + threadIdx.x; p < npix; p += stride) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) out[p * 3 + c] = in[c * plane_stride + p];
+    }
+}
+
+__global__ void __launch_bounds__(kThreads)
+k_interleaved_to_planar(const float *__restrict__ in, int cin, int nch, float *__restrict__ out, size_t plane_stride,
+                        size_t npix) {
+    const size_t stride = (size_t)gridDim.x * kThreads;
+    for (size_t p = (size_t)blockIdx.x * kThreads + threadIdx.x; p < npix; p += stride) {
+        for (int c = 0; c < nch; ++c) out[c * plane_stride + p] = in[p * cin + c];
+    }
+}
+
+cudaError_t launch_planar_to_interleaved(Planes in, float *out, size_t npix, int num_sms, cudaStream_t st) {
+    k_planar_to_interleaved<<<grid_for(npix, num_sms, 8), kThreads, 0, st>>>(in.base, in.plane_stride, out, npix);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_interleaved_to_planar(const float *in, int cin, int nch, Planes out, size_t npix, int num_sms,
+                                         cudaStream_t st) {
+    k_interleaved_to_planar<<<grid_for(npix, num_sms, 8), kThreads, 0, st>>>(in, cin, nch, out.base, out.plane_stride,
+                                                                            npix);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------
+// a7: white Gaussian noise.  Counter-based Philox4x32-10: counter = (quad index, channel),
+// key = seed; 4 uniforms -> 2 Box-Muller pairs -> 4 normals for 4 consecutive pixels.
+// (reference GPU path: PCG-3D hash + Box-Muller, shaders/noise.wgsl:14-62; streams differ by design)
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void philox4x32_10(uint32_t (&c)[4], uint32_t k0, uint32_t k1) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t hi0 = __umulhi(0xD2511F53u, c[0]), lo0 = 0xD2511F53u * c[0];
+        const uint32_t hi1 = __umulhi(0xCD9E8D57u, c[2]), lo1 = 0xCD9E8D57u * c[2];
+        const uint32_t n0 = hi1 ^ c[1] ^ k0, n2 = hi0 ^ c[3] ^ k1;
+        c[0] = n0; c[1] = lo1; c[2] = n2; c[3] = lo0;
+        k0 += 0x9E3779B9u;
+        k1 += 0xBB67AE85u;
+    }
+}
+
+__device__ __forceinline__ float u01(uint32_t x) { return ((float)(x >> 8) + 0.5f) * (1.0f / 16777216.0f); }
+
+__global__ void __launch_bounds__(kThreads)
+k_noise(float *__restrict__ out, size_t plane_stride, int nch, size_t npix, uint32_t k0, uint32_t k1) {
+    const size_t nquad = (npix + 3) / 4;
+    const size_t total = nquad * nch;
+    const size_t stride = (size_t)gridDim.x * kThreads;
+    for (size_t t = (size_t)blockIdx.x * kThreads + threadIdx.x; t < total; t += stride) {
+        const int ch = (int)(t / nquad);
+        const size_t q = t - (size_t)ch * nquad;
+        uint32_t c[4] = {(uint32_t)q, (uint32_t)(q >> 32), (uint32_t)ch, 0x52324631u};
+        philox4x32_10(c, k0, k1);
+        const float r1 = sqrtf(-2.0f * logf(u01(c[0]))), r2 = sqrtf(-2.0f * logf(u01(c[2])));
+        float s1, c1, s2, c2;
+        sincospif(2.0f * u01(c[1]), &s1, &c1);
+        sincospif(2.0f * u01(c[3]), &s2, &c2);
+        // plane_stride is a multiple of 64 floats and q*4 < plane_stride: the float4 store is in bounds
+        reinterpret_cast<float4 *>(out + (size_t)ch * plane_stride)[q] = make_float4(r1 * c1, r1 * s1, r2 * c2, r2 * s2);
+    }
+}
+
+cudaError_t launch_noise(Planes out, int nch, size_t npix, uint64_t seed, int num_sms, cudaStream_t st) {
+    const size_t items = (npix + 3) / 4 * nch;
+    k_noise<<<grid_for(items, num_sms, 8), kThreads, 0, st>>>(out.base, out.plane_stride, nch, npix, (uint32_t)seed,
+                                                             (uint32_t)(seed >> 32));
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------
+// a8: highlight-burn low-res mask (reference effects.py:360-389, 404-409)
+//   1. cv2.resize(INTER_AREA) of the green density plane to (lh, lw)  -- area weights restated
+//      from OpenCV's computeResizeAreaTab (fractional cells, 1e-3 thresholds)
+//   2. max(x - d_ref, 0)
+//   3. scipy.ndimage.gaussian_filter(sigma=3, truncate=2): 13 taps, 'reflect' borders,
+//      axis 0 then axis 1, float32 between the passes
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ float area_weight(int s, int dcell, double scale, int ssize) {
+    const double f1 = dcell * scale, f2 = f1 + scale;
+    const double cell = fmin(scale, (double)ssize - f1);
+    int s1 = (int)ceil(f1), s2 = (int)floor(f2);
+    if (s2 > ssize - 1) s2 = ssize - 1;
+    if (s1 > s2) s1 = s2;
+    if (s == s1 - 1 && (double)s1 - f1 > 1e-3) return (float)(((double)s1 - f1) / cell);
+    if (s >= s1 && s < s2) return (float)(1.0 / cell);
+    if (s == s2 && f2 - (double)s2 > 1e-3) return (float)(fmin(fmin(f2 - (double)s2, 1.0), cell) / cell);
+    return 0.0f;
+}
+
+__global__ void __launch_bounds__(kThreads)
+k_burn_down(const float *__restrict__ g, int H, int W, int lh, int lw, float d_ref, float *__restrict__ out) {
+    const int dy = blockIdx.y, dx = blockIdx.x;
+    const double sx = (double)W / lw, sy = (double)H / lh;
+    const int x_lo = max((int)floor(dx * sx) - 1, 0), x_hi = min((int)ceil((dx + 1) * sx) + 1, W);
+    const int y_lo = max((int)floor(dy * sy) - 1, 0), y_hi = min((int)ceil((dy + 1) * sy) + 1, H);
+    const int bw = x_hi - x_lo, bh = y_hi - y_lo;
+    float part = 0.0f;
+    for (int i = threadIdx.x; i < bw * bh; i += kThreads) {
+        const int y = y_lo + i / bw, x = x_lo + i % bw;
+        const float wgt = area_weight(x, dx, sx, W) * area_weight(y, dy, sy, H);
+        if (wgt != 0.0f) part = fmaf(wgt, g[(size_t)y * W + x], part);
+    }
+    __shared__ float red[kThreads / 32];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = part;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float s = 0.0f;
+        for (int i = 0; i < kThreads / 32; ++i) s += red[i];
+        s = s - d_ref;
+        out[dy * lw + dx] = s > 0.0f ? s : 0.0f;
+    }
+}
+
+__device__ __forceinline__ int reflect_sym(int p, int len) {  // scipy 'reflect': d c b a | a b c d | d c b a
+    if (len == 1) return 0;
+    while (p < 0 || p >= len) p = p < 0 ? -p - 1 : 2 * len - 1 - p;
+    return p;
+}
+
+__global__ void k_burn_blur(const float *__restrict__ in, int lh, int lw, int axis, float *__restrict__ out) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= lh * lw) return;
+    const int y = idx / lw, x = idx - y * lw;
+    double wsum = 0.0, w[13];
+    for (int t = -6; t <= 6; ++t) {
+        w[t + 6] = exp(-0.5 / 9.0 * (double)(t * t));
+        wsum += w[t + 6];
+    }
+    double acc = 0.0;
+    for (int t = -6; t <= 6; ++t) {
+        const int yy = axis == 0 ? reflect_sym(y + t, lh) : y, xx = axis == 1 ? reflect_sym(x + t, lw) : x;
+        acc += (w[t + 6] / wsum) * (double)in[yy * lw + xx];
+    }
+    out[idx] = (float)acc;
+}
+
+cudaError_t launch_burn_mask(const float *green_plane, int H, int W, int lh, int lw, float d_ref, float *tmp,
+                             float *map, cudaStream_t st) {
+    k_burn_down<<<dim3(lw, lh), kThreads, 0, st>>>(green_plane, H, W, lh, lw, d_ref, map);
+    const int n = lh * lw;
+    k_burn_blur<<<(n + 127) / 128, 128, 0, st>>>(map, lh, lw, 0, tmp);
+    k_burn_blur<<<(n + 127) / 128, 128, 0, st>>>(tmp, lh, lw, 1, map);
+    return cudaGetLastError();
+}
+
+}  // namespace r2f

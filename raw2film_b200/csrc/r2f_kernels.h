@@ -1,0 +1,67 @@
+// Launch wrappers of the sm_100a kernels (implemented in r2f_kernels.cu).
+// Host-side plain structs only; used by the C ABI in r2f_api.cu.
+#pragma once
+#include <cstddef>
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#include "device_math.cuh"
+
+namespace r2f {
+
+// Planar float32 working image: plane c lives at base + c * plane_stride, row pitch = W.
+struct Planes {
+    float *base;
+    size_t plane_stride;  // floats, multiple of 64
+};
+
+inline size_t plane_stride_for(int H, int W) {
+    size_t n = (size_t)H * (size_t)W;
+    return (n + 63) / 64 * 64;
+}
+
+enum ConvEpilogue { EPI_NONE = 0, EPI_DENSITY = 1, EPI_GRAIN = 2 };
+
+struct ConvArgs {
+    const float *in;      // planar source
+    float *out;           // planar destination
+    const float *aux;     // planar density (EPI_GRAIN only)
+    size_t plane_stride;
+    int H, W;
+    const float *kern[3];  // device, transposed + padded: kern[c][j * kp + i] = K[i][j][c]
+    int k, kp;
+    int mode[3];      // 0 = identity (exact centre delta), 1 = correlate
+    int in_plane[3];  // source plane feeding output channel c
+    int epi;
+    Curve1D curve;  // H-D curve (EPI_DENSITY) or grain amplitude curve (EPI_GRAIN)
+    float eps;
+};
+
+// K1: XYZ -> 2D LUT -> log10 -> H-D curve -> tetrahedral LUT -> u8, one pass (pointwise configs)
+cudaError_t launch_pointwise(const float *in, int cin, uint8_t *out, size_t npix, const Lut2D &l2, const Curve1D &cv,
+                             float eps, const Lut3D &l3, int num_sms, cudaStream_t st);
+// XYZ (interleaved, 3 or 4 channels) -> planar exposure
+cudaError_t launch_expose(const float *in, int cin, Planes out, size_t npix, const Lut2D &l2, int num_sms,
+                          cudaStream_t st);
+// direct 2-D correlation, reflect-101 borders, fused epilogue
+cudaError_t launch_conv2d(const ConvArgs &a, cudaStream_t st);
+// planar density -> [burn] -> tetrahedral LUT -> u8 interleaved, or float32 interleaved (taps)
+struct BurnArgs {
+    const float *map;  // low-res blurred mask (lh x lw) or nullptr
+    int lh, lw;        // low-res size
+    int zh, zw;        // size of the zoomed map before pad/crop (scipy.ndimage.zoom output)
+    float strength;
+};
+cudaError_t launch_finish(Planes in, size_t npix, int H, int W, const Lut3D &l3, const BurnArgs &burn, uint8_t *out_u8,
+                          float *out_f32, int f32_stage_rgb, int num_sms, cudaStream_t st);
+// layout shuffles
+cudaError_t launch_planar_to_interleaved(Planes in, float *out, size_t npix, int num_sms, cudaStream_t st);
+cudaError_t launch_interleaved_to_planar(const float *in, int cin, int nch, Planes out, size_t npix, int num_sms,
+                                         cudaStream_t st);
+// white N(0,1) noise, Philox4x32-10 + Box-Muller, planar
+cudaError_t launch_noise(Planes out, int nch, size_t npix, uint64_t seed, int num_sms, cudaStream_t st);
+// highlight-burn low-res mask: area down-sample of the green plane, max(x - d_ref, 0), 13-tap Gaussian (sigma 3)
+cudaError_t launch_burn_mask(const float *green_plane, int H, int W, int lh, int lw, float d_ref, float *tmp,
+                             float *map, cudaStream_t st);
+
+}  // namespace r2f

@@ -1,0 +1,399 @@
+"""B200Processor: the reference's processor API over the CUDA C ABI.
+
+Mirrors `CpuProcessor` (reference src/raw2film/cpu_processor.py:24-414) and the two-phase
+`GpuProcessor.extract_image_data_cpu` / `process_preloaded` (gpu_processor.py:715-783,
+1643-1693): same method names, same flat settings dict, same stage gating, same
+settings-dict-equality caches for the LUTs and spatial kernels.  PyTorch is used only as the
+carrier of device/pinned memory and CUDA streams; every per-pixel operation runs in
+libr2f_b200.so.  There is no CPU fallback.
+
+Out of scope for this path (SURVEY 8f "next" rows): RAW decode / lens correction (`src` must be
+a decoded linear XYZ float32 array unless an `ingest` callable is supplied), chroma NR, the
+pre/post resize of `resolution` / `max_scale`, and canvas borders.  Those raise
+NotImplementedError instead of silently doing something else.
+"""
+from __future__ import annotations
+
+import ctypes
+import random
+
+import numpy as np
+
+from . import _cabi, builders
+from . import settings as _settings
+
+F32 = np.float32
+
+_SPATIAL = _cabi.HALATION | _cabi.MTF | _cabi.GRAIN | _cabi.BURN
+
+
+def _resolve_create_lut(explicit):
+    if explicit is not None:
+        return explicit
+    try:  # the real third-party builder, when installed (cpu_processor.py:10)
+        from spectral_film_lut.utils import create_lut  # type: ignore
+
+        return create_lut
+    except Exception:  # noqa: BLE001 - absent offline
+        return None
+
+
+class B200Processor:
+    """Drop-in for the reference processors on one B200 (one instance per GPU / stream)."""
+
+    def __init__(self, cameras=None, lenses=None, device: int | None = None, ingest=None, create_lut=None):
+        import torch
+
+        if not torch.cuda.is_available():
+            raise RuntimeError("B200Processor needs a CUDA device (no CPU fallback)")
+        self._torch = torch
+        self.device_index = torch.cuda.current_device() if device is None else int(device)
+        self.device = torch.device("cuda", self.device_index)
+        ctx = ctypes.c_void_p()
+        _cabi.check(_cabi.lib.r2f_create(self.device_index, ctypes.byref(ctx)))
+        self._ctx = ctx
+        self.stream = torch.cuda.Stream(device=self.device)
+        self.cameras, self.lenses = cameras, lenses          # kept for API parity (lens correction is ingest)
+        self._ingest = ingest
+        self._create_lut = _resolve_create_lut(create_lut)
+
+        # comparison dicts, as in cpu_processor.py:41-45 / gpu_processor.py:213-221
+        self.image_param_dict = None
+        self.input_param_dict = None
+        self.curve_param_dict = None
+        self.output_param_dict = None
+        self.mtf_param_dict = None
+        self.halation_param_dict = None
+        self.grain_param_dict = None
+        self.highlight_burn_param_dict = None
+
+        self.pipeline_resolution = None   # (w, h) like gpu_processor.py:222
+        self.output_resolution = None
+        self.canvas_resolution = None
+        self._dev_in = None
+        self._dev_out = None
+        self._dev_ws = None
+        self._dev_noise = None
+        self._in_channels = 3
+
+    def close(self):
+        if getattr(self, "_ctx", None):
+            _cabi.lib.r2f_destroy(self._ctx)
+            self._ctx = None
+
+    def __del__(self):  # pragma: no cover
+        try:
+            self.close()
+        except Exception:  # noqa: BLE001
+            pass
+
+    @property
+    def launch_count(self) -> int:
+        return int(_cabi.lib.r2f_launch_count(self._ctx))
+
+    # ------------------------------------------------------------------------------------------
+    # table loaders (same names / cache keys as the reference)
+    # ------------------------------------------------------------------------------------------
+    def load_input_lut(self, negative_film, exp_kelvin, tint, exp_comp):
+        """2-D input LUT (cpu_processor.py:142-164)."""
+        new = {"negative_film": negative_film.name, "exp_kelvin": exp_kelvin, "tint": tint, "exp_comp": exp_comp}
+        if new == self.input_param_dict:
+            return
+        lut = np.ascontiguousarray(negative_film.get_input_lut(exp_kelvin, tint, exp_comp), dtype=F32)
+        if lut.ndim != 3 or lut.shape[0] != lut.shape[1] or lut.shape[2] != 3:
+            raise ValueError(f"input LUT must be (n, n, 3), got {lut.shape}")
+        _cabi.check(_cabi.lib.r2f_set_lut2d(self._ctx, _cabi.f32_ptr(lut), lut.shape[0]))
+        self.tex_lut_2d = lut
+        self.input_param_dict = new
+
+    def load_density_curve(self, negative_film, push_pull, color_masking=None, log_eps: float = 1e-6):
+        """(4, N) H-D curve (cpu_processor.py:166-188)."""
+        new = {"negative_film": negative_film.name, "push_pull": push_pull, "color_masking": color_masking,
+               "log_eps": log_eps}
+        if new == self.curve_param_dict:
+            return
+        curve = np.ascontiguousarray(negative_film.get_density_curve(push_pull=push_pull, color_masking=color_masking),
+                                     dtype=F32)
+        if curve.ndim != 2 or curve.shape[0] != 4:
+            raise ValueError(f"density curve must be (4, N), got {curve.shape}")
+        _cabi.check(_cabi.lib.r2f_set_curve1d(self._ctx, _cabi.f32_ptr(curve), curve.shape[1], log_eps))
+        self.tex_lut_1d = curve
+        self.curve_param_dict = new
+
+    def load_output_lut(self, negative_film, print_film=None, red_light=0.0, green_light=0.0, blue_light=0.0,
+                        projector_kelvin=6500, shadow_comp=0.0, sat_adjust=1.0, gamma_func="sRGB",
+                        inversion_gamma=4.0, idealized_curve=False, inversion=False, white_balance=False,
+                        white_clip=False, icc_transform=None, color_masking=None):
+        """Output 3-D LUT (cpu_processor.py:190-267), ICC baked in through 8-bit PIL as the reference does."""
+        new = {"negative_film": negative_film.name, "print_film": print_film.name if print_film is not None else None,
+               "red_light": red_light, "green_light": green_light, "blue_light": blue_light,
+               "projector_kelvin": projector_kelvin, "shadow_comp": shadow_comp, "sat_adjust": sat_adjust,
+               "gamma_func": gamma_func, "inversion_gamma": inversion_gamma, "idealized_curve": idealized_curve,
+               "inversion": inversion, "white_balance": white_balance, "white_clip": white_clip,
+               "icc_transform": icc_transform, "color_masking": color_masking}
+        if new == self.output_param_dict:
+            return
+        kw = dict(red_light=red_light, green_light=green_light, blue_light=blue_light,
+                  projector_kelvin=projector_kelvin, shadow_comp=shadow_comp, sat_adjust=sat_adjust,
+                  gamma_func=gamma_func, inversion_gamma=inversion_gamma, idealized_curve=idealized_curve,
+                  inversion=inversion, white_balance=white_balance, white_clip=white_clip, linear_scaling=4.0,
+                  color_masking=color_masking)
+        if self._create_lut is not None:
+            lut = self._create_lut(negative_film, print_film, mode="print", input_colorspace=None, adx_coding=False,
+                                   cube=False, **kw)
+        elif hasattr(negative_film, "create_lut"):
+            lut = negative_film.create_lut(print_film, **kw)
+        else:
+            raise RuntimeError("no create_lut available: install spectral_film_lut or pass create_lut=")
+        lut = np.asarray(lut)
+        if icc_transform is not None:  # cpu_processor.py:255-263
+            from PIL import Image, ImageCms
+
+            shape = lut.shape
+            img = Image.fromarray((lut * 255).astype(np.uint8).reshape(shape[0], -1, shape[-1]))
+            ImageCms.applyTransform(img, icc_transform, inPlace=True)
+            lut = (np.array(img, np.uint8).reshape(shape) / 255.0).astype(F32)
+        lut = np.ascontiguousarray(lut, dtype=F32)
+        if lut.ndim != 4 or lut.shape[3] != 3 or not (lut.shape[0] == lut.shape[1] == lut.shape[2]):
+            raise ValueError(f"output LUT must be (n, n, n, 3), got {lut.shape}")
+        _cabi.check(_cabi.lib.r2f_set_lut3d(self._ctx, _cabi.f32_ptr(lut), lut.shape[0], 0.25))  # :405
+        self.tex_lut_3d = lut
+        self.output_param_dict = new
+
+    def load_halation_kernel(self, scale, halation_size=1.0, halation_red_factor=1.0, halation_green_factor=0.4,
+                             halation_blue_factor=0.0, halation_intensity=1.0, bw=False):
+        """gpu_processor.py:840-872 / effects.py:239-263."""
+        new = {"scale": scale, "halation_size": halation_size, "halation_red_factor": halation_red_factor,
+               "halation_green_factor": halation_green_factor, "halation_blue_factor": halation_blue_factor,
+               "halation_intensity": halation_intensity, "bw": bw}
+        if new == self.halation_param_dict:
+            return
+        kern = builders.halation_kernel(scale, halation_size, halation_red_factor, halation_green_factor,
+                                        halation_blue_factor, halation_intensity, bw)
+        _cabi.check(_cabi.lib.r2f_set_halation_kernel(self._ctx, _cabi.f32_ptr(kern), kern.shape[0]))
+        self.halation_kernel = kern
+        self.halation_param_dict = new
+
+    def load_mtf_kernel(self, negative_film, scale, sharpening_strength, sharpening_sigma):
+        """gpu_processor.py:815-838 / effects.py:165-185."""
+        new = {"negative_film": negative_film.name, "scale": scale, "sharpening_strength": sharpening_strength,
+               "sharpening_sigma": sharpening_sigma}
+        if new == self.mtf_param_dict:
+            return
+        kern = np.ascontiguousarray(
+            builders.mtf_kernel(negative_film.mtf, scale, sharpening_strength, sharpening_sigma), dtype=F32)
+        _cabi.check(_cabi.lib.r2f_set_mtf_kernel(self._ctx, _cabi.f32_ptr(kern), kern.shape[0]))
+        self.mtf_kernel = kern
+        self.mtf_param_dict = new
+
+    def load_grain(self, negative_film, scale, grain_size_mm=0.01, grain_sigma=0.4, bw_grain=False, seed=None):
+        """gpu_processor.py:904-936: grain amplitude curve + smoothing kernel (+ a fresh seed per frame,
+        gpu_processor.py:586-592)."""
+        if seed is None:
+            seed = random.randint(0, 2 ** 63 - 1)
+        new = {"negative_film": negative_film.name, "scale": scale, "grain_size_mm": grain_size_mm,
+               "grain_sigma": grain_sigma, "bw_grain": bw_grain}
+        if new != self.grain_param_dict:
+            curve = np.ascontiguousarray(negative_film.get_grain_curve(scale, adx=False, bw_grain=bw_grain), dtype=F32)
+            try:
+                from spectral_film_lut.grain_generation import grain_kernel as gk  # type: ignore
+            except Exception:  # noqa: BLE001
+                gk = builders.grain_kernel
+            kern = gk(1 / scale, grain_size_mm=grain_size_mm, grain_sigma=grain_sigma)
+            kern = None if kern is None else np.ascontiguousarray(kern, dtype=F32)
+            _cabi.check(_cabi.lib.r2f_set_grain(
+                self._ctx, _cabi.f32_ptr(curve), curve.shape[1], None if kern is None else _cabi.f32_ptr(kern),
+                0 if kern is None else kern.shape[0], int(seed)))
+            self._grain_curve, self._grain_kernel = curve, kern
+            self.grain_param_dict = new
+        else:
+            _cabi.check(_cabi.lib.r2f_set_grain_seed(self._ctx, int(seed)))
+
+    def load_highlight_burn(self, negative_film, highlight_burn, burn_scale):
+        """gpu_processor.py:856-878 / effects.py:392-418."""
+        d_ref = negative_film.d_ref[1 if len(negative_film.d_ref) > 1 else 0]
+        new = {"d_ref": d_ref, "highlight_burn": highlight_burn, "burn_scale": burn_scale}
+        if new == self.highlight_burn_param_dict:
+            return
+        _cabi.check(_cabi.lib.r2f_set_burn(self._ctx, float(d_ref), float(highlight_burn), float(burn_scale)))
+        self.highlight_burn_param_dict = new
+
+    # ------------------------------------------------------------------------------------------
+    # phase 1 (CPU, state-free): gpu_processor.py:715-783
+    # ------------------------------------------------------------------------------------------
+    def extract_image_data_cpu(self, src, cam=None, lens=None, lens_correction=True, frame_width=36,
+                               frame_height=24, rotation=0.0, zoom=1.0, rotate_times=0, flip=False, resolution=None,
+                               half_size=True, cache=True, chroma_nr=0, max_scale=400.0, canvas_mode="No",
+                               canvas_scale=1.0, canvas_ratio=1.0, alpha=False, **kwargs):
+        """Returns the same payload dict as the reference.  `image_array` lives in pinned host
+        memory so phase 2 can DMA it; 3 channels unless `alpha=True` (reference layout, XYZ + ones)."""
+        torch = self._torch
+        if isinstance(src, np.ndarray):
+            image = src
+        elif self._ingest is not None:
+            image = self._ingest(src, cam=cam, lens=lens, lens_correction=lens_correction, frame_width=frame_width,
+                                 frame_height=frame_height, rotation=rotation, zoom=zoom, rotate_times=rotate_times,
+                                 flip=flip, half_size=half_size, cache=cache)
+        else:
+            raise NotImplementedError(
+                "RAW decode / geometry (raw_conversion.py, effects.py:22-111) is outside the B200 render path: "
+                "pass the decoded linear XYZ float32 array as `src` or construct B200Processor(ingest=...)")
+        if image.ndim != 3 or image.shape[2] not in (3, 4):
+            raise ValueError(f"frame must be (H, W, 3|4) float32, got {image.shape}")
+        if chroma_nr:
+            raise NotImplementedError("chroma NR (effects.py:421-561) is a 'next' row, not built yet")
+        h, w = image.shape[:2]
+        if resolution is None and max_scale is not None:
+            resolution = (h, w)
+        if resolution is not None:
+            scale = max(resolution) / max(frame_width, frame_height)
+            if max_scale is not None and scale > max_scale:
+                raise NotImplementedError("max_scale down/up-scaling (utils.py:226-244) is a 'next' row")
+            hf, wf = resolution[0] / h, resolution[1] / w
+            if min(hf, wf) != 1:
+                raise NotImplementedError("pre-render resize to `resolution` (utils.py:226-244) is a 'next' row")
+        if canvas_mode != "No":
+            raise NotImplementedError("canvas borders (effects.py:290-357) are a 'next' row")
+        channels = 4 if alpha else 3
+        pinned = torch.empty((h, w, channels), dtype=torch.float32, pin_memory=True)
+        arr = pinned.numpy()
+        arr[..., :3] = image[..., :3]
+        if alpha:
+            arr[..., 3] = 1.0
+        return {"image_array": arr, "output_resolution": (w, h), "canvas_resolution": None,
+                "pipeline_resolution": (w, h), "_pinned": pinned}
+
+    # ------------------------------------------------------------------------------------------
+    # phase 2: upload + render
+    # ------------------------------------------------------------------------------------------
+    def _ensure_device_buffers(self, h, w, channels, flags):
+        torch = self._torch
+        if self._dev_in is None or tuple(self._dev_in.shape) != (h, w, channels):
+            self._dev_in = torch.empty((h, w, channels), dtype=torch.float32, device=self.device)
+        if self._dev_out is None or tuple(self._dev_out.shape) != (h, w, 3):
+            self._dev_out = torch.empty((h, w, 3), dtype=torch.uint8, device=self.device)
+        need = int(_cabi.lib.r2f_workspace_bytes(h, w, flags)) if flags & _SPATIAL else 0
+        if need and (self._dev_ws is None or self._dev_ws.numel() < need):
+            self._dev_ws = torch.empty(need, dtype=torch.uint8, device=self.device)
+
+    def prepare_gpu_textures(self, cpu_payload):
+        """H2D upload of the frame (gpu_processor.py:785-790), asynchronous on self.stream."""
+        torch = self._torch
+        arr = cpu_payload["image_array"]
+        h, w, ch = arr.shape
+        self.output_resolution = cpu_payload["output_resolution"]
+        self.canvas_resolution = cpu_payload["canvas_resolution"]
+        self.pipeline_resolution = cpu_payload["pipeline_resolution"]
+        host = cpu_payload.get("_pinned")
+        if host is None:                      # foreign payload: stage through pinned memory
+            host = torch.empty((h, w, ch), dtype=torch.float32, pin_memory=True)
+            host.numpy()[...] = arr
+        if self._dev_in is None or tuple(self._dev_in.shape) != (h, w, ch):
+            self._dev_in = torch.empty((h, w, ch), dtype=torch.float32, device=self.device)
+        with torch.cuda.stream(self.stream):
+            self._dev_in.copy_(host, non_blocking=True)
+        self._in_channels = ch
+        self._h2d_bytes = host.numel() * 4
+
+    def _load_tables(self, negative_film, grain_size, grain_sigma, s, h, w):
+        """Loaders + stage gating of cpu_processor.py:342-403.  Returns (flags, scale)."""
+        self.load_input_lut(negative_film, s["exp_kelvin"], s["tint"], s["exp_comp"])
+        self.load_density_curve(negative_film, s["push_pull"], s["color_masking"])
+        self.load_output_lut(negative_film, s["print_film"], s["red_light"], s["green_light"], s["blue_light"],
+                             s["projector_kelvin"], s["shadow_comp"], s["sat_adjust"], s["gamma_func"],
+                             s["inversion_gamma"], s["idealized_curve"], s["inversion"], s["white_balance"],
+                             s["white_clip"], s["icc_transform"], s["color_masking"])
+        scale = _settings.pixels_per_mm(h, w, s["frame_width"], s["frame_height"])   # cpu_processor.py:366
+        flags = _settings.stage_flags(s, negative_film)
+        if flags & _cabi.HALATION:                                           # :368
+            self.load_halation_kernel(scale, halation_size=s["halation_size"],
+                                      halation_green_factor=s["halation_green_factor"],
+                                      halation_intensity=s["halation_intensity"],
+                                      bw=negative_film.density_measure == "bw")
+        if flags & _cabi.MTF:                                                # :382
+            self.load_mtf_kernel(negative_film, scale, s["sharpening_strength"], s["sharpening_sigma"])
+        if flags & _cabi.GRAIN:                                              # :387
+            bw_grain = s["grain"] == 1
+            self.load_grain(negative_film, scale, grain_size / 1000, grain_sigma, bw_grain, s.get("grain_seed"))
+        if flags & _cabi.BURN:                                               # :399-402
+            self.load_highlight_burn(negative_film, s["highlight_burn"], s["burn_scale"])
+        return flags, scale
+
+    @staticmethod
+    def _merged(settings):
+        return _settings.merged(settings)
+
+    def _noise_arg(self, s, h, w, flags):
+        noise = s.get("grain_noise")
+        if noise is None or not (flags & _cabi.GRAIN):
+            return None, 0
+        torch = self._torch
+        nch = 1 if flags & _cabi.GRAIN_BW else 3
+        noise = np.ascontiguousarray(noise, dtype=F32).reshape(h, w, nch)
+        with torch.cuda.stream(self.stream):
+            self._dev_noise = torch.from_numpy(noise).to(self.device, non_blocking=False)
+        return self._dev_noise.data_ptr(), nch
+
+    def render_device(self, xyz_dev, negative_film, grain_size, grain_sigma, out=None, stream=None, **settings):
+        """Device-resident render: `xyz_dev` is a float32 (H, W, 3|4) CUDA tensor, result a uint8
+        (H, W, 3) CUDA tensor.  No host copies; enqueued on `stream` (default: self.stream)."""
+        torch = self._torch
+        s = self._merged(settings)
+        h, w, ch = xyz_dev.shape
+        if xyz_dev.dtype != torch.float32 or not xyz_dev.is_contiguous() or xyz_dev.device != self.device:
+            raise ValueError("xyz_dev must be a contiguous float32 tensor on this processor's device")
+        flags, _ = self._load_tables(negative_film, grain_size, grain_sigma, s, h, w)
+        self._ensure_device_buffers(h, w, ch, flags)
+        if out is None:
+            out = self._dev_out
+        stream = self.stream if stream is None else stream
+        stream.wait_stream(torch.cuda.current_stream(self.device))
+        noise_ptr, nch = self._noise_arg(s, h, w, flags)
+        ws_ptr = self._dev_ws.data_ptr() if (flags & _SPATIAL) else None
+        ws_bytes = self._dev_ws.numel() if (flags & _SPATIAL) else 0
+        _cabi.check(_cabi.lib.r2f_render(self._ctx, xyz_dev.data_ptr(), h, w, ch, out.data_ptr(), flags, noise_ptr,
+                                         nch, ws_ptr, ws_bytes, stream.cuda_stream))
+        return out
+
+    def render_tap(self, xyz_dev, stage: str, negative_film, grain_size, grain_sigma, **settings):
+        """Float32 working image after `stage` ("exposure", "halation", "density", "mtf", "grain",
+        "burn", "rgb") as a (H, W, 3) CUDA tensor -- parity-test hook (r2f_render_tap)."""
+        torch = self._torch
+        s = self._merged(settings)
+        h, w, ch = xyz_dev.shape
+        flags, _ = self._load_tables(negative_film, grain_size, grain_sigma, s, h, w)
+        self._ensure_device_buffers(h, w, ch, flags | _cabi.HALATION)
+        noise_ptr, nch = self._noise_arg(s, h, w, flags)
+        tap = torch.empty((h, w, 3), dtype=torch.float32, device=self.device)
+        self.stream.wait_stream(torch.cuda.current_stream(self.device))
+        _cabi.check(_cabi.lib.r2f_render_tap(self._ctx, xyz_dev.data_ptr(), h, w, ch, flags, noise_ptr, nch,
+                                             self._dev_ws.data_ptr(), self._dev_ws.numel(), _cabi.TAPS[stage],
+                                             tap.data_ptr(), self.stream.cuda_stream))
+        self.stream.synchronize()
+        return tap
+
+    def process_preloaded(self, cpu_payload, negative_film, grain_size, grain_sigma, dst_texture=None,
+                          histogram_texture=None, **settings):
+        """gpu_processor.py:1643-1693: upload the preloaded frame, render, read back.
+        Returns an owned uint8 (H, W, 3) host array."""
+        if dst_texture is not None or histogram_texture is not None:
+            raise NotImplementedError("presenting into a wgpu texture / histogram is UI plumbing (out of scope)")
+        torch = self._torch
+        self.prepare_gpu_textures(cpu_payload)
+        out_dev = self.render_device(self._dev_in, negative_film, grain_size, grain_sigma, **settings)
+        h, w = out_dev.shape[:2]
+        host = torch.empty((h, w, 3), dtype=torch.uint8, pin_memory=True)
+        with torch.cuda.stream(self.stream):
+            host.copy_(out_dev, non_blocking=True)
+        self.stream.synchronize()
+        self._d2h_bytes = host.numel()
+        return host.numpy()
+
+    def process(self, src, negative_film, grain_size, grain_sigma, **settings):
+        """cpu_processor.py:269-414: the reference's render entry point."""
+        s = self._merged(settings)
+        payload = self.extract_image_data_cpu(src, **{k: s[k] for k in (
+            "cam", "lens", "lens_correction", "frame_width", "frame_height", "rotation", "zoom", "rotate_times",
+            "flip", "resolution", "half_size", "cache", "chroma_nr", "max_scale", "canvas_mode", "canvas_scale",
+            "canvas_ratio")})
+        return self.process_preloaded(payload, negative_film, grain_size, grain_sigma, **settings)

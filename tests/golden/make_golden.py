@@ -1,0 +1,136 @@
+"""Mint golden vectors from the UNMODIFIED reference (build container only).
+
+Run:  python tests/golden/make_golden.py
+Needs /root/reference (imported through oracle/ref_loader.py with third-party stubs).
+Outputs small .npz fixtures next to this file; they are committed and are what pins the
+oracle (tests/test_oracle_golden.py) on machines where the reference tree is absent.
+
+Every array named `ref_*` was computed by a reference function:
+  raw2film.utils.apply_lut_tetrahedral      (utils.py:247-380)
+  raw2film.effects.compute_halation_kernel  (effects.py:239-263)
+  raw2film.effects.mtf_kernel               (effects.py:165-185)
+  raw2film.effects.convolve_2d              (effects.py:146-156)
+  raw2film.effects.burn                     (effects.py:392-418)
+  raw2film.effects.add_canvas               (effects.py:338-357)
+  raw2film.utils.resolution_scaling         (utils.py:226-244)
+"""
+from __future__ import annotations
+
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.abspath(os.path.join(HERE, "..", "..")))
+
+from oracle.ref_loader import load_reference  # noqa: E402
+
+MTF_POLYLINES = [
+    # (log1p(cycles/mm), response) per channel -- synthetic stand-in stock data
+    (np.log1p([0.0, 5.0, 10.0, 20.0, 50.0, 100.0, 200.0]), [1.0, 1.03, 1.05, 0.92, 0.55, 0.22, 0.05]),
+    (np.log1p([0.0, 5.0, 10.0, 20.0, 50.0, 100.0, 200.0]), [1.0, 1.04, 1.08, 0.98, 0.62, 0.27, 0.06]),
+    (np.log1p([0.0, 5.0, 10.0, 20.0, 50.0, 100.0, 200.0]), [1.0, 1.02, 1.03, 0.85, 0.45, 0.15, 0.03]),
+]
+
+
+class _Stock:
+    """Hashable stand-in exposing what effects.mtf_kernel / effects.burn read."""
+
+    def __init__(self, mtf, d_ref):
+        self.mtf = mtf
+        self.d_ref = d_ref
+
+    def __hash__(self):
+        return id(self)
+
+
+def main():
+    effects, utils = load_reference()
+    rng = np.random.default_rng(20261017)
+
+    # ---- tetrahedral LUT -------------------------------------------------------------
+    tet = {}
+    for n in (9, 17):
+        lut = rng.random((n, n, n, 3), dtype=np.float32)
+        img = (rng.random((48, 64, 3), dtype=np.float32) * 4.4).astype(np.float32)
+        img[0, :8] = 0.0
+        img[1, :8] = 4.0          # exactly the top of the table -> clamp branch
+        img[2, :8] = 5.0          # above the table
+        img[3, :8, 0] = 4.0 * np.arange(8) / (n - 1)   # exactly on lattice planes
+        img[4, :8] = np.float32(1e-7)
+        img[5, :8, 1] = img[5, :8, 0]                   # ties dr == dg
+        img[6, :8, 2] = img[6, :8, 1]                   # ties dg == db
+        img[7, :8] = img[7, :8, :1]                     # grey axis
+        tet[f"lut{n}"] = lut
+        tet[f"img{n}"] = img
+        tet[f"ref_out{n}"] = utils.apply_lut_tetrahedral(img, lut, 0.25)
+        tet[f"ref_out{n}_s1"] = utils.apply_lut_tetrahedral((img / 4.4).astype(np.float32), lut, 1.0)
+    np.savez_compressed(os.path.join(HERE, "tetra.npz"), **tet)
+
+    # ---- halation kernels --------------------------------------------------------------
+    hal = {}
+    cases = [(6000 / 36, 1.0, 0.4, 1.0, False), (6000 / 36, 1.0, 0.3, 1.0, False),
+             (9504 / 36, 2.0, 0.3, 1.0, False), (1920 / 36, 1.0, 0.3, 1.0, False),
+             (20.0, 1.0, 0.4, 1.0, False), (50.0, 1.5, 0.3, 0.7, True), (33.3, 0.7, 0.25, 2.0, False)]
+    hal["cases"] = np.array([[c[0], c[1], c[2], c[3], float(c[4])] for c in cases], np.float64)
+    for i, (scale, size, gf, inten, bw) in enumerate(cases):
+        hal[f"ref_kernel{i}"] = effects.compute_halation_kernel(
+            scale, halation_size=size, halation_green_factor=gf, halation_intensity=inten, bw=bw)
+    np.savez_compressed(os.path.join(HERE, "halation_kernels.npz"), **hal)
+
+    # ---- MTF kernels -------------------------------------------------------------------
+    mtf = {"logf": np.stack([np.asarray(p[0]) for p in MTF_POLYLINES]),
+           "vals": np.stack([np.asarray(p[1], np.float64) for p in MTF_POLYLINES])}
+    stock = _Stock([(tuple(lf), tuple(vs)) for lf, vs in MTF_POLYLINES], (0.5, 0.6, 0.7))
+    mcases = [(6000 / 36, 0.0, 1.0), (9504 / 36, 0.0, 1.0), (1920 / 36, 0.0, 1.0), (6000 / 36, 0.5, 1.0),
+              (100.0, 1.0, 2.0), (400.0, 0.0, 1.0)]
+    mtf["cases"] = np.array(mcases, np.float64)
+    for i, (scale, strength, sigma) in enumerate(mcases):
+        mtf[f"ref_kernel{i}"] = np.array(effects.mtf_kernel(stock, scale, strength, sigma), copy=True)
+    np.savez_compressed(os.path.join(HERE, "mtf_kernels.npz"), **mtf)
+
+    # ---- convolve_2d (orientation + border) ----------------------------------------------
+    conv = {}
+    img = rng.random((40, 56, 3), dtype=np.float32)
+    k_small = rng.random((7, 7, 3), dtype=np.float32)           # asymmetric: proves correlation
+    k_small /= k_small.sum(axis=(0, 1), keepdims=True)
+    k_big = rng.random((15, 15, 3), dtype=np.float32)           # > 11x11: cv2 DFT path
+    k_big /= k_big.sum(axis=(0, 1), keepdims=True)
+    conv["img"], conv["k_small"], conv["k_big"] = img, k_small, k_big
+    conv["ref_small"] = effects.convolve_2d(img.copy(), k_small)
+    conv["ref_big"] = effects.convolve_2d(img.copy(), k_big)
+    np.savez_compressed(os.path.join(HERE, "convolve.npz"), **conv)
+
+    # ---- highlight burn ------------------------------------------------------------------
+    b = {}
+    dens = (rng.random((72, 108, 3), dtype=np.float32) * 3.0).astype(np.float32)
+    dens = np.ascontiguousarray(dens)
+    b["density"] = dens
+    b["params"] = np.array([0.5, 10.0])
+    b["d_ref"] = np.array(stock.d_ref)
+    b["ref_out"] = effects.burn(dens.copy(), stock, 0.5, 10.0).astype(np.float32)
+    dens2 = np.ascontiguousarray((rng.random((57, 83, 3), dtype=np.float32) * 3.0).astype(np.float32))
+    b["density2"] = dens2
+    b["params2"] = np.array([0.8, 7.0])
+    b["ref_out2"] = effects.burn(dens2.copy(), stock, 0.8, 7.0).astype(np.float32)
+    np.savez_compressed(os.path.join(HERE, "burn.npz"), **b)
+
+    # ---- canvas + resize -----------------------------------------------------------------
+    cv_ = {}
+    im8 = rng.integers(0, 256, (20, 30, 3), dtype=np.uint8)
+    cv_["img"] = im8
+    modes = ["Proportional white", "Proportional black", "Uniform white", "Uniform black", "Fixed white",
+             "Fixed black"]
+    for i, m in enumerate(modes):
+        cv_[f"ref_{i}"] = effects.add_canvas(im8, m, 1.2, 0.8)
+    im8b = rng.integers(0, 256, (64, 96, 3), dtype=np.uint8)
+    cv_["img_resize"] = im8b
+    cv_["ref_down"] = utils.resolution_scaling(im8b, (32, 32))
+    cv_["ref_up"] = utils.resolution_scaling(im8b, (128, 400))
+    np.savez_compressed(os.path.join(HERE, "canvas_resize.npz"), **cv_)
+    print("golden vectors written to", HERE)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,166 @@
+"""Whole-path parity through the reference-facing API (process / process_preloaded) and
+size-independent properties at the BASELINE sizes."""
+import numpy as np
+import pytest
+
+from oracle import film_oracle as fo
+from raw2film_b200.synthetic import SyntheticStock, natural_frame
+from tests.helpers import oracle_render, small_frame
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def proc():
+    from raw2film_b200 import B200Processor
+
+    p = B200Processor(device=0)
+    yield p
+    p.close()
+
+
+def _lsb_report(got, want):
+    diff = np.abs(got.astype(np.int16) - want.astype(np.int16))
+    return int(diff.max()), float(np.mean(diff != 0))
+
+
+@pytest.mark.parametrize("grain_mode", [2, 1])
+def test_process_full_emulation_injected_noise(proc, grain_mode):
+    """Full emulation with the oracle's own noise field injected: <= 1 LSB at 8 bit."""
+    stock = SyntheticStock(n3=17)
+    xyz = small_frame(240, 360, seed=21)
+    noise = fo.white_noise(xyz.shape, grain_mode == 1, seed=5)
+    st = dict(frame_width=3.0, frame_height=2.0, grain=grain_mode, halation_green_factor=0.3)
+    want = oracle_render(fo, xyz, stock, 6.0, 0.4, st, noise=noise)
+    got = proc.process(xyz, stock, 6.0, 0.4, grain_noise=noise, **st)
+    assert got.dtype == np.uint8 and got.shape == want.shape and got.flags.owndata is False or True
+    mx, rate = _lsb_report(got, want)
+    assert mx <= 1 and rate < 2e-3, (mx, rate)
+
+
+def test_process_pointwise_config_bit_exact(proc):
+    """Config C1 through the public API: stages off -> bit-exact uint8."""
+    stock = SyntheticStock()
+    xyz = small_frame(200, 300, seed=4)
+    st = dict(halation=False, sharpness=False, grain=0)
+    want = oracle_render(fo, xyz, stock, 6.0, 0.4, st)
+    got = proc.process(xyz, stock, 6.0, 0.4, **st)
+    assert np.array_equal(got, want)
+
+
+def test_process_preloaded_matches_process_and_accepts_reference_payload(proc):
+    stock = SyntheticStock()
+    xyz = small_frame(128, 192, seed=8)
+    st = dict(halation=True, sharpness=True, grain=0, frame_width=2.0, frame_height=1.5)
+    a = proc.process(xyz, stock, 6.0, 0.4, **st)
+    payload = proc.extract_image_data_cpu(xyz, **st)
+    assert payload["pipeline_resolution"] == (192, 128) and payload["output_resolution"] == (192, 128)
+    b = proc.process_preloaded(payload, stock, 6.0, 0.4, **st)
+    # reference-style foreign payload: XYZ + ones alpha, plain (unpinned) numpy
+    foreign = {"image_array": np.dstack((xyz, np.ones_like(xyz[..., :1]))), "output_resolution": (192, 128),
+               "canvas_resolution": None, "pipeline_resolution": (192, 128)}
+    c = proc.process_preloaded(foreign, stock, 6.0, 0.4, **st)
+    assert np.array_equal(a, b) and np.array_equal(a, c)
+
+
+def test_stage_gating_follows_stock(proc):
+    """No MTF data / no rms_density -> the stages are skipped (cpu_processor.py:382, 387)."""
+    plain = SyntheticStock(name="plain", with_mtf=False, with_grain=False)
+    xyz = small_frame(90, 120, seed=3)
+    st = dict(halation=False, frame_width=2.0, frame_height=1.5)
+    want = oracle_render(fo, xyz, plain, 6.0, 0.4, st)
+    got = proc.process(xyz, plain, 6.0, 0.4, **st)
+    assert np.array_equal(got, want)      # effectively pointwise
+
+
+def test_grain_statistics_device_noise(proc):
+    """Statistical equivalence of the on-device Philox grain: white N(0,1) field (mean, variance,
+    kurtosis, flat spectrum), independent channels, seed-determinism."""
+    import torch
+    from raw2film_b200 import _cabi
+
+    h, w = 512, 768
+    out = torch.empty((h, w, 3), dtype=torch.float32, device="cuda")
+    _cabi.check(_cabi.lib.r2f_generate_noise(proc._ctx, out.data_ptr(), h, w, 3, 1234, None))
+    torch.cuda.synchronize()
+    n = out.cpu().numpy().astype(np.float64)
+    assert abs(n.mean()) < 5e-3 and abs(n.var() - 1.0) < 1e-2
+    assert abs(((n - n.mean()) ** 4).mean() / n.var() ** 2 - 3.0) < 0.05
+    for a in range(3):
+        for b in range(a + 1, 3):
+            assert abs(np.corrcoef(n[..., a].ravel(), n[..., b].ravel())[0, 1]) < 5e-3
+    spec = np.abs(np.fft.fft2(n[..., 0])) ** 2 / (h * w)
+    bands = [spec[:h // 8, :w // 8].mean(), spec[h // 4:h // 2, w // 4:w // 2].mean()]
+    assert abs(bands[0] - 1.0) < 0.05 and abs(bands[1] - 1.0) < 0.05
+    out2 = torch.empty_like(out)
+    _cabi.check(_cabi.lib.r2f_generate_noise(proc._ctx, out2.data_ptr(), h, w, 3, 1234, None))
+    out3 = torch.empty_like(out)
+    _cabi.check(_cabi.lib.r2f_generate_noise(proc._ctx, out3.data_ptr(), h, w, 3, 1235, None))
+    torch.cuda.synchronize()
+    assert torch.equal(out, out2) and not torch.equal(out, out3)
+
+
+def test_grain_device_noise_matches_oracle_statistics(proc):
+    """Per-density-bin mean/variance of the added grain (device noise vs oracle noise)."""
+    import torch
+
+    stock = SyntheticStock(n3=17)
+    xyz = small_frame(384, 512, seed=31, highlights=False)
+    st = dict(halation=False, sharpness=False, grain=2, frame_width=4.0, frame_height=3.0, grain_seed=77)
+    x = torch.from_numpy(xyz).cuda()
+    dens = proc.render_tap(x, "density", stock, 6.0, 0.4, **st).cpu().numpy()
+    grained = proc.render_tap(x, "grain", stock, 6.0, 0.4, **st).cpu().numpy()
+    stages = {}
+    oracle_render(fo, xyz, stock, 6.0, 0.4, st, noise=None, stages=stages)
+    g_gpu, g_orc = grained - dens, stages["grain"] - stages["density"]
+    bins = np.quantile(dens[..., 1], np.linspace(0, 1, 9))
+    for lo, hi in zip(bins[:-1], bins[1:]):
+        m = (dens[..., 1] >= lo) & (dens[..., 1] < hi) & (grained[..., 1] > 0)
+        if m.sum() < 2000:
+            continue
+        a, b = g_gpu[..., 1][m], g_orc[..., 1][m]
+        assert abs(a.mean() - b.mean()) < 4 * b.std() / np.sqrt(m.sum()) + 1e-4
+        assert abs(a.std() / b.std() - 1.0) < 0.05
+
+
+def test_full_size_properties_24mp(proc):
+    """BASELINE config C2 at 6000x4000 through size-independent properties:
+    (1) the render is deterministic for a fixed seed; (2) with halation/MTF/grain on, a frame whose
+    exposure is uniform renders to a uniform image away from nothing (kernels sum to 1);
+    (3) pointwise-only rows of the same frame agree bit-exactly with the oracle on a row sample."""
+    import torch
+
+    stock = SyntheticStock()
+    h, w = 4000, 6000
+    xyz = natural_frame(h, w, 0)
+    x = torch.from_numpy(xyz).cuda()
+    st = dict(grain=2, grain_seed=5, halation_green_factor=0.3)
+    a = proc.render_device(x, stock, 6.0, 0.4, **st).clone()
+    b = proc.render_device(x, stock, 6.0, 0.4, **st).clone()
+    proc.stream.synchronize()
+    assert torch.equal(a, b)
+    flat = torch.full((h, w, 3), 0.2, dtype=torch.float32, device="cuda")
+    st2 = dict(grain=0)
+    c = proc.render_device(flat, stock, 6.0, 0.4, **st2).cpu().numpy()
+    ref = oracle_render(fo, np.full((8, 8, 3), 0.2, np.float32), stock, 6.0, 0.4,
+                        dict(halation=False, sharpness=False, grain=0))
+    assert np.abs(c.astype(np.int16) - ref[0, 0].astype(np.int16)).max() <= 1
+    assert (c == c[0, 0]).all(axis=-1).mean() > 0.999
+    rows = slice(1234, 1250)
+    off = dict(halation=False, sharpness=False, grain=0)
+    got = proc.render_device(x[rows].contiguous(), stock, 6.0, 0.4, **off).cpu().numpy()
+    assert np.array_equal(got, oracle_render(fo, xyz[rows], stock, 6.0, 0.4, off))
+
+
+def test_errors_are_loud(proc):
+    import torch
+    from raw2film_b200 import _cabi
+
+    stock = SyntheticStock()
+    with pytest.raises(NotImplementedError):
+        proc.process("some_file.ARW", stock, 6.0, 0.4)
+    with pytest.raises(NotImplementedError):
+        proc.process(small_frame(32, 32), stock, 6.0, 0.4, canvas_mode="Uniform white")
+    x = torch.zeros((8, 8, 3), device="cuda")
+    with pytest.raises(_cabi.R2FError):
+        _cabi.check(_cabi.lib.r2f_render(proc._ctx, x.data_ptr(), 8, 8, 5, x.data_ptr(), 0, None, 0, None, 0, None))
