@@ -191,7 +191,7 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     H, W, settings, desc = CONFIGS[args.config]
     mp = H * W / 1e6
-    stock = SyntheticStock(name=f"Synthetic {100 * (rank % 4 + 1)}", variant=rank % 4)   # mixed stocks across ranks
+    stock = SyntheticStock(variant=rank % 4)   # mixed stocks across ranks
     proc = B200Processor(device=local)
 
     # --- inputs: pinned host payloads (for e2e) and their device-resident copies (for value) ----------

@@ -31,8 +31,13 @@ class SyntheticStock:
     """Analytic negative stock.  `variant` selects one of the distinct parameter sets used for the
     mixed-stock batch config (BASELINE config 4)."""
 
-    def __init__(self, name: str = "Synthetic 400", variant: int = 0, n2: int = 64, n1: int = 1024, n3: int = 33,
+    def __init__(self, name: str | None = None, variant: int = 0, n2: int = 64, n1: int = 1024, n3: int = 33,
                  density_measure: str = "status_m", with_mtf: bool = True, with_grain: bool = True):
+        # The processors key their LUT caches on `.name` (reference cpu_processor.py:151, 174, 211), so two
+        # stocks with different tables must not share a name: the default name encodes every parameter.
+        if name is None:
+            name = (f"Synthetic {100 * (int(variant) + 1)} [{n2}/{n1}/{n3} {density_measure}"
+                    f"{'' if with_mtf else ' no-mtf'}{'' if with_grain else ' no-grain'}]")
         self.name = name
         self.variant = int(variant)
         self.n2, self.n1, self.n3 = int(n2), int(n1), int(n3)
@@ -137,7 +142,7 @@ class SyntheticStock:
 
 
 def mixed_stocks(count: int = 4, **kw) -> list[SyntheticStock]:
-    return [SyntheticStock(name=f"Synthetic {100 * (i + 1)}", variant=i, **kw) for i in range(count)]
+    return [SyntheticStock(variant=i, **kw) for i in range(count)]
 
 
 # -----------------------------------------------------------------------------------------------

@@ -33,7 +33,7 @@ def test_process_full_emulation_injected_noise(proc, grain_mode):
     st = dict(frame_width=3.0, frame_height=2.0, grain=grain_mode, halation_green_factor=0.3)
     want = oracle_render(fo, xyz, stock, 6.0, 0.4, st, noise=noise)
     got = proc.process(xyz, stock, 6.0, 0.4, grain_noise=noise, **st)
-    assert got.dtype == np.uint8 and got.shape == want.shape and got.flags.owndata is False or True
+    assert got.dtype == np.uint8 and got.shape == want.shape
     mx, rate = _lsb_report(got, want)
     assert mx <= 1 and rate < 2e-3, (mx, rate)
 
@@ -65,7 +65,7 @@ def test_process_preloaded_matches_process_and_accepts_reference_payload(proc):
 
 def test_stage_gating_follows_stock(proc):
     """No MTF data / no rms_density -> the stages are skipped (cpu_processor.py:382, 387)."""
-    plain = SyntheticStock(name="plain", with_mtf=False, with_grain=False)
+    plain = SyntheticStock(with_mtf=False, with_grain=False)
     xyz = small_frame(90, 120, seed=3)
     st = dict(halation=False, frame_width=2.0, frame_height=1.5)
     want = oracle_render(fo, xyz, plain, 6.0, 0.4, st)

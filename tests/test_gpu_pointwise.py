@@ -71,7 +71,7 @@ def test_pointwise_edge_values(proc):
 
 @pytest.mark.parametrize("variant", [0, 1, 2, 3])
 def test_pointwise_mixed_stocks_and_settings(proc, variant):
-    stock = SyntheticStock(name=f"S{variant}", variant=variant, n3=17 + 8 * (variant % 2))
+    stock = SyntheticStock(variant=variant, n3=17 + 8 * (variant % 2))
     xyz = small_frame(120, 200, seed=variant)
     st = dict(OFF, exp_comp=0.5 * variant - 0.5, exp_kelvin=5000 + 700 * variant, tint=variant - 1.0,
               push_pull=0.5 * (variant - 1), sat_adjust=1.0 + 0.1 * variant)

@@ -1,0 +1,67 @@
+"""The oracle against the golden vectors minted from the UNMODIFIED reference
+(tests/golden/make_golden.py).  This is what pins the oracle where /root/reference is absent."""
+import numpy as np
+import pytest
+
+from oracle import film_oracle as fo
+
+G = "tests/golden/"
+MODES = ["Proportional white", "Proportional black", "Uniform white", "Uniform black", "Fixed white", "Fixed black"]
+
+
+@pytest.mark.parametrize("n", [9, 17])
+def test_tetrahedral_lut_bit_exact(n):
+    """apply_lut_tetrahedral (utils.py:247-380): C restatement and NumPy twin, both bit-exact,
+    including the top-of-table clamp, lattice hits, ties and the grey axis."""
+    g = np.load(G + "tetra.npz")
+    img, lut = g[f"img{n}"], g[f"lut{n}"]
+    assert np.array_equal(fo.apply_lut_tetrahedral(img, lut, 0.25), g[f"ref_out{n}"])
+    assert np.array_equal(fo.apply_lut_tetrahedral_np(img, lut, 0.25), g[f"ref_out{n}"])
+    assert np.array_equal(fo.apply_lut_tetrahedral((img / 4.4).astype(np.float32), lut, 1.0), g[f"ref_out{n}_s1"])
+
+
+def test_halation_kernels_bit_exact():
+    """compute_halation_kernel (effects.py:239-263) at the BASELINE scales (43x43 @24MP, 133x133 @61MP x2)."""
+    g = np.load(G + "halation_kernels.npz")
+    sizes = []
+    for i, c in enumerate(g["cases"]):
+        k = fo.compute_halation_kernel(c[0], c[1], 1.0, c[2], 0.0, c[3], bool(c[4]))
+        assert np.array_equal(k, g[f"ref_kernel{i}"])
+        sizes.append(k.shape[0])
+    assert sizes[0] == 43 and sizes[2] == 133
+
+
+def test_mtf_kernels_bit_exact():
+    """mtf_kernel (effects.py:165-185) incl. the unsharp term; 17x17x3 @24MP, 27x27x3 @61MP."""
+    g = np.load(G + "mtf_kernels.npz")
+    mtf = [(g["logf"][c], g["vals"][c]) for c in range(3)]
+    sizes = []
+    for i, c in enumerate(g["cases"]):
+        k = fo.mtf_kernel(mtf, c[0], c[1], c[2])
+        assert np.array_equal(k, g[f"ref_kernel{i}"])
+        sizes.append(k.shape[0])
+    assert sizes[:2] == [17, 27]
+
+
+def test_convolve_2d_matches_reference_and_truth():
+    """convolve_2d (effects.py:146-156): same cv2 call; also the float64 'mirror' truth proves
+    correlation orientation + REFLECT_101."""
+    g = np.load(G + "convolve.npz")
+    for name in ("small", "big"):
+        out = fo.convolve_2d(g["img"].copy(), g["k_" + name])
+        assert np.array_equal(out, g["ref_" + name])
+        assert np.abs(out - fo.correlate_truth_f64(g["img"], g["k_" + name])).max() < 5e-7
+
+
+def test_burn_bit_exact():
+    g = np.load(G + "burn.npz")
+    assert np.array_equal(fo.burn(g["density"].copy(), g["d_ref"], *g["params"]), g["ref_out"])
+    assert np.array_equal(fo.burn(g["density2"].copy(), g["d_ref"], *g["params2"]), g["ref_out2"])
+
+
+def test_canvas_bit_exact():
+    g = np.load(G + "canvas_resize.npz")
+    for i, mode in enumerate(MODES):
+        assert np.array_equal(fo.add_canvas(g["img"], mode, 1.2, 0.8), g[f"ref_{i}"])
+    img = g["img"]
+    assert fo.add_canvas(img, "No") is img
