@@ -210,6 +210,36 @@ cudaError_t launch_expose(const float *in, int cin, Planes out, size_t npix, con
 // For kernel column j the thread slides a 16-row register window down the tile column:
 // one new LDS per 16 FMAs.
 // ------------------------------------------------------------------------------------------
+// One kernel row: 16 FMAs on the register window, then (unless LAST) slide the window down by
+// one tile row.  `u` is the compile-time slot of the row that leaves the window.
+template <int LAST>
+__device__ __forceinline__ void conv_step(float (&acc)[16], float (&v)[16], float w, int u, const float *&rowp,
+                                          int cols) {
+#pragma unroll
+    for (int o = 0; o < 16; ++o) acc[o] = fmaf(w, v[(o + u) & 15], acc[o]);
+    if (!LAST) {
+        v[u & 15] = *rowp;
+        rowp += cols;
+    }
+}
+
+// The last R (< 16) kernel rows of a kernel column, fully unrolled; the final row loads nothing.
+template <int R>
+__device__ __forceinline__ void conv_tail(float (&acc)[16], float (&v)[16], const float4 *wp, const float *rowp,
+                                          int cols) {
+    float w[16];
+#pragma unroll
+    for (int q = 0; q < (R + 3) / 4; ++q) {
+        const float4 w4 = wp[q];
+        w[4 * q] = w4.x; w[4 * q + 1] = w4.y; w[4 * q + 2] = w4.z; w[4 * q + 3] = w4.w;
+    }
+#pragma unroll
+    for (int u = 0; u < R; ++u) {
+        if (u + 1 < R) conv_step<0>(acc, v, w[u], u, rowp, cols);
+        else conv_step<1>(acc, v, w[u], u, rowp, cols);
+    }
+}
+
 template <int TW, int TH, bool W_SMEM>
 __global__ void __launch_bounds__((TW / 32) * (TH / 16) * 32)
 k_conv2d(ConvArgs a) {
@@ -251,25 +281,30 @@ k_conv2d(ConvArgs a) {
         __syncthreads();
 #pragma unroll
         for (int o = 0; o < 16; ++o) acc[o] = 0.0f;
+        const int nfull = k >> 4, rem = k & 15;
         for (int j = 0; j < k; ++j) {
             const float *col = tile + ly0 * cols + lx + j;
             float v[16];
 #pragma unroll
             for (int u = 0; u < 16; ++u) v[u] = col[u * cols];
-            const float *wj = wbase + j * kp;
-            for (int i0 = 0; i0 < k; i0 += 16) {
-                float4 w4 = make_float4(0.f, 0.f, 0.f, 0.f);
+            const float *rowp = col + 16 * cols;          // next tile row to enter the window
+            const float4 *wp = reinterpret_cast<const float4 *>(wbase + j * kp);
+            for (int b = 0; b < nfull; ++b) {             // 16 kernel rows per trip, no guards
 #pragma unroll
-                for (int u = 0; u < 16; ++u) {
-                    const int i = i0 + u;
-                    if (i < k) {
-                        if ((u & 3) == 0) w4 = *reinterpret_cast<const float4 *>(wj + i);
-                        const float w = (u & 3) == 0 ? w4.x : (u & 3) == 1 ? w4.y : (u & 3) == 2 ? w4.z : w4.w;
-#pragma unroll
-                        for (int o = 0; o < 16; ++o) acc[o] = fmaf(w, v[(o + u) & 15], acc[o]);
-                        if (i + 1 < k) v[u] = col[(16 + i) * cols];
-                    }
+                for (int u4 = 0; u4 < 4; ++u4) {
+                    const float4 w4 = *wp++;
+                    conv_step<0>(acc, v, w4.x, u4 * 4 + 0, rowp, cols);
+                    conv_step<0>(acc, v, w4.y, u4 * 4 + 1, rowp, cols);
+                    conv_step<0>(acc, v, w4.z, u4 * 4 + 2, rowp, cols);
+                    conv_step<0>(acc, v, w4.w, u4 * 4 + 3, rowp, cols);
                 }
+            }
+            switch (rem) {                                // k is odd: 1 <= rem <= 15
+#define R2F_REM(R) case R: conv_tail<R>(acc, v, wp, rowp, cols); break;
+                R2F_REM(1) R2F_REM(2) R2F_REM(3) R2F_REM(4) R2F_REM(5) R2F_REM(6) R2F_REM(7) R2F_REM(8)
+                R2F_REM(9) R2F_REM(10) R2F_REM(11) R2F_REM(12) R2F_REM(13) R2F_REM(14) R2F_REM(15)
+#undef R2F_REM
+                default: break;
             }
         }
     }

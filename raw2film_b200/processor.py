@@ -353,6 +353,8 @@ class B200Processor:
         ws_bytes = self._dev_ws.numel() if (flags & _SPATIAL) else 0
         _cabi.check(_cabi.lib.r2f_render(self._ctx, xyz_dev.data_ptr(), h, w, ch, out.data_ptr(), flags, noise_ptr,
                                          nch, ws_ptr, ws_bytes, stream.cuda_stream))
+        # order later work on the caller's stream after the render (asynchronous, no host sync)
+        torch.cuda.current_stream(self.device).wait_stream(stream)
         return out
 
     def render_tap(self, xyz_dev, stage: str, negative_film, grain_size, grain_sigma, **settings):
