@@ -88,6 +88,12 @@ int r2f_set_mtf_kernel(r2f_ctx *ctx, const float *kernel, int k);
  * (the reference draws a fresh seed per frame, gpu_processor.py:586-592). */
 int r2f_set_grain(r2f_ctx *ctx, const float *curve, int N, const float *kernel, int k, uint64_t seed);
 
+/* Tuning / test options.  R2F_OPT_CONV_PATH selects the halation correlation path:
+ * 0 = auto (FFT for wide even-symmetric kernels, direct otherwise), 1 = force direct,
+ * 2 = force FFT (render fails if the kernel or frame is not eligible). */
+#define R2F_OPT_CONV_PATH 1
+int r2f_set_option(r2f_ctx *ctx, int key, int value);
+
 /* Re-seed the on-device noise stream only (no table upload, no synchronisation). */
 int r2f_set_grain_seed(r2f_ctx *ctx, uint64_t seed);
 

@@ -14,11 +14,12 @@ ABI_VERSION = 1
 
 EXPORTS = [
     "r2f_abi_version", "r2f_last_error", "r2f_create", "r2f_destroy", "r2f_set_lut2d", "r2f_set_curve1d",
-    "r2f_set_lut3d", "r2f_set_halation_kernel", "r2f_set_mtf_kernel", "r2f_set_grain", "r2f_set_grain_seed",
+    "r2f_set_lut3d", "r2f_set_halation_kernel", "r2f_set_mtf_kernel", "r2f_set_grain", "r2f_set_grain_seed", "r2f_set_option",
     "r2f_set_burn",
     "r2f_workspace_bytes", "r2f_render", "r2f_render_tap", "r2f_render_host", "r2f_convolve2d",
     "r2f_generate_noise", "r2f_launch_count", "r2f_profile_enable", "r2f_profile_read",
 ]
+OPT_CONV_PATH = 1
 PROF_NAMES = ["pointwise", "expose", "halation", "density", "mtf", "noise", "grain", "burn", "finish"]
 
 
@@ -47,6 +48,7 @@ def _load():
         "r2f_set_mtf_kernel": (ci, [vp, fp, ci]),
         "r2f_set_grain": (ci, [vp, fp, ci, fp, ci, u64]),
         "r2f_set_grain_seed": (ci, [vp, u64]),
+        "r2f_set_option": (ci, [vp, ci, ci]),
         "r2f_set_burn": (ci, [vp, cf, cf, cf]),
         "r2f_workspace_bytes": (sz, [ci, ci, cu]),
         "r2f_render": (ci, [vp, vp, ci, ci, ci, u8p, cu, vp, ci, vp, sz, vp]),

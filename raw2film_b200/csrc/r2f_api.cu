@@ -7,7 +7,10 @@
 #include <vector>
 
 #include "../../include/r2f_b200.h"
+#include "r2f_fft.h"
 #include "r2f_kernels.h"
+#include <map>
+#include <memory>
 
 using namespace r2f;
 
@@ -57,6 +60,27 @@ struct KernelSet {
     int mode[3] = {0, 0, 0};
     const float *chan[3] = {nullptr, nullptr, nullptr};
     bool set = false;
+    // FFT eligibility (r2f_fft.cu): exactly two filtered layers that share one even-symmetric base
+    // kernel, K_c = alpha_c * base + beta_c * delta, third layer an exact delta.
+    bool fft_ok = false;
+    int fft_chan[2] = {0, 1};
+    float fft_alpha[2] = {1.f, 1.f}, fft_beta[2] = {0.f, 0.f};
+    DevBuf base;            // k x k base kernel, row-major, device
+    uint64_t generation = 0;  // bumped on every upload (keys the spectrum cache)
+};
+
+// device copies of the per-length FFT tables
+struct FftLineDev {
+    FftLineHost host;
+    DevBuf roots, cosines;
+    FftLine line() const {
+        FftLine l{};
+        l.n = host.n;
+        l.nrad = (int)host.rad.size();
+        for (int i = 0; i < l.nrad; ++i) l.rad[i] = host.rad[i];
+        l.tw = static_cast<const float2 *>(roots.p);
+        return l;
+    }
 };
 
 }  // namespace
@@ -88,6 +112,13 @@ struct r2f_ctx {
     // r2f_render_host staging
     DevBuf h_in, h_out, h_ws, h_noise;
     cudaStream_t host_stream = nullptr;
+
+    // FFT halation path: per-length tables, cached kernel spectrum
+    std::map<int, std::unique_ptr<FftLineDev>> fft_lines;
+    DevBuf khat, khat_scratch;
+    uint64_t khat_generation = 0;
+    int khat_hp = 0, khat_wp = 0;
+    int conv_path = 0;  // R2F_OPT_CONV_PATH: 0 auto, 1 direct, 2 fft
 
     // per-kernel profiling (r2f_profile_*)
     bool profiling = false;
@@ -151,7 +182,126 @@ int upload_kernel(KernelSet &ks, const float *kernel, int k, int channels) {
         ks.chan[c] = static_cast<const float *>(ks.buf.p) + per * src;
     }
     ks.set = true;
+    ks.generation += 1;
+    ks.fft_ok = false;
+    if (channels == 3 && k >= 3) {
+        int conv[3], nconv = 0;
+        for (int c = 0; c < 3; ++c)
+            if (mode[c]) conv[nconv++] = c;
+        if (nconv == 2) {
+            const int c0 = conv[0], c1 = conv[1], mid = k / 2;
+            auto at = [&](int i, int j, int c) { return (double)kernel[((size_t)i * k + j) * 3 + c]; };
+            bool even = true;
+            for (int i = 0; i < k && even; ++i)
+                for (int j = 0; j < k; ++j)
+                    if (at(i, j, c0) != at(k - 1 - i, j, c0) || at(i, j, c0) != at(i, k - 1 - j, c0)) {
+                        even = false;
+                        break;
+                    }
+            double num = 0.0, den = 0.0;
+            for (int i = 0; i < k; ++i)
+                for (int j = 0; j < k; ++j)
+                    if (i != mid || j != mid) {
+                        num += at(i, j, c1) * at(i, j, c0);
+                        den += at(i, j, c0) * at(i, j, c0);
+                    }
+            if (even && den > 0.0) {
+                const double alpha = num / den, beta = at(mid, mid, c1) - alpha * at(mid, mid, c0);
+                double resid = 0.0;
+                for (int i = 0; i < k; ++i)
+                    for (int j = 0; j < k; ++j)
+                        if (i != mid || j != mid) resid += std::fabs(at(i, j, c1) - alpha * at(i, j, c0));
+                if (resid <= 1e-6) {
+                    std::vector<float> base((size_t)k * k);
+                    for (int i = 0; i < k; ++i)
+                        for (int j = 0; j < k; ++j) base[(size_t)i * k + j] = kernel[((size_t)i * k + j) * 3 + c0];
+                    rc = upload(ks.base, base.data(), base.size() * sizeof(float));
+                    if (rc != R2F_OK) return rc;
+                    ks.fft_ok = true;
+                    ks.fft_chan[0] = c0;
+                    ks.fft_chan[1] = c1;
+                    ks.fft_alpha[0] = 1.f;
+                    ks.fft_beta[0] = 0.f;
+                    ks.fft_alpha[1] = (float)alpha;
+                    ks.fft_beta[1] = (float)beta;
+                }
+            }
+        }
+    }
     return R2F_OK;
+}
+
+// ---- FFT path plumbing ------------------------------------------------------------------------
+constexpr int kFftMinKernel = 9;  // below this the direct kernel is cheaper
+
+FftLineDev *fft_line_for(r2f_ctx *c, int n);
+
+struct FftGeometry {
+    int Hp = 0, Wp = 0;
+    bool ok = false;
+};
+
+FftGeometry fft_geometry(int H, int W, int k) {
+    FftGeometry g;
+    const int r = k / 2;
+    g.Wp = fft_good_size(W + 2 * r, kFftColsPerBlock);
+    g.Hp = fft_good_size(H + 2 * r, 1);
+    if (!g.Wp || !g.Hp) return g;
+    if (fft_rows_smem(g.Wp) > 227 * 1024 || fft_cols_smem(g.Hp) > 227 * 1024) return g;
+    // the spectrum scratch must fit in one planar working image (3 planes of float32)
+    if ((size_t)g.Wp * H * sizeof(float2) > plane_stride_for(H, W) * 3 * sizeof(float)) return g;
+    g.ok = true;
+    return g;
+}
+
+
+FftLineDev *fft_line_for(r2f_ctx *c, int n) {
+    auto it = c->fft_lines.find(n);
+    if (it != c->fft_lines.end()) return it->second.get();
+    std::unique_ptr<FftLineDev> d(new FftLineDev());
+    if (!fft_make_line(n, d->host)) return nullptr;
+    if (upload(d->roots, d->host.roots.data(), d->host.roots.size() * sizeof(float2)) != R2F_OK) return nullptr;
+    if (upload(d->cosines, d->host.cosines.data(), d->host.cosines.size() * sizeof(double)) != R2F_OK) return nullptr;
+    FftLineDev *raw = d.get();
+    c->fft_lines[n] = std::move(d);
+    return raw;
+}
+
+// Fills the geometry-dependent parts of FftConvArgs (tables, cached kernel spectrum).
+int fft_prepare(r2f_ctx *c, const KernelSet &ks, int H, int W, const FftGeometry &g, FftConvArgs &a, cudaStream_t st) {
+    FftLineDev *row = fft_line_for(c, g.Wp), *col = fft_line_for(c, g.Hp);
+    if (!row || !col) return fail(R2F_ERR_INVALID, "FFT plan construction failed");
+    if (c->khat_generation != ks.generation || c->khat_hp != g.Hp || c->khat_wp != g.Wp || !c->khat.p) {
+        CU(c->khat.ensure((size_t)g.Hp * g.Wp * sizeof(float)));
+        CU(c->khat_scratch.ensure((size_t)ks.k * g.Wp * sizeof(double)));
+        CU(launch_khat(static_cast<const float *>(ks.base.p), ks.k, g.Hp, g.Wp,
+                       static_cast<const double *>(col->cosines.p), static_cast<const double *>(row->cosines.p),
+                       static_cast<double *>(c->khat_scratch.p), static_cast<float *>(c->khat.p), st));
+        c->launches += 2;
+        c->khat_generation = ks.generation;
+        c->khat_hp = g.Hp;
+        c->khat_wp = g.Wp;
+    }
+    a.H = H;
+    a.W = W;
+    a.r = ks.k / 2;
+    a.row = row->line();
+    a.col = col->line();
+    a.khat = static_cast<const float *>(c->khat.p);
+    for (int i = 0; i < 2; ++i) {
+        a.chan[i] = ks.fft_chan[i];
+        a.alpha[i] = ks.fft_alpha[i];
+        a.beta[i] = ks.fft_beta[i];
+    }
+    a.plane_stride = plane_stride_for(H, W);
+    return R2F_OK;
+}
+
+bool want_fft(const r2f_ctx *c, const KernelSet &ks, int H, int W, FftGeometry &g) {
+    if (c->conv_path == 1 || !ks.fft_ok) return false;
+    if (c->conv_path == 0 && ks.k < kFftMinKernel) return false;
+    g = fft_geometry(H, W, ks.k);
+    return g.ok;
 }
 
 Lut2D lut2d_of(const r2f_ctx *c) { return Lut2D{static_cast<const float *>(c->lut2d.p), c->n2}; }
@@ -287,35 +437,60 @@ int render_impl(r2f_ctx *c, const float *in, int H, int W, int cin, uint8_t *out
         return R2F_OK;
     };
 
-    // a2: exposure
-    {
-        ProfScope ps_(c, st, R2F_PROF_EXPOSE);
-        CU(launch_expose(in, cin, P[0], npix, l2, c->num_sms, st));
-    }
-    c->launches += 1;
-    if (tap_stage == R2F_TAP_EXPOSURE) return export_tap(P[0]);
-
-    // a3 (+ a4 + a5 fused in the epilogue)
-    if (flags & R2F_HALATION) {
-        ConvArgs a = conv_args(c->hal, P[0].base, P[1].base, ps, H, W);
+    // a2 (+ a3 + a4 + a5): exposure, halation, density
+    FftGeometry geo;
+    const bool hal_fft = (flags & R2F_HALATION) && want_fft(c, c->hal, H, W, geo);
+    if (c->conv_path == 2 && (flags & R2F_HALATION) && !hal_fft)
+        return fail(R2F_ERR_INVALID, "FFT path forced (R2F_OPT_CONV_PATH=2) but this kernel/frame is not eligible");
+    if (hal_fft && tap_stage != R2F_TAP_EXPOSURE) {
+        // XYZ -> 2-D LUT is fused into the row transforms; the exposure image is never materialised
+        FftConvArgs fa{};
+        rc = fft_prepare(c, c->hal, H, W, geo, fa, st);
+        if (rc != R2F_OK) return rc;
+        fa.S = reinterpret_cast<float2 *>(P[2].base);
+        fa.src_planar = nullptr;
+        fa.src_xyz = in;
+        fa.lut2d = l2;
+        fa.dst_planar = P[1].base;
+        fa.curve = cv;
+        fa.eps = c->eps;
+        {
+            ProfScope ps_(c, st, R2F_PROF_HALATION);
+            CU(launch_fft_conv(fa, cin == 3 ? 1 : 2, tap_stage != R2F_TAP_HALATION, st));
+        }
+        c->launches += 2;  // + the one counted below
         if (tap_stage == R2F_TAP_HALATION) {
-            CU(launch_conv2d(a, st));
             c->launches += 1;
             return export_tap(P[1]);
         }
-        a.epi = EPI_DENSITY;
-        a.curve = cv;
-        a.eps = c->eps;
-        ProfScope ps_(c, st, R2F_PROF_HALATION);
-        CU(launch_conv2d(a, st));
     } else {
-        if (tap_stage == R2F_TAP_HALATION) return fail(R2F_ERR_INVALID, "halation tap requested but stage is off");
-        ConvArgs a = identity_args(P[0].base, P[1].base, ps, H, W);
-        a.epi = EPI_DENSITY;
-        a.curve = cv;
-        a.eps = c->eps;
-        ProfScope ps_(c, st, R2F_PROF_DENSITY);
-        CU(launch_conv2d(a, st));
+        {
+            ProfScope ps_(c, st, R2F_PROF_EXPOSE);
+            CU(launch_expose(in, cin, P[0], npix, l2, c->num_sms, st));
+        }
+        c->launches += 1;
+        if (tap_stage == R2F_TAP_EXPOSURE) return export_tap(P[0]);
+        if (flags & R2F_HALATION) {
+            ConvArgs a = conv_args(c->hal, P[0].base, P[1].base, ps, H, W);
+            if (tap_stage == R2F_TAP_HALATION) {
+                CU(launch_conv2d(a, st));
+                c->launches += 1;
+                return export_tap(P[1]);
+            }
+            a.epi = EPI_DENSITY;
+            a.curve = cv;
+            a.eps = c->eps;
+            ProfScope ps_(c, st, R2F_PROF_HALATION);
+            CU(launch_conv2d(a, st));
+        } else {
+            if (tap_stage == R2F_TAP_HALATION) return fail(R2F_ERR_INVALID, "halation tap requested but stage is off");
+            ConvArgs a = identity_args(P[0].base, P[1].base, ps, H, W);
+            a.epi = EPI_DENSITY;
+            a.curve = cv;
+            a.eps = c->eps;
+            ProfScope ps_(c, st, R2F_PROF_DENSITY);
+            CU(launch_conv2d(a, st));
+        }
     }
     c->launches += 1;
     int cur = 1;
@@ -417,8 +592,13 @@ int r2f_destroy(r2f_ctx *c) {
     if (!c) return R2F_OK;
     DeviceGuard guard(c->device);
     for (DevBuf *b : {&c->lut2d, &c->curve, &c->lut3d, &c->hal.buf, &c->mtf.buf, &c->grain.buf, &c->gcurve,
-                      &c->burn_buf, &c->h_in, &c->h_out, &c->h_ws, &c->h_noise})
+                      &c->burn_buf, &c->h_in, &c->h_out, &c->h_ws, &c->h_noise, &c->hal.base, &c->mtf.base,
+                      &c->grain.base, &c->khat, &c->khat_scratch})
         b->release();
+    for (auto &kv : c->fft_lines) {
+        kv.second->roots.release();
+        kv.second->cosines.release();
+    }
     if (c->host_stream) cudaStreamDestroy(c->host_stream);
     delete c;
     return R2F_OK;
@@ -487,6 +667,15 @@ int r2f_set_grain(r2f_ctx *c, const float *curve, int N, const float *kernel, in
     if (rc != R2F_OK) return rc;
     c->seed = seed;
     return R2F_OK;
+}
+
+int r2f_set_option(r2f_ctx *c, int key, int value) {
+    if (!c) return fail(R2F_ERR_INVALID, "null context");
+    if (key == R2F_OPT_CONV_PATH && value >= 0 && value <= 2) {
+        c->conv_path = value;
+        return R2F_OK;
+    }
+    return fail(R2F_ERR_INVALID, "r2f_set_option: unknown key or value");
 }
 
 int r2f_set_grain_seed(r2f_ctx *c, uint64_t seed) {
@@ -568,10 +757,33 @@ int r2f_convolve2d(r2f_ctx *c, const float *in_dev, float *out_dev, int H, int W
     Planes a{static_cast<float *>(workspace_dev), ps}, b{static_cast<float *>(workspace_dev) + 3 * ps, ps};
     const size_t npix = (size_t)H * W;
     cudaError_t e = launch_interleaved_to_planar(in_dev, 3, 3, a, npix, c->num_sms, st);
-    if (e == cudaSuccess) e = launch_conv2d(conv_args(ks, a.base, b.base, ps, H, W), st);
+    FftGeometry geo;
+    const bool use_fft = want_fft(c, ks, H, W, geo) && workspace_bytes >= ps * 9 * sizeof(float);
+    if (c->conv_path == 2 && !use_fft) {
+        ks.buf.release();
+        ks.base.release();
+        return fail(R2F_ERR_INVALID, "FFT path forced but this kernel/frame/workspace is not eligible");
+    }
+    if (e == cudaSuccess && use_fft) {
+        FftConvArgs fa{};
+        ks.generation = ~0ull - (c->launches & 0xffff);  // never collides with a cached halation spectrum
+        c->khat_generation = 0;
+        rc = fft_prepare(c, ks, H, W, geo, fa, st);
+        if (rc == R2F_OK) {
+            fa.S = reinterpret_cast<float2 *>(static_cast<float *>(workspace_dev) + 6 * ps);
+            fa.src_planar = a.base;
+            fa.dst_planar = b.base;
+            e = launch_fft_conv(fa, 0, false, st);
+        }
+        c->khat_generation = 0;  // the cached spectrum belongs to a temporary kernel: invalidate
+    } else if (e == cudaSuccess) {
+        e = launch_conv2d(conv_args(ks, a.base, b.base, ps, H, W), st);
+    }
     if (e == cudaSuccess) e = launch_planar_to_interleaved(b, out_dev, npix, c->num_sms, st);
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);
     ks.buf.release();
+    ks.base.release();
+    if (rc != R2F_OK) return rc;
     if (e != cudaSuccess) return fail_cuda(e, "r2f_convolve2d");
     c->launches += 3;
     return R2F_OK;

@@ -86,13 +86,15 @@ __device__ __forceinline__ void butterfly<5>(float2 (&v)[5]) {
     v[3] = csub(r2, n2);
 }
 
-constexpr int kMaxElemsPerThread = 16;
+// complex elements a thread may hold during one pass: 16 with 512 threads (<=128 registers),
+// 12 with 1024 threads (<=64 registers)
+__host__ __device__ constexpr int max_elems_for(int threads) { return threads <= 512 ? 16 : 12; }
 
 // One in-place Stockham pass of radix R over buf[0..n): every thread first pulls its butterflies
 // into registers, the CTA synchronises, then results go back to their auto-sorted positions.
-template <int R>
+template <int R, int MAXE>
 __device__ __forceinline__ void fft_pass(float2 *buf, int n, int Ns, const float2 *__restrict__ tw) {
-    constexpr int IT = kMaxElemsPerThread / R;
+    constexpr int IT = MAXE / R;
     const int nb = n / R;
     const int tws = n / (Ns * R);
     const int tid = threadIdx.x, T = blockDim.x;
@@ -125,15 +127,17 @@ __device__ __forceinline__ void fft_pass(float2 *buf, int n, int Ns, const float
 }
 
 // Forward FFT of buf[0..n) by the whole CTA (all threads must call; ends synchronised).
+template <int T>
 __device__ __forceinline__ void fft_forward(float2 *buf, const FftLine &L) {
+    constexpr int M = max_elems_for(T);
     int Ns = 1;
     for (int s = 0; s < L.nrad; ++s) {
         const int R = L.rad[s];
         switch (R) {
-            case 2: fft_pass<2>(buf, L.n, Ns, L.tw); break;
-            case 3: fft_pass<3>(buf, L.n, Ns, L.tw); break;
-            case 4: fft_pass<4>(buf, L.n, Ns, L.tw); break;
-            default: fft_pass<5>(buf, L.n, Ns, L.tw); break;
+            case 2: fft_pass<2, M>(buf, L.n, Ns, L.tw); break;
+            case 3: fft_pass<3, M>(buf, L.n, Ns, L.tw); break;
+            case 4: fft_pass<4, M>(buf, L.n, Ns, L.tw); break;
+            default: fft_pass<5, M>(buf, L.n, Ns, L.tw); break;
         }
         Ns *= R;
     }
@@ -152,9 +156,9 @@ __device__ __forceinline__ void pad_line(float2 *buf, int len, int r, int n) {
 // ------------------------------------------------------------------------------------------
 // rows, forward
 // ------------------------------------------------------------------------------------------
-template <int SRC>  // 0: planar source planes, 1: interleaved XYZ through the 2-D LUT (cin 3), 2: same, cin 4
-__global__ void __launch_bounds__(1024)
-k_fft_rows_fwd(FftConvArgs a) {
+template <int SRC, int T>  // SRC 0: planar planes, 1: interleaved XYZ through the 2-D LUT (cin 3), 2: same, cin 4
+__global__ void __launch_bounds__(T, 1)
+k_fft_rows_fwd(const __grid_constant__ FftConvArgs a) {
     extern __shared__ __align__(16) float2 fsm[];
     const int W = a.W, H = a.H, r = a.r, n = a.row.n;
     const int y0 = blockIdx.x * 2;
@@ -182,7 +186,7 @@ k_fft_rows_fwd(FftConvArgs a) {
     __syncthreads();
     for (int row = 0; row < nrows; ++row) pad_line(fsm + (size_t)row * n, W, r, n);
     __syncthreads();
-    for (int row = 0; row < nrows; ++row) fft_forward(fsm + (size_t)row * n, a.row);
+    for (int row = 0; row < nrows; ++row) fft_forward<T>(fsm + (size_t)row * n, a.row);
     // blocked store: S[(b*H + y)*NC + c], NC columns of one row are contiguous (NC*8 bytes)
     constexpr int NC = kFftColsPerBlock;
     const int per_row = n;  // n % NC == 0
@@ -197,8 +201,9 @@ k_fft_rows_fwd(FftConvArgs a) {
 // ------------------------------------------------------------------------------------------
 // columns: forward FFT, * Khat, inverse FFT, fused
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(1024)
-k_fft_cols(FftConvArgs a) {
+template <int T>
+__global__ void __launch_bounds__(T, 1)
+k_fft_cols(const __grid_constant__ FftConvArgs a) {
     extern __shared__ __align__(16) float2 fsm[];
     constexpr int NC = kFftColsPerBlock;
     const int H = a.H, r = a.r, n = a.col.n;
@@ -212,7 +217,7 @@ k_fft_cols(FftConvArgs a) {
     __syncthreads();
     for (int c = 0; c < NC; ++c) pad_line(fsm + (size_t)c * pitch, H, r, n);
     __syncthreads();
-    for (int c = 0; c < NC; ++c) fft_forward(fsm + (size_t)c * pitch, a.col);
+    for (int c = 0; c < NC; ++c) fft_forward<T>(fsm + (size_t)c * pitch, a.col);
     // product with the real kernel spectrum; swap re/im so the next forward FFT is the inverse
     for (int idx = threadIdx.x; idx < n * NC; idx += blockDim.x) {
         const int c = idx / n, u = idx - c * n;
@@ -222,7 +227,7 @@ k_fft_cols(FftConvArgs a) {
         *p = make_float2(z.y * kh, z.x * kh);
     }
     __syncthreads();
-    for (int c = 0; c < NC; ++c) fft_forward(fsm + (size_t)c * pitch, a.col);
+    for (int c = 0; c < NC; ++c) fft_forward<T>(fsm + (size_t)c * pitch, a.col);
     // keep the swapped form: k_fft_rows_inv consumes swap(x) directly
     for (int idx = threadIdx.x; idx < H * NC; idx += blockDim.x) {
         const int c = idx % NC, y = idx / NC;
@@ -233,9 +238,9 @@ k_fft_cols(FftConvArgs a) {
 // ------------------------------------------------------------------------------------------
 // rows, inverse + epilogue
 // ------------------------------------------------------------------------------------------
-template <int SRC, int DENSITY>
-__global__ void __launch_bounds__(1024)
-k_fft_rows_inv(FftConvArgs a) {
+template <int SRC, int DENSITY, int T>
+__global__ void __launch_bounds__(T, 1)
+k_fft_rows_inv(const __grid_constant__ FftConvArgs a) {
     extern __shared__ __align__(16) float2 fsm[];
     constexpr int NC = kFftColsPerBlock;
     const int W = a.W, H = a.H, r = a.r, n = a.row.n;
@@ -249,7 +254,7 @@ k_fft_rows_inv(FftConvArgs a) {
         fsm[(size_t)row * n + b * NC + c] = a.S[((size_t)b * H + (y0 + row)) * NC + c];
     }
     __syncthreads();
-    for (int row = 0; row < nrows; ++row) fft_forward(fsm + (size_t)row * n, a.row);
+    for (int row = 0; row < nrows; ++row) fft_forward<T>(fsm + (size_t)row * n, a.row);
     const size_t ps = a.plane_stride;
     for (int row = 0; row < nrows; ++row) {
         const int y = y0 + row;
@@ -339,7 +344,7 @@ static bool line_feasible(int n, const std::vector<int> &rad) {
     for (int R : rad) {
         const int nb = n / R;
         const int per = (nb + T - 1) / T;
-        if (per * R > kMaxElemsPerThread) return false;
+        if (per * R > max_elems_for(T)) return false;
     }
     return true;
 }
@@ -386,24 +391,27 @@ static cudaError_t set_smem(K kfn, size_t bytes) {
     return cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
 }
 
-cudaError_t launch_fft_conv(const FftConvArgs &a, int src_mode, bool density, cudaStream_t st) {
-    const size_t rs = fft_rows_smem(a.row.n), cs = fft_cols_smem(a.col.n);
-    const int tr = fft_threads_for(a.row.n), tc = fft_threads_for(a.col.n);
-    const int row_ctas = (a.H + 1) / 2, col_ctas = a.row.n / kFftColsPerBlock;
+template <int T>
+static cudaError_t launch_rows_fwd(const FftConvArgs &a, int src_mode, int ctas, size_t smem, cudaStream_t st) {
     cudaError_t e;
-#define R2F_FWD(M)                                                        \
-    do {                                                                  \
-        if ((e = set_smem(k_fft_rows_fwd<M>, rs)) != cudaSuccess) return e; \
-        k_fft_rows_fwd<M><<<row_ctas, tr, rs, st>>>(a);                   \
+#define R2F_FWD(M)                                                              \
+    do {                                                                        \
+        if ((e = set_smem(k_fft_rows_fwd<M, T>, smem)) != cudaSuccess) return e; \
+        k_fft_rows_fwd<M, T><<<ctas, T, smem, st>>>(a);                         \
     } while (0)
     if (src_mode == 0) R2F_FWD(0); else if (src_mode == 1) R2F_FWD(1); else R2F_FWD(2);
 #undef R2F_FWD
-    if ((e = set_smem(k_fft_cols, cs)) != cudaSuccess) return e;
-    k_fft_cols<<<col_ctas, tc, cs, st>>>(a);
-#define R2F_INV(M, D)                                                          \
-    do {                                                                       \
-        if ((e = set_smem(k_fft_rows_inv<M, D>, rs)) != cudaSuccess) return e; \
-        k_fft_rows_inv<M, D><<<row_ctas, tr, rs, st>>>(a);                     \
+    return cudaGetLastError();
+}
+
+template <int T>
+static cudaError_t launch_rows_inv(const FftConvArgs &a, int src_mode, bool density, int ctas, size_t smem,
+                                   cudaStream_t st) {
+    cudaError_t e;
+#define R2F_INV(M, D)                                                              \
+    do {                                                                           \
+        if ((e = set_smem(k_fft_rows_inv<M, D, T>, smem)) != cudaSuccess) return e; \
+        k_fft_rows_inv<M, D, T><<<ctas, T, smem, st>>>(a);                         \
     } while (0)
     if (density) {
         if (src_mode == 0) R2F_INV(0, 1); else if (src_mode == 1) R2F_INV(1, 1); else R2F_INV(2, 1);
@@ -412,6 +420,27 @@ cudaError_t launch_fft_conv(const FftConvArgs &a, int src_mode, bool density, cu
     }
 #undef R2F_INV
     return cudaGetLastError();
+}
+
+template <int T>
+static cudaError_t launch_cols(const FftConvArgs &a, int ctas, size_t smem, cudaStream_t st) {
+    cudaError_t e;
+    if ((e = set_smem(k_fft_cols<T>, smem)) != cudaSuccess) return e;
+    k_fft_cols<T><<<ctas, T, smem, st>>>(a);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_fft_conv(const FftConvArgs &a, int src_mode, bool density, cudaStream_t st) {
+    const size_t rs = fft_rows_smem(a.row.n), cs = fft_cols_smem(a.col.n);
+    const int tr = fft_threads_for(a.row.n), tc = fft_threads_for(a.col.n);
+    const int row_ctas = (a.H + 1) / 2, col_ctas = a.row.n / kFftColsPerBlock;
+    cudaError_t e = tr == 512 ? launch_rows_fwd<512>(a, src_mode, row_ctas, rs, st)
+                              : launch_rows_fwd<1024>(a, src_mode, row_ctas, rs, st);
+    if (e != cudaSuccess) return e;
+    e = tc == 512 ? launch_cols<512>(a, col_ctas, cs, st) : launch_cols<1024>(a, col_ctas, cs, st);
+    if (e != cudaSuccess) return e;
+    return tr == 512 ? launch_rows_inv<512>(a, src_mode, density, row_ctas, rs, st)
+                     : launch_rows_inv<1024>(a, src_mode, density, row_ctas, rs, st);
 }
 
 }  // namespace r2f

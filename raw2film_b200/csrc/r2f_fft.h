@@ -1,0 +1,64 @@
+// FFT-based 2-D correlation for wide, even-symmetric kernels (halation).  See r2f_fft.cu.
+#pragma once
+#include <cstddef>
+#include <cstdint>
+#include <vector>
+
+#include <cuda_runtime.h>
+
+#include "device_math.cuh"
+
+namespace r2f {
+
+constexpr int kFftColsPerBlock = 4;   // columns per CTA in the column pass (32-byte row segments)
+constexpr int kFftMaxPasses = 12;
+constexpr int kFftMaxLen = 14336;
+
+// One FFT length as the device sees it.
+struct FftLine {
+    int n;
+    int nrad;
+    int rad[kFftMaxPasses];
+    const float2 *tw;  // exp(-2 pi i q / n), q < n
+};
+
+// Host-side description of one FFT length (factorisation + double-built root / cosine tables).
+struct FftLineHost {
+    int n = 0;
+    std::vector<int> rad;
+    std::vector<float2> roots;
+    std::vector<double> cosines;
+};
+
+struct FftConvArgs {
+    int H, W, r;        // frame size, kernel radius (k/2)
+    FftLine row, col;   // lengths Wp (>= W + 2r, multiple of kFftColsPerBlock) and Hp (>= H + 2r)
+    float2 *S;          // spectrum scratch, (Wp / NC) x H x NC complex
+    const float *khat;  // [Wp][Hp] real kernel spectrum, 1/(Hp*Wp) folded in
+    int chan[2];        // the two planes filtered together (R, G)
+    float alpha[2], beta[2];  // out_c = alpha * (K (*) x_c) + beta * x_c
+    // source: planar planes or interleaved XYZ through the 2-D input LUT
+    const float *src_planar;
+    const float *src_xyz;
+    Lut2D lut2d;
+    size_t plane_stride;
+    // destination: planar planes, optionally through log10 + H-D curve
+    float *dst_planar;
+    Curve1D curve;
+    float eps;
+};
+
+int fft_good_size(int min_n, int multiple_of);
+int fft_threads_for(int n);
+bool fft_make_line(int n, FftLineHost &out);
+size_t fft_rows_smem(int Wp);
+size_t fft_cols_smem(int Hp);
+
+// Kernel spectrum of an even-symmetric k x k base kernel (device, row-major) -> khat [Wp][Hp].
+cudaError_t launch_khat(const float *base_kernel_dev, int k, int Hp, int Wp, const double *cosH_dev,
+                        const double *cosW_dev, double *scratchA_dev, float *khat_dev, cudaStream_t st);
+
+// src_mode: 0 planar, 1 XYZ interleaved (3 channels) + 2-D LUT, 2 same with 4 channels.
+cudaError_t launch_fft_conv(const FftConvArgs &a, int src_mode, bool density, cudaStream_t st);
+
+}  // namespace r2f

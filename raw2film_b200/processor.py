@@ -87,6 +87,10 @@ class B200Processor:
         except Exception:  # noqa: BLE001
             pass
 
+    def set_conv_path(self, mode: str = "auto") -> None:
+        """Halation correlation path: "auto" (FFT for wide even-symmetric kernels), "direct" or "fft"."""
+        _cabi.check(_cabi.lib.r2f_set_option(self._ctx, _cabi.OPT_CONV_PATH, {"auto": 0, "direct": 1, "fft": 2}[mode]))
+
     @property
     def launch_count(self) -> int:
         return int(_cabi.lib.r2f_launch_count(self._ctx))

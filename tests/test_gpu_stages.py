@@ -33,9 +33,11 @@ def _tap(proc, xyz, stage, stock, **settings):
     return proc.render_tap(x, stage, stock, 6.0, 0.4, **settings).cpu().numpy()
 
 
-def _gpu_convolve(proc, img, kernel):
+def _gpu_convolve(proc, img, kernel, path="auto"):
     import torch
     from raw2film_b200 import _cabi
+
+    proc.set_conv_path(path)
 
     h, w = img.shape[:2]
     x = torch.from_numpy(np.ascontiguousarray(img)).cuda()
@@ -46,7 +48,42 @@ def _gpu_convolve(proc, img, kernel):
     _cabi.check(_cabi.lib.r2f_convolve2d(proc._ctx, x.data_ptr(), out.data_ptr(), h, w, _cabi.f32_ptr(kernel),
                                          kernel.shape[0], ws.data_ptr(), ws.numel(), None))
     torch.cuda.synchronize()
+    proc.set_conv_path("auto")
     return out.cpu().numpy()
+
+
+@pytest.mark.parametrize("shape,scale,size", [((300, 200), 150.0, 1.0), ((211, 307), 102.0, 1.0), ((97, 130), 40.0, 1.0),
+                                              ((402, 603), 6000 / 36, 1.0), ((530, 801), 9504 / 36, 2.0)])
+def test_halation_fft_path_vs_truth_and_direct(proc, shape, scale, size):
+    """The FFT path (packed R+iG, real kernel spectrum) against the float64 direct truth and against
+    the direct CUDA kernel, on ragged sizes (odd H -> single-row tail CTA, W % 4 != 0) with real
+    halation kernels up to 133x133 and point highlights 200x above the surround."""
+    rng = np.random.default_rng(shape[0])
+    img = (rng.random((*shape, 3), dtype=np.float32) * 0.5).astype(np.float32)
+    for _ in range(12):
+        img[rng.integers(0, shape[0]), rng.integers(0, shape[1])] = 100.0
+    kern = fo.compute_halation_kernel(scale, size, 1.0, 0.3, 0.0, 1.0)
+    truth = fo.correlate_truth_f64(img, kern)
+    fft = _gpu_convolve(proc, img, kern, "fft")
+    direct = _gpu_convolve(proc, img, kern, "direct")
+    lim = 2e-6 * 100.0
+    assert np.abs(direct - truth).max() <= lim
+    assert np.abs(fft - truth).max() <= lim, f"fft err {np.abs(fft - truth).max()}"
+    assert np.array_equal(fft[..., 2], img[..., 2])          # blue layer untouched
+    # relative accuracy in the dark surround, where halation from the highlights dominates
+    rel = np.abs(fft - truth) / np.maximum(np.abs(truth), 1e-3)
+    assert rel.max() <= 2e-4
+
+
+def test_fft_path_refuses_ineligible_kernel(proc):
+    from raw2film_b200 import _cabi
+
+    rng = np.random.default_rng(0)
+    img = rng.random((64, 64, 3), dtype=np.float32)
+    kern = rng.random((9, 9, 3), dtype=np.float32)            # asymmetric, three filtered layers
+    with pytest.raises(_cabi.R2FError):
+        _gpu_convolve(proc, img, kern, "fft")
+    proc.set_conv_path("auto")
 
 
 def test_convolve_matches_reference_golden(proc):
