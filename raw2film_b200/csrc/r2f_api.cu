@@ -237,17 +237,17 @@ constexpr int kFftMinKernel = 9;  // below this the direct kernel is cheaper
 FftLineDev *fft_line_for(r2f_ctx *c, int n);
 
 struct FftGeometry {
-    int Hp = 0, Wp = 0;
+    int Hp = 0, Wp = 0, nc = 0, groups = 0;
     bool ok = false;
 };
 
 FftGeometry fft_geometry(int H, int W, int k) {
     FftGeometry g;
     const int r = k / 2;
-    g.Wp = fft_good_size(W + 2 * r, kFftColsPerBlock);
+    g.Wp = fft_good_size(W + 2 * r, 2);
     g.Hp = fft_good_size(H + 2 * r, 1);
     if (!g.Wp || !g.Hp) return g;
-    if (fft_rows_smem(g.Wp) > 227 * 1024 || fft_cols_smem(g.Hp) > 227 * 1024) return g;
+    if (fft_rows_smem(g.Wp) > 227 * 1024 || !fft_col_geometry(g.Hp, g.Wp, g.nc, g.groups)) return g;
     // the spectrum scratch must fit in one planar working image (3 planes of float32)
     if ((size_t)g.Wp * H * sizeof(float2) > plane_stride_for(H, W) * 3 * sizeof(float)) return g;
     g.ok = true;
@@ -287,6 +287,8 @@ int fft_prepare(r2f_ctx *c, const KernelSet &ks, int H, int W, const FftGeometry
     a.r = ks.k / 2;
     a.row = row->line();
     a.col = col->line();
+    a.nc = g.nc;
+    a.col_groups = g.groups;
     a.khat = static_cast<const float *>(c->khat.p);
     for (int i = 0; i < 2; ++i) {
         a.chan[i] = ks.fft_chan[i];

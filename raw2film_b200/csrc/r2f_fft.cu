@@ -86,87 +86,103 @@ __device__ __forceinline__ void butterfly<5>(float2 (&v)[5]) {
     v[3] = csub(r2, n2);
 }
 
-// complex elements a thread may hold during one pass: 16 with 512 threads (<=128 registers),
-// 12 with 1024 threads (<=64 registers)
-__host__ __device__ constexpr int max_elems_for(int threads) { return threads <= 512 ? 16 : 12; }
-
-// One in-place Stockham pass of radix R over buf[0..n): every thread first pulls its butterflies
-// into registers, the CTA synchronises, then results go back to their auto-sorted positions.
-template <int R, int MAXE>
-__device__ __forceinline__ void fft_pass(float2 *buf, int n, int Ns, const float2 *__restrict__ tw) {
-    constexpr int IT = MAXE / R;
-    const int nb = n / R;
-    const int tws = n / (Ns * R);
-    const int tid = threadIdx.x, T = blockDim.x;
-    float2 v[IT][R];
-#pragma unroll
-    for (int it = 0; it < IT; ++it) {
-        const int j = tid + it * T;
-        if (j < nb) {
-#pragma unroll
-            for (int t = 0; t < R; ++t) v[it][t] = buf[j + t * nb];
-        }
-    }
-    __syncthreads();
-#pragma unroll
-    for (int it = 0; it < IT; ++it) {
-        const int j = tid + it * T;
-        if (j < nb) {
-            const int k = j % Ns;
-            if (k != 0) {
-#pragma unroll
-                for (int t = 1; t < R; ++t) v[it][t] = cmul(v[it][t], __ldg(tw + t * k * tws));
-            }
-            butterfly<R>(v[it]);
-            const int j0 = (j - k) * R + k;
-#pragma unroll
-            for (int t = 0; t < R; ++t) buf[j0 + t * Ns] = v[it][t];
-        }
-    }
-    __syncthreads();
+// A group of threads that cooperates on one FFT line and synchronises on its own named barrier.
+struct Group {
+    int tid, size, bar;
+};
+__device__ __forceinline__ void group_sync(const Group &g) {
+    asm volatile("bar.sync %0, %1;" ::"r"(g.bar), "r"(g.size) : "memory");
 }
 
-// Forward FFT of buf[0..n) by the whole CTA (all threads must call; ends synchronised).
-template <int T>
-__device__ __forceinline__ void fft_forward(float2 *buf, const FftLine &L) {
-    constexpr int M = max_elems_for(T);
+// One out-of-place Stockham pass of radix R: src[0..n) -> dst[0..n) (auto-sorting, no bit reversal).
+// Butterfly j reads src[j + t*n/R] (contiguous across lanes) and writes dst[j0 + t*Ns].
+template <int R>
+__device__ __forceinline__ void fft_pass(const float2 *__restrict__ src, float2 *__restrict__ dst, int n, int Ns,
+                                         const float2 *__restrict__ tw, const Group &g) {
+    const int nb = n / R;
+    const int tws = n / (Ns * R);
+    const bool pow2 = (Ns & (Ns - 1)) == 0;
+    for (int j = g.tid; j < nb; j += g.size) {
+        const int k = pow2 ? (j & (Ns - 1)) : (j % Ns);
+        float2 v[R];
+#pragma unroll
+        for (int t = 0; t < R; ++t) v[t] = src[j + t * nb];
+        if (k != 0) {
+            const int q = k * tws;
+#pragma unroll
+            for (int t = 1; t < R; ++t) v[t] = cmul(v[t], __ldg(tw + t * q));
+        }
+        butterfly<R>(v);
+        const int j0 = (j - k) * R + k;
+        if (Ns == 1 && R == 4) {  // outputs are 4 consecutive elements: two 16-byte stores
+            float4 *d4 = reinterpret_cast<float4 *>(dst + j0);
+            d4[0] = make_float4(v[0].x, v[0].y, v[1].x, v[1].y);
+            d4[1] = make_float4(v[2].x, v[2].y, v[3].x, v[3].y);
+        } else if (Ns == 1 && R == 2) {
+            *reinterpret_cast<float4 *>(dst + j0) = make_float4(v[0].x, v[0].y, v[1].x, v[1].y);
+        } else {
+#pragma unroll
+            for (int t = 0; t < R; ++t) dst[j0 + t * Ns] = v[t];
+        }
+    }
+    group_sync(g);
+}
+
+// Forward FFT of a[0..n) using b as the ping-pong partner.  The data in `a` must already be visible
+// to the whole group.  Returns the buffer holding the result (a if the pass count is even).
+__device__ __forceinline__ float2 *fft_forward(float2 *a, float2 *b, const FftLine &L, const Group &g) {
+    float2 *src = a, *dst = b;
     int Ns = 1;
     for (int s = 0; s < L.nrad; ++s) {
         const int R = L.rad[s];
         switch (R) {
-            case 2: fft_pass<2, M>(buf, L.n, Ns, L.tw); break;
-            case 3: fft_pass<3, M>(buf, L.n, Ns, L.tw); break;
-            case 4: fft_pass<4, M>(buf, L.n, Ns, L.tw); break;
-            default: fft_pass<5, M>(buf, L.n, Ns, L.tw); break;
+            case 2: fft_pass<2>(src, dst, L.n, Ns, L.tw, g); break;
+            case 3: fft_pass<3>(src, dst, L.n, Ns, L.tw, g); break;
+            case 4: fft_pass<4>(src, dst, L.n, Ns, L.tw, g); break;
+            default: fft_pass<5>(src, dst, L.n, Ns, L.tw, g); break;
         }
+        float2 *t = src;
+        src = dst;
+        dst = t;
         Ns *= R;
     }
+    return src;
 }
 
 // reflect-101 fill of the r-wide borders of a padded line whose interior [r, r+len) is loaded,
-// and zero fill of the tail [len+2r, n).  `stride` = distance between consecutive elements.
-__device__ __forceinline__ void pad_line(float2 *buf, int len, int r, int n) {
-    for (int p = threadIdx.x; p < r; p += blockDim.x) {
+// and zero fill of the tail [len+2r, n).
+__device__ __forceinline__ void pad_line(float2 *buf, int len, int r, int n, const Group &g) {
+    for (int p = g.tid; p < r; p += g.size) {
         buf[p] = buf[r + reflect101(p - r, len)];
         buf[r + len + p] = buf[r + reflect101(len + p, len)];
     }
-    for (int p = len + 2 * r + threadIdx.x; p < n; p += blockDim.x) buf[p] = make_float2(0.f, 0.f);
+    for (int p = len + 2 * r + g.tid; p < n; p += g.size) buf[p] = make_float2(0.f, 0.f);
+}
+
+// Row kernels: ROWS image rows per CTA, one thread group per row (ROWS == 2: two 512-thread groups
+// on named barriers 1 and 2; ROWS == 1: the whole CTA).  Each row owns two line buffers.
+template <int ROWS>
+__device__ __forceinline__ Group row_group() {
+    if (ROWS == 2) return Group{(int)(threadIdx.x & 511), 512, 1 + (int)(threadIdx.x >> 9)};
+    return Group{(int)threadIdx.x, (int)blockDim.x, 0};
 }
 
 // ------------------------------------------------------------------------------------------
 // rows, forward
 // ------------------------------------------------------------------------------------------
-template <int SRC, int T>  // SRC 0: planar planes, 1: interleaved XYZ through the 2-D LUT (cin 3), 2: same, cin 4
-__global__ void __launch_bounds__(T, 1)
+template <int SRC, int ROWS>  // SRC 0: planar planes, 1: interleaved XYZ through the 2-D LUT (cin 3), 2: same, cin 4
+__global__ void __launch_bounds__(1024, 1)
 k_fft_rows_fwd(const __grid_constant__ FftConvArgs a) {
     extern __shared__ __align__(16) float2 fsm[];
-    const int W = a.W, H = a.H, r = a.r, n = a.row.n;
-    const int y0 = blockIdx.x * 2;
-    const int nrows = min(2, H - y0);
-    for (int row = 0; row < nrows; ++row) {
-        float2 *buf = fsm + (size_t)row * n;
-        const int y = y0 + row;
-        for (int x = threadIdx.x; x < W; x += blockDim.x) {
+    const int W = a.W, H = a.H, r = a.r, n = a.row.n, NC = a.nc;
+    const Group g = row_group<ROWS>();
+    const int half = ROWS == 2 ? (int)(threadIdx.x >> 9) : 0;
+    const int y0 = blockIdx.x * ROWS;
+    const int nrows = min(ROWS, H - y0);
+    float2 *bufA = fsm + (size_t)half * 2 * n, *bufB = bufA + n;
+    const int y = y0 + half;
+    if (half < nrows) {
+        for (int x = g.tid; x < W; x += g.size) {
             float2 z;
             if (SRC == 0) {
                 const size_t idx = (size_t)y * W + x;
@@ -180,34 +196,33 @@ k_fft_rows_fwd(const __grid_constant__ FftConvArgs a) {
                 z.x = e0;
                 z.y = e1;
             }
-            buf[r + x] = z;
+            bufA[r + x] = z;
         }
+        group_sync(g);
+        pad_line(bufA, W, r, n, g);
+        group_sync(g);
+        fft_forward(bufA, bufB, a.row, g);
     }
     __syncthreads();
-    for (int row = 0; row < nrows; ++row) pad_line(fsm + (size_t)row * n, W, r, n);
-    __syncthreads();
-    for (int row = 0; row < nrows; ++row) fft_forward<T>(fsm + (size_t)row * n, a.row);
-    // blocked store: S[(b*H + y)*NC + c], NC columns of one row are contiguous (NC*8 bytes)
-    constexpr int NC = kFftColsPerBlock;
-    const int per_row = n;  // n % NC == 0
-    for (int idx = threadIdx.x; idx < per_row * nrows; idx += blockDim.x) {
+    // blocked store: S[(b*H + y)*NC + c]; the NC columns of the CTA's rows are contiguous
+    const size_t res_off = (a.row.nrad & 1) ? (size_t)n : 0;  // result buffer by pass parity
+    for (int idx = threadIdx.x; idx < n * nrows; idx += blockDim.x) {
         const int c = idx % NC;
         const int row = (idx / NC) % nrows;
         const int b = idx / (NC * nrows);
-        a.S[((size_t)b * H + (y0 + row)) * NC + c] = fsm[(size_t)row * n + b * NC + c];
+        a.S[((size_t)b * H + (y0 + row)) * NC + c] = fsm[(size_t)row * 2 * n + res_off + b * NC + c];
     }
 }
 
 // ------------------------------------------------------------------------------------------
-// columns: forward FFT, * Khat, inverse FFT, fused
+// columns: forward FFT, * Khat, inverse FFT, fused.  NC columns per CTA (one contiguous block of
+// S), a.col_groups thread groups, each with its own ping-pong buffer.
 // ------------------------------------------------------------------------------------------
-template <int T>
-__global__ void __launch_bounds__(T, 1)
+__global__ void __launch_bounds__(1024, 1)
 k_fft_cols(const __grid_constant__ FftConvArgs a) {
     extern __shared__ __align__(16) float2 fsm[];
-    constexpr int NC = kFftColsPerBlock;
-    const int H = a.H, r = a.r, n = a.col.n;
-    const int pitch = n + 1;  // de-phase the NC column buffers across banks
+    const int H = a.H, r = a.r, n = a.col.n, NC = a.nc, NG = a.col_groups;
+    const int pitch = n + 2;  // even (16-byte aligned lines), de-phases the column buffers across banks
     const int b = blockIdx.x;
     float2 *blk = a.S + (size_t)b * H * NC;
     for (int idx = threadIdx.x; idx < H * NC; idx += blockDim.x) {
@@ -215,19 +230,27 @@ k_fft_cols(const __grid_constant__ FftConvArgs a) {
         fsm[(size_t)c * pitch + r + y] = blk[idx];
     }
     __syncthreads();
-    for (int c = 0; c < NC; ++c) pad_line(fsm + (size_t)c * pitch, H, r, n);
-    __syncthreads();
-    for (int c = 0; c < NC; ++c) fft_forward<T>(fsm + (size_t)c * pitch, a.col);
-    // product with the real kernel spectrum; swap re/im so the next forward FFT is the inverse
-    for (int idx = threadIdx.x; idx < n * NC; idx += blockDim.x) {
-        const int c = idx / n, u = idx - c * n;
-        const float kh = __ldg(a.khat + (size_t)(b * NC + c) * n + u);
-        float2 *p = fsm + (size_t)c * pitch + u;
-        const float2 z = *p;
-        *p = make_float2(z.y * kh, z.x * kh);
+    const int gsize = (int)blockDim.x / NG;
+    const int gi = (int)threadIdx.x / gsize;
+    const Group g{(int)threadIdx.x % gsize, gsize, NG == 1 ? 0 : 1 + gi};
+    float2 *tmp = fsm + (size_t)(NC + gi) * pitch;
+    for (int c = gi; c < NC; c += NG) {
+        float2 *home = fsm + (size_t)c * pitch;
+        pad_line(home, H, r, n, g);
+        group_sync(g);
+        float2 *spec = fft_forward(home, tmp, a.col, g);
+        float2 *other = spec == home ? tmp : home;
+        // product with the real kernel spectrum; swap re/im so the next forward FFT is the inverse
+        const float *kh = a.khat + (size_t)(b * NC + c) * n;
+        for (int u = g.tid; u < n; u += g.size) {
+            const float2 z = spec[u];
+            const float w = __ldg(kh + u);
+            spec[u] = make_float2(z.y * w, z.x * w);
+        }
+        group_sync(g);
+        fft_forward(spec, other, a.col, g);  // 2 * nrad passes in total: the result is back in `home`
     }
     __syncthreads();
-    for (int c = 0; c < NC; ++c) fft_forward<T>(fsm + (size_t)c * pitch, a.col);
     // keep the swapped form: k_fft_rows_inv consumes swap(x) directly
     for (int idx = threadIdx.x; idx < H * NC; idx += blockDim.x) {
         const int c = idx % NC, y = idx / NC;
@@ -238,48 +261,48 @@ k_fft_cols(const __grid_constant__ FftConvArgs a) {
 // ------------------------------------------------------------------------------------------
 // rows, inverse + epilogue
 // ------------------------------------------------------------------------------------------
-template <int SRC, int DENSITY, int T>
-__global__ void __launch_bounds__(T, 1)
+template <int SRC, int DENSITY, int ROWS>
+__global__ void __launch_bounds__(1024, 1)
 k_fft_rows_inv(const __grid_constant__ FftConvArgs a) {
     extern __shared__ __align__(16) float2 fsm[];
-    constexpr int NC = kFftColsPerBlock;
-    const int W = a.W, H = a.H, r = a.r, n = a.row.n;
-    const int y0 = blockIdx.x * 2;
-    const int nrows = min(2, H - y0);
+    const int W = a.W, H = a.H, r = a.r, n = a.row.n, NC = a.nc;
+    const Group g = row_group<ROWS>();
+    const int half = ROWS == 2 ? (int)(threadIdx.x >> 9) : 0;
+    const int y0 = blockIdx.x * ROWS;
+    const int nrows = min(ROWS, H - y0);
     // S holds swap(column-inverse); one more forward FFT along the row completes swap(IFFT2)
     for (int idx = threadIdx.x; idx < n * nrows; idx += blockDim.x) {
         const int c = idx % NC;
         const int row = (idx / NC) % nrows;
         const int b = idx / (NC * nrows);
-        fsm[(size_t)row * n + b * NC + c] = a.S[((size_t)b * H + (y0 + row)) * NC + c];
+        fsm[(size_t)row * 2 * n + b * NC + c] = a.S[((size_t)b * H + (y0 + row)) * NC + c];
     }
     __syncthreads();
-    for (int row = 0; row < nrows; ++row) fft_forward<T>(fsm + (size_t)row * n, a.row);
+    if (half >= nrows) return;
+    float2 *bufA = fsm + (size_t)half * 2 * n, *bufB = bufA + n;
+    const float2 *buf = fft_forward(bufA, bufB, a.row, g);
     const size_t ps = a.plane_stride;
-    for (int row = 0; row < nrows; ++row) {
-        const int y = y0 + row;
-        const float2 *buf = fsm + (size_t)row * n;
-        for (int x = threadIdx.x; x < W; x += blockDim.x) {
-            const size_t idx = (size_t)y * W + x;
-            const float2 zs = buf[r + x];  // swapped: .y = K(*)chan0, .x = K(*)chan1
-            float src[3];
-            if (SRC == 0) {
+    const int y = y0 + half;
+    for (int x = g.tid; x < W; x += g.size) {
+        const size_t idx = (size_t)y * W + x;
+        const float2 zs = buf[r + x];  // swapped: .y = K(*)chan0, .x = K(*)chan1
+        float src[3];
+        if (SRC == 0) {
 #pragma unroll
-                for (int c = 0; c < 3; ++c) src[c] = a.src_planar[c * ps + idx];
-            } else {
-                const int cin = SRC == 1 ? 3 : 4;
-                const float *px = a.src_xyz + idx * cin;
-                lut2d_eval(a.lut2d, __ldg(px), __ldg(px + 1), __ldg(px + 2), src[0], src[1], src[2]);
-            }
-            float out[3] = {src[0], src[1], src[2]};
-            out[a.chan[0]] = fmaf(a.alpha[0], zs.y, a.beta[0] * src[a.chan[0]]);
-            out[a.chan[1]] = fmaf(a.alpha[1], zs.x, a.beta[1] * src[a.chan[1]]);
+            for (int c = 0; c < 3; ++c) src[c] = a.src_planar[c * ps + idx];
+        } else {
+            const int cin = SRC == 1 ? 3 : 4;
+            const float *px = a.src_xyz + idx * cin;
+            lut2d_eval(a.lut2d, __ldg(px), __ldg(px + 1), __ldg(px + 2), src[0], src[1], src[2]);
+        }
+        float out[3] = {src[0], src[1], src[2]};
+        out[a.chan[0]] = fmaf(a.alpha[0], zs.y, a.beta[0] * src[a.chan[0]]);
+        out[a.chan[1]] = fmaf(a.alpha[1], zs.x, a.beta[1] * src[a.chan[1]]);
 #pragma unroll
-            for (int c = 0; c < 3; ++c) {
-                float val = out[c];
-                if (DENSITY) val = density_eval(a.curve, c, val, a.eps);
-                a.dst_planar[c * ps + idx] = val;
-            }
+        for (int c = 0; c < 3; ++c) {
+            float val = out[c];
+            if (DENSITY) val = density_eval(a.curve, c, val, a.eps);
+            a.dst_planar[c * ps + idx] = val;
         }
     }
 }
@@ -337,30 +360,18 @@ static bool factor_235(int n, std::vector<int> &rad) {
     return (int)rad.size() <= kFftMaxPasses;
 }
 
-int fft_threads_for(int n) { return n <= 6656 ? 512 : 1024; }
-
-static bool line_feasible(int n, const std::vector<int> &rad) {
-    const int T = fft_threads_for(n);
-    for (int R : rad) {
-        const int nb = n / R;
-        const int per = (nb + T - 1) / T;
-        if (per * R > max_elems_for(T)) return false;
-    }
-    return true;
-}
-
 int fft_good_size(int min_n, int multiple_of) {
     for (int n = min_n; n <= kFftMaxLen; ++n) {
         if (n % multiple_of) continue;
         std::vector<int> rad;
-        if (factor_235(n, rad) && line_feasible(n, rad)) return n;
+        if (factor_235(n, rad)) return n;
     }
     return 0;
 }
 
 bool fft_make_line(int n, FftLineHost &out) {
     std::vector<int> rad;
-    if (!factor_235(n, rad) || !line_feasible(n, rad)) return false;
+    if (!factor_235(n, rad)) return false;
     out.n = n;
     out.rad = rad;
     out.roots.resize(n);
@@ -374,8 +385,29 @@ bool fft_make_line(int n, FftLineHost &out) {
     return true;
 }
 
-size_t fft_rows_smem(int Wp) { return (size_t)2 * Wp * sizeof(float2); }
-size_t fft_cols_smem(int Hp) { return (size_t)kFftColsPerBlock * (Hp + 1) * sizeof(float2); }
+constexpr size_t kFftMaxSmem = 227 * 1024;
+
+// rows per CTA: two when both rows' ping-pong pairs fit in shared memory
+static int rows_per_cta(int Wp) { return (size_t)4 * Wp * sizeof(float2) <= kFftMaxSmem ? 2 : 1; }
+size_t fft_rows_smem(int Wp) { return (size_t)rows_per_cta(Wp) * 2 * Wp * sizeof(float2); }
+size_t fft_cols_smem(int Hp, int nc, int groups) { return (size_t)(nc + groups) * (Hp + 2) * sizeof(float2); }
+
+// Column-pass geometry: the widest column block (<= 4) dividing Wp that fits, with two thread
+// groups when their ping-pong buffers fit too.
+bool fft_col_geometry(int Hp, int Wp, int &nc, int &groups) {
+    for (int c = 4; c >= 2; --c) {
+        if (Wp % c) continue;
+        for (int gcount = 2; gcount >= 1; --gcount) {
+            if (gcount > c) continue;
+            if (fft_cols_smem(Hp, c, gcount) <= kFftMaxSmem) {
+                nc = c;
+                groups = gcount;
+                return true;
+            }
+        }
+    }
+    return false;
+}
 
 cudaError_t launch_khat(const float *base_kernel_dev, int k, int Hp, int Wp, const double *cosH_dev,
                         const double *cosW_dev, double *scratchA_dev, float *khat_dev, cudaStream_t st) {
@@ -391,27 +423,28 @@ static cudaError_t set_smem(K kfn, size_t bytes) {
     return cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
 }
 
-template <int T>
-static cudaError_t launch_rows_fwd(const FftConvArgs &a, int src_mode, int ctas, size_t smem, cudaStream_t st) {
+template <int ROWS>
+static cudaError_t launch_rows_fwd(const FftConvArgs &a, int src_mode, int ctas, int threads, size_t smem,
+                                   cudaStream_t st) {
     cudaError_t e;
-#define R2F_FWD(M)                                                              \
-    do {                                                                        \
-        if ((e = set_smem(k_fft_rows_fwd<M, T>, smem)) != cudaSuccess) return e; \
-        k_fft_rows_fwd<M, T><<<ctas, T, smem, st>>>(a);                         \
+#define R2F_FWD(M)                                                                 \
+    do {                                                                           \
+        if ((e = set_smem(k_fft_rows_fwd<M, ROWS>, smem)) != cudaSuccess) return e; \
+        k_fft_rows_fwd<M, ROWS><<<ctas, threads, smem, st>>>(a);                   \
     } while (0)
     if (src_mode == 0) R2F_FWD(0); else if (src_mode == 1) R2F_FWD(1); else R2F_FWD(2);
 #undef R2F_FWD
     return cudaGetLastError();
 }
 
-template <int T>
-static cudaError_t launch_rows_inv(const FftConvArgs &a, int src_mode, bool density, int ctas, size_t smem,
-                                   cudaStream_t st) {
+template <int ROWS>
+static cudaError_t launch_rows_inv(const FftConvArgs &a, int src_mode, bool density, int ctas, int threads,
+                                   size_t smem, cudaStream_t st) {
     cudaError_t e;
-#define R2F_INV(M, D)                                                              \
-    do {                                                                           \
-        if ((e = set_smem(k_fft_rows_inv<M, D, T>, smem)) != cudaSuccess) return e; \
-        k_fft_rows_inv<M, D, T><<<ctas, T, smem, st>>>(a);                         \
+#define R2F_INV(M, D)                                                                 \
+    do {                                                                              \
+        if ((e = set_smem(k_fft_rows_inv<M, D, ROWS>, smem)) != cudaSuccess) return e; \
+        k_fft_rows_inv<M, D, ROWS><<<ctas, threads, smem, st>>>(a);                   \
     } while (0)
     if (density) {
         if (src_mode == 0) R2F_INV(0, 1); else if (src_mode == 1) R2F_INV(1, 1); else R2F_INV(2, 1);
@@ -422,25 +455,18 @@ static cudaError_t launch_rows_inv(const FftConvArgs &a, int src_mode, bool dens
     return cudaGetLastError();
 }
 
-template <int T>
-static cudaError_t launch_cols(const FftConvArgs &a, int ctas, size_t smem, cudaStream_t st) {
-    cudaError_t e;
-    if ((e = set_smem(k_fft_cols<T>, smem)) != cudaSuccess) return e;
-    k_fft_cols<T><<<ctas, T, smem, st>>>(a);
-    return cudaGetLastError();
-}
-
 cudaError_t launch_fft_conv(const FftConvArgs &a, int src_mode, bool density, cudaStream_t st) {
-    const size_t rs = fft_rows_smem(a.row.n), cs = fft_cols_smem(a.col.n);
-    const int tr = fft_threads_for(a.row.n), tc = fft_threads_for(a.col.n);
-    const int row_ctas = (a.H + 1) / 2, col_ctas = a.row.n / kFftColsPerBlock;
-    cudaError_t e = tr == 512 ? launch_rows_fwd<512>(a, src_mode, row_ctas, rs, st)
-                              : launch_rows_fwd<1024>(a, src_mode, row_ctas, rs, st);
+    const int rows = rows_per_cta(a.row.n);
+    const size_t rs = fft_rows_smem(a.row.n), cs = fft_cols_smem(a.col.n, a.nc, a.col_groups);
+    const int row_ctas = (a.H + rows - 1) / rows, col_ctas = a.row.n / a.nc;
+    cudaError_t e = rows == 2 ? launch_rows_fwd<2>(a, src_mode, row_ctas, 1024, rs, st)
+                              : launch_rows_fwd<1>(a, src_mode, row_ctas, 1024, rs, st);
     if (e != cudaSuccess) return e;
-    e = tc == 512 ? launch_cols<512>(a, col_ctas, cs, st) : launch_cols<1024>(a, col_ctas, cs, st);
-    if (e != cudaSuccess) return e;
-    return tr == 512 ? launch_rows_inv<512>(a, src_mode, density, row_ctas, rs, st)
-                     : launch_rows_inv<1024>(a, src_mode, density, row_ctas, rs, st);
+    if ((e = set_smem(k_fft_cols, cs)) != cudaSuccess) return e;
+    k_fft_cols<<<col_ctas, 1024, cs, st>>>(a);
+    if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    return rows == 2 ? launch_rows_inv<2>(a, src_mode, density, row_ctas, 1024, rs, st)
+                     : launch_rows_inv<1>(a, src_mode, density, row_ctas, 1024, rs, st);
 }
 
 }  // namespace r2f

@@ -10,7 +10,7 @@
 
 namespace r2f {
 
-constexpr int kFftColsPerBlock = 4;   // columns per CTA in the column pass (32-byte row segments)
+constexpr int kFftColsPerBlock = 4;   // preferred columns per CTA in the column pass (32-byte row segments)
 constexpr int kFftMaxPasses = 12;
 constexpr int kFftMaxLen = 14336;
 
@@ -33,7 +33,9 @@ struct FftLineHost {
 struct FftConvArgs {
     int H, W, r;        // frame size, kernel radius (k/2)
     FftLine row, col;   // lengths Wp (>= W + 2r, multiple of kFftColsPerBlock) and Hp (>= H + 2r)
-    float2 *S;          // spectrum scratch, (Wp / NC) x H x NC complex
+    int nc;             // columns per CTA / per block of S (2..4, divides Wp)
+    int col_groups;     // thread groups per column CTA (1 or 2)
+    float2 *S;          // spectrum scratch, (Wp / nc) x H x nc complex
     const float *khat;  // [Wp][Hp] real kernel spectrum, 1/(Hp*Wp) folded in
     int chan[2];        // the two planes filtered together (R, G)
     float alpha[2], beta[2];  // out_c = alpha * (K (*) x_c) + beta * x_c
@@ -49,10 +51,10 @@ struct FftConvArgs {
 };
 
 int fft_good_size(int min_n, int multiple_of);
-int fft_threads_for(int n);
 bool fft_make_line(int n, FftLineHost &out);
 size_t fft_rows_smem(int Wp);
-size_t fft_cols_smem(int Hp);
+size_t fft_cols_smem(int Hp, int nc, int groups);
+bool fft_col_geometry(int Hp, int Wp, int &nc, int &groups);
 
 // Kernel spectrum of an even-symmetric k x k base kernel (device, row-major) -> khat [Wp][Hp].
 cudaError_t launch_khat(const float *base_kernel_dev, int k, int Hp, int Wp, const double *cosH_dev,
