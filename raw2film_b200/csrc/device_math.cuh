@@ -8,6 +8,8 @@
 #include <cstdint>
 #include <cuda_runtime.h>
 
+#include "log10_tables.h"
+
 namespace r2f {
 
 struct Lut2D {
@@ -26,6 +28,11 @@ struct Lut3D {
     const float4 *tab;  // (n, n, n) vertices padded to float4
     int n;
     double s;  // scale * (n - 1)
+    // guarded float32 fast path for uint8 outputs (tetra_quant_u8): sf = (float)s, `margin` = proven
+    // bound on |255 * (fast - exact)|; fast_exact_d != 0 when s is a power of two (fractions exact)
+    float sf;
+    float margin;
+    int fast_ok;
 };
 
 // ---- a2: chromaticity-indexed input LUT (reference shaders/lut_2d.wgsl:18-108) ---------
@@ -70,10 +77,50 @@ __device__ __forceinline__ void lut2d_eval(const Lut2D &L, float X, float Y, flo
 }
 
 // ---- a4: log10 with lower clip (shaders/lut_1d.wgsl:23-26) -------------------------------
-// binary64 log10 rounded once to binary32 (see oracle/pointwise_oracle.c log10_clip1).
+// The oracle defines log10 as binary64 log10 rounded once to binary32 (pointwise_oracle.c
+// log10_clip1), i.e. a correctly rounded log10f.  CUDA's generic double log10 costs ~100
+// instructions; log10_exact gets the same bits from a 256-entry table + degree-7 series:
+//   x = 2^k * z, z in [0.699, 1.398);  r = fma(z, invc_i, -1)  (|r| <= 2^-8, error 2^-62)
+//   y = (k*log10(2) + T_i) + r * P(r),  relative error <= ~3 * 2^-53.
+// If y lies within 64 binary64-ulps of a binary32 rounding tie the generic routine decides
+// (probability 2^-22).  Validated on the host against glibc on 3.3e8 inputs: 0 mismatches
+// (tools/gen_log10_tables.py documents the tables).
+static __device__ __noinline__ float log10_slow(float c) { return (float)log10((double)c); }
+
+__device__ __forceinline__ float log10_exact(float c) {
+    const uint32_t ix = __float_as_uint(c);
+    if (ix - 0x00800000u >= 0x7f000000u) return log10_slow(c);  // zero, subnormal, negative, inf, nan
+    const uint32_t tmp = ix - 0x3f330000u;
+    const int i = (tmp >> 15) & 255;
+    const int k = (int)tmp >> 23;
+    const uint32_t iz = ix - (tmp & 0xff800000u);
+    // z widened to binary64 by bit construction (z is a normal float): no F2F conversion
+    const double z = __hiloint2double((int)((iz >> 3) + 0x38000000u), (int)(iz << 29));
+    const double2 tab = __ldg(&kLog10Tab[i]);
+    const double r = fma(z, tab.x, -1.0);
+    double p = R2F_LOG10_A7;
+    p = fma(p, r, R2F_LOG10_A6);
+    p = fma(p, r, R2F_LOG10_A5);
+    p = fma(p, r, R2F_LOG10_A4);
+    p = fma(p, r, R2F_LOG10_A3);
+    p = fma(p, r, R2F_LOG10_A2);
+    p = fma(p, r, R2F_LOG10_A1);
+    const double y = fma(r, p, __ldg(&kLog10Exp[k + 160]) + tab.y);
+    const uint32_t t = (uint32_t)__double2loint(y) & 0x1fffffffu;
+    if ((uint32_t)(t - (0x10000000u - 64u)) < 128u) return log10_slow(c);
+    return __double2float_rn(y);
+}
+
 __device__ __forceinline__ float log10_clip(float v, float eps) {
     const float c = v > eps ? v : eps;
-    return (float)log10((double)c);
+    return log10_exact(c);
+}
+
+// Approximate variant (MUFU.LG2, abs error ~1e-6 at |log10| = 6) for stages whose input already
+// carries float32 convolution noise (tolerance 1e-4 in density).
+__device__ __forceinline__ float log10_clip_fast(float v, float eps) {
+    const float c = v > eps ? v : eps;
+    return __log2f(c) * 0.30102999566398119521f;
 }
 
 // ---- a5: per-channel curve, uniform abscissa, clamped ends (lut_1d.wgsl:43-47) -----------
@@ -92,6 +139,9 @@ __device__ __forceinline__ float curve_eval(const Curve1D &C, int ch, float v) {
 
 __device__ __forceinline__ float density_eval(const Curve1D &C, int ch, float exposure, float eps) {
     return curve_eval(C, ch, log10_clip(exposure, eps));
+}
+__device__ __forceinline__ float density_eval_fast(const Curve1D &C, int ch, float exposure, float eps) {
+    return curve_eval(C, ch, log10_clip_fast(exposure, eps));
 }
 
 // ---- a9: tetrahedral 3-D LUT (reference utils.py:247-380) -----------------------------------
@@ -160,6 +210,67 @@ __device__ __forceinline__ uint32_t quantise_u8(float v) {
     if (!(q > 0.0f)) return 0u;
     if (q >= 255.0f) return 255u;
     return (uint32_t)(int)q;
+}
+
+// a9 + a10 for uint8 outputs: float32 evaluation of the same tetrahedral formula, accepted only
+// when 255*value is provably on the same side of every quantisation boundary as the exact
+// binary64 path (|255*(fast - exact)| <= L.margin, bound derived in r2f_set_lut3d); otherwise the
+// exact path decides.  Interpolation is continuous across cells and tetrahedra, so a different
+// cell choice of the float32 coordinates is covered by the same bound.
+__device__ __forceinline__ bool quant_safe(float q, float m, uint32_t &out) {
+    if (q < -m) { out = 0u; return true; }
+    if (q >= 255.0f + m) { out = 255u; return true; }
+    const float fl = floorf(q);
+    const float fr = q - fl;
+    out = (uint32_t)(int)fl;
+    return q > 0.0f && q < 255.0f && fr > m && fr < 1.0f - m;
+}
+
+__device__ __forceinline__ void tetra_quant_u8(const Lut3D &L, float dr_in, float dg_in, float db_in, uint32_t &q0,
+                                               uint32_t &q1, uint32_t &q2) {
+    bool ok = L.fast_ok != 0;
+    if (ok) {
+        const int n = L.n;
+        const float vr = dr_in * L.sf, vg = dg_in * L.sf, vb = db_in * L.sf;
+        ok = vr >= 0.0f && vg >= 0.0f && vb >= 0.0f && vr < 1.0e6f && vg < 1.0e6f && vb < 1.0e6f;  // also NaN
+        if (ok) {
+            int r0 = (int)vr, g0 = (int)vg, b0 = (int)vb;
+            float dr = vr - (float)r0, dg = vg - (float)g0, db = vb - (float)b0;
+            if (r0 >= n - 1) { r0 = n - 2; dr = 1.0f; }
+            if (g0 >= n - 1) { g0 = n - 2; dg = 1.0f; }
+            if (b0 >= n - 1) { b0 = n - 2; db = 1.0f; }
+            const int sr = n * n, sg = n;  // vertex strides
+            int o1, o2;
+            float d1, d2, d3;
+            if (dr >= dg) {
+                if (dg >= db) { o1 = sr; o2 = sr + sg; d1 = dr; d2 = dg; d3 = db; }
+                else if (dr >= db) { o1 = sr; o2 = sr + 1; d1 = dr; d2 = db; d3 = dg; }
+                else { o1 = 1; o2 = sr + 1; d1 = db; d2 = dr; d3 = dg; }
+            } else {
+                if (db >= dg) { o1 = 1; o2 = sg + 1; d1 = db; d2 = dg; d3 = dr; }
+                else if (db >= dr) { o1 = sg; o2 = sg + 1; d1 = dg; d2 = db; d3 = dr; }
+                else { o1 = sg; o2 = sr + sg; d1 = dg; d2 = dr; d3 = db; }
+            }
+            const float4 *base = L.tab + (r0 * n + g0) * n + b0;
+            const float4 c000 = __ldg(base), cm1 = __ldg(base + o1), cm2 = __ldg(base + o2);
+            const float4 c111 = __ldg(base + sr + sg + 1);
+            const float s0 = fmaf(d3, c111.x - cm2.x, fmaf(d2, cm2.x - cm1.x, fmaf(d1, cm1.x - c000.x, c000.x)));
+            const float s1 = fmaf(d3, c111.y - cm2.y, fmaf(d2, cm2.y - cm1.y, fmaf(d1, cm1.y - c000.y, c000.y)));
+            const float s2 = fmaf(d3, c111.z - cm2.z, fmaf(d2, cm2.z - cm1.z, fmaf(d1, cm1.z - c000.z, c000.z)));
+            const float m = L.margin;
+            const bool a0 = quant_safe(s0 * 255.0f, m, q0);
+            const bool a1 = quant_safe(s1 * 255.0f, m, q1);
+            const bool a2 = quant_safe(s2 * 255.0f, m, q2);
+            ok = a0 && a1 && a2;
+        }
+    }
+    if (!ok) {
+        float o0, o1f, o2f;
+        tetra_eval(L, dr_in, dg_in, db_in, o0, o1f, o2f);
+        q0 = quantise_u8(o0);
+        q1 = quantise_u8(o1f);
+        q2 = quantise_u8(o2f);
+    }
 }
 
 // ---- BORDER_REFLECT_101 index (cv2.filter2D default, reference effects.py:146-156) -----------

@@ -98,6 +98,8 @@ struct r2f_ctx {
     DevBuf lut3d;
     int n3 = 0;
     double s3 = 0.0;
+    float s3f = 0.f, margin3 = 0.f;
+    int fast3 = 0;
 
     KernelSet hal, mtf, grain;
     DevBuf gcurve;
@@ -313,7 +315,9 @@ Curve1D curve_of(const r2f_ctx *c) {
 Curve1D gcurve_of(const r2f_ctx *c) {
     return Curve1D{static_cast<const float *>(c->gcurve.p), c->ng, c->gx0, c->ginv};
 }
-Lut3D lut3d_of(const r2f_ctx *c) { return Lut3D{static_cast<const float4 *>(c->lut3d.p), c->n3, c->s3}; }
+Lut3D lut3d_of(const r2f_ctx *c) {
+    return Lut3D{static_cast<const float4 *>(c->lut3d.p), c->n3, c->s3, c->s3f, c->margin3, c->fast3};
+}
 
 ConvArgs conv_args(const KernelSet &ks, const float *in, float *out, size_t ps, int H, int W) {
     ConvArgs a{};
@@ -479,7 +483,7 @@ int render_impl(r2f_ctx *c, const float *in, int H, int W, int cin, uint8_t *out
                 c->launches += 1;
                 return export_tap(P[1]);
             }
-            a.epi = EPI_DENSITY;
+            a.epi = EPI_DENSITY_FAST;
             a.curve = cv;
             a.eps = c->eps;
             ProfScope ps_(c, st, R2F_PROF_HALATION);
@@ -641,6 +645,23 @@ int r2f_set_lut3d(r2f_ctx *c, const float *lut, int n, double scale) {
     if (rc != R2F_OK) return rc;
     c->n3 = n;
     c->s3 = scale * (double)(n - 1);  // utils.py:258
+    // Error bound of the float32 fast path (device_math.cuh tetra_quant_u8), in units of the
+    // quantised output: three fused roundings of partial sums bounded by 1 + 2*range, the final
+    // binary32 rounding of the exact path, the float32 product with 255, and -- when s is not a
+    // power of two -- the rounding of the coordinate v = d*s propagated through the edge slopes.
+    double absmax = 0.0;
+    for (size_t i = 0; i < verts * 3; ++i) absmax = std::fmax(absmax, std::fabs((double)lut[i]));
+    const double u = std::ldexp(1.0, -24);
+    const double partial = absmax + 3.0 * 2.0 * absmax + 1e-30;
+    double err = 3.0 * u * partial + u * absmax;           // accumulation + final rounding
+    int e2 = 0;
+    const bool pow2 = std::frexp(c->s3, &e2) == 0.5 && c->s3 > 0.0;
+    if (!pow2) err += 3.0 * (2.0 * absmax) * (2.0 * u * (double)n);  // coordinate rounding x slopes
+    double margin = 255.0 * err + 2.0 * u * 255.0 * std::fmax(1.0, absmax);
+    margin *= 1.5;                                          // safety factor
+    c->s3f = (float)c->s3;
+    c->margin3 = (float)margin;
+    c->fast3 = (margin < 0.2 && (double)c->s3f == c->s3 && std::isfinite(absmax)) ? 1 : 0;
     return R2F_OK;
 }
 

@@ -301,7 +301,7 @@ k_fft_rows_inv(const __grid_constant__ FftConvArgs a) {
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
             float val = out[c];
-            if (DENSITY) val = density_eval(a.curve, c, val, a.eps);
+            if (DENSITY) val = density_eval_fast(a.curve, c, val, a.eps);
             a.dst_planar[c * ps + idx] = val;
         }
     }

@@ -69,11 +69,7 @@ __device__ __forceinline__ void pixel_chain(const float (&xyz)[3], const Lut2D &
     const float d0 = density_eval(cv, 0, e0, eps);
     const float d1 = density_eval(cv, 1, e1, eps);
     const float d2 = density_eval(cv, 2, e2, eps);
-    float o0, o1, o2;
-    tetra_eval(l3, d0, d1, d2, o0, o1, o2);
-    r = quantise_u8(o0);
-    g = quantise_u8(o1);
-    b = quantise_u8(o2);
+    tetra_quant_u8(l3, d0, d1, d2, r, g, b);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -318,6 +314,8 @@ k_conv2d(ConvArgs a) {
             float val = acc[o];
             if (a.epi == EPI_DENSITY) {
                 val = density_eval(a.curve, c, val, a.eps);
+            } else if (a.epi == EPI_DENSITY_FAST) {
+                val = density_eval_fast(a.curve, c, val, a.eps);
             } else if (a.epi == EPI_GRAIN) {
                 const float d = a.aux[c * ps + idx];
                 const float g = val * curve_eval(a.curve, c, d);
@@ -405,11 +403,10 @@ k_finish(const float *__restrict__ in, size_t plane_stride, size_t npix, int W, 
             }
             if (F32_OUT && !f32_stage_rgb) {
                 f[3 * p] = d0; f[3 * p + 1] = d1; f[3 * p + 2] = d2;
+            } else if (F32_OUT) {
+                tetra_eval(l3, d0, d1, d2, f[3 * p], f[3 * p + 1], f[3 * p + 2]);
             } else {
-                float o0, o1, o2;
-                tetra_eval(l3, d0, d1, d2, o0, o1, o2);
-                if (F32_OUT) { f[3 * p] = o0; f[3 * p + 1] = o1; f[3 * p + 2] = o2; }
-                else { b[3 * p] = quantise_u8(o0); b[3 * p + 1] = quantise_u8(o1); b[3 * p + 2] = quantise_u8(o2); }
+                tetra_quant_u8(l3, d0, d1, d2, b[3 * p], b[3 * p + 1], b[3 * p + 2]);
             }
         }
         if (q * 4 + 4 <= npix) {

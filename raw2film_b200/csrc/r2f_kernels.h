@@ -20,7 +20,7 @@ inline size_t plane_stride_for(int H, int W) {
     return (n + 63) / 64 * 64;
 }
 
-enum ConvEpilogue { EPI_NONE = 0, EPI_DENSITY = 1, EPI_GRAIN = 2 };
+enum ConvEpilogue { EPI_NONE = 0, EPI_DENSITY = 1, EPI_GRAIN = 2, EPI_DENSITY_FAST = 3 };
 
 struct ConvArgs {
     const float *in;      // planar source
