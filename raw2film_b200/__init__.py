@@ -2,7 +2,7 @@
 render path behind the reference's processor API.  See DESIGN.md."""
 from __future__ import annotations
 
-__all__ = ["B200Processor", "SyntheticStock", "BatchExporter"]
+__all__ = ["B200Processor", "SyntheticStock", "BatchExporter", "PipelinedRenderer"]
 
 
 def __getattr__(name):  # lazy: importing the package does not need CUDA, using the processor does
@@ -18,4 +18,8 @@ def __getattr__(name):  # lazy: importing the package does not need CUDA, using 
         from .batch import BatchExporter
 
         return BatchExporter
+    if name == "PipelinedRenderer":
+        from .pipeline import PipelinedRenderer
+
+        return PipelinedRenderer
     raise AttributeError(name)

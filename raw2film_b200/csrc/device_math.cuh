@@ -15,6 +15,8 @@ namespace r2f {
 struct Lut2D {
     const float *tab;  // (n, n, 3) lut[x_idx][y_idx]
     int n;
+    __host__ __device__ Lut2D() : tab(nullptr), n(0) {}
+    __host__ __device__ Lut2D(const float *t, int n_) : tab(t), n(n_) {}
 };
 
 struct Curve1D {
@@ -36,44 +38,36 @@ struct Lut3D {
 };
 
 // ---- a2: chromaticity-indexed input LUT (reference shaders/lut_2d.wgsl:18-108) ---------
-__device__ __forceinline__ int clamp_floor_idx(float fl, int hi) {
-    if (!(fl >= 0.0f)) return 0;
-    if (fl > (float)hi) return hi;
-    return (int)fl;
-}
-
+// Branch-free; the float operations and their order are exactly those of
+// oracle/pointwise_oracle.c lut2d_pixel (index clamps and selects do not round).
 __device__ __forceinline__ void lut2d_eval(const Lut2D &L, float X, float Y, float Z, float &e0, float &e1,
                                            float &e2) {
     const float S = (X + Y) + Z;
-    if (S < 1e-12f) {
-        e0 = e1 = e2 = 0.0f;
-        return;
-    }
+    const bool dark = S < 1e-12f;
     const int n = L.n;
-    const float inv_sum = __fdiv_rn((float)(n - 1), S);
+    const float inv_sum = __fdiv_rn((float)(n - 1), dark ? 1.0f : S);
     const float r = X * inv_sum, g = Y * inv_sum;
     const float rfl = floorf(r), gfl = floorf(g);
-    const int ri = clamp_floor_idx(rfl, n - 2), gi = clamp_floor_idx(gfl, n - 2);
+    const float hi = (float)(n - 2);
+    const int ri = (int)fminf(fmaxf(rfl, 0.0f), hi);  // NaN -> 0, like the oracle's clamp
+    const int gi = (int)fminf(fmaxf(gfl, 0.0f), hi);
     const float rf = r - rfl, gf = g - gfl;
     const float fs = rf + gf;
-    const float *a = L.tab + ((ri + 1) * n + gi) * 3;
-    const float *b = L.tab + (ri * n + gi + 1) * 3;
-    const float *c;
-    float wa, wb, wc;
-    if (fs <= 1.0f) {
-        c = L.tab + (ri * n + gi) * 3;
-        wa = rf;
-        wb = gf;
-        wc = 1.0f - fs;
-    } else {
-        c = L.tab + ((ri + 1) * n + gi + 1) * 3;
-        wa = 1.0f - gf;
-        wb = 1.0f - rf;
-        wc = fs - 1.0f;
-    }
-    e0 = ((a[0] * wa + b[0] * wb) + c[0] * wc) * S;
-    e1 = ((a[1] * wa + b[1] * wb) + c[1] * wc) * S;
-    e2 = ((a[2] * wa + b[2] * wb) + c[2] * wc) * S;
+    const bool lower = fs <= 1.0f;
+    const int n3 = 3 * n;
+    const float *base = L.tab + (ri * n3 + gi * 3);
+    const float *a = base + n3;                       // lut[ri+1][gi]
+    const float *b = base + 3;                        // lut[ri][gi+1]
+    const float *c = base + (lower ? 0 : n3 + 3);     // lut[ri][gi] or lut[ri+1][gi+1]
+    const float wa = lower ? rf : 1.0f - gf;
+    const float wb = lower ? gf : 1.0f - rf;
+    const float wc = lower ? 1.0f - fs : fs - 1.0f;
+    const float v0 = ((a[0] * wa + b[0] * wb) + c[0] * wc) * S;
+    const float v1 = ((a[1] * wa + b[1] * wb) + c[1] * wc) * S;
+    const float v2 = ((a[2] * wa + b[2] * wb) + c[2] * wc) * S;
+    e0 = dark ? 0.0f : v0;
+    e1 = dark ? 0.0f : v1;
+    e2 = dark ? 0.0f : v2;
 }
 
 // ---- a4: log10 with lower clip (shaders/lut_1d.wgsl:23-26) -------------------------------
@@ -126,14 +120,12 @@ __device__ __forceinline__ float log10_clip_fast(float v, float eps) {
 // ---- a5: per-channel curve, uniform abscissa, clamped ends (lut_1d.wgsl:43-47) -----------
 __device__ __forceinline__ float curve_eval(const Curve1D &C, int ch, float v) {
     float t = (v - C.x0) * C.inv_range;
-    t = t < 0.0f ? 0.0f : (t > 1.0f ? 1.0f : t);
-    if (!(t == t)) t = 0.0f;
+    t = fminf(fmaxf(t, 0.0f), 1.0f);  // clamp; NaN -> 0 (fmaxf returns the non-NaN operand)
     const float p = t * (float)(C.N - 1);
-    int i = (int)p;
-    if (i > C.N - 2) i = C.N - 2;
+    const int i = min((int)p, C.N - 2);
     const float f = p - (float)i;
-    const float *row = C.rows + ch * C.N;
-    const float lo = row[i], hi = row[i + 1];
+    const float *row = C.rows + ch * C.N + i;
+    const float lo = row[0], hi = row[1];
     return lo + f * (hi - lo);
 }
 
@@ -218,42 +210,36 @@ __device__ __forceinline__ uint32_t quantise_u8(float v) {
 // exact path decides.  Interpolation is continuous across cells and tetrahedra, so a different
 // cell choice of the float32 coordinates is covered by the same bound.
 __device__ __forceinline__ bool quant_safe(float q, float m, uint32_t &out) {
-    if (q < -m) { out = 0u; return true; }
-    if (q >= 255.0f + m) { out = 255u; return true; }
-    const float fl = floorf(q);
-    const float fr = q - fl;
-    out = (uint32_t)(int)fl;
-    return q > 0.0f && q < 255.0f && fr > m && fr < 1.0f - m;
+    // every value in [q-m, q+m] truncates (after the [0,255] clamp) to the same integer
+    const int lo = __float2int_rd(q - m), hi = __float2int_rd(q + m);
+    out = (uint32_t)min(max(lo, 0), 255);
+    return lo == hi;  // NaN: both conversions give 0 -> "safe" 0, same as the exact path's !(q > 0) -> 0
 }
 
 __device__ __forceinline__ void tetra_quant_u8(const Lut3D &L, float dr_in, float dg_in, float db_in, uint32_t &q0,
                                                uint32_t &q1, uint32_t &q2) {
-    bool ok = L.fast_ok != 0;
-    if (ok) {
+    bool ok = false;
+    if (L.fast_ok) {
         const int n = L.n;
         const float vr = dr_in * L.sf, vg = dg_in * L.sf, vb = db_in * L.sf;
-        ok = vr >= 0.0f && vg >= 0.0f && vb >= 0.0f && vr < 1.0e6f && vg < 1.0e6f && vb < 1.0e6f;  // also NaN
-        if (ok) {
-            int r0 = (int)vr, g0 = (int)vg, b0 = (int)vb;
-            float dr = vr - (float)r0, dg = vg - (float)g0, db = vb - (float)b0;
-            if (r0 >= n - 1) { r0 = n - 2; dr = 1.0f; }
-            if (g0 >= n - 1) { g0 = n - 2; dg = 1.0f; }
-            if (b0 >= n - 1) { b0 = n - 2; db = 1.0f; }
-            const int sr = n * n, sg = n;  // vertex strides
-            int o1, o2;
-            float d1, d2, d3;
-            if (dr >= dg) {
-                if (dg >= db) { o1 = sr; o2 = sr + sg; d1 = dr; d2 = dg; d3 = db; }
-                else if (dr >= db) { o1 = sr; o2 = sr + 1; d1 = dr; d2 = db; d3 = dg; }
-                else { o1 = 1; o2 = sr + 1; d1 = db; d2 = dr; d3 = dg; }
-            } else {
-                if (db >= dg) { o1 = 1; o2 = sg + 1; d1 = db; d2 = dg; d3 = dr; }
-                else if (db >= dr) { o1 = sg; o2 = sg + 1; d1 = dg; d2 = db; d3 = dr; }
-                else { o1 = sg; o2 = sr + sg; d1 = dg; d2 = dr; d3 = db; }
-            }
+        const float vmin = fminf(fminf(vr, vg), vb), vmax = fmaxf(fmaxf(vr, vg), vb);
+        if (vmin >= 0.0f && vmax < 1.0e6f && vr == vr && vg == vg && vb == vb) {
+            const int top = n - 2;
+            const int r0 = min((int)vr, top), g0 = min((int)vg, top), b0 = min((int)vb, top);
+            // fraction; at or above the last lattice plane the reference pins it to 1 (utils.py:273-289)
+            const float dr = fminf(vr - (float)r0, 1.0f), dg = fminf(vg - (float)g0, 1.0f);
+            const float db = fminf(vb - (float)b0, 1.0f);
+            // ordered fractions d1 >= d2 >= d3 and the lattice steps of their axes (ties: any consistent
+            // order gives the same interpolant; the exact path keeps the reference's branch order)
+            const float d1 = fmaxf(fmaxf(dr, dg), db), d3 = fminf(fminf(dr, dg), db);
+            const float d2 = fmaxf(fminf(dr, dg), fminf(fmaxf(dr, dg), db));
+            const int sr = n * n, sg = n;
+            const int o1 = dr == d1 ? sr : (dg == d1 ? sg : 1);
+            const int o3 = db == d3 ? 1 : (dg == d3 ? sg : sr);
+            const int o111 = sr + sg + 1;
             const float4 *base = L.tab + (r0 * n + g0) * n + b0;
-            const float4 c000 = __ldg(base), cm1 = __ldg(base + o1), cm2 = __ldg(base + o2);
-            const float4 c111 = __ldg(base + sr + sg + 1);
+            const float4 c000 = __ldg(base), cm1 = __ldg(base + o1), cm2 = __ldg(base + (o111 - o3));
+            const float4 c111 = __ldg(base + o111);
             const float s0 = fmaf(d3, c111.x - cm2.x, fmaf(d2, cm2.x - cm1.x, fmaf(d1, cm1.x - c000.x, c000.x)));
             const float s1 = fmaf(d3, c111.y - cm2.y, fmaf(d2, cm2.y - cm1.y, fmaf(d1, cm1.y - c000.y, c000.y)));
             const float s2 = fmaf(d3, c111.z - cm2.z, fmaf(d2, cm2.z - cm1.z, fmaf(d1, cm1.z - c000.z, c000.z)));

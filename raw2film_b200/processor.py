@@ -338,7 +338,8 @@ class B200Processor:
             self._dev_noise = torch.from_numpy(noise).to(self.device, non_blocking=False)
         return self._dev_noise.data_ptr(), nch
 
-    def render_device(self, xyz_dev, negative_film, grain_size, grain_sigma, out=None, stream=None, **settings):
+    def render_device(self, xyz_dev, negative_film, grain_size, grain_sigma, out=None, stream=None,
+                      sync_caller=True, **settings):
         """Device-resident render: `xyz_dev` is a float32 (H, W, 3|4) CUDA tensor, result a uint8
         (H, W, 3) CUDA tensor.  No host copies; enqueued on `stream` (default: self.stream)."""
         torch = self._torch
@@ -351,14 +352,15 @@ class B200Processor:
         if out is None:
             out = self._dev_out
         stream = self.stream if stream is None else stream
-        stream.wait_stream(torch.cuda.current_stream(self.device))
+        if sync_caller:
+            stream.wait_stream(torch.cuda.current_stream(self.device))
         noise_ptr, nch = self._noise_arg(s, h, w, flags)
         ws_ptr = self._dev_ws.data_ptr() if (flags & _SPATIAL) else None
         ws_bytes = self._dev_ws.numel() if (flags & _SPATIAL) else 0
         _cabi.check(_cabi.lib.r2f_render(self._ctx, xyz_dev.data_ptr(), h, w, ch, out.data_ptr(), flags, noise_ptr,
                                          nch, ws_ptr, ws_bytes, stream.cuda_stream))
-        # order later work on the caller's stream after the render (asynchronous, no host sync)
-        torch.cuda.current_stream(self.device).wait_stream(stream)
+        if sync_caller:  # order later work on the caller's stream after the render (asynchronous, no host sync)
+            torch.cuda.current_stream(self.device).wait_stream(stream)
         return out
 
     def render_tap(self, xyz_dev, stage: str, negative_film, grain_size, grain_sigma, **settings):

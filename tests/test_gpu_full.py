@@ -164,3 +164,25 @@ def test_errors_are_loud(proc):
     x = torch.zeros((8, 8, 3), device="cuda")
     with pytest.raises(_cabi.R2FError):
         _cabi.check(_cabi.lib.r2f_render(proc._ctx, x.data_ptr(), 8, 8, 5, x.data_ptr(), 0, None, 0, None, 0, None))
+
+
+@pytest.mark.parametrize("depth", [2, 3])
+def test_pipelined_renderer_matches_synchronous_calls(proc, depth):
+    """Overlapped H2D / render / D2H (PipelinedRenderer) returns, in order, exactly what
+    process_preloaded returns frame by frame (fixed grain seed), for more frames than slots."""
+    from raw2film_b200 import PipelinedRenderer
+
+    stock = SyntheticStock(n3=17)
+    st = dict(frame_width=2.0, frame_height=1.5, grain=2, grain_seed=11)
+    frames = [small_frame(120, 180, seed=100 + i) for i in range(7)]
+    want = [proc.process_preloaded(proc.extract_image_data_cpu(f, **st), stock, 6.0, 0.4, **st).copy() for f in frames]
+    pipe = PipelinedRenderer(proc, depth=depth)
+    got = {}
+    n = pipe.run((proc.extract_image_data_cpu(f, **st) for f in frames), stock, 6.0, 0.4,
+                 sink=lambda i, img: got.__setitem__(i, img.copy()), **st)
+    assert n == len(frames) and sorted(got) == list(range(len(frames)))
+    for i in range(len(frames)):
+        assert np.array_equal(got[i], want[i]), f"frame {i}"
+    assert pipe.h2d_bytes == len(frames) * 120 * 180 * 3 * 4 and pipe.d2h_bytes == len(frames) * 120 * 180 * 3
+    with pytest.raises(ValueError):
+        pipe.result(0)
