@@ -117,10 +117,25 @@ int r2f_render(r2f_ctx *ctx, const float *in_dev, int H, int W, int in_channels,
                unsigned flags, const float *noise_dev, int noise_channels, void *workspace_dev,
                size_t workspace_bytes, void *stream);
 
+/* Input-format variant ("u16 ingest on device").  in_format R2F_IN_U16: `in_dev` is the
+ * uint16 H x W x in_channels frame rawpy hands over (reference raw_conversion.py:38-48); the device
+ * applies the reference's own ingest arithmetic `astype(float32) / 65535.0` then `*= gain`
+ * (raw_conversion.py:51-53, gain = 2**calc_exposure) before the 2-D LUT, bit-identically.
+ * R2F_IN_F32 ignores in_gain and equals r2f_render. */
+#define R2F_IN_F32 0
+#define R2F_IN_U16 1
+int r2f_render_ex(r2f_ctx *ctx, const void *in_dev, int in_format, float in_gain, int H, int W, int in_channels,
+                  uint8_t *out_dev, unsigned flags, const float *noise_dev, int noise_channels,
+                  void *workspace_dev, size_t workspace_bytes, void *stream);
+
 /* Same pipeline, stopped after `tap_stage`; writes the float32 H x W x 3 working image. */
 int r2f_render_tap(r2f_ctx *ctx, const float *in_dev, int H, int W, int in_channels, unsigned flags,
                    const float *noise_dev, int noise_channels, void *workspace_dev, size_t workspace_bytes,
                    int tap_stage, float *tap_dev, void *stream);
+
+int r2f_render_tap_ex(r2f_ctx *ctx, const void *in_dev, int in_format, float in_gain, int H, int W,
+                      int in_channels, unsigned flags, const float *noise_dev, int noise_channels,
+                      void *workspace_dev, size_t workspace_bytes, int tap_stage, float *tap_dev, void *stream);
 
 /* Host-buffer variant for non-torch callers (what a cgo/JNI/ctypes binding of
  * GpuProcessor.process_preloaded, gpu_processor.py:1643-1693, would call): copies in,

@@ -16,10 +16,11 @@ EXPORTS = [
     "r2f_abi_version", "r2f_last_error", "r2f_create", "r2f_destroy", "r2f_set_lut2d", "r2f_set_curve1d",
     "r2f_set_lut3d", "r2f_set_halation_kernel", "r2f_set_mtf_kernel", "r2f_set_grain", "r2f_set_grain_seed", "r2f_set_option",
     "r2f_set_burn",
-    "r2f_workspace_bytes", "r2f_render", "r2f_render_tap", "r2f_render_host", "r2f_convolve2d",
+    "r2f_workspace_bytes", "r2f_render", "r2f_render_ex", "r2f_render_tap", "r2f_render_tap_ex", "r2f_render_host", "r2f_convolve2d",
     "r2f_generate_noise", "r2f_launch_count", "r2f_profile_enable", "r2f_profile_read",
 ]
 OPT_CONV_PATH = 1
+IN_F32, IN_U16 = 0, 1
 PROF_NAMES = ["pointwise", "expose", "halation", "density", "mtf", "noise", "grain", "burn", "finish"]
 
 
@@ -52,7 +53,9 @@ def _load():
         "r2f_set_burn": (ci, [vp, cf, cf, cf]),
         "r2f_workspace_bytes": (sz, [ci, ci, cu]),
         "r2f_render": (ci, [vp, vp, ci, ci, ci, u8p, cu, vp, ci, vp, sz, vp]),
+        "r2f_render_ex": (ci, [vp, vp, ci, cf, ci, ci, ci, u8p, cu, vp, ci, vp, sz, vp]),
         "r2f_render_tap": (ci, [vp, vp, ci, ci, ci, cu, vp, ci, vp, sz, ci, vp, vp]),
+        "r2f_render_tap_ex": (ci, [vp, vp, ci, cf, ci, ci, ci, cu, vp, ci, vp, sz, ci, vp, vp]),
         "r2f_render_host": (ci, [vp, vp, ci, ci, ci, vp, cu, vp, ci]),
         "r2f_convolve2d": (ci, [vp, vp, vp, ci, ci, fp, ci, vp, sz, vp]),
         "r2f_generate_noise": (ci, [vp, vp, ci, ci, ci, u64, vp]),

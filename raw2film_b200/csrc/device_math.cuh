@@ -37,6 +37,84 @@ struct Lut3D {
     int fast_ok;
 };
 
+// ---- frame input formats -------------------------------------------------------------------
+// FMT 0: float32 x3 (XYZ), 1: float32 x4 (XYZ + alpha, reference GPU payload gpu_processor.py:765),
+//     2: uint16 x3, 3: uint16 x4 -- what rawpy hands over (reference raw_conversion.py:38-51); the
+//     device then does the reference's `astype(float32) / 65535.0` and `*= 2**calc_exposure`
+//     (raw_conversion.py:51-53) itself, halving the PCIe bytes per frame.
+constexpr int kFmtF32x3 = 0, kFmtF32x4 = 1, kFmtU16x3 = 2, kFmtU16x4 = 3;
+template <int FMT>
+struct InFmt {
+    static constexpr int cin = (FMT & 1) ? 4 : 3;
+    static constexpr bool u16 = FMT >= 2;
+};
+
+// float32(u) / 65535 correctly rounded (checked for all 65536 inputs: q = u*rcp refined by one FMA
+// remainder step), then the float32 product with the exposure gain.
+__device__ __forceinline__ float u16_to_linear(uint32_t u, float gain) {
+    const float x = (float)u;
+    const float rcp = 1.0f / 65535.0f;
+    const float q = x * rcp;
+    const float r = fmaf(-q, 65535.0f, x);
+    return fmaf(r, rcp, q) * gain;
+}
+
+template <int FMT>
+__device__ __forceinline__ void load_px(const void *__restrict__ in, size_t pix, float gain, float &X, float &Y,
+                                        float &Z) {
+    constexpr int cin = InFmt<FMT>::cin;
+    if (InFmt<FMT>::u16) {
+        const uint16_t *p = static_cast<const uint16_t *>(in) + pix * cin;
+        X = u16_to_linear(__ldg(p), gain);
+        Y = u16_to_linear(__ldg(p + 1), gain);
+        Z = u16_to_linear(__ldg(p + 2), gain);
+    } else {
+        const float *p = static_cast<const float *>(in) + pix * cin;
+        X = __ldg(p);
+        Y = __ldg(p + 1);
+        Z = __ldg(p + 2);
+    }
+}
+
+// four consecutive pixels with vector loads (q = quad index; the frame base is 16-byte aligned)
+template <int FMT>
+__device__ __forceinline__ void load_quad(const void *__restrict__ in, size_t q, float gain, float (&px)[4][3]) {
+    if (FMT == kFmtF32x3) {
+        const float4 *p = static_cast<const float4 *>(in) + 3 * q;
+        const float4 a = __ldcs(p), b = __ldcs(p + 1), c = __ldcs(p + 2);
+        px[0][0] = a.x; px[0][1] = a.y; px[0][2] = a.z;
+        px[1][0] = a.w; px[1][1] = b.x; px[1][2] = b.y;
+        px[2][0] = b.z; px[2][1] = b.w; px[2][2] = c.x;
+        px[3][0] = c.y; px[3][1] = c.z; px[3][2] = c.w;
+    } else if (FMT == kFmtF32x4) {
+        const float4 *p = static_cast<const float4 *>(in) + 4 * q;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const float4 a = __ldcs(p + i);
+            px[i][0] = a.x; px[i][1] = a.y; px[i][2] = a.z;
+        }
+    } else if (FMT == kFmtU16x3) {
+        const uint2 *p = static_cast<const uint2 *>(in) + 3 * q;  // 12 halfwords = 24 bytes
+        const uint2 a = __ldcs(p), b = __ldcs(p + 1), c = __ldcs(p + 2);
+        const uint32_t w[6] = {a.x, a.y, b.x, b.y, c.x, c.y};
+#pragma unroll
+        for (int i = 0; i < 12; ++i) {
+            const uint32_t h = (i & 1) ? (w[i >> 1] >> 16) : (w[i >> 1] & 0xffffu);
+            px[i / 3][i % 3] = u16_to_linear(h, gain);
+        }
+    } else {
+        const uint4 *p = static_cast<const uint4 *>(in) + 2 * q;  // 16 halfwords = 32 bytes
+        const uint4 a = __ldcs(p), b = __ldcs(p + 1);
+        const uint32_t w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            px[i][0] = u16_to_linear(w[2 * i] & 0xffffu, gain);
+            px[i][1] = u16_to_linear(w[2 * i] >> 16, gain);
+            px[i][2] = u16_to_linear(w[2 * i + 1] & 0xffffu, gain);
+        }
+    }
+}
+
 // ---- a2: chromaticity-indexed input LUT (reference shaders/lut_2d.wgsl:18-108) ---------
 // Branch-free; the float operations and their order are exactly those of
 // oracle/pointwise_oracle.c lut2d_pixel (index clamps and selects do not round).

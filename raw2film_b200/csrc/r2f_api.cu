@@ -403,11 +403,13 @@ int check_tables(const r2f_ctx *c, unsigned flags) {
 }
 
 // The whole pipeline.  tap_stage == 0: normal render to out_u8.
-int render_impl(r2f_ctx *c, const float *in, int H, int W, int cin, uint8_t *out_u8, unsigned flags,
-                const float *noise, int noise_ch, void *ws, size_t ws_bytes, int tap_stage, float *tap,
-                cudaStream_t st) {
+int render_impl(r2f_ctx *c, const void *in, int in_format, float in_gain, int H, int W, int cin, uint8_t *out_u8,
+                unsigned flags, const float *noise, int noise_ch, void *ws, size_t ws_bytes, int tap_stage,
+                float *tap, cudaStream_t st) {
     if (!c) return fail(R2F_ERR_INVALID, "null context");
     if (!in || H < 1 || W < 1 || (cin != 3 && cin != 4)) return fail(R2F_ERR_INVALID, "bad input image arguments");
+    if (in_format != R2F_IN_F32 && in_format != R2F_IN_U16) return fail(R2F_ERR_INVALID, "unknown input format");
+    const int fmt = (in_format == R2F_IN_U16 ? 2 : 0) + (cin == 4 ? 1 : 0);  // kFmt* of device_math.cuh
     if (tap_stage == 0 && !out_u8) return fail(R2F_ERR_INVALID, "null output");
     if (tap_stage != 0 && (!tap || tap_stage < R2F_TAP_EXPOSURE || tap_stage > R2F_TAP_RGB))
         return fail(R2F_ERR_INVALID, "bad tap arguments");
@@ -426,7 +428,7 @@ int render_impl(r2f_ctx *c, const float *in, int H, int W, int cin, uint8_t *out
 
     if (tap_stage == 0 && spatial == 0) {  // configs C1 / C5: one fused pass
         ProfScope ps_(c, st, R2F_PROF_POINTWISE);
-        CU(launch_pointwise(in, cin, out_u8, npix, l2, cv, c->eps, l3, c->num_sms, st));
+        CU(launch_pointwise(in, fmt, in_gain, out_u8, npix, l2, cv, c->eps, l3, c->num_sms, st));
         c->launches += 1;
         return R2F_OK;
     }
@@ -456,13 +458,14 @@ int render_impl(r2f_ctx *c, const float *in, int H, int W, int cin, uint8_t *out
         fa.S = reinterpret_cast<float2 *>(P[2].base);
         fa.src_planar = nullptr;
         fa.src_xyz = in;
+        fa.gain = in_gain;
         fa.lut2d = l2;
         fa.dst_planar = P[1].base;
         fa.curve = cv;
         fa.eps = c->eps;
         {
             ProfScope ps_(c, st, R2F_PROF_HALATION);
-            CU(launch_fft_conv(fa, cin == 3 ? 1 : 2, tap_stage != R2F_TAP_HALATION, st));
+            CU(launch_fft_conv(fa, 1 + fmt, tap_stage != R2F_TAP_HALATION, st));
         }
         c->launches += 2;  // + the one counted below
         if (tap_stage == R2F_TAP_HALATION) {
@@ -472,7 +475,7 @@ int render_impl(r2f_ctx *c, const float *in, int H, int W, int cin, uint8_t *out
     } else {
         {
             ProfScope ps_(c, st, R2F_PROF_EXPOSE);
-            CU(launch_expose(in, cin, P[0], npix, l2, c->num_sms, st));
+            CU(launch_expose(in, fmt, in_gain, P[0], npix, l2, c->num_sms, st));
         }
         c->launches += 1;
         if (tap_stage == R2F_TAP_EXPOSURE) return export_tap(P[0]);
@@ -724,16 +727,31 @@ size_t r2f_workspace_bytes(int H, int W, unsigned flags) {
 
 int r2f_render(r2f_ctx *c, const float *in_dev, int H, int W, int in_channels, uint8_t *out_dev, unsigned flags,
                const float *noise_dev, int noise_channels, void *workspace_dev, size_t workspace_bytes, void *stream) {
-    return render_impl(c, in_dev, H, W, in_channels, out_dev, flags, noise_dev, noise_channels, workspace_dev,
-                       workspace_bytes, 0, nullptr, static_cast<cudaStream_t>(stream));
+    return render_impl(c, in_dev, R2F_IN_F32, 1.0f, H, W, in_channels, out_dev, flags, noise_dev, noise_channels,
+                       workspace_dev, workspace_bytes, 0, nullptr, static_cast<cudaStream_t>(stream));
+}
+
+int r2f_render_ex(r2f_ctx *c, const void *in_dev, int in_format, float in_gain, int H, int W, int in_channels,
+                  uint8_t *out_dev, unsigned flags, const float *noise_dev, int noise_channels, void *workspace_dev,
+                  size_t workspace_bytes, void *stream) {
+    return render_impl(c, in_dev, in_format, in_gain, H, W, in_channels, out_dev, flags, noise_dev, noise_channels,
+                       workspace_dev, workspace_bytes, 0, nullptr, static_cast<cudaStream_t>(stream));
 }
 
 int r2f_render_tap(r2f_ctx *c, const float *in_dev, int H, int W, int in_channels, unsigned flags,
                    const float *noise_dev, int noise_channels, void *workspace_dev, size_t workspace_bytes,
                    int tap_stage, float *tap_dev, void *stream) {
     if (tap_stage == 0) return fail(R2F_ERR_INVALID, "tap_stage must be one of R2F_TAP_*");
-    return render_impl(c, in_dev, H, W, in_channels, nullptr, flags, noise_dev, noise_channels, workspace_dev,
-                       workspace_bytes, tap_stage, tap_dev, static_cast<cudaStream_t>(stream));
+    return render_impl(c, in_dev, R2F_IN_F32, 1.0f, H, W, in_channels, nullptr, flags, noise_dev, noise_channels,
+                       workspace_dev, workspace_bytes, tap_stage, tap_dev, static_cast<cudaStream_t>(stream));
+}
+
+int r2f_render_tap_ex(r2f_ctx *c, const void *in_dev, int in_format, float in_gain, int H, int W, int in_channels,
+                      unsigned flags, const float *noise_dev, int noise_channels, void *workspace_dev,
+                      size_t workspace_bytes, int tap_stage, float *tap_dev, void *stream) {
+    if (tap_stage == 0) return fail(R2F_ERR_INVALID, "tap_stage must be one of R2F_TAP_*");
+    return render_impl(c, in_dev, in_format, in_gain, H, W, in_channels, nullptr, flags, noise_dev, noise_channels,
+                       workspace_dev, workspace_bytes, tap_stage, tap_dev, static_cast<cudaStream_t>(stream));
 }
 
 int r2f_render_host(r2f_ctx *c, const float *in_host, int H, int W, int in_channels, uint8_t *out_host, unsigned flags,
@@ -756,9 +774,8 @@ int r2f_render_host(r2f_ctx *c, const float *in_host, int H, int W, int in_chann
         CU(cudaMemcpyAsync(c->h_noise.p, noise_host, nb, cudaMemcpyHostToDevice, c->host_stream));
         noise_dev = static_cast<const float *>(c->h_noise.p);
     }
-    int rc = render_impl(c, static_cast<const float *>(c->h_in.p), H, W, in_channels,
-                         static_cast<uint8_t *>(c->h_out.p), flags, noise_dev, noise_channels, c->h_ws.p,
-                         c->h_ws.bytes, 0, nullptr, c->host_stream);
+    int rc = render_impl(c, c->h_in.p, R2F_IN_F32, 1.0f, H, W, in_channels, static_cast<uint8_t *>(c->h_out.p), flags,
+                         noise_dev, noise_channels, c->h_ws.p, c->h_ws.bytes, 0, nullptr, c->host_stream);
     if (rc != R2F_OK) return rc;
     CU(cudaMemcpyAsync(out_host, c->h_out.p, out_bytes, cudaMemcpyDeviceToHost, c->host_stream));
     CU(cudaStreamSynchronize(c->host_stream));

@@ -170,7 +170,7 @@ __device__ __forceinline__ Group row_group() {
 // ------------------------------------------------------------------------------------------
 // rows, forward
 // ------------------------------------------------------------------------------------------
-template <int SRC, int ROWS>  // SRC 0: planar planes, 1: interleaved XYZ through the 2-D LUT (cin 3), 2: same, cin 4
+template <int SRC, int ROWS>  // SRC 0: planar planes, 1 + FMT: interleaved frame (kFmt*) through the 2-D LUT
 __global__ void __launch_bounds__(1024, 1)
 k_fft_rows_fwd(const __grid_constant__ FftConvArgs a) {
     extern __shared__ __align__(16) float2 fsm[];
@@ -189,10 +189,9 @@ k_fft_rows_fwd(const __grid_constant__ FftConvArgs a) {
                 z.x = a.src_planar[(size_t)a.chan[0] * a.plane_stride + idx];
                 z.y = a.src_planar[(size_t)a.chan[1] * a.plane_stride + idx];
             } else {
-                const int cin = SRC == 1 ? 3 : 4;
-                const float *px = a.src_xyz + ((size_t)y * W + x) * cin;
-                float e0, e1, e2;
-                lut2d_eval(a.lut2d, __ldg(px), __ldg(px + 1), __ldg(px + 2), e0, e1, e2);
+                float X, Y, Z, e0, e1, e2;
+                load_px<(SRC > 0 ? SRC - 1 : 0)>(a.src_xyz, (size_t)y * W + x, a.gain, X, Y, Z);
+                lut2d_eval(a.lut2d, X, Y, Z, e0, e1, e2);
                 z.x = e0;
                 z.y = e1;
             }
@@ -291,9 +290,9 @@ k_fft_rows_inv(const __grid_constant__ FftConvArgs a) {
 #pragma unroll
             for (int c = 0; c < 3; ++c) src[c] = a.src_planar[c * ps + idx];
         } else {
-            const int cin = SRC == 1 ? 3 : 4;
-            const float *px = a.src_xyz + idx * cin;
-            lut2d_eval(a.lut2d, __ldg(px), __ldg(px + 1), __ldg(px + 2), src[0], src[1], src[2]);
+            float X, Y, Z;
+            load_px<(SRC > 0 ? SRC - 1 : 0)>(a.src_xyz, idx, a.gain, X, Y, Z);
+            lut2d_eval(a.lut2d, X, Y, Z, src[0], src[1], src[2]);
         }
         float out[3] = {src[0], src[1], src[2]};
         out[a.chan[0]] = fmaf(a.alpha[0], zs.y, a.beta[0] * src[a.chan[0]]);
@@ -432,7 +431,13 @@ static cudaError_t launch_rows_fwd(const FftConvArgs &a, int src_mode, int ctas,
         if ((e = set_smem(k_fft_rows_fwd<M, ROWS>, smem)) != cudaSuccess) return e; \
         k_fft_rows_fwd<M, ROWS><<<ctas, threads, smem, st>>>(a);                   \
     } while (0)
-    if (src_mode == 0) R2F_FWD(0); else if (src_mode == 1) R2F_FWD(1); else R2F_FWD(2);
+    switch (src_mode) {
+        case 0: R2F_FWD(0); break;
+        case 1: R2F_FWD(1); break;
+        case 2: R2F_FWD(2); break;
+        case 3: R2F_FWD(3); break;
+        default: R2F_FWD(4); break;
+    }
 #undef R2F_FWD
     return cudaGetLastError();
 }
@@ -446,10 +451,17 @@ static cudaError_t launch_rows_inv(const FftConvArgs &a, int src_mode, bool dens
         if ((e = set_smem(k_fft_rows_inv<M, D, ROWS>, smem)) != cudaSuccess) return e; \
         k_fft_rows_inv<M, D, ROWS><<<ctas, threads, smem, st>>>(a);                   \
     } while (0)
-    if (density) {
-        if (src_mode == 0) R2F_INV(0, 1); else if (src_mode == 1) R2F_INV(1, 1); else R2F_INV(2, 1);
-    } else {
-        if (src_mode == 0) R2F_INV(0, 0); else if (src_mode == 1) R2F_INV(1, 0); else R2F_INV(2, 0);
+    switch (src_mode * 2 + (density ? 1 : 0)) {
+        case 0: R2F_INV(0, 0); break;
+        case 1: R2F_INV(0, 1); break;
+        case 2: R2F_INV(1, 0); break;
+        case 3: R2F_INV(1, 1); break;
+        case 4: R2F_INV(2, 0); break;
+        case 5: R2F_INV(2, 1); break;
+        case 6: R2F_INV(3, 0); break;
+        case 7: R2F_INV(3, 1); break;
+        case 8: R2F_INV(4, 0); break;
+        default: R2F_INV(4, 1); break;
     }
 #undef R2F_INV
     return cudaGetLastError();

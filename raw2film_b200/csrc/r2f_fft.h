@@ -41,7 +41,8 @@ struct FftConvArgs {
     float alpha[2], beta[2];  // out_c = alpha * (K (*) x_c) + beta * x_c
     // source: planar planes or interleaved XYZ through the 2-D input LUT
     const float *src_planar;
-    const float *src_xyz;
+    const void *src_xyz;  // interleaved frame in one of the kFmt* formats
+    float gain;           // exposure gain of uint16 frames
     Lut2D lut2d;
     size_t plane_stride;
     // destination: planar planes, optionally through log10 + H-D curve
@@ -60,7 +61,7 @@ bool fft_col_geometry(int Hp, int Wp, int &nc, int &groups);
 cudaError_t launch_khat(const float *base_kernel_dev, int k, int Hp, int Wp, const double *cosH_dev,
                         const double *cosW_dev, double *scratchA_dev, float *khat_dev, cudaStream_t st);
 
-// src_mode: 0 planar, 1 XYZ interleaved (3 channels) + 2-D LUT, 2 same with 4 channels.
+// src_mode: 0 planar, 1 + kFmt* for an interleaved frame routed through the 2-D LUT.
 cudaError_t launch_fft_conv(const FftConvArgs &a, int src_mode, bool density, cudaStream_t st);
 
 }  // namespace r2f

@@ -14,30 +14,6 @@ namespace r2f {
 
 constexpr int kThreads = 256;
 
-__device__ __forceinline__ float4 ld_stream(const float4 *p) { return __ldcs(p); }
-
-// ------------------------------------------------------------------------------------------
-// quad (4-pixel) loads of interleaved input
-// ------------------------------------------------------------------------------------------
-template <int CIN>
-__device__ __forceinline__ void load_quad(const float *__restrict__ in, size_t q, float (&px)[4][3]) {
-    if (CIN == 3) {
-        const float4 *p = reinterpret_cast<const float4 *>(in) + 3 * q;
-        const float4 a = ld_stream(p), b = ld_stream(p + 1), c = ld_stream(p + 2);
-        px[0][0] = a.x; px[0][1] = a.y; px[0][2] = a.z;
-        px[1][0] = a.w; px[1][1] = b.x; px[1][2] = b.y;
-        px[2][0] = b.z; px[2][1] = b.w; px[2][2] = c.x;
-        px[3][0] = c.y; px[3][1] = c.z; px[3][2] = c.w;
-    } else {
-        const float4 *p = reinterpret_cast<const float4 *>(in) + 4 * q;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const float4 a = ld_stream(p + i);
-            px[i][0] = a.x; px[i][1] = a.y; px[i][2] = a.z;
-        }
-    }
-}
-
 __device__ __forceinline__ void store_quad_u8(uint8_t *__restrict__ out, size_t q, const uint32_t (&b)[12]) {
     uint32_t *o = reinterpret_cast<uint32_t *>(out) + 3 * q;
     __stcs(o + 0, b[0] | (b[1] << 8) | (b[2] << 16) | (b[3] << 24));
@@ -75,17 +51,17 @@ __device__ __forceinline__ void pixel_chain(const float (&xyz)[3], const Lut2D &
 // ------------------------------------------------------------------------------------------
 // K1: fused pointwise chain
 // ------------------------------------------------------------------------------------------
-template <int CIN, bool SMEM_TABLES>
+template <int FMT, bool SMEM_TABLES>
 __global__ void __launch_bounds__(kThreads)
-k_pointwise(const float *__restrict__ in, uint8_t *__restrict__ out, size_t npix, Lut2D l2, Curve1D cv, float eps,
-            Lut3D l3) {
+k_pointwise(const void *__restrict__ in, float gain, uint8_t *__restrict__ out, size_t npix, Lut2D l2, Curve1D cv,
+            float eps, Lut3D l3) {
     extern __shared__ __align__(16) float smem[];
     if (SMEM_TABLES) stage_tables(smem, l2, cv, true, true);
     const size_t nquad = npix / 4;
     const size_t stride = (size_t)gridDim.x * kThreads;
     for (size_t q = (size_t)blockIdx.x * kThreads + threadIdx.x; q < nquad; q += stride) {
         float px[4][3];
-        load_quad<CIN>(in, q, px);
+        load_quad<FMT>(in, q, gain, px);
         uint32_t b[12];
 #pragma unroll
         for (int p = 0; p < 4; ++p) pixel_chain(px[p], l2, cv, eps, l3, b[3 * p], b[3 * p + 1], b[3 * p + 2]);
@@ -93,7 +69,8 @@ k_pointwise(const float *__restrict__ in, uint8_t *__restrict__ out, size_t npix
     }
     if (blockIdx.x == 0 && threadIdx.x < (npix & 3)) {
         const size_t p = nquad * 4 + threadIdx.x;
-        const float xyz[3] = {in[p * CIN], in[p * CIN + 1], in[p * CIN + 2]};
+        float xyz[3];
+        load_px<FMT>(in, p, gain, xyz[0], xyz[1], xyz[2]);
         uint32_t r, g, b;
         pixel_chain(xyz, l2, cv, eps, l3, r, g, b);
         out[p * 3] = (uint8_t)r;
@@ -118,8 +95,8 @@ static size_t table_smem_bytes(const Lut2D &l2, const Curve1D &cv, bool want2d, 
 
 constexpr size_t kMaxTableSmem = 96 * 1024;  // keep >= 2 CTAs/SM resident
 
-cudaError_t launch_pointwise(const float *in, int cin, uint8_t *out, size_t npix, const Lut2D &l2, const Curve1D &cv,
-                             float eps, const Lut3D &l3, int num_sms, cudaStream_t st) {
+cudaError_t launch_pointwise(const void *in, int fmt, float gain, uint8_t *out, size_t npix, const Lut2D &l2,
+                             const Curve1D &cv, float eps, const Lut3D &l3, int num_sms, cudaStream_t st) {
     const size_t sm = table_smem_bytes(l2, cv, true, true);
     const bool use_smem = sm <= kMaxTableSmem;
     const int grid = grid_for(npix / 4 + 1, num_sms, 8);
@@ -130,12 +107,18 @@ cudaError_t launch_pointwise(const float *in, int cin, uint8_t *out, size_t npix
             cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm); \
             if (e != cudaSuccess) return e;                                                                \
         }                                                                                                  \
-        kfn<<<grid, kThreads, S ? sm : 0, st>>>(in, out, npix, l2, cv, eps, l3);                           \
+        kfn<<<grid, kThreads, S ? sm : 0, st>>>(in, gain, out, npix, l2, cv, eps, l3);                     \
     } while (0)
-    if (cin == 3) {
-        if (use_smem) R2F_LAUNCH_PW(3, true); else R2F_LAUNCH_PW(3, false);
-    } else {
-        if (use_smem) R2F_LAUNCH_PW(4, true); else R2F_LAUNCH_PW(4, false);
+    switch (fmt * 2 + (use_smem ? 1 : 0)) {
+        case 0: R2F_LAUNCH_PW(0, false); break;
+        case 1: R2F_LAUNCH_PW(0, true); break;
+        case 2: R2F_LAUNCH_PW(1, false); break;
+        case 3: R2F_LAUNCH_PW(1, true); break;
+        case 4: R2F_LAUNCH_PW(2, false); break;
+        case 5: R2F_LAUNCH_PW(2, true); break;
+        case 6: R2F_LAUNCH_PW(3, false); break;
+        case 7: R2F_LAUNCH_PW(3, true); break;
+        default: return cudaErrorInvalidValue;
     }
 #undef R2F_LAUNCH_PW
     return cudaGetLastError();
@@ -144,9 +127,10 @@ cudaError_t launch_pointwise(const float *in, int cin, uint8_t *out, size_t npix
 // ------------------------------------------------------------------------------------------
 // a2: XYZ -> planar exposure
 // ------------------------------------------------------------------------------------------
-template <int CIN, bool SMEM_TABLES>
+template <int FMT, bool SMEM_TABLES>
 __global__ void __launch_bounds__(kThreads)
-k_expose(const float *__restrict__ in, float *__restrict__ out, size_t plane_stride, size_t npix, Lut2D l2) {
+k_expose(const void *__restrict__ in, float gain, float *__restrict__ out, size_t plane_stride, size_t npix,
+         Lut2D l2) {
     extern __shared__ __align__(16) float smem[];
     Curve1D none{};
     if (SMEM_TABLES) stage_tables(smem, l2, none, true, false);
@@ -154,7 +138,7 @@ k_expose(const float *__restrict__ in, float *__restrict__ out, size_t plane_str
     const size_t stride = (size_t)gridDim.x * kThreads;
     for (size_t q = (size_t)blockIdx.x * kThreads + threadIdx.x; q < nquad; q += stride) {
         float px[4][3];
-        load_quad<CIN>(in, q, px);
+        load_quad<FMT>(in, q, gain, px);
         float e[3][4];
 #pragma unroll
         for (int p = 0; p < 4; ++p) lut2d_eval(l2, px[p][0], px[p][1], px[p][2], e[0][p], e[1][p], e[2][p]);
@@ -164,15 +148,16 @@ k_expose(const float *__restrict__ in, float *__restrict__ out, size_t plane_str
     }
     if (blockIdx.x == 0 && threadIdx.x < (npix & 3)) {
         const size_t p = nquad * 4 + threadIdx.x;
-        float e0, e1, e2;
-        lut2d_eval(l2, in[p * CIN], in[p * CIN + 1], in[p * CIN + 2], e0, e1, e2);
+        float X, Y, Z, e0, e1, e2;
+        load_px<FMT>(in, p, gain, X, Y, Z);
+        lut2d_eval(l2, X, Y, Z, e0, e1, e2);
         out[p] = e0;
         out[plane_stride + p] = e1;
         out[2 * plane_stride + p] = e2;
     }
 }
 
-cudaError_t launch_expose(const float *in, int cin, Planes out, size_t npix, const Lut2D &l2, int num_sms,
+cudaError_t launch_expose(const void *in, int fmt, float gain, Planes out, size_t npix, const Lut2D &l2, int num_sms,
                           cudaStream_t st) {
     Curve1D none{};
     const size_t sm = table_smem_bytes(l2, none, true, false);
@@ -185,12 +170,18 @@ cudaError_t launch_expose(const float *in, int cin, Planes out, size_t npix, con
             cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm); \
             if (e != cudaSuccess) return e;                                                                \
         }                                                                                                  \
-        kfn<<<grid, kThreads, S ? sm : 0, st>>>(in, out.base, out.plane_stride, npix, l2);                 \
+        kfn<<<grid, kThreads, S ? sm : 0, st>>>(in, gain, out.base, out.plane_stride, npix, l2);           \
     } while (0)
-    if (cin == 3) {
-        if (use_smem) R2F_LAUNCH_EX(3, true); else R2F_LAUNCH_EX(3, false);
-    } else {
-        if (use_smem) R2F_LAUNCH_EX(4, true); else R2F_LAUNCH_EX(4, false);
+    switch (fmt * 2 + (use_smem ? 1 : 0)) {
+        case 0: R2F_LAUNCH_EX(0, false); break;
+        case 1: R2F_LAUNCH_EX(0, true); break;
+        case 2: R2F_LAUNCH_EX(1, false); break;
+        case 3: R2F_LAUNCH_EX(1, true); break;
+        case 4: R2F_LAUNCH_EX(2, false); break;
+        case 5: R2F_LAUNCH_EX(2, true); break;
+        case 6: R2F_LAUNCH_EX(3, false); break;
+        case 7: R2F_LAUNCH_EX(3, true); break;
+        default: return cudaErrorInvalidValue;
     }
 #undef R2F_LAUNCH_EX
     return cudaGetLastError();

@@ -38,10 +38,11 @@ struct ConvArgs {
 };
 
 // K1: XYZ -> 2D LUT -> log10 -> H-D curve -> tetrahedral LUT -> u8, one pass (pointwise configs)
-cudaError_t launch_pointwise(const float *in, int cin, uint8_t *out, size_t npix, const Lut2D &l2, const Curve1D &cv,
-                             float eps, const Lut3D &l3, int num_sms, cudaStream_t st);
+// `fmt` = kFmt* (device_math.cuh); `gain` is the exposure gain applied to uint16 input only.
+cudaError_t launch_pointwise(const void *in, int fmt, float gain, uint8_t *out, size_t npix, const Lut2D &l2,
+                             const Curve1D &cv, float eps, const Lut3D &l3, int num_sms, cudaStream_t st);
 // XYZ (interleaved, 3 or 4 channels) -> planar exposure
-cudaError_t launch_expose(const float *in, int cin, Planes out, size_t npix, const Lut2D &l2, int num_sms,
+cudaError_t launch_expose(const void *in, int fmt, float gain, Planes out, size_t npix, const Lut2D &l2, int num_sms,
                           cudaStream_t st);
 // direct 2-D correlation, reflect-101 borders, fused epilogue
 cudaError_t launch_conv2d(const ConvArgs &a, cudaStream_t st);

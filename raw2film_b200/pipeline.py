@@ -32,11 +32,11 @@ class PipelinedRenderer:
         self.h2d_bytes = 0
         self.d2h_bytes = 0
 
-    def _slot_buffers(self, slot, shape_in):
+    def _slot_buffers(self, slot, shape_in, tdtype):
         torch = self._torch
         h, w, ch = shape_in
-        if slot["dev_in"] is None or tuple(slot["dev_in"].shape) != (h, w, ch):
-            slot["dev_in"] = torch.empty((h, w, ch), dtype=torch.float32, device=self.proc.device)
+        if slot["dev_in"] is None or tuple(slot["dev_in"].shape) != (h, w, ch) or slot["dev_in"].dtype != tdtype:
+            slot["dev_in"] = torch.empty((h, w, ch), dtype=tdtype, device=self.proc.device)
             slot["dev_out"] = torch.empty((h, w, 3), dtype=torch.uint8, device=self.proc.device)
             slot["host_out"] = torch.empty((h, w, 3), dtype=torch.uint8, pin_memory=True)
             for k in ("h2d", "done", "d2h"):
@@ -47,12 +47,13 @@ class PipelinedRenderer:
         torch = self._torch
         arr = cpu_payload["image_array"]
         host = cpu_payload.get("_pinned")
+        tdtype = torch.uint16 if arr.dtype == np.uint16 else torch.float32
         if host is None:  # foreign payload: stage through pinned memory (extra host copy)
-            host = torch.empty(arr.shape, dtype=torch.float32, pin_memory=True)
+            host = torch.empty(arr.shape, dtype=tdtype, pin_memory=True)
             host.numpy()[...] = arr
         ticket = self._count
         slot = self._slots[ticket % self.depth]
-        self._slot_buffers(slot, arr.shape)
+        self._slot_buffers(slot, arr.shape, tdtype)
         if slot["used"]:
             slot["d2h"].synchronize()          # the slot's previous result has left the device
         with torch.cuda.stream(self.s_in):
@@ -64,7 +65,8 @@ class PipelinedRenderer:
         if slot["used"]:
             self.s_compute.wait_event(slot["d2h"])
         self.proc.render_device(slot["dev_in"], negative_film, grain_size, grain_sigma, out=slot["dev_out"],
-                                stream=self.s_compute, sync_caller=False, **settings)
+                                stream=self.s_compute, sync_caller=False,
+                                input_gain=cpu_payload.get("input_gain", 1.0), **settings)
         slot["done"].record(self.s_compute)
         with torch.cuda.stream(self.s_out):
             self.s_out.wait_event(slot["done"])
@@ -73,7 +75,7 @@ class PipelinedRenderer:
         slot["used"] = True
         slot["keep"] = host                       # keep the pinned source alive until the copy ran
         self._count += 1
-        self.h2d_bytes += host.numel() * 4
+        self.h2d_bytes += host.numel() * host.element_size()
         self.d2h_bytes += slot["host_out"].numel()
         return ticket
 

@@ -228,9 +228,13 @@ class B200Processor:
     def extract_image_data_cpu(self, src, cam=None, lens=None, lens_correction=True, frame_width=36,
                                frame_height=24, rotation=0.0, zoom=1.0, rotate_times=0, flip=False, resolution=None,
                                half_size=True, cache=True, chroma_nr=0, max_scale=400.0, canvas_mode="No",
-                               canvas_scale=1.0, canvas_ratio=1.0, alpha=False, **kwargs):
+                               canvas_scale=1.0, canvas_ratio=1.0, alpha=False, input_gain=1.0, **kwargs):
         """Returns the same payload dict as the reference.  `image_array` lives in pinned host
-        memory so phase 2 can DMA it; 3 channels unless `alpha=True` (reference layout, XYZ + ones)."""
+        memory so phase 2 can DMA it; 3 channels unless `alpha=True` (reference layout, XYZ + ones).
+
+        A uint16 frame (what rawpy's postprocess returns, raw_conversion.py:38-48) is kept as uint16:
+        the device applies `/ 65535` and `* input_gain` (= 2**calc_exposure, raw_conversion.py:51-53)
+        itself, so only 6 bytes per pixel cross PCIe."""
         torch = self._torch
         if isinstance(src, np.ndarray):
             image = src
@@ -259,21 +263,20 @@ class B200Processor:
         if canvas_mode != "No":
             raise NotImplementedError("canvas borders (effects.py:290-357) are a 'next' row")
         channels = 4 if alpha else 3
-        pinned = torch.empty((h, w, channels), dtype=torch.float32, pin_memory=True)
+        is_u16 = image.dtype == np.uint16
+        pinned = torch.empty((h, w, channels), dtype=torch.uint16 if is_u16 else torch.float32, pin_memory=True)
         arr = pinned.numpy()
         arr[..., :3] = image[..., :3]
         if alpha:
-            arr[..., 3] = 1.0
+            arr[..., 3] = 65535 if is_u16 else 1.0
         return {"image_array": arr, "output_resolution": (w, h), "canvas_resolution": None,
-                "pipeline_resolution": (w, h), "_pinned": pinned}
+                "pipeline_resolution": (w, h), "_pinned": pinned, "input_gain": float(np.float32(input_gain))}
 
     # ------------------------------------------------------------------------------------------
     # phase 2: upload + render
     # ------------------------------------------------------------------------------------------
     def _ensure_device_buffers(self, h, w, channels, flags):
         torch = self._torch
-        if self._dev_in is None or tuple(self._dev_in.shape) != (h, w, channels):
-            self._dev_in = torch.empty((h, w, channels), dtype=torch.float32, device=self.device)
         if self._dev_out is None or tuple(self._dev_out.shape) != (h, w, 3):
             self._dev_out = torch.empty((h, w, 3), dtype=torch.uint8, device=self.device)
         need = int(_cabi.lib.r2f_workspace_bytes(h, w, flags)) if flags & _SPATIAL else 0
@@ -289,15 +292,17 @@ class B200Processor:
         self.canvas_resolution = cpu_payload["canvas_resolution"]
         self.pipeline_resolution = cpu_payload["pipeline_resolution"]
         host = cpu_payload.get("_pinned")
+        tdtype = torch.uint16 if arr.dtype == np.uint16 else torch.float32
         if host is None:                      # foreign payload: stage through pinned memory
-            host = torch.empty((h, w, ch), dtype=torch.float32, pin_memory=True)
+            host = torch.empty((h, w, ch), dtype=tdtype, pin_memory=True)
             host.numpy()[...] = arr
-        if self._dev_in is None or tuple(self._dev_in.shape) != (h, w, ch):
-            self._dev_in = torch.empty((h, w, ch), dtype=torch.float32, device=self.device)
+        if self._dev_in is None or tuple(self._dev_in.shape) != (h, w, ch) or self._dev_in.dtype != tdtype:
+            self._dev_in = torch.empty((h, w, ch), dtype=tdtype, device=self.device)
         with torch.cuda.stream(self.stream):
             self._dev_in.copy_(host, non_blocking=True)
         self._in_channels = ch
-        self._h2d_bytes = host.numel() * 4
+        self._in_gain = float(cpu_payload.get("input_gain", 1.0))
+        self._h2d_bytes = host.numel() * host.element_size()
 
     def _load_tables(self, negative_film, grain_size, grain_sigma, s, h, w):
         """Loaders + stage gating of cpu_processor.py:342-403.  Returns (flags, scale)."""
@@ -339,14 +344,17 @@ class B200Processor:
         return self._dev_noise.data_ptr(), nch
 
     def render_device(self, xyz_dev, negative_film, grain_size, grain_sigma, out=None, stream=None,
-                      sync_caller=True, **settings):
-        """Device-resident render: `xyz_dev` is a float32 (H, W, 3|4) CUDA tensor, result a uint8
-        (H, W, 3) CUDA tensor.  No host copies; enqueued on `stream` (default: self.stream)."""
+                      sync_caller=True, input_gain=1.0, **settings):
+        """Device-resident render: `xyz_dev` is a float32 -- or uint16 with `input_gain` -- (H, W, 3|4)
+        CUDA tensor, result a uint8 (H, W, 3) CUDA tensor.  No host copies; enqueued on `stream`
+        (default: self.stream)."""
         torch = self._torch
         s = self._merged(settings)
         h, w, ch = xyz_dev.shape
-        if xyz_dev.dtype != torch.float32 or not xyz_dev.is_contiguous() or xyz_dev.device != self.device:
-            raise ValueError("xyz_dev must be a contiguous float32 tensor on this processor's device")
+        if xyz_dev.dtype not in (torch.float32, torch.uint16) or not xyz_dev.is_contiguous() \
+                or xyz_dev.device != self.device:
+            raise ValueError("xyz_dev must be a contiguous float32 / uint16 tensor on this processor's device")
+        in_fmt = _cabi.IN_U16 if xyz_dev.dtype == torch.uint16 else _cabi.IN_F32
         flags, _ = self._load_tables(negative_film, grain_size, grain_sigma, s, h, w)
         self._ensure_device_buffers(h, w, ch, flags)
         if out is None:
@@ -357,13 +365,16 @@ class B200Processor:
         noise_ptr, nch = self._noise_arg(s, h, w, flags)
         ws_ptr = self._dev_ws.data_ptr() if (flags & _SPATIAL) else None
         ws_bytes = self._dev_ws.numel() if (flags & _SPATIAL) else 0
-        _cabi.check(_cabi.lib.r2f_render(self._ctx, xyz_dev.data_ptr(), h, w, ch, out.data_ptr(), flags, noise_ptr,
-                                         nch, ws_ptr, ws_bytes, stream.cuda_stream))
+        if out is None or tuple(out.shape) != (h, w, 3):
+            out = self._dev_out = torch.empty((h, w, 3), dtype=torch.uint8, device=self.device)
+        _cabi.check(_cabi.lib.r2f_render_ex(self._ctx, xyz_dev.data_ptr(), in_fmt, float(input_gain), h, w, ch,
+                                            out.data_ptr(), flags, noise_ptr, nch, ws_ptr, ws_bytes,
+                                            stream.cuda_stream))
         if sync_caller:  # order later work on the caller's stream after the render (asynchronous, no host sync)
             torch.cuda.current_stream(self.device).wait_stream(stream)
         return out
 
-    def render_tap(self, xyz_dev, stage: str, negative_film, grain_size, grain_sigma, **settings):
+    def render_tap(self, xyz_dev, stage: str, negative_film, grain_size, grain_sigma, input_gain=1.0, **settings):
         """Float32 working image after `stage` ("exposure", "halation", "density", "mtf", "grain",
         "burn", "rgb") as a (H, W, 3) CUDA tensor -- parity-test hook (r2f_render_tap)."""
         torch = self._torch
@@ -374,9 +385,11 @@ class B200Processor:
         noise_ptr, nch = self._noise_arg(s, h, w, flags)
         tap = torch.empty((h, w, 3), dtype=torch.float32, device=self.device)
         self.stream.wait_stream(torch.cuda.current_stream(self.device))
-        _cabi.check(_cabi.lib.r2f_render_tap(self._ctx, xyz_dev.data_ptr(), h, w, ch, flags, noise_ptr, nch,
-                                             self._dev_ws.data_ptr(), self._dev_ws.numel(), _cabi.TAPS[stage],
-                                             tap.data_ptr(), self.stream.cuda_stream))
+        in_fmt = _cabi.IN_U16 if xyz_dev.dtype == torch.uint16 else _cabi.IN_F32
+        _cabi.check(_cabi.lib.r2f_render_tap_ex(self._ctx, xyz_dev.data_ptr(), in_fmt, float(input_gain), h, w, ch,
+                                                flags, noise_ptr, nch, self._dev_ws.data_ptr(),
+                                                self._dev_ws.numel(), _cabi.TAPS[stage], tap.data_ptr(),
+                                                self.stream.cuda_stream))
         self.stream.synchronize()
         return tap
 
@@ -388,7 +401,8 @@ class B200Processor:
             raise NotImplementedError("presenting into a wgpu texture / histogram is UI plumbing (out of scope)")
         torch = self._torch
         self.prepare_gpu_textures(cpu_payload)
-        out_dev = self.render_device(self._dev_in, negative_film, grain_size, grain_sigma, **settings)
+        out_dev = self.render_device(self._dev_in, negative_film, grain_size, grain_sigma,
+                                     input_gain=self._in_gain, **settings)
         h, w = out_dev.shape[:2]
         host = torch.empty((h, w, 3), dtype=torch.uint8, pin_memory=True)
         with torch.cuda.stream(self.stream):
