@@ -515,6 +515,41 @@ int render_impl(r2f_ctx *c, const void *in, int in_format, float in_gain, int H,
     }
     if (tap_stage == R2F_TAP_MTF) return export_tap(P[cur]);
 
+    // a7 + a8 + a9 + a10 fused (normal render): noise regenerated per tile, nothing but the density
+    // read and the uint8 write touches HBM.  Taps keep the staged kernels below.
+    if (tap_stage == 0 && (flags & R2F_GRAIN) && !(flags & R2F_BURN) &&
+        (size_t)(64 + c->grain.k - 1) * (64 + c->grain.k - 1) * 4 + (size_t)c->grain.k * c->grain.kp * 4 + 16384 <=
+            200 * 1024) {
+        const int nch = (flags & R2F_GRAIN_BW) ? 1 : 3;
+        GrainFinishArgs ga{};
+        ga.dens = P[cur].base;
+        ga.noise = nullptr;
+        if (noise) {
+            if (noise_ch != nch) return fail(R2F_ERR_INVALID, "injected noise has the wrong channel count");
+            ProfScope ps_(c, st, R2F_PROF_NOISE);
+            CU(launch_interleaved_to_planar(noise, nch, nch, P[2], npix, c->num_sms, st));
+            c->launches += 1;
+            ga.noise = P[2].base;
+        }
+        ga.plane_stride = ps;
+        ga.H = H;
+        ga.W = W;
+        ga.gk = c->grain.chan[0];
+        ga.k = c->grain.k;
+        ga.kp = c->grain.kp;
+        ga.bw = nch == 1;
+        ga.seed_lo = (uint32_t)c->seed;
+        ga.seed_hi = (uint32_t)(c->seed >> 32);
+        ga.gcurve = gcurve_of(c);
+        ga.l3 = l3;
+        ga.burn = BurnArgs{};
+        ga.out_u8 = out_u8;
+        ProfScope ps_(c, st, R2F_PROF_GRAIN);
+        CU(launch_grain_finish(ga, st));
+        c->launches += 1;
+        return R2F_OK;
+    }
+
     // a7: grain (noise -> grain-kernel correlation -> amplitude from density -> add -> clip >= 0)
     if (flags & R2F_GRAIN) {
         const int nch = (flags & R2F_GRAIN_BW) ? 1 : 3;
@@ -524,7 +559,7 @@ int render_impl(r2f_ctx *c, const void *in, int in_format, float in_gain, int H,
             CU(launch_interleaved_to_planar(noise, nch, nch, P[2], npix, c->num_sms, st));
         } else {
             ProfScope ps_(c, st, R2F_PROF_NOISE);
-            CU(launch_noise(P[2], nch, npix, c->seed, c->num_sms, st));
+            CU(launch_noise(P[2], nch, H, W, c->seed, c->num_sms, st));
         }
         ConvArgs a = conv_args(c->grain, P[2].base, P[1 - cur].base, ps, H, W);
         for (int ch = 0; ch < 3; ++ch) a.in_plane[ch] = nch == 1 ? 0 : ch;
@@ -837,7 +872,7 @@ int r2f_generate_noise(r2f_ctx *c, float *out_dev, int H, int W, int channels, u
     const size_t ps = plane_stride_for(H, W), npix = (size_t)H * W;
     CU(c->h_noise.ensure(ps * 3 * sizeof(float)));
     Planes p{static_cast<float *>(c->h_noise.p), ps};
-    CU(launch_noise(p, channels, npix, seed, c->num_sms, st));
+    CU(launch_noise(p, channels, H, W, seed, c->num_sms, st));
     if (channels == 3) {
         CU(launch_planar_to_interleaved(p, out_dev, npix, c->num_sms, st));
     } else {

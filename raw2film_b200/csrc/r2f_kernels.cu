@@ -485,29 +485,203 @@ __device__ __forceinline__ void philox4x32_10(uint32_t (&c)[4], uint32_t k0, uin
 
 __device__ __forceinline__ float u01(uint32_t x) { return ((float)(x >> 8) + 0.5f) * (1.0f / 16777216.0f); }
 
+// Four unit normals for pixels x = 4*qx .. 4*qx+3 of row y, channel ch.  The stream is a pure
+// function of (qx, y, ch, seed), so any kernel can regenerate any part of the field.
+__device__ __forceinline__ float4 noise_quad(uint32_t qx, uint32_t y, uint32_t ch, uint32_t k0, uint32_t k1) {
+    uint32_t c[4] = {qx, y, ch, 0x52324631u};
+    philox4x32_10(c, k0, k1);
+    const float r1 = sqrtf(-2.0f * __logf(u01(c[0]))), r2 = sqrtf(-2.0f * __logf(u01(c[2])));
+    float s1, c1, s2, c2;
+    sincospif(2.0f * u01(c[1]), &s1, &c1);
+    sincospif(2.0f * u01(c[3]), &s2, &c2);
+    return make_float4(r1 * c1, r1 * s1, r2 * c2, r2 * s2);
+}
+
+__device__ __forceinline__ float noise_at(int x, int y, int ch, uint32_t k0, uint32_t k1) {
+    const float4 q = noise_quad((uint32_t)x >> 2, (uint32_t)y, (uint32_t)ch, k0, k1);
+    const int l = x & 3;
+    return l == 0 ? q.x : l == 1 ? q.y : l == 2 ? q.z : q.w;
+}
+
 __global__ void __launch_bounds__(kThreads)
-k_noise(float *__restrict__ out, size_t plane_stride, int nch, size_t npix, uint32_t k0, uint32_t k1) {
-    const size_t nquad = (npix + 3) / 4;
-    const size_t total = nquad * nch;
+k_noise(float *__restrict__ out, size_t plane_stride, int nch, int H, int W, uint32_t k0, uint32_t k1) {
+    const int qw = (W + 3) >> 2;
+    const size_t per_ch = (size_t)H * qw, total = per_ch * nch;
     const size_t stride = (size_t)gridDim.x * kThreads;
     for (size_t t = (size_t)blockIdx.x * kThreads + threadIdx.x; t < total; t += stride) {
-        const int ch = (int)(t / nquad);
-        const size_t q = t - (size_t)ch * nquad;
-        uint32_t c[4] = {(uint32_t)q, (uint32_t)(q >> 32), (uint32_t)ch, 0x52324631u};
-        philox4x32_10(c, k0, k1);
-        const float r1 = sqrtf(-2.0f * logf(u01(c[0]))), r2 = sqrtf(-2.0f * logf(u01(c[2])));
-        float s1, c1, s2, c2;
-        sincospif(2.0f * u01(c[1]), &s1, &c1);
-        sincospif(2.0f * u01(c[3]), &s2, &c2);
-        // plane_stride is a multiple of 64 floats and q*4 < plane_stride: the float4 store is in bounds
-        reinterpret_cast<float4 *>(out + (size_t)ch * plane_stride)[q] = make_float4(r1 * c1, r1 * s1, r2 * c2, r2 * s2);
+        const int ch = (int)(t / per_ch);
+        const size_t rem = t - (size_t)ch * per_ch;
+        const int y = (int)(rem / qw), qx = (int)(rem - (size_t)y * qw);
+        const float4 v = noise_quad(qx, y, ch, k0, k1);
+        float *row = out + (size_t)ch * plane_stride + (size_t)y * W + 4 * qx;
+        const float vals[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int l = 0; l < 4; ++l)
+            if (4 * qx + l < W) row[l] = vals[l];
     }
 }
 
-cudaError_t launch_noise(Planes out, int nch, size_t npix, uint64_t seed, int num_sms, cudaStream_t st) {
-    const size_t items = (npix + 3) / 4 * nch;
-    k_noise<<<grid_for(items, num_sms, 8), kThreads, 0, st>>>(out.base, out.plane_stride, nch, npix, (uint32_t)seed,
+cudaError_t launch_noise(Planes out, int nch, int H, int W, uint64_t seed, int num_sms, cudaStream_t st) {
+    const size_t items = (size_t)H * ((W + 3) / 4) * nch;
+    k_noise<<<grid_for(items, num_sms, 8), kThreads, 0, st>>>(out.base, out.plane_stride, nch, H, W, (uint32_t)seed,
                                                              (uint32_t)(seed >> 32));
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------
+// a7 + a8 + a9 + a10 fused: grain (noise regenerated per tile, correlated with the grain kernel,
+// scaled by the density-dependent amplitude, added, clipped), burn, tetrahedral LUT, quantise.
+// Replaces k_noise + k_conv2d(EPI_GRAIN) + k_finish: the noise field and the grained density never
+// touch HBM (reads 12 B/px of density, writes 3 B/px).
+// Same thread mapping as k_conv2d: 64x64 tile, 256 threads, a 16-row strip per thread.
+// ------------------------------------------------------------------------------------------
+constexpr int kGfTile = 64;
+
+template <bool GEN>
+__global__ void __launch_bounds__(256)
+k_grain_finish(GrainFinishArgs a) {
+    extern __shared__ __align__(16) float smem[];
+    const int H = a.H, W = a.W, k = a.k, kp = a.kp, rad = k / 2;
+    const int cols = kGfTile + k - 1, rows = kGfTile + k - 1;
+    float *tile = smem;
+    float *wsm = smem + ((rows * cols + 3) / 4) * 4;
+    uint8_t *stage = reinterpret_cast<uint8_t *>(wsm + k * kp);  // 64 x 64 x 3 output bytes
+    const int tx0 = blockIdx.x * kGfTile, ty0 = blockIdx.y * kGfTile;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int lx = (warp & 1) * 32 + lane, ly0 = (warp >> 1) * 16;
+    const int gx = tx0 + lx;
+    const size_t ps = a.plane_stride;
+    for (int idx = threadIdx.x; idx < k * kp; idx += 256) wsm[idx] = __ldg(a.gk + idx);
+
+    float dens[3][16];
+    float g[16];
+    const int nch = a.bw ? 1 : 3;
+    const int xs = tx0 - rad;                                  // global x of tile column 0
+    const bool interior = xs >= 0 && xs + cols <= W;           // no horizontal reflection needed
+    const int q0 = xs >> 2, nq = ((xs + cols - 1) >> 2) - q0 + 1;  // aligned noise quads covering the tile row
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        if (c < nch) {
+            __syncthreads();  // previous channel's window reads are done
+            if (GEN) {
+                if (interior) {  // one Philox call per aligned quad of four samples
+                    for (int idx = threadIdx.x; idx < rows * nq; idx += 256) {
+                        const int ty = idx / nq, tq = idx - ty * nq;
+                        const int gy = reflect101(ty0 - rad + ty, H);
+                        const float4 v = noise_quad((uint32_t)(q0 + tq), gy, c, a.seed_lo, a.seed_hi);
+                        const float vals[4] = {v.x, v.y, v.z, v.w};
+                        const int tx = 4 * (q0 + tq) - xs;
+#pragma unroll
+                        for (int l = 0; l < 4; ++l)
+                            if (tx + l >= 0 && tx + l < cols) tile[ty * cols + tx + l] = vals[l];
+                    }
+                } else {
+                    for (int idx = threadIdx.x; idx < rows * cols; idx += 256) {
+                        const int ty = idx / cols, tx = idx - ty * cols;
+                        tile[idx] = noise_at(reflect101(tx0 - rad + tx, W), reflect101(ty0 - rad + ty, H), c, a.seed_lo,
+                                             a.seed_hi);
+                    }
+                }
+            } else {
+                const float *src = a.noise + (size_t)c * ps;
+                for (int idx = threadIdx.x; idx < rows * cols; idx += 256) {
+                    const int ty = idx / cols, tx = idx - ty * cols;
+                    tile[idx] = __ldg(src + (size_t)reflect101(ty0 - rad + ty, H) * W + reflect101(tx0 - rad + tx, W));
+                }
+            }
+            __syncthreads();
+#pragma unroll
+            for (int o = 0; o < 16; ++o) g[o] = 0.0f;
+            const int nfull = k >> 4, rem = k & 15;
+            for (int j = 0; j < k; ++j) {
+                const float *col = tile + ly0 * cols + lx + j;
+                float v[16];
+#pragma unroll
+                for (int u = 0; u < 16; ++u) v[u] = col[u * cols];
+                const float *rowp = col + 16 * cols;
+                const float4 *wp = reinterpret_cast<const float4 *>(wsm + j * kp);
+                for (int b = 0; b < nfull; ++b) {
+#pragma unroll
+                    for (int u4 = 0; u4 < 4; ++u4) {
+                        const float4 w4 = *wp++;
+                        conv_step<0>(g, v, w4.x, u4 * 4 + 0, rowp, cols);
+                        conv_step<0>(g, v, w4.y, u4 * 4 + 1, rowp, cols);
+                        conv_step<0>(g, v, w4.z, u4 * 4 + 2, rowp, cols);
+                        conv_step<0>(g, v, w4.w, u4 * 4 + 3, rowp, cols);
+                    }
+                }
+                switch (rem) {
+#define R2F_REM(R) case R: conv_tail<R>(g, v, wp, rowp, cols); break;
+                    R2F_REM(1) R2F_REM(2) R2F_REM(3) R2F_REM(4) R2F_REM(5) R2F_REM(6) R2F_REM(7) R2F_REM(8)
+                    R2F_REM(9) R2F_REM(10) R2F_REM(11) R2F_REM(12) R2F_REM(13) R2F_REM(14) R2F_REM(15)
+#undef R2F_REM
+                    default: break;
+                }
+            }
+        }
+        // grain apply on channel c (black-and-white grain reuses the single field)
+#pragma unroll
+        for (int o = 0; o < 16; ++o) {
+            const int gy = ty0 + ly0 + o;
+            float val = 0.0f;
+            if (gx < W && gy < H) {
+                const float d = __ldcs(a.dens + c * ps + (size_t)gy * W + gx);
+                val = d + g[o] * curve_eval(a.gcurve, c, d);
+                val = val > 0.0f ? val : 0.0f;
+            }
+            dens[c][o] = val;
+        }
+    }
+    __syncthreads();
+    // burn, tetrahedral LUT, quantise; stage the tile's bytes so rows leave as 16-byte stores
+#pragma unroll
+    for (int o = 0; o < 16; ++o) {
+        const int gy = ty0 + ly0 + o;
+        float d0 = dens[0][o], d1 = dens[1][o], d2 = dens[2][o];
+        if (a.burn.map != nullptr && gx < W && gy < H) {
+            const float m = a.burn.strength * burn_sample(a.burn, gy, gx);
+            d0 = d0 - m; d1 = d1 - m; d2 = d2 - m;
+            d0 = d0 > 0.f ? d0 : 0.f; d1 = d1 > 0.f ? d1 : 0.f; d2 = d2 > 0.f ? d2 : 0.f;
+        }
+        uint32_t q0, q1, q2;
+        tetra_quant_u8(a.l3, d0, d1, d2, q0, q1, q2);
+        uint8_t *sp = stage + ((ly0 + o) * kGfTile + lx) * 3;
+        sp[0] = (uint8_t)q0; sp[1] = (uint8_t)q1; sp[2] = (uint8_t)q2;
+    }
+    __syncthreads();
+    const int tw = min(kGfTile, W - tx0), th = min(kGfTile, H - ty0);
+    const int row_bytes = tw * 3;
+    if (tw == kGfTile && ((size_t)W * 3 % 16) == 0 && (reinterpret_cast<uintptr_t>(a.out_u8) & 15) == 0) {
+        for (int idx = threadIdx.x; idx < th * 12; idx += 256) {  // 192 bytes = 12 x 16 per row
+            const int r = idx / 12, s16 = idx - r * 12;
+            const uint4 v = *reinterpret_cast<const uint4 *>(stage + r * 192 + s16 * 16);
+            __stcs(reinterpret_cast<uint4 *>(a.out_u8 + ((size_t)(ty0 + r) * W + tx0) * 3) + s16, v);
+        }
+    } else {
+        for (int idx = threadIdx.x; idx < th * row_bytes; idx += 256) {
+            const int r = idx / row_bytes, bcol = idx - r * row_bytes;
+            a.out_u8[((size_t)(ty0 + r) * W + tx0) * 3 + bcol] = stage[r * 192 + bcol];
+        }
+    }
+}
+
+cudaError_t launch_grain_finish(const GrainFinishArgs &a, cudaStream_t st) {
+    const int ext = kGfTile + a.k - 1;
+    const size_t smem = (((size_t)ext * ext + 3) / 4 * 4 + (size_t)a.k * a.kp) * sizeof(float) + kGfTile * kGfTile * 3;
+    if (smem > kMaxDynSmem) return cudaErrorInvalidValue;
+    dim3 grid((a.W + kGfTile - 1) / kGfTile, (a.H + kGfTile - 1) / kGfTile);
+    cudaError_t e;
+    if (a.noise == nullptr) {
+        if ((e = cudaFuncSetAttribute(k_grain_finish<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) !=
+            cudaSuccess)
+            return e;
+        k_grain_finish<true><<<grid, 256, smem, st>>>(a);
+    } else {
+        if ((e = cudaFuncSetAttribute(k_grain_finish<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)smem)) != cudaSuccess)
+            return e;
+        k_grain_finish<false><<<grid, 256, smem, st>>>(a);
+    }
     return cudaGetLastError();
 }
 

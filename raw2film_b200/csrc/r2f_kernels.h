@@ -37,6 +37,13 @@ struct ConvArgs {
     float eps;
 };
 
+struct BurnArgs {
+    const float *map;  // low-res blurred mask (lh x lw) or nullptr
+    int lh, lw;        // low-res size
+    int zh, zw;        // size of the zoomed map before pad/crop (scipy.ndimage.zoom output)
+    float strength;
+};
+
 // K1: XYZ -> 2D LUT -> log10 -> H-D curve -> tetrahedral LUT -> u8, one pass (pointwise configs)
 // `fmt` = kFmt* (device_math.cuh); `gain` is the exposure gain applied to uint16 input only.
 cudaError_t launch_pointwise(const void *in, int fmt, float gain, uint8_t *out, size_t npix, const Lut2D &l2,
@@ -47,12 +54,7 @@ cudaError_t launch_expose(const void *in, int fmt, float gain, Planes out, size_
 // direct 2-D correlation, reflect-101 borders, fused epilogue
 cudaError_t launch_conv2d(const ConvArgs &a, cudaStream_t st);
 // planar density -> [burn] -> tetrahedral LUT -> u8 interleaved, or float32 interleaved (taps)
-struct BurnArgs {
-    const float *map;  // low-res blurred mask (lh x lw) or nullptr
-    int lh, lw;        // low-res size
-    int zh, zw;        // size of the zoomed map before pad/crop (scipy.ndimage.zoom output)
-    float strength;
-};
+
 cudaError_t launch_finish(Planes in, size_t npix, int H, int W, const Lut3D &l3, const BurnArgs &burn, uint8_t *out_u8,
                           float *out_f32, int f32_stage_rgb, int num_sms, cudaStream_t st);
 // layout shuffles
@@ -60,7 +62,23 @@ cudaError_t launch_planar_to_interleaved(Planes in, float *out, size_t npix, int
 cudaError_t launch_interleaved_to_planar(const float *in, int cin, int nch, Planes out, size_t npix, int num_sms,
                                          cudaStream_t st);
 // white N(0,1) noise, Philox4x32-10 + Box-Muller, planar
-cudaError_t launch_noise(Planes out, int nch, size_t npix, uint64_t seed, int num_sms, cudaStream_t st);
+cudaError_t launch_noise(Planes out, int nch, int H, int W, uint64_t seed, int num_sms, cudaStream_t st);
+// fused grain + burn apply + tetrahedral LUT + quantise (normal render path)
+struct GrainFinishArgs {
+    const float *dens;   // planar density (after MTF)
+    const float *noise;  // planar injected white noise, or nullptr: regenerate from the seed per tile
+    size_t plane_stride;
+    int H, W;
+    const float *gk;     // grain kernel, transposed + padded: gk[j * kp + i]
+    int k, kp;
+    int bw;              // one noise field for all three layers
+    uint32_t seed_lo, seed_hi;
+    Curve1D gcurve;
+    Lut3D l3;
+    BurnArgs burn;
+    uint8_t *out_u8;
+};
+cudaError_t launch_grain_finish(const GrainFinishArgs &a, cudaStream_t st);
 // highlight-burn low-res mask: area down-sample of the green plane, max(x - d_ref, 0), 13-tap Gaussian (sigma 3)
 cudaError_t launch_burn_mask(const float *green_plane, int H, int W, int lh, int lw, float d_ref, float *tmp,
                              float *map, cudaStream_t st);

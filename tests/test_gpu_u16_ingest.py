@@ -25,7 +25,9 @@ def _u16_frame(h, w, seed):
     rng = np.random.default_rng(seed)
     lum = np.exp2(rng.uniform(-9, 0, (h, w, 1)))
     frame = np.clip(lum * rng.uniform(0.6, 1.0, (h, w, 3)) * 65535, 0, 65535).astype(np.uint16)
-    frame[0, :8] = [[0, 0, 0], [65535] * 3, [1, 0, 0], [0, 1, 0], [0, 0, 1], [65535, 0, 0], [2, 3, 5], [32768] * 3]
+    edge = np.array([[0, 0, 0], [65535] * 3, [1, 0, 0], [0, 1, 0], [0, 0, 1], [65535, 0, 0], [2, 3, 5], [32768] * 3],
+                    np.uint16)
+    frame[0, :min(8, w)] = edge[:min(8, w)]
     return frame
 
 
