@@ -197,6 +197,24 @@ cudaError_t launch_expose(const void *in, int fmt, float gain, Planes out, size_
 // For kernel column j the thread slides a 16-row register window down the tile column:
 // one new LDS per 16 FMAs.
 // ------------------------------------------------------------------------------------------
+// Cooperative load of a (rows x cols) tile whose top-left corner is (gy0, gx0) in a W x H plane,
+// BORDER_REFLECT_101 outside the plane.  One warp per tile row, lanes along x: no div/mod, and the
+// reflection is only evaluated for tiles that actually cross the frame border.
+__device__ __forceinline__ void fill_tile(float *__restrict__ tile, const float *__restrict__ src, int rows, int cols,
+                                          int gy0, int gx0, int H, int W, int nthreads) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = nthreads >> 5;
+    const bool inside_x = gx0 >= 0 && gx0 + cols <= W;
+    for (int ty = warp; ty < rows; ty += nwarps) {
+        const float *row = src + (size_t)reflect101(gy0 + ty, H) * W;
+        float *dst = tile + ty * cols;
+        if (inside_x) {
+            for (int tx = lane; tx < cols; tx += 32) dst[tx] = __ldg(row + gx0 + tx);
+        } else {
+            for (int tx = lane; tx < cols; tx += 32) dst[tx] = __ldg(row + reflect101(gx0 + tx, W));
+        }
+    }
+}
+
 // One kernel row: 16 FMAs on the register window, then (unless LAST) slide the window down by
 // one tile row.  `u` is the compile-time slot of the row that leaves the window.
 template <int LAST>
@@ -254,12 +272,7 @@ k_conv2d(ConvArgs a) {
         const int cols = TW + k - 1, rows = TH + k - 1;
         float *tile = smem;
         float *wsm = smem + ((rows * cols + 3) / 4) * 4;
-        for (int idx = threadIdx.x; idx < rows * cols; idx += NT) {
-            const int ty = idx / cols, tx = idx - ty * cols;
-            const int gy = reflect101(ty0 - rad + ty, H);
-            const int gxx = reflect101(tx0 - rad + tx, W);
-            tile[idx] = __ldg(src + (size_t)gy * W + gxx);
-        }
+        fill_tile(tile, src, rows, cols, ty0 - rad, tx0 - rad, H, W, NT);
         const float *__restrict__ wbase = a.kern[c];
         if (W_SMEM) {
             for (int idx = threadIdx.x; idx < k * kp; idx += NT) wsm[idx] = __ldg(wbase + idx);
@@ -490,10 +503,12 @@ __device__ __forceinline__ float u01(uint32_t x) { return ((float)(x >> 8) + 0.5
 __device__ __forceinline__ float4 noise_quad(uint32_t qx, uint32_t y, uint32_t ch, uint32_t k0, uint32_t k1) {
     uint32_t c[4] = {qx, y, ch, 0x52324631u};
     philox4x32_10(c, k0, k1);
-    const float r1 = sqrtf(-2.0f * __logf(u01(c[0]))), r2 = sqrtf(-2.0f * __logf(u01(c[2])));
+    // Box-Muller on MUFU approximations (relative error ~1e-6: irrelevant for a noise field)
+    const float l1 = -2.0f * __logf(u01(c[0])), l2 = -2.0f * __logf(u01(c[2]));
+    const float r1 = l1 * rsqrtf(l1), r2 = l2 * rsqrtf(l2);  // sqrt(l); l > 0 since u01 < 1
     float s1, c1, s2, c2;
-    sincospif(2.0f * u01(c[1]), &s1, &c1);
-    sincospif(2.0f * u01(c[3]), &s2, &c2);
+    __sincosf(6.28318530717958647692f * (u01(c[1]) - 0.5f), &s1, &c1);  // angle in [-pi, pi)
+    __sincosf(6.28318530717958647692f * (u01(c[3]) - 0.5f), &s2, &c2);
     return make_float4(r1 * c1, r1 * s1, r2 * c2, r2 * s2);
 }
 
@@ -538,14 +553,14 @@ cudaError_t launch_noise(Planes out, int nch, int H, int W, uint64_t seed, int n
 constexpr int kGfTile = 64;
 
 template <bool GEN>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 3)
 k_grain_finish(GrainFinishArgs a) {
     extern __shared__ __align__(16) float smem[];
     const int H = a.H, W = a.W, k = a.k, kp = a.kp, rad = k / 2;
     const int cols = kGfTile + k - 1, rows = kGfTile + k - 1;
-    float *tile = smem;
-    float *wsm = smem + ((rows * cols + 3) / 4) * 4;
-    uint8_t *stage = reinterpret_cast<uint8_t *>(wsm + k * kp);  // 64 x 64 x 3 output bytes
+    float *tile = smem;                                   // noise tile; later the byte staging area
+    float *wsm = smem + ((rows * cols + 3) / 4) * 4;      // grain kernel
+    float *priv = wsm + k * kp;                           // [3][16][256] grained densities, thread-private slots
     const int tx0 = blockIdx.x * kGfTile, ty0 = blockIdx.y * kGfTile;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int lx = (warp & 1) * 32 + lane, ly0 = (warp >> 1) * 16;
@@ -553,13 +568,12 @@ k_grain_finish(GrainFinishArgs a) {
     const size_t ps = a.plane_stride;
     for (int idx = threadIdx.x; idx < k * kp; idx += 256) wsm[idx] = __ldg(a.gk + idx);
 
-    float dens[3][16];
     float g[16];
     const int nch = a.bw ? 1 : 3;
     const int xs = tx0 - rad;                                  // global x of tile column 0
     const bool interior = xs >= 0 && xs + cols <= W;           // no horizontal reflection needed
     const int q0 = xs >> 2, nq = ((xs + cols - 1) >> 2) - q0 + 1;  // aligned noise quads covering the tile row
-#pragma unroll
+#pragma unroll 1
     for (int c = 0; c < 3; ++c) {
         if (c < nch) {
             __syncthreads();  // previous channel's window reads are done
@@ -583,11 +597,7 @@ k_grain_finish(GrainFinishArgs a) {
                     }
                 }
             } else {
-                const float *src = a.noise + (size_t)c * ps;
-                for (int idx = threadIdx.x; idx < rows * cols; idx += 256) {
-                    const int ty = idx / cols, tx = idx - ty * cols;
-                    tile[idx] = __ldg(src + (size_t)reflect101(ty0 - rad + ty, H) * W + reflect101(tx0 - rad + tx, W));
-                }
+                fill_tile(tile, a.noise + (size_t)c * ps, rows, cols, ty0 - rad, xs, H, W, 256);
             }
             __syncthreads();
 #pragma unroll
@@ -620,33 +630,36 @@ k_grain_finish(GrainFinishArgs a) {
             }
         }
         // grain apply on channel c (black-and-white grain reuses the single field)
+        const float *dplane = a.dens + c * ps;
 #pragma unroll
         for (int o = 0; o < 16; ++o) {
             const int gy = ty0 + ly0 + o;
             float val = 0.0f;
             if (gx < W && gy < H) {
-                const float d = __ldcs(a.dens + c * ps + (size_t)gy * W + gx);
+                const float d = __ldcs(dplane + (size_t)gy * W + gx);
                 val = d + g[o] * curve_eval(a.gcurve, c, d);
                 val = val > 0.0f ? val : 0.0f;
             }
-            dens[c][o] = val;
+            priv[(c * 16 + o) * 256 + threadIdx.x] = val;
         }
     }
-    __syncthreads();
+    __syncthreads();  // all noise-tile reads done: its storage becomes the output staging area
+    uint8_t *stage = reinterpret_cast<uint8_t *>(tile);
     // burn, tetrahedral LUT, quantise; stage the tile's bytes so rows leave as 16-byte stores
-#pragma unroll
+#pragma unroll 4
     for (int o = 0; o < 16; ++o) {
         const int gy = ty0 + ly0 + o;
-        float d0 = dens[0][o], d1 = dens[1][o], d2 = dens[2][o];
+        float d0 = priv[(0 * 16 + o) * 256 + threadIdx.x], d1 = priv[(1 * 16 + o) * 256 + threadIdx.x];
+        float d2 = priv[(2 * 16 + o) * 256 + threadIdx.x];
         if (a.burn.map != nullptr && gx < W && gy < H) {
             const float m = a.burn.strength * burn_sample(a.burn, gy, gx);
             d0 = d0 - m; d1 = d1 - m; d2 = d2 - m;
             d0 = d0 > 0.f ? d0 : 0.f; d1 = d1 > 0.f ? d1 : 0.f; d2 = d2 > 0.f ? d2 : 0.f;
         }
-        uint32_t q0, q1, q2;
-        tetra_quant_u8(a.l3, d0, d1, d2, q0, q1, q2);
+        uint32_t q0b, q1b, q2b;
+        tetra_quant_u8(a.l3, d0, d1, d2, q0b, q1b, q2b);
         uint8_t *sp = stage + ((ly0 + o) * kGfTile + lx) * 3;
-        sp[0] = (uint8_t)q0; sp[1] = (uint8_t)q1; sp[2] = (uint8_t)q2;
+        sp[0] = (uint8_t)q0b; sp[1] = (uint8_t)q1b; sp[2] = (uint8_t)q2b;
     }
     __syncthreads();
     const int tw = min(kGfTile, W - tx0), th = min(kGfTile, H - ty0);
@@ -667,7 +680,10 @@ k_grain_finish(GrainFinishArgs a) {
 
 cudaError_t launch_grain_finish(const GrainFinishArgs &a, cudaStream_t st) {
     const int ext = kGfTile + a.k - 1;
-    const size_t smem = (((size_t)ext * ext + 3) / 4 * 4 + (size_t)a.k * a.kp) * sizeof(float) + kGfTile * kGfTile * 3;
+    // noise tile (>= 12 KB so it can hold the staged output bytes) + grain kernel + private slots
+    size_t tile_f = ((size_t)ext * ext + 3) / 4 * 4;
+    if (tile_f < (size_t)kGfTile * kGfTile * 3 / 4) tile_f = (size_t)kGfTile * kGfTile * 3 / 4;
+    const size_t smem = (tile_f + (size_t)a.k * a.kp + 3 * 16 * 256) * sizeof(float);
     if (smem > kMaxDynSmem) return cudaErrorInvalidValue;
     dim3 grid((a.W + kGfTile - 1) / kGfTile, (a.H + kGfTile - 1) / kGfTile);
     cudaError_t e;
