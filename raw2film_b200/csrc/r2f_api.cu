@@ -77,7 +77,10 @@ struct FftLineDev {
         FftLine l{};
         l.n = host.n;
         l.nrad = (int)host.rad.size();
-        for (int i = 0; i < l.nrad; ++i) l.rad[i] = host.rad[i];
+        for (int i = 0; i < l.nrad; ++i) {
+            l.rad[i] = host.rad[i];
+            l.tw_off[i] = host.tw_off[i];
+        }
         l.tw = static_cast<const float2 *>(roots.p);
         return l;
     }

@@ -86,6 +86,21 @@ __device__ __forceinline__ void butterfly<5>(float2 (&v)[5]) {
     v[3] = csub(r2, n2);
 }
 
+template <>
+__device__ __forceinline__ void butterfly<8>(float2 (&v)[8]) {
+    const float h = 0.70710678118654752440f;
+    float2 e[4] = {v[0], v[2], v[4], v[6]}, o[4] = {v[1], v[3], v[5], v[7]};
+    butterfly<4>(e);
+    butterfly<4>(o);
+    const float2 o1 = make_float2((o[1].x + o[1].y) * h, (o[1].y - o[1].x) * h);   // * exp(-i pi/4)
+    const float2 o2 = mul_neg_i(o[2]);                                             // * exp(-i pi/2)
+    const float2 o3 = make_float2((o[3].y - o[3].x) * h, -(o[3].x + o[3].y) * h);  // * exp(-3i pi/4)
+    v[0] = cadd(e[0], o[0]); v[4] = csub(e[0], o[0]);
+    v[1] = cadd(e[1], o1);   v[5] = csub(e[1], o1);
+    v[2] = cadd(e[2], o2);   v[6] = csub(e[2], o2);
+    v[3] = cadd(e[3], o3);   v[7] = csub(e[3], o3);
+}
+
 // A group of threads that cooperates on one FFT line and synchronises on its own named barrier.
 struct Group {
     int tid, size, bar;
@@ -96,30 +111,29 @@ __device__ __forceinline__ void group_sync(const Group &g) {
 
 // One out-of-place Stockham pass of radix R: src[0..n) -> dst[0..n) (auto-sorting, no bit reversal).
 // Butterfly j reads src[j + t*n/R] (contiguous across lanes) and writes dst[j0 + t*Ns].
+// `tw` is this pass's twiddle table: tw[(t-1)*Ns + k] = exp(-2 pi i t k / (Ns R)), so lanes with
+// consecutive j read consecutive twiddles.
 template <int R>
 __device__ __forceinline__ void fft_pass(const float2 *__restrict__ src, float2 *__restrict__ dst, int n, int Ns,
                                          const float2 *__restrict__ tw, const Group &g) {
     const int nb = n / R;
-    const int tws = n / (Ns * R);
     const bool pow2 = (Ns & (Ns - 1)) == 0;
+#pragma unroll 2
     for (int j = g.tid; j < nb; j += g.size) {
         const int k = pow2 ? (j & (Ns - 1)) : (j % Ns);
         float2 v[R];
 #pragma unroll
         for (int t = 0; t < R; ++t) v[t] = src[j + t * nb];
-        if (k != 0) {
-            const int q = k * tws;
+        if (Ns > 1) {
 #pragma unroll
-            for (int t = 1; t < R; ++t) v[t] = cmul(v[t], __ldg(tw + t * q));
+            for (int t = 1; t < R; ++t) v[t] = cmul(v[t], __ldg(tw + (t - 1) * Ns + k));
         }
         butterfly<R>(v);
         const int j0 = (j - k) * R + k;
-        if (Ns == 1 && R == 4) {  // outputs are 4 consecutive elements: two 16-byte stores
+        if (Ns == 1 && (R & 1) == 0) {  // R consecutive outputs: 16-byte stores
             float4 *d4 = reinterpret_cast<float4 *>(dst + j0);
-            d4[0] = make_float4(v[0].x, v[0].y, v[1].x, v[1].y);
-            d4[1] = make_float4(v[2].x, v[2].y, v[3].x, v[3].y);
-        } else if (Ns == 1 && R == 2) {
-            *reinterpret_cast<float4 *>(dst + j0) = make_float4(v[0].x, v[0].y, v[1].x, v[1].y);
+#pragma unroll
+            for (int t = 0; t < R / 2; ++t) d4[t] = make_float4(v[2 * t].x, v[2 * t].y, v[2 * t + 1].x, v[2 * t + 1].y);
         } else {
 #pragma unroll
             for (int t = 0; t < R; ++t) dst[j0 + t * Ns] = v[t];
@@ -135,11 +149,13 @@ __device__ __forceinline__ float2 *fft_forward(float2 *a, float2 *b, const FftLi
     int Ns = 1;
     for (int s = 0; s < L.nrad; ++s) {
         const int R = L.rad[s];
+        const float2 *tw = L.tw + L.tw_off[s];
         switch (R) {
-            case 2: fft_pass<2>(src, dst, L.n, Ns, L.tw, g); break;
-            case 3: fft_pass<3>(src, dst, L.n, Ns, L.tw, g); break;
-            case 4: fft_pass<4>(src, dst, L.n, Ns, L.tw, g); break;
-            default: fft_pass<5>(src, dst, L.n, Ns, L.tw, g); break;
+            case 2: fft_pass<2>(src, dst, L.n, Ns, tw, g); break;
+            case 3: fft_pass<3>(src, dst, L.n, Ns, tw, g); break;
+            case 4: fft_pass<4>(src, dst, L.n, Ns, tw, g); break;
+            case 5: fft_pass<5>(src, dst, L.n, Ns, tw, g); break;
+            default: fft_pass<8>(src, dst, L.n, Ns, tw, g); break;
         }
         float2 *t = src;
         src = dst;
@@ -205,11 +221,19 @@ k_fft_rows_fwd(const __grid_constant__ FftConvArgs a) {
     __syncthreads();
     // blocked store: S[(b*H + y)*NC + c]; the NC columns of the CTA's rows are contiguous
     const size_t res_off = (a.row.nrad & 1) ? (size_t)n : 0;  // result buffer by pass parity
-    for (int idx = threadIdx.x; idx < n * nrows; idx += blockDim.x) {
-        const int c = idx % NC;
-        const int row = (idx / NC) % nrows;
-        const int b = idx / (NC * nrows);
-        a.S[((size_t)b * H + (y0 + row)) * NC + c] = fsm[(size_t)row * 2 * n + res_off + b * NC + c];
+    const int nblk = n / NC;
+    for (int b = threadIdx.x; b < nblk; b += blockDim.x) {  // one column block per thread: no div/mod
+        for (int row = 0; row < nrows; ++row) {
+            const float2 *sp = fsm + (size_t)row * 2 * n + res_off + b * NC;
+            float2 *dp = a.S + ((size_t)b * H + (y0 + row)) * NC;
+            if (NC == 4) {
+                const float4 lo = *reinterpret_cast<const float4 *>(sp), hi = *reinterpret_cast<const float4 *>(sp + 2);
+                *reinterpret_cast<float4 *>(dp) = lo;
+                *reinterpret_cast<float4 *>(dp + 2) = hi;
+            } else {
+                for (int c = 0; c < NC; ++c) dp[c] = sp[c];
+            }
+        }
     }
 }
 
@@ -224,9 +248,17 @@ k_fft_cols(const __grid_constant__ FftConvArgs a) {
     const int pitch = n + 2;  // even (16-byte aligned lines), de-phases the column buffers across banks
     const int b = blockIdx.x;
     float2 *blk = a.S + (size_t)b * H * NC;
-    for (int idx = threadIdx.x; idx < H * NC; idx += blockDim.x) {
-        const int c = idx % NC, y = idx / NC;
-        fsm[(size_t)c * pitch + r + y] = blk[idx];
+    for (int y = threadIdx.x; y < H; y += blockDim.x) {  // one spectrum row (NC values) per thread
+        const float2 *sp = blk + (size_t)y * NC;
+        if (NC == 4) {
+            const float4 lo = *reinterpret_cast<const float4 *>(sp), hi = *reinterpret_cast<const float4 *>(sp + 2);
+            fsm[r + y] = make_float2(lo.x, lo.y);
+            fsm[(size_t)pitch + r + y] = make_float2(lo.z, lo.w);
+            fsm[(size_t)2 * pitch + r + y] = make_float2(hi.x, hi.y);
+            fsm[(size_t)3 * pitch + r + y] = make_float2(hi.z, hi.w);
+        } else {
+            for (int c = 0; c < NC; ++c) fsm[(size_t)c * pitch + r + y] = sp[c];
+        }
     }
     __syncthreads();
     const int gsize = (int)blockDim.x / NG;
@@ -251,9 +283,16 @@ k_fft_cols(const __grid_constant__ FftConvArgs a) {
     }
     __syncthreads();
     // keep the swapped form: k_fft_rows_inv consumes swap(x) directly
-    for (int idx = threadIdx.x; idx < H * NC; idx += blockDim.x) {
-        const int c = idx % NC, y = idx / NC;
-        blk[idx] = fsm[(size_t)c * pitch + r + y];
+    for (int y = threadIdx.x; y < H; y += blockDim.x) {
+        float2 *dp = blk + (size_t)y * NC;
+        if (NC == 4) {
+            const float2 c0 = fsm[r + y], c1 = fsm[(size_t)pitch + r + y];
+            const float2 c2 = fsm[(size_t)2 * pitch + r + y], c3 = fsm[(size_t)3 * pitch + r + y];
+            *reinterpret_cast<float4 *>(dp) = make_float4(c0.x, c0.y, c1.x, c1.y);
+            *reinterpret_cast<float4 *>(dp + 2) = make_float4(c2.x, c2.y, c3.x, c3.y);
+        } else {
+            for (int c = 0; c < NC; ++c) dp[c] = fsm[(size_t)c * pitch + r + y];
+        }
     }
 }
 
@@ -270,11 +309,19 @@ k_fft_rows_inv(const __grid_constant__ FftConvArgs a) {
     const int y0 = blockIdx.x * ROWS;
     const int nrows = min(ROWS, H - y0);
     // S holds swap(column-inverse); one more forward FFT along the row completes swap(IFFT2)
-    for (int idx = threadIdx.x; idx < n * nrows; idx += blockDim.x) {
-        const int c = idx % NC;
-        const int row = (idx / NC) % nrows;
-        const int b = idx / (NC * nrows);
-        fsm[(size_t)row * 2 * n + b * NC + c] = a.S[((size_t)b * H + (y0 + row)) * NC + c];
+    const int nblk = n / NC;
+    for (int b = threadIdx.x; b < nblk; b += blockDim.x) {
+        for (int row = 0; row < nrows; ++row) {
+            const float2 *sp = a.S + ((size_t)b * H + (y0 + row)) * NC;
+            float2 *dp = fsm + (size_t)row * 2 * n + b * NC;
+            if (NC == 4) {
+                const float4 lo = *reinterpret_cast<const float4 *>(sp), hi = *reinterpret_cast<const float4 *>(sp + 2);
+                *reinterpret_cast<float4 *>(dp) = lo;
+                *reinterpret_cast<float4 *>(dp + 2) = hi;
+            } else {
+                for (int c = 0; c < NC; ++c) dp[c] = sp[c];
+            }
+        }
     }
     __syncthreads();
     if (half >= nrows) return;
@@ -353,19 +400,33 @@ static bool factor_235(int n, std::vector<int> &rad) {
     while (m % 3 == 0) { m /= 3; odd.push_back(3); }
     while (m % 5 == 0) { m /= 5; odd.push_back(5); }
     if (m != 1) return false;
-    for (int i = 0; i + 1 < twos; i += 2) rad.push_back(4);
-    if (twos & 1) rad.push_back(2);
+    while (twos >= 3) { rad.push_back(8); twos -= 3; }
+    if (twos == 2) rad.push_back(4);
+    if (twos == 1) rad.push_back(2);
     rad.insert(rad.end(), odd.begin(), odd.end());
     return (int)rad.size() <= kFftMaxPasses;
 }
 
+// Padded FFT length: among the 2^a 3^b 5^c sizes in [min_n, 1.3 min_n] pick the one with the lowest
+// estimated cost  n * sum_passes(weight(radix))  -- a power of two a few percent larger (radix-8
+// passes) beats the smallest smooth size made of many radix-3/5 passes.
 int fft_good_size(int min_n, int multiple_of) {
-    for (int n = min_n; n <= kFftMaxLen; ++n) {
+    int best = 0;
+    double best_cost = 0.0;
+    const int hi = min_n + min_n * 3 / 10 + 64;
+    for (int n = min_n; n <= hi && n <= kFftMaxLen; ++n) {
         if (n % multiple_of) continue;
         std::vector<int> rad;
-        if (factor_235(n, rad)) return n;
+        if (!factor_235(n, rad)) continue;
+        double w = 0.0;
+        for (int R : rad) w += R == 8 ? 1.3 : R == 5 ? 1.25 : R == 2 ? 0.9 : 1.0;
+        const double cost = w * (double)n;
+        if (!best || cost < best_cost) {
+            best = n;
+            best_cost = cost;
+        }
     }
-    return 0;
+    return best;
 }
 
 bool fft_make_line(int n, FftLineHost &out) {
@@ -373,13 +434,21 @@ bool fft_make_line(int n, FftLineHost &out) {
     if (!factor_235(n, rad)) return false;
     out.n = n;
     out.rad = rad;
-    out.roots.resize(n);
     out.cosines.resize(n);
     const double two_pi = 6.283185307179586476925286766559;
-    for (int q = 0; q < n; ++q) {
-        const double ang = two_pi * (double)q / (double)n;
-        out.roots[q] = make_float2((float)std::cos(ang), (float)(-std::sin(ang)));  // exp(-2 pi i q / n)
-        out.cosines[q] = std::cos(ang);
+    for (int q = 0; q < n; ++q) out.cosines[q] = std::cos(two_pi * (double)q / (double)n);
+    // per-pass twiddles, laid out [t-1][k] so that a warp reads consecutive entries
+    out.roots.clear();
+    out.tw_off.clear();
+    int Ns = 1;
+    for (int R : rad) {
+        out.tw_off.push_back((int)out.roots.size());
+        for (int t = 1; t < R; ++t)
+            for (int k = 0; k < Ns; ++k) {
+                const double ang = two_pi * (double)t * (double)k / ((double)Ns * (double)R);
+                out.roots.push_back(make_float2((float)std::cos(ang), (float)(-std::sin(ang))));
+            }
+        Ns *= R;
     }
     return true;
 }

@@ -19,13 +19,15 @@ struct FftLine {
     int n;
     int nrad;
     int rad[kFftMaxPasses];
-    const float2 *tw;  // exp(-2 pi i q / n), q < n
+    int tw_off[kFftMaxPasses];  // start of each pass's twiddle table inside tw
+    const float2 *tw;           // per-pass tables, pass p: tw[tw_off[p] + (t-1)*Ns + k] = exp(-2 pi i t k / (Ns R))
 };
 
 // Host-side description of one FFT length (factorisation + double-built root / cosine tables).
 struct FftLineHost {
     int n = 0;
     std::vector<int> rad;
+    std::vector<int> tw_off;
     std::vector<float2> roots;
     std::vector<double> cosines;
 };
