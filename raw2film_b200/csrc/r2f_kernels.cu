@@ -201,12 +201,13 @@ cudaError_t launch_expose(const void *in, int fmt, float gain, Planes out, size_
 // BORDER_REFLECT_101 outside the plane.  One warp per tile row, lanes along x: no div/mod, and the
 // reflection is only evaluated for tiles that actually cross the frame border.
 __device__ __forceinline__ void fill_tile(float *__restrict__ tile, const float *__restrict__ src, int rows, int cols,
-                                          int gy0, int gx0, int H, int W, int nthreads) {
+                                          int gy0, int gx0, int H, int W, int nthreads, int pitch = 0) {
+    if (pitch == 0) pitch = cols;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = nthreads >> 5;
     const bool inside_x = gx0 >= 0 && gx0 + cols <= W;
     for (int ty = warp; ty < rows; ty += nwarps) {
         const float *row = src + (size_t)reflect101(gy0 + ty, H) * W;
-        float *dst = tile + ty * cols;
+        float *dst = tile + ty * pitch;
         if (inside_x) {
             for (int tx = lane; tx < cols; tx += 32) dst[tx] = __ldg(row + gx0 + tx);
         } else {
@@ -245,7 +246,9 @@ __device__ __forceinline__ void conv_tail(float (&acc)[16], float (&v)[16], cons
     }
 }
 
-template <int TW, int TH, bool W_SMEM>
+// PITCH > 0: compile-time tile row pitch (floats), so the window loads of the unrolled inner loop
+// become LDS with immediate offsets (no per-step pointer arithmetic); PITCH == 0: pitch = TW + k - 1.
+template <int TW, int TH, bool W_SMEM, int PITCH>
 __global__ void __launch_bounds__((TW / 32) * (TH / 16) * 32)
 k_conv2d(ConvArgs a) {
     constexpr int NWX = TW / 32;
@@ -269,10 +272,10 @@ k_conv2d(ConvArgs a) {
         }
     } else {
         const int k = a.k, kp = a.kp, rad = k / 2;
-        const int cols = TW + k - 1, rows = TH + k - 1;
+        const int cols = PITCH ? PITCH : TW + k - 1, rows = TH + k - 1;
         float *tile = smem;
         float *wsm = smem + ((rows * cols + 3) / 4) * 4;
-        fill_tile(tile, src, rows, cols, ty0 - rad, tx0 - rad, H, W, NT);
+        fill_tile(tile, src, rows, TW + k - 1, ty0 - rad, tx0 - rad, H, W, NT, cols);
         const float *__restrict__ wbase = a.kern[c];
         if (W_SMEM) {
             for (int idx = threadIdx.x; idx < k * kp; idx += NT) wsm[idx] = __ldg(wbase + idx);
@@ -331,9 +334,9 @@ k_conv2d(ConvArgs a) {
     }
 }
 
-template <int TW, int TH, bool W_SMEM>
+template <int TW, int TH, bool W_SMEM, int PITCH>
 static cudaError_t launch_conv_cfg(const ConvArgs &a, size_t smem_bytes, cudaStream_t st) {
-    auto kfn = k_conv2d<TW, TH, W_SMEM>;
+    auto kfn = k_conv2d<TW, TH, W_SMEM, PITCH>;
     cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
     if (e != cudaSuccess) return e;
     dim3 grid((a.W + TW - 1) / TW, (a.H + TH - 1) / TH, 3);
@@ -343,20 +346,26 @@ static cudaError_t launch_conv_cfg(const ConvArgs &a, size_t smem_bytes, cudaStr
 
 constexpr size_t kMaxDynSmem = 227 * 1024;
 
-static size_t conv_smem_bytes(int tw, int th, int k, int kp, bool w_smem) {
-    size_t tile = ((size_t)(tw + k - 1) * (th + k - 1) + 3) / 4 * 4;
+static size_t conv_smem_bytes(int tw, int th, int k, int kp, bool w_smem, int pitch = 0) {
+    const size_t cols = pitch ? (size_t)pitch : (size_t)(tw + k - 1);
+    size_t tile = (cols * (th + k - 1) + 3) / 4 * 4;
     return (tile + (w_smem ? (size_t)k * kp : 0)) * sizeof(float);
 }
 
 cudaError_t launch_conv2d(const ConvArgs &a, cudaStream_t st) {
     const bool any_conv = a.mode[0] || a.mode[1] || a.mode[2];
-    if (!any_conv) return launch_conv_cfg<64, 64, true>(a, 16, st);
-    size_t s = conv_smem_bytes(64, 64, a.k, a.kp, true);
-    if (s <= kMaxDynSmem) return launch_conv_cfg<64, 64, true>(a, s, st);
+    if (!any_conv) return launch_conv_cfg<64, 64, true, 0>(a, 16, st);
+    size_t s;
+    if (64 + a.k - 1 <= 128) {  // fixed 128-float pitch: immediate-offset window loads
+        s = conv_smem_bytes(64, 64, a.k, a.kp, true, 128);
+        if (s <= 100 * 1024) return launch_conv_cfg<64, 64, true, 128>(a, s, st);
+    }
+    s = conv_smem_bytes(64, 64, a.k, a.kp, true);
+    if (s <= kMaxDynSmem) return launch_conv_cfg<64, 64, true, 0>(a, s, st);
     s = conv_smem_bytes(64, 64, a.k, a.kp, false);
-    if (s <= kMaxDynSmem) return launch_conv_cfg<64, 64, false>(a, s, st);
+    if (s <= kMaxDynSmem) return launch_conv_cfg<64, 64, false, 0>(a, s, st);
     s = conv_smem_bytes(32, 32, a.k, a.kp, false);
-    if (s <= kMaxDynSmem) return launch_conv_cfg<32, 32, false>(a, s, st);
+    if (s <= kMaxDynSmem) return launch_conv_cfg<32, 32, false, 0>(a, s, st);
     return cudaErrorInvalidValue;  // kernel wider than ~205 taps: needs the FFT path
 }
 
