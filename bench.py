@@ -141,6 +141,7 @@ def run_reference(args, world, rank):
 
     H, W, settings, desc = CONFIGS[args.config]
     stock = SyntheticStock()
+    fo.use_all_host_threads()
     xyz, st, sample = cpu_sample(args.config, H, W, settings)
     mp = xyz.shape[0] * xyz.shape[1] / 1e6
     for _ in range(max(1, min(args.warmup, 1))):
@@ -150,7 +151,7 @@ def run_reference(args, world, rank):
         cpu_render_once(fo, xyz, stock, st)
     dt = time.perf_counter() - t0
     val = mp * args.steps / dt
-    cores = os.cpu_count()
+    cores = fo.num_threads()
     line = {
         "impl": "reference", "metric": "megapixels_per_second", "value": val, "unit": "MP/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
@@ -238,6 +239,19 @@ def main():
     prof_n = (ctypes.c_uint64 * len(_cabi.PROF_NAMES))()
     _cabi.check(_cabi.lib.r2f_profile_read(proc._ctx, prof_ms, prof_n))
     _cabi.check(_cabi.lib.r2f_profile_enable(proc._ctx, 0))
+
+    # --- per-call latency (BASELINE config 5 asks for p50/p99): synchronous device-resident calls ----
+    lat_n = 1000 if args.config == "C5" else 50
+    lat = []
+    for i in range(lat_n):
+        t0 = time.perf_counter()
+        step_device(i)
+        proc.stream.synchronize()
+        lat.append((time.perf_counter() - t0) * 1e3)
+    lat = np.sort(np.asarray(lat))
+    latency = {"p50_ms": float(lat[len(lat) // 2]), "p99_ms": float(lat[min(len(lat) - 1, int(len(lat) * 0.99))]),
+               "min_ms": float(lat[0]), "calls": lat_n,
+               "what": "wall time of one synchronous B200Processor.render_device call (device-resident frame)"}
 
     # --- timed, end to end through the public API (pinned host in, host out) ---------------------
     # (a) synchronous per-frame call, as the reference's single export makes it
@@ -332,12 +346,13 @@ def main():
         if world == 1 and not args.no_cpu_baseline:
             from oracle import film_oracle as fo
 
+            fo.use_all_host_threads()
             xyz, st, sample = cpu_sample(args.config, H, W, settings, frac=2)
             cpu_render_once(fo, xyz[:64].copy(), stock, st)          # warm caches / thread pools
             t0 = time.perf_counter()
             cpu_render_once(fo, xyz, stock, st)
             dt = time.perf_counter() - t0
-            cpu = {"value": xyz.shape[0] * xyz.shape[1] / 1e6 / dt, "unit": "MP/s", "cores": os.cpu_count(),
+            cpu = {"value": xyz.shape[0] * xyz.shape[1] / 1e6 / dt, "unit": "MP/s", "cores": fo.num_threads(),
                    "kind": "port", "sample": sample, "seconds": dt}
         line = {
             "metric": "megapixels_per_second", "value": value, "unit": "MP/s", "n_gpus": world, "steps": args.steps,
@@ -357,7 +372,7 @@ def main():
                         "ms_per_step": ms_e2e16 / args.steps,
                         "note": "same batch from uint16 XYZ frames (what rawpy hands over); /65535 and exposure "
                                 "gain applied on the device (SURVEY 8f-1)"},
-            "gpu_launches": launches, "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu, "clocks": clocks,
+            "latency": latency, "gpu_launches": launches, "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu, "clocks": clocks,
             "checksum": checksum,
         }
         print(json.dumps(line))

@@ -65,6 +65,8 @@ def _c():
         fp, u8p = ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_uint8)
         i64, ci, cf, cd = ctypes.c_int64, ctypes.c_int, ctypes.c_float, ctypes.c_double
         lib.orc_num_threads.restype = ci
+        lib.orc_set_num_threads.argtypes = [ci]
+        lib.orc_set_num_threads.restype = None
         lib.orc_apply_2d_lut.argtypes = [fp, i64, ci, fp, ci, fp]
         lib.orc_log_clip.argtypes = [fp, i64, cf]
         lib.orc_curve_interp.argtypes = [fp, i64, fp, ci, cf, fp]
@@ -89,6 +91,14 @@ def _c32(a):
 
 def num_threads() -> int:
     return int(_c().orc_num_threads())
+
+
+def use_all_host_threads() -> int:
+    """Give the OpenMP stages and cv2 every host core (torchrun exports OMP_NUM_THREADS=1)."""
+    n = os.cpu_count() or 1
+    _c().orc_set_num_threads(n)
+    cv.setNumThreads(n)
+    return n
 
 
 # --------------------------------------------------------------------------------------

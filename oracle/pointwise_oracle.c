@@ -37,6 +37,15 @@
 #include <omp.h>
 #endif
 
+/* torchrun exports OMP_NUM_THREADS=1; the CPU baseline asks for every host thread explicitly. */
+void orc_set_num_threads(int n) {
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+
 int orc_num_threads(void) {
 #ifdef _OPENMP
     return omp_get_max_threads();
