@@ -45,7 +45,22 @@ CONFIGS = {
 ALG_BYTES_PER_PX = {"C1": 15, "C2": 63, "C3": 63, "C5": 15}
 # per-kernel algorithmic bytes/px: own input + output tensors (SURVEY 8d "same rule per kernel")
 KERNEL_BYTES_PER_PX = {"pointwise": 15, "expose": 24, "halation": 24, "density": 24, "mtf": 24, "noise": 12,
-                       "grain": 36, "burn": 4, "finish": 15}
+                       "grain": 15, "burn": 4, "finish": 15,
+                       # FFT halation: 12 B/px frame read + 8 B/px spectrum write | spectrum r+w + 4 B/px kernel
+                       # spectrum | spectrum read + frame re-read + 12 B/px density write (padding excluded)
+                       "fft_rows_fwd": 20, "fft_cols": 20, "fft_rows_inv": 32}
+KERNEL_SASS_NAME = {"pointwise": "k_pointwise", "mtf": "k_conv2d", "halation": "k_conv2d", "grain": "k_grain_finish",
+                    "fft_rows_fwd": "k_fft_rows_fwd", "fft_cols": "k_fft_cols", "fft_rows_inv": "k_fft_rows_inv",
+                    "finish": "k_finish", "expose": "k_expose", "noise": "k_noise", "density": "k_conv2d"}
+
+
+def load_traffic(config, kernel):
+    """DRAM bytes per launch of `kernel` from the committed ncu --set full capture (profiles/traffic.json)."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            return json.load(f)[config][kernel]
+    except Exception:  # noqa: BLE001
+        return None
 GRAIN_SIZE, GRAIN_SIGMA = 6.0, 0.4                                  # gui.py:498, 509
 
 
@@ -330,13 +345,14 @@ def main():
         roofline = None
         if dom:
             ach = kernels[dom]["gbs"]
-            roofline = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s",
-                        "frac": ach / peak, "traffic": None, "peak_source": peak_src,
+            roofline = {"bound": "hbm", "kernel": dom, "sass_name": KERNEL_SASS_NAME.get(dom), "achieved": ach,
+                        "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": load_traffic(args.config, dom),
+                        "peak_source": peak_src,
                         "ms_per_launch": kernels[dom]["ms"],
                         "share_of_step": kernels[dom]["ms"] * kernels[dom]["launches_per_step"] / (ms_total / args.steps),
                         "step_alg_gbs": ALG_BYTES_PER_PX[args.config] * H * W / (ms_total / args.steps * 1e-3) / 1e9,
                         "step_frac": ALG_BYTES_PER_PX[args.config] * H * W / (ms_total / args.steps * 1e-3) / 1e9 / peak}
-            if dom in ("halation", "mtf", "grain"):
+            if dom in ("halation", "mtf"):
                 k = {"halation": proc.halation_kernel, "mtf": proc.mtf_kernel}.get(dom)
                 if k is not None:
                     taps = sum(int(np.count_nonzero(k[..., c])) > 1 for c in range(3)) * k.shape[0] * k.shape[1]

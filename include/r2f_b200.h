@@ -153,6 +153,11 @@ int r2f_convolve2d(r2f_ctx *ctx, const float *in_dev, float *out_dev, int H, int
 /* White N(0,1) field from the context's Philox stream: float32 H x W x channels (1 or 3). */
 int r2f_generate_noise(r2f_ctx *ctx, float *out_dev, int H, int W, int channels, uint64_t seed, void *stream);
 
+/* add_canvas (effects.py:338-357): fill a canvas_h x canvas_w x 3 uint8 image with (r, g, b) and paste
+ * the H x W x 3 render at (off_y, off_x); geometry from get_canvas_data (effects.py:290-335). */
+int r2f_canvas_paste(r2f_ctx *ctx, const uint8_t *src_dev, int H, int W, uint8_t *dst_dev, int canvas_h, int canvas_w,
+                     int off_y, int off_x, int r, int g, int b, void *stream);
+
 /* Number of kernel launches issued by this context since creation (bench.py gpu_launches). */
 uint64_t r2f_launch_count(const r2f_ctx *ctx);
 
@@ -162,14 +167,17 @@ uint64_t r2f_launch_count(const r2f_ctx *ctx);
  * arrays (length R2F_PROF_COUNT) and clears the recorded events. */
 #define R2F_PROF_POINTWISE 0 /* k_pointwise (fused a2+a4+a5+a9+a10)        */
 #define R2F_PROF_EXPOSE 1    /* k_expose (a2)                              */
-#define R2F_PROF_HALATION 2  /* k_conv2d halation + density epilogue (a3-5) */
+#define R2F_PROF_HALATION 2  /* direct k_conv2d halation + density epilogue (a3-5) */
 #define R2F_PROF_DENSITY 3   /* pointwise density pass when halation is off */
 #define R2F_PROF_MTF 4       /* k_conv2d MTF (a6)                           */
 #define R2F_PROF_NOISE 5     /* k_noise / noise upload shuffle (a7)        */
 #define R2F_PROF_GRAIN 6     /* k_conv2d grain + apply epilogue (a7)       */
 #define R2F_PROF_BURN 7      /* burn mask kernels (a8)                     */
 #define R2F_PROF_FINISH 8    /* k_finish (a8 apply + a9 + a10)             */
-#define R2F_PROF_COUNT 9
+#define R2F_PROF_FFT_ROWS_FWD 9  /* k_fft_rows_fwd (a2 + row FFT)          */
+#define R2F_PROF_FFT_COLS 10     /* k_fft_cols (column FFT x Khat, inverse) */
+#define R2F_PROF_FFT_ROWS_INV 11 /* k_fft_rows_inv (row IFFT + a4 + a5)    */
+#define R2F_PROF_COUNT 12
 int r2f_profile_enable(r2f_ctx *ctx, int on);
 int r2f_profile_read(r2f_ctx *ctx, double *ms_accum, uint64_t *count_accum);
 

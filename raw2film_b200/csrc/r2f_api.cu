@@ -466,9 +466,9 @@ int render_impl(r2f_ctx *c, const void *in, int in_format, float in_gain, int H,
         fa.dst_planar = P[1].base;
         fa.curve = cv;
         fa.eps = c->eps;
-        {
-            ProfScope ps_(c, st, R2F_PROF_HALATION);
-            CU(launch_fft_conv(fa, 1 + fmt, tap_stage != R2F_TAP_HALATION, st));
+        for (int stage = 1; stage <= 3; ++stage) {
+            ProfScope ps_(c, st, R2F_PROF_FFT_ROWS_FWD + stage - 1);
+            CU(launch_fft_conv(fa, 1 + fmt, tap_stage != R2F_TAP_HALATION, st, stage));
         }
         c->launches += 2;  // + the one counted below
         if (tap_stage == R2F_TAP_HALATION) {
@@ -882,6 +882,17 @@ int r2f_generate_noise(r2f_ctx *c, float *out_dev, int H, int W, int channels, u
         CU(cudaMemcpyAsync(out_dev, p.base, npix * sizeof(float), cudaMemcpyDeviceToDevice, st));
     }
     c->launches += 2;
+    return R2F_OK;
+}
+
+int r2f_canvas_paste(r2f_ctx *c, const uint8_t *src_dev, int H, int W, uint8_t *dst_dev, int canvas_h, int canvas_w,
+                     int off_y, int off_x, int r, int g, int b, void *stream) {
+    if (!c || !src_dev || !dst_dev || H < 1 || W < 1 || canvas_h < 1 || canvas_w < 1)
+        return fail(R2F_ERR_INVALID, "r2f_canvas_paste: bad arguments");
+    DeviceGuard guard(c->device);
+    CU(launch_canvas_paste(src_dev, H, W, dst_dev, canvas_h, canvas_w, off_y, off_x, r, g, b, c->num_sms,
+                           static_cast<cudaStream_t>(stream)));
+    c->launches += 1;
     return R2F_OK;
 }
 

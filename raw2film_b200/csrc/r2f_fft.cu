@@ -536,18 +536,26 @@ static cudaError_t launch_rows_inv(const FftConvArgs &a, int src_mode, bool dens
     return cudaGetLastError();
 }
 
-cudaError_t launch_fft_conv(const FftConvArgs &a, int src_mode, bool density, cudaStream_t st) {
+cudaError_t launch_fft_conv(const FftConvArgs &a, int src_mode, bool density, cudaStream_t st, int stage) {
     const int rows = rows_per_cta(a.row.n);
     const size_t rs = fft_rows_smem(a.row.n), cs = fft_cols_smem(a.col.n, a.nc, a.col_groups);
     const int row_ctas = (a.H + rows - 1) / rows, col_ctas = a.row.n / a.nc;
-    cudaError_t e = rows == 2 ? launch_rows_fwd<2>(a, src_mode, row_ctas, 1024, rs, st)
-                              : launch_rows_fwd<1>(a, src_mode, row_ctas, 1024, rs, st);
-    if (e != cudaSuccess) return e;
-    if ((e = set_smem(k_fft_cols, cs)) != cudaSuccess) return e;
-    k_fft_cols<<<col_ctas, 1024, cs, st>>>(a);
-    if ((e = cudaGetLastError()) != cudaSuccess) return e;
-    return rows == 2 ? launch_rows_inv<2>(a, src_mode, density, row_ctas, 1024, rs, st)
-                     : launch_rows_inv<1>(a, src_mode, density, row_ctas, 1024, rs, st);
+    cudaError_t e = cudaSuccess;
+    if (stage == 0 || stage == 1) {
+        e = rows == 2 ? launch_rows_fwd<2>(a, src_mode, row_ctas, 1024, rs, st)
+                      : launch_rows_fwd<1>(a, src_mode, row_ctas, 1024, rs, st);
+        if (e != cudaSuccess) return e;
+    }
+    if (stage == 0 || stage == 2) {
+        if ((e = set_smem(k_fft_cols, cs)) != cudaSuccess) return e;
+        k_fft_cols<<<col_ctas, 1024, cs, st>>>(a);
+        if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    }
+    if (stage == 0 || stage == 3) {
+        e = rows == 2 ? launch_rows_inv<2>(a, src_mode, density, row_ctas, 1024, rs, st)
+                      : launch_rows_inv<1>(a, src_mode, density, row_ctas, 1024, rs, st);
+    }
+    return e;
 }
 
 }  // namespace r2f

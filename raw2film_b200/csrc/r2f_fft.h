@@ -64,6 +64,7 @@ cudaError_t launch_khat(const float *base_kernel_dev, int k, int Hp, int Wp, con
                         const double *cosW_dev, double *scratchA_dev, float *khat_dev, cudaStream_t st);
 
 // src_mode: 0 planar, 1 + kFmt* for an interleaved frame routed through the 2-D LUT.
-cudaError_t launch_fft_conv(const FftConvArgs &a, int src_mode, bool density, cudaStream_t st);
+// stage: 0 = all three kernels, 1 = rows forward, 2 = columns, 3 = rows inverse (for per-kernel timing)
+cudaError_t launch_fft_conv(const FftConvArgs &a, int src_mode, bool density, cudaStream_t st, int stage = 0);
 
 }  // namespace r2f

@@ -476,6 +476,33 @@ k_interleaved_to_planar(const float *__restrict__ in, int cin, int nch, float *_
     }
 }
 
+// Canvas border (reference effects.py:338-357 add_canvas): fill the canvas with one colour and
+// paste the rendered image at (off_y, off_x).  One thread per canvas byte triple.
+__global__ void __launch_bounds__(kThreads)
+k_canvas_paste(const uint8_t *__restrict__ src, int H, int W, uint8_t *__restrict__ dst, int CH, int CW, int off_y,
+               int off_x, uchar3 colour) {
+    const size_t total = (size_t)CH * CW;
+    const size_t stride = (size_t)gridDim.x * kThreads;
+    for (size_t p = (size_t)blockIdx.x * kThreads + threadIdx.x; p < total; p += stride) {
+        const int y = (int)(p / CW), x = (int)(p - (size_t)y * CW);
+        const int sy = y - off_y, sx = x - off_x;
+        uchar3 v = colour;
+        if (sy >= 0 && sy < H && sx >= 0 && sx < W) {
+            const uint8_t *q = src + ((size_t)sy * W + sx) * 3;
+            v = make_uchar3(q[0], q[1], q[2]);
+        }
+        uint8_t *d = dst + p * 3;
+        d[0] = v.x; d[1] = v.y; d[2] = v.z;
+    }
+}
+
+cudaError_t launch_canvas_paste(const uint8_t *src, int H, int W, uint8_t *dst, int CH, int CW, int off_y, int off_x,
+                                int r, int g, int b, int num_sms, cudaStream_t st) {
+    k_canvas_paste<<<grid_for((size_t)CH * CW, num_sms, 8), kThreads, 0, st>>>(
+        src, H, W, dst, CH, CW, off_y, off_x, make_uchar3((unsigned char)r, (unsigned char)g, (unsigned char)b));
+    return cudaGetLastError();
+}
+
 cudaError_t launch_planar_to_interleaved(Planes in, float *out, size_t npix, int num_sms, cudaStream_t st) {
     k_planar_to_interleaved<<<grid_for(npix, num_sms, 8), kThreads, 0, st>>>(in.base, in.plane_stride, out, npix);
     return cudaGetLastError();

@@ -57,6 +57,9 @@ cudaError_t launch_conv2d(const ConvArgs &a, cudaStream_t st);
 
 cudaError_t launch_finish(Planes in, size_t npix, int H, int W, const Lut3D &l3, const BurnArgs &burn, uint8_t *out_u8,
                           float *out_f32, int f32_stage_rgb, int num_sms, cudaStream_t st);
+// canvas border: colour fill + paste (reference effects.py:338-357)
+cudaError_t launch_canvas_paste(const uint8_t *src, int H, int W, uint8_t *dst, int CH, int CW, int off_y, int off_x,
+                                int r, int g, int b, int num_sms, cudaStream_t st);
 // layout shuffles
 cudaError_t launch_planar_to_interleaved(Planes in, float *out, size_t npix, int num_sms, cudaStream_t st);
 cudaError_t launch_interleaved_to_planar(const float *in, int cin, int nch, Planes out, size_t npix, int num_sms,

@@ -45,6 +45,10 @@ class PipelinedRenderer:
 
     def submit(self, cpu_payload, negative_film, grain_size, grain_sigma, **settings) -> int:
         torch = self._torch
+        if cpu_payload.get("_canvas") is not None or (
+                cpu_payload.get("_orig_resolution") is not None
+                and tuple(cpu_payload["_orig_resolution"]) != tuple(cpu_payload["image_array"].shape[:2])):
+            raise NotImplementedError("canvas / post-resize frames go through B200Processor.process_preloaded")
         arr = cpu_payload["image_array"]
         host = cpu_payload.get("_pinned")
         tdtype = torch.uint16 if arr.dtype == np.uint16 else torch.float32

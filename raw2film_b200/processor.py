@@ -8,9 +8,10 @@ carrier of device/pinned memory and CUDA streams; every per-pixel operation runs
 libr2f_b200.so.  There is no CPU fallback.
 
 Out of scope for this path (SURVEY 8f "next" rows): RAW decode / lens correction (`src` must be
-a decoded linear XYZ float32 array unless an `ingest` callable is supplied), chroma NR, the
-pre/post resize of `resolution` / `max_scale`, and canvas borders.  Those raise
-NotImplementedError instead of silently doing something else.
+a decoded linear XYZ float32 / uint16 array unless an `ingest` callable is supplied) and chroma
+NR; they raise NotImplementedError instead of silently doing something else.  The
+`resolution` / `max_scale` resizes run on the host with cv2 exactly where both reference
+processors run them (their "CPU phase"); canvas borders are pasted on the device.
 """
 from __future__ import annotations
 
@@ -19,7 +20,7 @@ import random
 
 import numpy as np
 
-from . import _cabi, builders
+from . import _cabi, builders, hostops
 from . import settings as _settings
 
 F32 = np.float32
@@ -251,17 +252,33 @@ class B200Processor:
         if chroma_nr:
             raise NotImplementedError("chroma NR (effects.py:421-561) is a 'next' row, not built yet")
         h, w = image.shape[:2]
+        # resolution / max_scale handling of the reference's CPU phase (gpu_processor.py:748-760,
+        # cpu_processor.py:122-134): host cv2, exactly where both reference processors do it
         if resolution is None and max_scale is not None:
             resolution = (h, w)
+        orig_resolution = None if resolution is None else tuple(resolution)
+        scale_factor = 1.0
         if resolution is not None:
+            resolution = list(resolution)
             scale = max(resolution) / max(frame_width, frame_height)
             if max_scale is not None and scale > max_scale:
-                raise NotImplementedError("max_scale down/up-scaling (utils.py:226-244) is a 'next' row")
-            hf, wf = resolution[0] / h, resolution[1] / w
-            if min(hf, wf) != 1:
-                raise NotImplementedError("pre-render resize to `resolution` (utils.py:226-244) is a 'next' row")
+                scale_factor = max_scale / scale
+                resolution = [round(x * scale_factor) for x in resolution]
+            if min(resolution[0] / h, resolution[1] / w) != 1:
+                if image.dtype == np.uint16:      # the reference resizes the float frame (after ingest)
+                    image = image[..., :3].astype(F32) / F32(65535.0)
+                    image *= F32(input_gain)
+                    input_gain = 1.0
+                image = hostops.resolution_scaling(np.ascontiguousarray(image[..., :3]), resolution)
+                h, w = image.shape[:2]
+        output_res = tuple(round(x / scale_factor) for x in (h, w))
+        canvas = None
+        canvas_res = None
         if canvas_mode != "No":
-            raise NotImplementedError("canvas borders (effects.py:290-357) are a 'next' row")
+            size, colour, offset = hostops.canvas_geometry((h, w), canvas_mode, canvas_scale, canvas_ratio)
+            canvas = {"size": size, "colour": colour, "offset": offset}
+            out_size, _, _ = hostops.canvas_geometry(output_res, canvas_mode, canvas_scale, canvas_ratio)
+            canvas_res = (out_size[1], out_size[0])
         channels = 4 if alpha else 3
         is_u16 = image.dtype == np.uint16
         pinned = torch.empty((h, w, channels), dtype=torch.uint16 if is_u16 else torch.float32, pin_memory=True)
@@ -269,8 +286,9 @@ class B200Processor:
         arr[..., :3] = image[..., :3]
         if alpha:
             arr[..., 3] = 65535 if is_u16 else 1.0
-        return {"image_array": arr, "output_resolution": (w, h), "canvas_resolution": None,
-                "pipeline_resolution": (w, h), "_pinned": pinned, "input_gain": float(np.float32(input_gain))}
+        return {"image_array": arr, "output_resolution": (output_res[1], output_res[0]),
+                "canvas_resolution": canvas_res, "pipeline_resolution": (w, h), "_pinned": pinned,
+                "input_gain": float(np.float32(input_gain)), "_canvas": canvas, "_orig_resolution": orig_resolution}
 
     # ------------------------------------------------------------------------------------------
     # phase 2: upload + render
@@ -403,13 +421,27 @@ class B200Processor:
         self.prepare_gpu_textures(cpu_payload)
         out_dev = self.render_device(self._dev_in, negative_film, grain_size, grain_sigma,
                                      input_gain=self._in_gain, **settings)
+        canvas = cpu_payload.get("_canvas")
+        if canvas is not None:                       # add_canvas (cpu_processor.py:409) on the device
+            h, w = out_dev.shape[:2]
+            ch, cw = canvas["size"]
+            canvas_dev = torch.empty((ch, cw, 3), dtype=torch.uint8, device=self.device)
+            r, g, b = canvas["colour"]
+            _cabi.check(_cabi.lib.r2f_canvas_paste(self._ctx, out_dev.data_ptr(), h, w, canvas_dev.data_ptr(), ch, cw,
+                                                   int(canvas["offset"][0]), int(canvas["offset"][1]), r, g, b,
+                                                   self.stream.cuda_stream))
+            out_dev = canvas_dev
         h, w = out_dev.shape[:2]
         host = torch.empty((h, w, 3), dtype=torch.uint8, pin_memory=True)
         with torch.cuda.stream(self.stream):
             host.copy_(out_dev, non_blocking=True)
         self.stream.synchronize()
         self._d2h_bytes = host.numel()
-        return host.numpy()
+        image = host.numpy()
+        orig = cpu_payload.get("_orig_resolution")
+        if orig is not None:                         # post-step of cpu_processor.py:411-412 (host cv2)
+            image = hostops.resolution_scaling(image, orig)
+        return image
 
     def process(self, src, negative_film, grain_size, grain_sigma, **settings):
         """cpu_processor.py:269-414: the reference's render entry point."""

@@ -160,7 +160,7 @@ def test_errors_are_loud(proc):
     with pytest.raises(NotImplementedError):
         proc.process("some_file.ARW", stock, 6.0, 0.4)
     with pytest.raises(NotImplementedError):
-        proc.process(small_frame(32, 32), stock, 6.0, 0.4, canvas_mode="Uniform white")
+        proc.process(small_frame(32, 32), stock, 6.0, 0.4, chroma_nr=2)
     x = torch.zeros((8, 8, 3), device="cuda")
     with pytest.raises(_cabi.R2FError):
         _cabi.check(_cabi.lib.r2f_render(proc._ctx, x.data_ptr(), 8, 8, 5, x.data_ptr(), 0, None, 0, None, 0, None))
@@ -186,3 +186,41 @@ def test_pipelined_renderer_matches_synchronous_calls(proc, depth):
     assert pipe.h2d_bytes == len(frames) * 120 * 180 * 3 * 4 and pipe.d2h_bytes == len(frames) * 120 * 180 * 3
     with pytest.raises(ValueError):
         pipe.result(0)
+
+
+@pytest.mark.parametrize("mode", ["Proportional white", "Uniform black", "Fixed white"])
+def test_canvas_modes_match_oracle(proc, mode):
+    """add_canvas (effects.py:338-357) pasted on the device, then the reference's post-step
+    resolution_scaling(image, resolution) (cpu_processor.py:409-412) on the host."""
+    from raw2film_b200 import hostops
+
+    stock = SyntheticStock(n3=17)
+    xyz = small_frame(90, 140, seed=17)
+    st = dict(halation=False, sharpness=False, grain=0, canvas_mode=mode, canvas_scale=1.2, canvas_ratio=0.8)
+    core = oracle_render(fo, xyz, stock, 6.0, 0.4, {k: v for k, v in st.items() if not k.startswith("canvas")})
+    want = hostops.resolution_scaling(fo.add_canvas(core, mode, 1.2, 0.8), (90, 140))
+    got = proc.process(xyz, stock, 6.0, 0.4, **st)
+    assert got.shape == want.shape and np.array_equal(got, want)
+
+
+def test_preview_resolution_and_max_scale(proc):
+    """`resolution` (preview) and `max_scale` (dense frames) resize on the host before / after the
+    path exactly like cpu_processor.py:122-134 and :411-412."""
+    from raw2film_b200 import hostops
+
+    stock = SyntheticStock(n3=17)
+    xyz = small_frame(240, 360, seed=23)
+    st = dict(halation=False, sharpness=False, grain=0)
+    # preview: fit into 100 x 100
+    small = hostops.resolution_scaling(xyz, (100, 100))
+    want = hostops.resolution_scaling(oracle_render(fo, small, stock, 6.0, 0.4, st), (100, 100))
+    got = proc.process(xyz, stock, 6.0, 0.4, resolution=(100, 100), **st)
+    assert got.shape == want.shape and np.array_equal(got, want)
+    # max_scale: 360 px over a 0.5 mm frame = 720 px/mm > 400 -> render at 400 px/mm, Lanczos back up
+    st2 = dict(st, frame_width=0.5, frame_height=0.3333, max_scale=400.0)
+    sf = 400.0 / (360 / 0.5)
+    res = [round(240 * sf), round(360 * sf)]
+    small = hostops.resolution_scaling(xyz, res)
+    want = hostops.resolution_scaling(oracle_render(fo, small, stock, 6.0, 0.4, st2), (240, 360))
+    got = proc.process(xyz, stock, 6.0, 0.4, **st2)
+    assert got.shape == (240, 360, 3) and np.array_equal(got, want)

@@ -75,3 +75,22 @@ def test_synthetic_frames():
     assert a.min() >= 0 and a[..., 1].max() == 16.0
     adv = adversarial_frame(16, 16, 0)
     assert adv.min() >= 0 and adv.max() <= 2
+
+
+def test_hostops_match_reference_goldens():
+    """resolution_scaling (utils.py:226-244) and get_canvas_data (effects.py:290-335) restated in
+    raw2film_b200/hostops.py against outputs of the reference functions."""
+    from raw2film_b200 import hostops
+
+    g = np.load("tests/golden/canvas_resize.npz")
+    assert np.array_equal(hostops.resolution_scaling(g["img_resize"], (32, 32)), g["ref_down"])
+    assert np.array_equal(hostops.resolution_scaling(g["img_resize"], (128, 400)), g["ref_up"])
+    same = g["img_resize"]
+    assert hostops.resolution_scaling(same, same.shape[:2]) is same
+    modes = ["Proportional white", "Proportional black", "Uniform white", "Uniform black", "Fixed white", "Fixed black"]
+    for i, m in enumerate(modes):
+        size, colour, off = hostops.canvas_geometry(g["img"].shape, m, 1.2, 0.8)
+        ref = g[f"ref_{i}"]
+        assert tuple(size) == ref.shape[:2]
+        assert tuple(ref[0, 0]) == colour
+        assert np.array_equal(ref[off[0]:off[0] + 20, off[1]:off[1] + 30], g["img"])
