@@ -153,6 +153,12 @@ int r2f_convolve2d(r2f_ctx *ctx, const float *in_dev, float *out_dev, int H, int
 /* White N(0,1) field from the context's Philox stream: float32 H x W x channels (1 or 3). */
 int r2f_generate_noise(r2f_ctx *ctx, float *out_dev, int H, int W, int channels, uint64_t seed, void *stream);
 
+/* chroma_nr_filter (effects.py:547-561): the pre-path chroma noise reduction.  in_dev: float32
+ * H x W x in_channels XYZ; out_dev: float32 H x W x 3; taps: HOST Gaussian taps (odd count) as built by
+ * gaussian_kernel_1d (effects.py:421-435); scratch >= 6 planes (r2f_workspace_bytes suffices). */
+int r2f_chroma_nr(r2f_ctx *ctx, const float *in_dev, int in_channels, float *out_dev, int H, int W,
+                  const float *taps, int ntaps, void *workspace_dev, size_t workspace_bytes, void *stream);
+
 /* add_canvas (effects.py:338-357): fill a canvas_h x canvas_w x 3 uint8 image with (r, g, b) and paste
  * the H x W x 3 render at (off_y, off_x); geometry from get_canvas_data (effects.py:290-335). */
 int r2f_canvas_paste(r2f_ctx *ctx, const uint8_t *src_dev, int H, int W, uint8_t *dst_dev, int canvas_h, int canvas_w,

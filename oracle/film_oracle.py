@@ -420,6 +420,54 @@ def burn(image: np.ndarray, d_ref, highlight_burn: float, burn_scale: float) -> 
 
 
 # --------------------------------------------------------------------------------------
+# chroma NR (effects.py:421-561)  -- "next" row, PINNED by tests/golden/chroma_nr.npz
+# --------------------------------------------------------------------------------------
+def gaussian_kernel_1d(size: int, sigma: float) -> np.ndarray:
+    """float32 taps, normalised by their float32 running sum (effects.py:421-435 under numba)."""
+    half = size // 2
+    taps = np.array([math.exp(-((i - half) * (i - half)) / (2.0 * sigma * sigma)) for i in range(size)], dtype=F32)
+    total = F32(0.0)
+    for v in taps:
+        total = F32(total + v)
+    return (taps / total).astype(F32)
+
+
+def _blur_axis_clamped(plane: np.ndarray, taps: np.ndarray, axis: int) -> np.ndarray:
+    """float32 products accumulated in binary64 in tap order, edge-clamped (effects.py:438-482)."""
+    half = taps.shape[0] // 2
+    n = plane.shape[axis]
+    acc = np.zeros(plane.shape, np.float64)
+    for i in range(-half, half + 1):
+        idx = np.clip(np.arange(n) + i, 0, n - 1)
+        acc += (np.take(plane, idx, axis=axis) * taps[i + half]).astype(np.float64)
+    return acc.astype(F32)
+
+
+def chroma_nr_filter(image: np.ndarray, size: int = 0) -> np.ndarray:
+    """XYZ -> xyY, Gaussian blur of the two chromaticity planes, back to XYZ (effects.py:497-561)."""
+    image = np.asarray(image, dtype=F32)
+    X, Y, Z = image[..., 0], image[..., 1], image[..., 2]
+    denom = (X + Y) + Z
+    ok = denom > 1e-8
+    with np.errstate(divide="ignore", invalid="ignore"):
+        cx = np.where(ok, X / denom, F32(0)).astype(F32)
+        cy = np.where(ok, Y / denom, F32(0)).astype(F32)
+    taps_n = int(size) * 2 + 1
+    taps = gaussian_kernel_1d(taps_n, 0.3 * ((taps_n - 1) * 0.5 - 1) + 0.8)
+    cx = _blur_axis_clamped(_blur_axis_clamped(cx, taps, 1), taps, 0)
+    cy = _blur_axis_clamped(_blur_axis_clamped(cy, taps, 1), taps, 0)
+    good = cy > 1e-8
+    with np.errstate(divide="ignore", invalid="ignore"):
+        inv = (Y / cy).astype(F32)
+        out = np.zeros(image.shape, F32)
+        out[..., 0] = np.where(good, cx * inv, F32(0))
+        out[..., 1] = np.where(good, Y, F32(0))
+        # `1.0 - cx - cy` is binary64 under numba (float64 literal), times the float32 `inv`
+        out[..., 2] = np.where(good, ((1.0 - cx.astype(np.float64) - cy.astype(np.float64)) * inv.astype(np.float64)), 0.0)
+    return out
+
+
+# --------------------------------------------------------------------------------------
 # canvas (effects.py:290-357)  -- "next" row (SURVEY 8f-2)
 # --------------------------------------------------------------------------------------
 def get_canvas_data(shape, canvas_mode: str, canvas_scale: float = 1.0, canvas_ratio: float = 1.0):

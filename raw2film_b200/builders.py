@@ -84,3 +84,17 @@ def grain_kernel(pixel_size_mm: float, grain_size_mm: float = 0.01, grain_sigma:
         kern += weight * np.exp(-d2 / (2 * s * s)) / (2 * math.pi * s * s)
     kern /= math.sqrt(float(np.sum(kern * kern)))
     return kern.astype(F32)
+
+
+def chroma_nr_taps(chroma_nr: int) -> np.ndarray:
+    """float32 Gaussian taps of the chroma noise reduction (reference effects.py:421-435, 552-554):
+    size = 2*chroma_nr + 1, sigma = 0.3*((size-1)/2 - 1) + 0.8, normalised by the float32 running
+    sum (numba sums a float32 array in float32)."""
+    size = int(chroma_nr) * 2 + 1
+    sigma = 0.3 * ((size - 1) * 0.5 - 1) + 0.8
+    half = size // 2
+    taps = np.array([math.exp(-((i - half) * (i - half)) / (2.0 * sigma * sigma)) for i in range(size)], dtype=F32)
+    total = F32(0.0)
+    for v in taps:
+        total = F32(total + v)
+    return (taps / total).astype(F32)

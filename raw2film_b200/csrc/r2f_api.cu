@@ -113,6 +113,7 @@ struct r2f_ctx {
     bool burn_set = false;
     float d_ref = 0.f, burn_strength = 0.f, burn_scale = 50.f;
     DevBuf burn_buf;
+    DevBuf cnr_taps;
 
     // r2f_render_host staging
     DevBuf h_in, h_out, h_ws, h_noise;
@@ -640,7 +641,7 @@ int r2f_destroy(r2f_ctx *c) {
     DeviceGuard guard(c->device);
     for (DevBuf *b : {&c->lut2d, &c->curve, &c->lut3d, &c->hal.buf, &c->mtf.buf, &c->grain.buf, &c->gcurve,
                       &c->burn_buf, &c->h_in, &c->h_out, &c->h_ws, &c->h_noise, &c->hal.base, &c->mtf.base,
-                      &c->grain.base, &c->khat, &c->khat_scratch})
+                      &c->grain.base, &c->khat, &c->khat_scratch, &c->cnr_taps})
         b->release();
     for (auto &kv : c->fft_lines) {
         kv.second->roots.release();
@@ -882,6 +883,24 @@ int r2f_generate_noise(r2f_ctx *c, float *out_dev, int H, int W, int channels, u
         CU(cudaMemcpyAsync(out_dev, p.base, npix * sizeof(float), cudaMemcpyDeviceToDevice, st));
     }
     c->launches += 2;
+    return R2F_OK;
+}
+
+int r2f_chroma_nr(r2f_ctx *c, const float *in_dev, int in_channels, float *out_dev, int H, int W, const float *taps,
+                  int ntaps, void *workspace_dev, size_t workspace_bytes, void *stream) {
+    if (!c || !in_dev || !out_dev || !taps || H < 1 || W < 1 || ntaps < 1 || (ntaps & 1) == 0 ||
+        (in_channels != 3 && in_channels != 4))
+        return fail(R2F_ERR_INVALID, "r2f_chroma_nr: bad arguments");
+    DeviceGuard guard(c->device);
+    const size_t ps = plane_stride_for(H, W);
+    if (!workspace_dev || workspace_bytes < ps * 6 * sizeof(float))
+        return fail(R2F_ERR_NOMEM, "workspace too small (see r2f_workspace_bytes)");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    CU(c->cnr_taps.ensure((size_t)ntaps * sizeof(float)));
+    CU(cudaMemcpyAsync(c->cnr_taps.p, taps, (size_t)ntaps * sizeof(float), cudaMemcpyHostToDevice, st));
+    CU(launch_chroma_nr(in_dev, in_channels, out_dev, H, W, static_cast<const float *>(c->cnr_taps.p), ntaps,
+                        static_cast<float *>(workspace_dev), ps, c->num_sms, st));
+    c->launches += 3;
     return R2F_OK;
 }
 

@@ -476,6 +476,81 @@ k_interleaved_to_planar(const float *__restrict__ in, int cin, int nch, float *_
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// chroma noise reduction (reference effects.py:421-561; SURVEY 8f-3, runs BEFORE the render path)
+//   k_cnr_to_xyY : XYZ -> planar (x, y, Y)                      effects.py:497-519
+//   k_cnr_blur   : edge-clamped 1-D Gaussian on the x and y planes; float32 products accumulated
+//                  in binary64 in tap order, like the numba loops   effects.py:438-482
+//   k_cnr_finish : vertical pass + xyY -> XYZ                    effects.py:463-482, 522-544
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads)
+k_cnr_to_xyY(const float *__restrict__ in, int cin, float *__restrict__ out, size_t ps, size_t npix) {
+    const size_t stride = (size_t)gridDim.x * kThreads;
+    for (size_t p = (size_t)blockIdx.x * kThreads + threadIdx.x; p < npix; p += stride) {
+        const float X = in[p * cin], Y = in[p * cin + 1], Z = in[p * cin + 2];
+        const float denom = (X + Y) + Z;
+        const bool ok = denom > 1e-8f;
+        out[p] = ok ? __fdiv_rn(X, denom) : 0.0f;
+        out[ps + p] = ok ? __fdiv_rn(Y, denom) : 0.0f;
+        out[2 * ps + p] = Y;
+    }
+}
+
+__device__ __forceinline__ float cnr_tap_sum(const float *__restrict__ plane, int y, int x, int H, int W,
+                                             const float *__restrict__ taps, int half, bool vertical) {
+    double acc = 0.0;
+    for (int i = -half; i <= half; ++i) {
+        const int yy = vertical ? min(max(y + i, 0), H - 1) : y;
+        const int xx = vertical ? x : min(max(x + i, 0), W - 1);
+        acc += (double)(plane[(size_t)yy * W + xx] * taps[i + half]);  // float32 product, binary64 sum
+    }
+    return (float)acc;
+}
+
+__global__ void __launch_bounds__(kThreads)
+k_cnr_blur_h(const float *__restrict__ in, float *__restrict__ out, size_t ps, int H, int W,
+             const float *__restrict__ taps, int half) {
+    const size_t npix = (size_t)H * W, stride = (size_t)gridDim.x * kThreads;
+    for (size_t p = (size_t)blockIdx.x * kThreads + threadIdx.x; p < 2 * npix; p += stride) {
+        const int c = (int)(p / npix);
+        const size_t q = p - (size_t)c * npix;
+        const int y = (int)(q / W), x = (int)(q - (size_t)y * W);
+        out[c * ps + q] = cnr_tap_sum(in + c * ps, y, x, H, W, taps, half, false);
+    }
+}
+
+__global__ void __launch_bounds__(kThreads)
+k_cnr_finish(const float *__restrict__ blurred_h, const float *__restrict__ xyY, float *__restrict__ out, size_t ps,
+             int H, int W, const float *__restrict__ taps, int half) {
+    const size_t npix = (size_t)H * W, stride = (size_t)gridDim.x * kThreads;
+    for (size_t p = (size_t)blockIdx.x * kThreads + threadIdx.x; p < npix; p += stride) {
+        const int y = (int)(p / W), x = (int)(p - (size_t)y * W);
+        const float cx = cnr_tap_sum(blurred_h, y, x, H, W, taps, half, true);
+        const float cy = cnr_tap_sum(blurred_h + ps, y, x, H, W, taps, half, true);
+        const float Y = xyY[2 * ps + p];
+        float X = 0.0f, Yo = 0.0f, Z = 0.0f;
+        if (cy > 1e-8f) {
+            const float inv = __fdiv_rn(Y, cy);
+            X = cx * inv;
+            Yo = Y;
+            Z = (float)(((1.0 - (double)cx) - (double)cy) * (double)inv);  // binary64 like numba's typing
+        }
+        out[p * 3] = X;
+        out[p * 3 + 1] = Yo;
+        out[p * 3 + 2] = Z;
+    }
+}
+
+cudaError_t launch_chroma_nr(const float *in, int cin, float *out, int H, int W, const float *taps_dev, int ntaps,
+                             float *ws /* 6 planes */, size_t ps, int num_sms, cudaStream_t st) {
+    const size_t npix = (size_t)H * W;
+    float *xyY = ws, *tmp = ws + 3 * ps;
+    k_cnr_to_xyY<<<grid_for(npix, num_sms, 8), kThreads, 0, st>>>(in, cin, xyY, ps, npix);
+    k_cnr_blur_h<<<grid_for(2 * npix, num_sms, 8), kThreads, 0, st>>>(xyY, tmp, ps, H, W, taps_dev, ntaps / 2);
+    k_cnr_finish<<<grid_for(npix, num_sms, 8), kThreads, 0, st>>>(tmp, xyY, out, ps, H, W, taps_dev, ntaps / 2);
+    return cudaGetLastError();
+}
+
 // Canvas border (reference effects.py:338-357 add_canvas): fill the canvas with one colour and
 // paste the rendered image at (off_y, off_x).  One thread per canvas byte triple.
 __global__ void __launch_bounds__(kThreads)

@@ -57,6 +57,9 @@ cudaError_t launch_conv2d(const ConvArgs &a, cudaStream_t st);
 
 cudaError_t launch_finish(Planes in, size_t npix, int H, int W, const Lut3D &l3, const BurnArgs &burn, uint8_t *out_u8,
                           float *out_f32, int f32_stage_rgb, int num_sms, cudaStream_t st);
+// chroma NR pre-stage (reference effects.py:421-561): needs 6 float planes of scratch
+cudaError_t launch_chroma_nr(const float *in, int cin, float *out, int H, int W, const float *taps_dev, int ntaps,
+                             float *ws, size_t ps, int num_sms, cudaStream_t st);
 // canvas border: colour fill + paste (reference effects.py:338-357)
 cudaError_t launch_canvas_paste(const uint8_t *src, int H, int W, uint8_t *dst, int CH, int CW, int off_y, int off_x,
                                 int r, int g, int b, int num_sms, cudaStream_t st);

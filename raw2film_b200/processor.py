@@ -8,8 +8,8 @@ carrier of device/pinned memory and CUDA streams; every per-pixel operation runs
 libr2f_b200.so.  There is no CPU fallback.
 
 Out of scope for this path (SURVEY 8f "next" rows): RAW decode / lens correction (`src` must be
-a decoded linear XYZ float32 / uint16 array unless an `ingest` callable is supplied) and chroma
-NR; they raise NotImplementedError instead of silently doing something else.  The
+a decoded linear XYZ float32 / uint16 array unless an `ingest` callable is supplied); it raises
+NotImplementedError instead of silently doing something else.  Chroma NR runs on the device.  The
 `resolution` / `max_scale` resizes run on the host with cv2 exactly where both reference
 processors run them (their "CPU phase"); canvas borders are pasted on the device.
 """
@@ -223,6 +223,27 @@ class B200Processor:
         _cabi.check(_cabi.lib.r2f_set_burn(self._ctx, float(d_ref), float(highlight_burn), float(burn_scale)))
         self.highlight_burn_param_dict = new
 
+    def chroma_nr_filter(self, image: np.ndarray, chroma_nr: int) -> np.ndarray:
+        """Chroma noise reduction (reference effects.py:547-561) on the device: XYZ -> xyY, Gaussian
+        blur of the chromaticity planes, back to XYZ.  Host array in, host array out; uses its own
+        stream and buffers so it can run on a producer thread next to a render."""
+        torch = self._torch
+        if getattr(self, "_ingest_stream", None) is None:
+            self._ingest_stream = torch.cuda.Stream(device=self.device)
+        frame = np.ascontiguousarray(image[..., :3], dtype=F32)
+        h, w = frame.shape[:2]
+        taps = builders.chroma_nr_taps(chroma_nr)
+        with torch.cuda.stream(self._ingest_stream):
+            x = torch.from_numpy(frame).to(self.device, non_blocking=False)
+            out = torch.empty_like(x)
+            ws = torch.empty(int(_cabi.lib.r2f_workspace_bytes(h, w, 0)), dtype=torch.uint8, device=self.device)
+            _cabi.check(_cabi.lib.r2f_chroma_nr(self._ctx, x.data_ptr(), 3, out.data_ptr(), h, w, _cabi.f32_ptr(taps),
+                                                taps.shape[0], ws.data_ptr(), ws.numel(),
+                                                self._ingest_stream.cuda_stream))
+            result = out.cpu().numpy()
+        self._ingest_stream.synchronize()
+        return result
+
     # ------------------------------------------------------------------------------------------
     # phase 1 (CPU, state-free): gpu_processor.py:715-783
     # ------------------------------------------------------------------------------------------
@@ -249,8 +270,12 @@ class B200Processor:
                 "pass the decoded linear XYZ float32 array as `src` or construct B200Processor(ingest=...)")
         if image.ndim != 3 or image.shape[2] not in (3, 4):
             raise ValueError(f"frame must be (H, W, 3|4) float32, got {image.shape}")
-        if chroma_nr:
-            raise NotImplementedError("chroma NR (effects.py:421-561) is a 'next' row, not built yet")
+        if chroma_nr:                                  # before the resize, like the reference (:744-745)
+            if image.dtype == np.uint16:               # the filter works on the ingested float frame
+                image = image[..., :3].astype(F32) / F32(65535.0)
+                image *= F32(input_gain)
+                input_gain = 1.0
+            image = self.chroma_nr_filter(image, chroma_nr)
         h, w = image.shape[:2]
         # resolution / max_scale handling of the reference's CPU phase (gpu_processor.py:748-760,
         # cpu_processor.py:122-134): host cv2, exactly where both reference processors do it

@@ -13,6 +13,7 @@ Every array named `ref_*` was computed by a reference function:
   raw2film.effects.burn                     (effects.py:392-418)
   raw2film.effects.add_canvas               (effects.py:338-357)
   raw2film.utils.resolution_scaling         (utils.py:226-244)
+  raw2film.effects.chroma_nr_filter         (effects.py:421-561)
 """
 from __future__ import annotations
 
@@ -129,6 +130,17 @@ def main():
     cv_["ref_down"] = utils.resolution_scaling(im8b, (32, 32))
     cv_["ref_up"] = utils.resolution_scaling(im8b, (128, 400))
     np.savez_compressed(os.path.join(HERE, "canvas_resize.npz"), **cv_)
+    # ---- chroma NR (effects.py:421-561) ---------------------------------------------------
+    cn = {}
+    xyz = (rng.random((61, 83, 3), dtype=np.float32) * np.float32(1.5)).astype(np.float32)
+    xyz[0, :4] = 0.0                      # denom <= eps branch
+    xyz[1, :4, 1] = 0.0                   # y chromaticity 0 -> xyY_to_XYZ zero branch
+    cn["xyz"] = xyz
+    for size in (1, 3, 8):
+        cn[f"ref_out{size}"] = np.asarray(effects.chroma_nr_filter(xyz.copy(), size))
+        sz = int(size) * 2 + 1
+        cn[f"ref_kernel{size}"] = np.asarray(effects.gaussian_kernel_1d(sz, 0.3 * ((sz - 1) * 0.5 - 1) + 0.8))
+    np.savez_compressed(os.path.join(HERE, "chroma_nr.npz"), **cn)
     print("golden vectors written to", HERE)
 
 

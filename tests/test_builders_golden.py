@@ -22,6 +22,12 @@ def test_mtf_builder_bit_exact():
         assert k.dtype == np.float32 and np.array_equal(k, g[f"ref_kernel{i}"])
 
 
+def test_chroma_nr_taps_bit_exact():
+    g = np.load(G + "chroma_nr.npz")
+    for size in (1, 3, 8):
+        assert np.array_equal(builders.chroma_nr_taps(size), g[f"ref_kernel{size}"])
+
+
 def test_builders_do_not_import_oracle():
     import sys
 
@@ -31,7 +37,7 @@ def test_builders_do_not_import_oracle():
 
     src = open(builders.__file__).read()
     assert "oracle" not in src.replace("# oracle", "")
-    for mod in ("processor", "batch", "_cabi", "settings", "synthetic", "builders"):
+    for mod in ("processor", "batch", "_cabi", "settings", "synthetic", "builders", "pipeline", "hostops"):
         text = open(builders.__file__.replace("builders.py", mod + ".py")).read()
         assert "import oracle" not in text and "from oracle" not in text, mod
     assert "raw2film_b200" in sys.modules

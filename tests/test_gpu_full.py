@@ -159,8 +159,6 @@ def test_errors_are_loud(proc):
     stock = SyntheticStock()
     with pytest.raises(NotImplementedError):
         proc.process("some_file.ARW", stock, 6.0, 0.4)
-    with pytest.raises(NotImplementedError):
-        proc.process(small_frame(32, 32), stock, 6.0, 0.4, chroma_nr=2)
     x = torch.zeros((8, 8, 3), device="cuda")
     with pytest.raises(_cabi.R2FError):
         _cabi.check(_cabi.lib.r2f_render(proc._ctx, x.data_ptr(), 8, 8, 5, x.data_ptr(), 0, None, 0, None, 0, None))
@@ -224,3 +222,20 @@ def test_preview_resolution_and_max_scale(proc):
     want = hostops.resolution_scaling(oracle_render(fo, small, stock, 6.0, 0.4, st2), (240, 360))
     got = proc.process(xyz, stock, 6.0, 0.4, **st2)
     assert got.shape == (240, 360, 3) and np.array_equal(got, want)
+
+
+@pytest.mark.parametrize("size", [1, 3, 8])
+def test_chroma_nr_bit_exact_vs_reference_golden(proc, size):
+    """tests/golden/chroma_nr.npz holds outputs of the reference's own chroma_nr_filter (effects.py:547-561)."""
+    g = np.load("tests/golden/chroma_nr.npz")
+    got = proc.chroma_nr_filter(g["xyz"], size)
+    assert got.dtype == np.float32 and np.array_equal(got, g[f"ref_out{size}"])
+
+
+def test_process_with_chroma_nr_matches_oracle(proc):
+    stock = SyntheticStock(n3=17)
+    xyz = small_frame(100, 150, seed=41)
+    st = dict(halation=False, sharpness=False, grain=0, chroma_nr=4)
+    want = oracle_render(fo, fo.chroma_nr_filter(xyz, 4), stock, 6.0, 0.4, st)
+    got = proc.process(xyz, stock, 6.0, 0.4, **st)
+    assert np.array_equal(got, want)

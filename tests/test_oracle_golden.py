@@ -65,3 +65,12 @@ def test_canvas_bit_exact():
         assert np.array_equal(fo.add_canvas(g["img"], mode, 1.2, 0.8), g[f"ref_{i}"])
     img = g["img"]
     assert fo.add_canvas(img, "No") is img
+
+
+def test_chroma_nr_bit_exact():
+    """chroma_nr_filter + gaussian_kernel_1d (effects.py:421-561) incl. the zero-denominator branches."""
+    g = np.load(G + "chroma_nr.npz")
+    for size in (1, 3, 8):
+        n = size * 2 + 1
+        assert np.array_equal(fo.gaussian_kernel_1d(n, 0.3 * ((n - 1) * 0.5 - 1) + 0.8), g[f"ref_kernel{size}"])
+        assert np.array_equal(fo.chroma_nr_filter(g["xyz"], size), g[f"ref_out{size}"])
