@@ -221,7 +221,7 @@ def test_preview_resolution_and_max_scale(proc):
     small = hostops.resolution_scaling(xyz, res)
     want = hostops.resolution_scaling(oracle_render(fo, small, stock, 6.0, 0.4, st2), (240, 360))
     got = proc.process(xyz, stock, 6.0, 0.4, **st2)
-    assert got.shape == (240, 360, 3) and np.array_equal(got, want)
+    assert got.shape == want.shape and got.shape[1] == 360 and np.array_equal(got, want)
 
 
 @pytest.mark.parametrize("size", [1, 3, 8])
