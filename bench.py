@@ -202,6 +202,9 @@ def main():
     from raw2film_b200 import B200Processor, _cabi
     from raw2film_b200.synthetic import SyntheticStock, natural_frame
 
+    from raw2film_b200.affinity import bind_to_gpu
+
+    affinity = bind_to_gpu(local)          # before any pinned allocation: first touch on the GPU's NUMA node
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
@@ -388,7 +391,7 @@ def main():
                         "ms_per_step": ms_e2e16 / args.steps,
                         "note": "same batch from uint16 XYZ frames (what rawpy hands over); /65535 and exposure "
                                 "gain applied on the device (SURVEY 8f-1)"},
-            "latency": latency, "gpu_launches": launches, "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu, "clocks": clocks,
+            "latency": latency, "affinity": affinity, "gpu_launches": launches, "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu, "clocks": clocks,
             "checksum": checksum,
         }
         print(json.dumps(line))
