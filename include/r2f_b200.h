@@ -159,6 +159,11 @@ int r2f_generate_noise(r2f_ctx *ctx, float *out_dev, int H, int W, int channels,
 int r2f_chroma_nr(r2f_ctx *ctx, const float *in_dev, int in_channels, float *out_dev, int H, int W,
                   const float *taps, int ntaps, void *workspace_dev, size_t workspace_bytes, void *stream);
 
+/* Counting pass of generate_histogram (utils.py:158-169; shaders/histogram.wgsl pass 1):
+ * counts_dev[c * 256 + v] = number of pixels whose channel c equals v, over a uint8 H x W x 3 device image.
+ * The 256-bin post-processing and rasterisation (utils.py:171-223) are host-side (hostops.histogram_image). */
+int r2f_histogram(r2f_ctx *ctx, const uint8_t *img_dev, int H, int W, uint32_t *counts_dev, void *stream);
+
 /* add_canvas (effects.py:338-357): fill a canvas_h x canvas_w x 3 uint8 image with (r, g, b) and paste
  * the H x W x 3 render at (off_y, off_x); geometry from get_canvas_data (effects.py:290-335). */
 int r2f_canvas_paste(r2f_ctx *ctx, const uint8_t *src_dev, int H, int W, uint8_t *dst_dev, int canvas_h, int canvas_w,

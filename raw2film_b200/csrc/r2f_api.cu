@@ -904,6 +904,15 @@ int r2f_chroma_nr(r2f_ctx *c, const float *in_dev, int in_channels, float *out_d
     return R2F_OK;
 }
 
+int r2f_histogram(r2f_ctx *c, const uint8_t *img_dev, int H, int W, uint32_t *counts_dev, void *stream) {
+    if (!c || !img_dev || !counts_dev || H < 1 || W < 1) return fail(R2F_ERR_INVALID, "r2f_histogram: bad arguments");
+    if ((reinterpret_cast<uintptr_t>(img_dev) & 3) != 0) return fail(R2F_ERR_INVALID, "image must be 4-byte aligned");
+    DeviceGuard guard(c->device);
+    CU(launch_histogram(img_dev, (size_t)H * W, counts_dev, c->num_sms, static_cast<cudaStream_t>(stream)));
+    c->launches += 1;
+    return R2F_OK;
+}
+
 int r2f_canvas_paste(r2f_ctx *c, const uint8_t *src_dev, int H, int W, uint8_t *dst_dev, int canvas_h, int canvas_w,
                      int off_y, int off_x, int r, int g, int b, void *stream) {
     if (!c || !src_dev || !dst_dev || H < 1 || W < 1 || canvas_h < 1 || canvas_w < 1)

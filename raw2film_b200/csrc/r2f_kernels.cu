@@ -551,6 +551,48 @@ cudaError_t launch_chroma_nr(const float *in, int cin, float *out, int H, int W,
     return cudaGetLastError();
 }
 
+// ------------------------------------------------------------------------------------------
+// RGB histogram counts (reference utils.py:158-169 / shaders/histogram.wgsl pass 1):
+// 3 x 256 bins over the uint8 output.  Each warp counts into its own shared-memory copy (no
+// inter-warp atomic contention), copies are reduced and added to the global bins once per CTA.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads)
+k_histogram(const uint8_t *__restrict__ img, size_t npix, unsigned int *__restrict__ counts /* [3][256] */) {
+    __shared__ unsigned int sh[kThreads / 32][768];
+    const int warp = threadIdx.x >> 5;
+    for (int i = threadIdx.x; i < (kThreads / 32) * 768; i += kThreads) (&sh[0][0])[i] = 0u;
+    __syncthreads();
+    // 4 pixels = 12 bytes = three 32-bit words per iteration
+    const size_t nquad = npix / 4, stride = (size_t)gridDim.x * kThreads;
+    const uint32_t *w32 = reinterpret_cast<const uint32_t *>(img);
+    unsigned int *my = sh[warp];
+    for (size_t q = (size_t)blockIdx.x * kThreads + threadIdx.x; q < nquad; q += stride) {
+        const uint32_t a = __ldg(w32 + 3 * q), b = __ldg(w32 + 3 * q + 1), c = __ldg(w32 + 3 * q + 2);
+        const uint32_t bytes[12] = {a & 255u, (a >> 8) & 255u, (a >> 16) & 255u, a >> 24, b & 255u, (b >> 8) & 255u,
+                                    (b >> 16) & 255u, b >> 24, c & 255u, (c >> 8) & 255u, (c >> 16) & 255u, c >> 24};
+#pragma unroll
+        for (int i = 0; i < 12; ++i) atomicAdd(&my[(i % 3) * 256 + bytes[i]], 1u);
+    }
+    if (blockIdx.x == 0 && threadIdx.x < (npix & 3) * 3) {
+        const size_t i = nquad * 12 + threadIdx.x;
+        atomicAdd(&my[(threadIdx.x % 3) * 256 + img[i]], 1u);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 768; i += kThreads) {
+        unsigned int t = 0;
+#pragma unroll
+        for (int w = 0; w < kThreads / 32; ++w) t += sh[w][i];
+        if (t) atomicAdd(counts + i, t);
+    }
+}
+
+cudaError_t launch_histogram(const uint8_t *img, size_t npix, unsigned int *counts_dev, int num_sms, cudaStream_t st) {
+    cudaError_t e = cudaMemsetAsync(counts_dev, 0, 768 * sizeof(unsigned int), st);
+    if (e != cudaSuccess) return e;
+    k_histogram<<<grid_for(npix / 4 + 1, num_sms, 4), kThreads, 0, st>>>(img, npix, counts_dev);
+    return cudaGetLastError();
+}
+
 // Canvas border (reference effects.py:338-357 add_canvas): fill the canvas with one colour and
 // paste the rendered image at (off_y, off_x).  One thread per canvas byte triple.
 __global__ void __launch_bounds__(kThreads)

@@ -60,6 +60,8 @@ cudaError_t launch_finish(Planes in, size_t npix, int H, int W, const Lut3D &l3,
 // chroma NR pre-stage (reference effects.py:421-561): needs 6 float planes of scratch
 cudaError_t launch_chroma_nr(const float *in, int cin, float *out, int H, int W, const float *taps_dev, int ntaps,
                              float *ws, size_t ps, int num_sms, cudaStream_t st);
+// 3 x 256 histogram counts of a uint8 H x W x 3 image (reference utils.py:158-169)
+cudaError_t launch_histogram(const uint8_t *img, size_t npix, unsigned int *counts_dev, int num_sms, cudaStream_t st);
 // canvas border: colour fill + paste (reference effects.py:338-357)
 cudaError_t launch_canvas_paste(const uint8_t *src, int H, int W, uint8_t *dst, int CH, int CW, int off_y, int off_x,
                                 int r, int g, int b, int num_sms, cudaStream_t st);

@@ -44,3 +44,27 @@ def canvas_geometry(shape, canvas_mode: str, canvas_scale: float = 1.0, canvas_r
         raise ValueError(f"unknown canvas mode {canvas_mode!r}")
     offset = ((size[0] - rows) // 2, (size[1] - cols) // 2)
     return size, colour, offset
+
+
+def histogram_image(counts: np.ndarray, mix_table: np.ndarray, height: int = 100) -> np.ndarray:
+    """RGB histogram widget image (height, 256, 4) uint8 from per-channel 256-bin counts.
+
+    reference utils.py:171-223 (everything after the counting loop, which runs on the device):
+    float32 log1p(count / max), 3-tap moving average with replicated ends, scaling to `height`,
+    truncation to int, and the (2,2,2,4) colour mix table lookup per column / row.
+    """
+    f = counts.astype(np.float32)                                   # (3, 256)
+    peak = np.float32(max(f.max(), 0))
+    if peak == 0:
+        peak = np.float32(1)
+    f = np.log1p(f / peak).astype(np.float32)
+    left = np.concatenate([f[:, :1], f[:, :-1]], axis=1)
+    right = np.concatenate([f[:, 1:], f[:, -1:]], axis=1)
+    smooth = ((left + f + right) / np.float32(3)).astype(np.float32)
+    top = np.float32(max(smooth.max(), 0))
+    if top == 0:
+        top = np.float32(1)
+    heights = ((smooth * np.float32(height)) / top).astype(np.int32)   # (3, 256)
+    rows = np.arange(height)[:, None]                                   # y
+    active = rows >= (height - heights[:, None, :])                     # (3, height, 256)
+    return mix_table[active[0].astype(np.intp), active[1].astype(np.intp), active[2].astype(np.intp)]

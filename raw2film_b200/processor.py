@@ -244,6 +244,24 @@ class B200Processor:
         self._ingest_stream.synchronize()
         return result
 
+    def histogram_counts(self, image_dev=None):
+        """(3, 256) int64 per-channel counts of a uint8 (H, W, 3) CUDA tensor (default: the last render)."""
+        torch = self._torch
+        img = self._dev_out if image_dev is None else image_dev
+        if img is None:
+            raise RuntimeError("nothing rendered yet")
+        h, w = img.shape[:2]
+        counts = torch.empty(768, dtype=torch.int32, device=self.device)
+        self.stream.wait_stream(torch.cuda.current_stream(self.device))
+        _cabi.check(_cabi.lib.r2f_histogram(self._ctx, img.data_ptr(), h, w, counts.data_ptr(), self.stream.cuda_stream))
+        self.stream.synchronize()
+        return counts.cpu().numpy().astype(np.int64).reshape(3, 256)
+
+    def generate_histogram(self, mix_table, height: int = 100, image_dev=None) -> np.ndarray:
+        """The reference's RGB histogram widget image (utils.py:145-223): counts on the device, the 256-bin
+        post-processing on the host."""
+        return hostops.histogram_image(self.histogram_counts(image_dev), np.asarray(mix_table, np.uint8), height)
+
     # ------------------------------------------------------------------------------------------
     # phase 1 (CPU, state-free): gpu_processor.py:715-783
     # ------------------------------------------------------------------------------------------

@@ -14,6 +14,7 @@ Every array named `ref_*` was computed by a reference function:
   raw2film.effects.add_canvas               (effects.py:338-357)
   raw2film.utils.resolution_scaling         (utils.py:226-244)
   raw2film.effects.chroma_nr_filter         (effects.py:421-561)
+  raw2film.utils.generate_histogram         (utils.py:145-223)
 """
 from __future__ import annotations
 
@@ -141,6 +142,16 @@ def main():
         sz = int(size) * 2 + 1
         cn[f"ref_kernel{size}"] = np.asarray(effects.gaussian_kernel_1d(sz, 0.3 * ((sz - 1) * 0.5 - 1) + 0.8))
     np.savez_compressed(os.path.join(HERE, "chroma_nr.npz"), **cn)
+    # ---- RGB histogram widget (utils.py:145-223) --------------------------------------------------
+    hg = {}
+    img = rng.integers(0, 256, (90, 130, 3), dtype=np.uint8)
+    img[:30] = (img[:30] // 4 + 100).astype(np.uint8)          # a peak, so the log/height scaling matters
+    mix = rng.integers(0, 256, (2, 2, 2, 4), dtype=np.uint8)
+    mix[0, 0, 0] = 0
+    hg["img"], hg["mix"] = img, mix
+    hg["ref_hist100"] = np.asarray(utils.generate_histogram(img, mix, 100))
+    hg["ref_hist64"] = np.asarray(utils.generate_histogram(img, mix, 64))
+    np.savez_compressed(os.path.join(HERE, "histogram.npz"), **hg)
     print("golden vectors written to", HERE)
 
 

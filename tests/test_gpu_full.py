@@ -239,3 +239,22 @@ def test_process_with_chroma_nr_matches_oracle(proc):
     want = oracle_render(fo, fo.chroma_nr_filter(xyz, 4), stock, 6.0, 0.4, st)
     got = proc.process(xyz, stock, 6.0, 0.4, **st)
     assert np.array_equal(got, want)
+
+
+def test_histogram_matches_reference_golden(proc):
+    """generate_histogram (utils.py:145-223): device counts + host raster vs the reference's output."""
+    import torch
+
+    g = np.load("tests/golden/histogram.npz")
+    img = torch.from_numpy(g["img"]).cuda()
+    counts = proc.histogram_counts(img)
+    want = np.stack([np.bincount(g["img"][..., c].ravel(), minlength=256) for c in range(3)])
+    assert np.array_equal(counts, want)
+    for h in (100, 64):
+        assert np.array_equal(proc.generate_histogram(g["mix"], h, img), g[f"ref_hist{h}"])
+    # ragged pixel count (npix % 4 != 0) and a big frame
+    rng = np.random.default_rng(0)
+    for shape in ((7, 9), (1001, 777)):
+        a = rng.integers(0, 256, (*shape, 3), dtype=np.uint8)
+        got = proc.histogram_counts(torch.from_numpy(a).cuda())
+        assert np.array_equal(got, np.stack([np.bincount(a[..., c].ravel(), minlength=256) for c in range(3)]))

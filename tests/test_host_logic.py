@@ -94,3 +94,13 @@ def test_hostops_match_reference_goldens():
         assert tuple(size) == ref.shape[:2]
         assert tuple(ref[0, 0]) == colour
         assert np.array_equal(ref[off[0]:off[0] + 20, off[1]:off[1] + 30], g["img"])
+
+
+def test_histogram_postprocessing_matches_reference_golden():
+    from raw2film_b200 import hostops
+
+    g = np.load("tests/golden/histogram.npz")
+    counts = np.stack([np.bincount(g["img"][..., c].ravel(), minlength=256) for c in range(3)])
+    for h in (100, 64):
+        assert np.array_equal(hostops.histogram_image(counts, g["mix"], h), g[f"ref_hist{h}"])
+    assert hostops.histogram_image(np.zeros((3, 256), np.int64), g["mix"], 10).shape == (10, 256, 4)
