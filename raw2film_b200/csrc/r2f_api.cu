@@ -694,8 +694,9 @@ int r2f_set_lut3d(r2f_ctx *c, const float *lut, int n, double scale) {
     double absmax = 0.0;
     for (size_t i = 0; i < verts * 3; ++i) absmax = std::fmax(absmax, std::fabs((double)lut[i]));
     const double u = std::ldexp(1.0, -24);
-    const double partial = absmax + 3.0 * 2.0 * absmax + 1e-30;
-    double err = 3.0 * u * partial + u * absmax;           // accumulation + final rounding
+    // d1 >= d2 >= d3 in [0,1] make every partial sum a convex combination of vertex values, so each of
+    // the three fused roundings (and the exact path's final rounding) is at most u * absmax
+    double err = 3.0 * u * absmax + u * absmax + 1e-30;
     int e2 = 0;
     const bool pow2 = std::frexp(c->s3, &e2) == 0.5 && c->s3 > 0.0;
     if (!pow2) err += 3.0 * (2.0 * absmax) * (2.0 * u * (double)n);  // coordinate rounding x slopes

@@ -706,7 +706,7 @@ cudaError_t launch_noise(Planes out, int nch, int H, int W, uint64_t seed, int n
 constexpr int kGfTile = 64;
 
 template <bool GEN>
-__global__ void __launch_bounds__(256, 3)
+__global__ void __launch_bounds__(256, 2)
 k_grain_finish(GrainFinishArgs a) {
     extern __shared__ __align__(16) float smem[];
     const int H = a.H, W = a.W, k = a.k, kp = a.kp, rad = k / 2;
@@ -728,6 +728,15 @@ k_grain_finish(GrainFinishArgs a) {
     const int q0 = xs >> 2, nq = ((xs + cols - 1) >> 2) - q0 + 1;  // aligned noise quads covering the tile row
 #pragma unroll 1
     for (int c = 0; c < 3; ++c) {
+        // issue this channel's 16 density loads first: their latency hides behind the noise generation
+        // and the correlation below
+        const float *dplane = a.dens + c * ps;
+        float dval[16];
+#pragma unroll
+        for (int o = 0; o < 16; ++o) {
+            const int gy = ty0 + ly0 + o;
+            dval[o] = (gx < W && gy < H) ? __ldcs(dplane + (size_t)gy * W + gx) : 0.0f;
+        }
         if (c < nch) {
             __syncthreads();  // previous channel's window reads are done
             if (GEN) {
@@ -783,16 +792,11 @@ k_grain_finish(GrainFinishArgs a) {
             }
         }
         // grain apply on channel c (black-and-white grain reuses the single field)
-        const float *dplane = a.dens + c * ps;
 #pragma unroll
         for (int o = 0; o < 16; ++o) {
-            const int gy = ty0 + ly0 + o;
-            float val = 0.0f;
-            if (gx < W && gy < H) {
-                const float d = __ldcs(dplane + (size_t)gy * W + gx);
-                val = d + g[o] * curve_eval(a.gcurve, c, d);
-                val = val > 0.0f ? val : 0.0f;
-            }
+            const float d = dval[o];
+            float val = d + g[o] * curve_eval(a.gcurve, c, d);
+            val = val > 0.0f ? val : 0.0f;
             priv[(c * 16 + o) * 256 + threadIdx.x] = val;
         }
     }
