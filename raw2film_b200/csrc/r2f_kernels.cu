@@ -334,6 +334,15 @@ k_conv2d(ConvArgs a) {
     }
 }
 
+// Two alternative inner loops were built, measured at 24 MP / 17x17x3 and rejected (all 1.04-1.06 ms):
+//  * horizontal 16-pixel strips with 128-bit window and weight loads (13 LDS per 272 FFMA): the vector
+//    loads pin the window to consecutive registers and the FFMA register-bank conflicts cost what the
+//    saved LDS gained;
+//  * weights through the constant bank (kernel parameters, uniform-register FFMA operand): 62 vs 54
+//    TFLOP/s in an isolated loop (scratch microbenchmark), but inside the kernel the extra guards and
+//    ULDCs kept the issue slots just as busy (88 %).
+// The kernel is issue-slot bound: ~66 % of its instructions are FFMA at ~84-88 % issue utilisation.
+
 template <int TW, int TH, bool W_SMEM, int PITCH>
 static cudaError_t launch_conv_cfg(const ConvArgs &a, size_t smem_bytes, cudaStream_t st) {
     auto kfn = k_conv2d<TW, TH, W_SMEM, PITCH>;
