@@ -258,3 +258,63 @@ def test_histogram_matches_reference_golden(proc):
         a = rng.integers(0, 256, (*shape, 3), dtype=np.uint8)
         got = proc.histogram_counts(torch.from_numpy(a).cuda())
         assert np.array_equal(got, np.stack([np.bincount(a[..., c].ravel(), minlength=256) for c in range(3)]))
+
+
+def test_c_abi_host_entry_point_matches_device_path(proc):
+    """r2f_render_host (the host-buffer C-ABI call a non-torch binding of process_preloaded would make):
+    plain pageable numpy buffers in and out, staging owned by the context."""
+    import ctypes
+
+    from raw2film_b200 import _cabi
+
+    stock = SyntheticStock(n3=17)
+    xyz = small_frame(150, 222, seed=55)
+    noise = fo.white_noise(xyz.shape, False, seed=2)
+    st = dict(frame_width=2.5, frame_height=1.7, grain=2, grain_noise=noise)
+    want = proc.process(xyz, stock, 6.0, 0.4, **st)          # also loads every table into the context
+    out = np.empty(xyz.shape, np.uint8)
+    flags = _cabi.HALATION | _cabi.MTF | _cabi.GRAIN
+    _cabi.check(_cabi.lib.r2f_render_host(proc._ctx, xyz.ctypes.data_as(ctypes.c_void_p), 150, 222, 3,
+                                          out.ctypes.data_as(ctypes.c_void_p), flags,
+                                          noise.ctypes.data_as(ctypes.c_void_p), 3))
+    assert np.array_equal(out, want)
+    # pointwise flags = 0 through the same entry point
+    off = dict(halation=False, sharpness=False, grain=0)
+    want0 = proc.process(xyz, stock, 6.0, 0.4, **off)
+    _cabi.check(_cabi.lib.r2f_render_host(proc._ctx, xyz.ctypes.data_as(ctypes.c_void_p), 150, 222, 3,
+                                          out.ctypes.data_as(ctypes.c_void_p), 0, None, 0))
+    assert np.array_equal(out, want0)
+
+
+def test_black_and_white_stock_halation(proc):
+    """density_measure == "bw": the halation kernel uses the green factor on all three layers
+    (effects.py:248-250), so no layer is a pass-through and the direct correlation runs on all three."""
+    stock = SyntheticStock(n3=17, density_measure="bw")
+    xyz = small_frame(130, 170, seed=9)
+    st = dict(frame_width=2.0, frame_height=1.5, grain=0, sharpness=False)
+    stages = {}
+    want = oracle_render(fo, xyz, stock, 6.0, 0.4, st, stages=stages)
+    got = proc.process(xyz, stock, 6.0, 0.4, **st)
+    diff = np.abs(got.astype(np.int16) - want.astype(np.int16))
+    assert diff.max() <= 1 and np.mean(diff != 0) < 2e-3
+    assert not np.array_equal(stages["halation"][..., 2], stages["exposure"][..., 2])
+
+
+def test_fused_grain_kernel_matches_staged_kernels(proc):
+    """The fused grain+finish kernel (normal render) and the staged k_noise / k_conv2d / k_finish kernels
+    (tap path) implement the same stream and arithmetic: with device-generated Philox noise and a fixed
+    seed, the uint8 render equals quantise(tetra(grain tap)) within 1 LSB, and the RGB tap agrees."""
+    import torch
+
+    stock = SyntheticStock(n3=17)
+    xyz = small_frame(200, 264, seed=77)
+    for grain_mode in (2, 1):
+        st = dict(frame_width=1.2, frame_height=0.8, grain=grain_mode, grain_seed=1234)
+        x = torch.from_numpy(xyz).cuda()
+        rgb = proc.render_tap(x, "rgb", stock, 6.0, 0.4, **st).cpu().numpy()
+        want = fo.quantise_u8(rgb)
+        got = proc.render_device(x, stock, 6.0, 0.4, **st)
+        proc.stream.synchronize()
+        got = got.cpu().numpy()
+        diff = np.abs(got.astype(np.int16) - want.astype(np.int16))
+        assert diff.max() <= 1 and np.mean(diff != 0) < 1e-3, (grain_mode, diff.max(), np.mean(diff != 0))
