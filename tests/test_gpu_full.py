@@ -318,3 +318,34 @@ def test_fused_grain_kernel_matches_staged_kernels(proc):
         got = got.cpu().numpy()
         diff = np.abs(got.astype(np.int16) - want.astype(np.int16))
         assert diff.max() <= 1 and np.mean(diff != 0) < 1e-3, (grain_mode, diff.max(), np.mean(diff != 0))
+
+
+def test_process_skips_ingest_when_image_parameters_are_unchanged(proc):
+    """cpu_processor.py:88-105: same image parameters -> the frame on the device is reused; a changed
+    effect setting still re-renders, a changed image parameter (or cache=False) re-ingests."""
+    stock = SyntheticStock(n3=17)
+    xyz = small_frame(64, 96, seed=61)
+    calls = {"n": 0}
+    real = proc.extract_image_data_cpu
+
+    def counting(*a, **k):
+        calls["n"] += 1
+        return real(*a, **k)
+
+    proc.extract_image_data_cpu = counting
+    try:
+        st = dict(halation=False, sharpness=False, grain=0)
+        a = proc.process(xyz, stock, 6.0, 0.4, **st)
+        b = proc.process(xyz, stock, 6.0, 0.4, **st)
+        c = proc.process(xyz, stock, 6.0, 0.4, exp_comp=1.0, **st)          # effect setting only
+        assert calls["n"] == 1 and np.array_equal(a, b) and not np.array_equal(a, c)
+        assert np.array_equal(c, oracle_render(fo, xyz, stock, 6.0, 0.4, dict(st, exp_comp=1.0)))
+        proc.process(xyz, stock, 6.0, 0.4, canvas_mode="Uniform white", canvas_scale=1.1, **st)   # image parameter
+        assert calls["n"] == 2
+        proc.process(xyz, stock, 6.0, 0.4, cache=False, **st)
+        assert calls["n"] == 3
+        other = small_frame(64, 96, seed=62)
+        d = proc.process(other, stock, 6.0, 0.4, **st)
+        assert calls["n"] == 4 and np.array_equal(d, oracle_render(fo, other, stock, 6.0, 0.4, st))
+    finally:
+        proc.extract_image_data_cpu = real
