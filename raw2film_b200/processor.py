@@ -463,6 +463,7 @@ class B200Processor:
             raise NotImplementedError("presenting into a wgpu texture / histogram is UI plumbing (out of scope)")
         torch = self._torch
         if _upload:
+            self.image_param_dict = None      # the device frame changes: process() re-validates its cache
             self.prepare_gpu_textures(cpu_payload)
         out_dev = self.render_device(self._dev_in, negative_film, grain_size, grain_sigma,
                                      input_gain=self._in_gain, **settings)
