@@ -349,3 +349,43 @@ def test_process_skips_ingest_when_image_parameters_are_unchanged(proc):
         assert calls["n"] == 4 and np.array_equal(d, oracle_render(fo, other, stock, 6.0, 0.4, st))
     finally:
         proc.extract_image_data_cpu = real
+
+
+@pytest.mark.parametrize("shape", [(9, 13), (4, 40), (33, 5)])
+def test_full_emulation_on_tiny_frames(proc, shape):
+    """Frames smaller than the halation / MTF kernels (multiple REFLECT_101 folds at every border)."""
+    stock = SyntheticStock(n3=9)
+    xyz = small_frame(*shape, seed=shape[0], highlights=False)
+    noise = fo.white_noise((*shape, 3), False, seed=1)
+    st = dict(frame_width=0.3, frame_height=0.2, grain=2, grain_noise=noise)     # 43..133 px/mm -> kernels > frame
+    want = oracle_render(fo, xyz, stock, 6.0, 0.4, {k: v for k, v in st.items() if k != "grain_noise"}, noise=noise)
+    got = proc.process(xyz, stock, 6.0, 0.4, **st)
+    diff = np.abs(got.astype(np.int16) - want.astype(np.int16))
+    assert got.shape == want.shape and diff.max() <= 1
+
+
+def test_full_size_61mp_fft_halation_agrees_with_direct_correlation(proc):
+    """BASELINE config C3 at full size (9504x6336, halation_size=2 -> 133x133 kernel): the FFT path
+    (padded 10240 x 6912 transforms) against the direct 17 689-tap correlation on the same frame, through
+    the halation tap; plus determinism of the whole render."""
+    import torch
+
+    stock = SyntheticStock()
+    h, w = 6336, 9504
+    xyz = natural_frame(h, w, 3)
+    x = torch.from_numpy(xyz).cuda()
+    st = dict(halation_size=2.0, halation_green_factor=0.3, grain=2, grain_seed=9)
+    proc.set_conv_path("fft")
+    a = proc.render_tap(x, "halation", stock, 6.0, 0.4, **st)
+    proc.set_conv_path("direct")
+    b = proc.render_tap(x, "halation", stock, 6.0, 0.4, **st)
+    proc.set_conv_path("auto")
+    assert proc.halation_kernel.shape[0] == 133
+    rel = (a - b).abs() / b.abs().clamp_min(1e-3)
+    assert float(rel.max()) <= 2e-4, float(rel.max())
+    assert torch.equal(a[..., 2], b[..., 2])
+    del a, b, rel
+    o1 = proc.render_device(x, stock, 6.0, 0.4, **st).clone()
+    o2 = proc.render_device(x, stock, 6.0, 0.4, **st).clone()
+    proc.stream.synchronize()
+    assert torch.equal(o1, o2)
