@@ -204,6 +204,11 @@ int upload_kernel(KernelSet &ks, const float *kernel, int k, int channels) {
                         even = false;
                         break;
                     }
+            // Split every filtered layer as K_c = alpha_c * B + beta_c * delta with ONE smooth base B: B is
+            // layer c0 with its centre spike (the identity part of (f K + delta)/(f + 1), effects.py:255-262)
+            // replaced by the largest neighbour.  Only B goes through the FFT -- its spectrum decays, so the
+            // transform's rounding noise is filtered instead of passing through the delta plateau -- and
+            // the identity part beta_c * x is applied exactly in float32 in the row epilogue.
             double num = 0.0, den = 0.0;
             for (int i = 0; i < k; ++i)
                 for (int j = 0; j < k; ++j)
@@ -212,7 +217,7 @@ int upload_kernel(KernelSet &ks, const float *kernel, int k, int channels) {
                         den += at(i, j, c0) * at(i, j, c0);
                     }
             if (even && den > 0.0) {
-                const double alpha = num / den, beta = at(mid, mid, c1) - alpha * at(mid, mid, c0);
+                const double alpha = num / den;
                 double resid = 0.0;
                 for (int i = 0; i < k; ++i)
                     for (int j = 0; j < k; ++j)
@@ -221,15 +226,23 @@ int upload_kernel(KernelSet &ks, const float *kernel, int k, int channels) {
                     std::vector<float> base((size_t)k * k);
                     for (int i = 0; i < k; ++i)
                         for (int j = 0; j < k; ++j) base[(size_t)i * k + j] = kernel[((size_t)i * k + j) * 3 + c0];
+                    double smooth_centre = at(mid, mid, c0);
+                    if (k >= 3) {
+                        const double nb = std::fmax(std::fmax(at(mid - 1, mid, c0), at(mid + 1, mid, c0)),
+                                                    std::fmax(at(mid, mid - 1, c0), at(mid, mid + 1, c0)));
+                        if (nb < smooth_centre) smooth_centre = nb;
+                    }
+                    base[(size_t)mid * k + mid] = (float)smooth_centre;
+                    const double bc = (double)base[(size_t)mid * k + mid];
                     rc = upload(ks.base, base.data(), base.size() * sizeof(float));
                     if (rc != R2F_OK) return rc;
                     ks.fft_ok = true;
                     ks.fft_chan[0] = c0;
                     ks.fft_chan[1] = c1;
                     ks.fft_alpha[0] = 1.f;
-                    ks.fft_beta[0] = 0.f;
+                    ks.fft_beta[0] = (float)(at(mid, mid, c0) - bc);
                     ks.fft_alpha[1] = (float)alpha;
-                    ks.fft_beta[1] = (float)beta;
+                    ks.fft_beta[1] = (float)(at(mid, mid, c1) - alpha * bc);
                 }
             }
         }

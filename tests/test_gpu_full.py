@@ -389,3 +389,31 @@ def test_full_size_61mp_fft_halation_agrees_with_direct_correlation(proc):
     o2 = proc.render_device(x, stock, 6.0, 0.4, **st).clone()
     proc.stream.synchronize()
     assert torch.equal(o1, o2)
+
+
+def test_full_size_24mp_full_emulation_against_oracle(proc):
+    """BASELINE config C2 at full size against the oracle itself (cv2.filter2D halation 43x43 and MTF
+    17x17x3, injected noise field): <= 1 LSB at 8 bit, LSB flip rate reported and bounded, and the
+    density working image within 1e-4 on a row band."""
+    import torch
+
+    stock = SyntheticStock()
+    h, w = 4000, 6000
+    xyz = natural_frame(h, w, 1)
+    noise = fo.white_noise((h, w, 3), False, seed=4)
+    st = dict(grain=2, halation_green_factor=0.3)
+    fo.use_all_host_threads()
+    stages = {}
+    want = oracle_render(fo, xyz, stock, 6.0, 0.4, st, noise=noise, stages=stages)
+    got = proc.process(xyz, stock, 6.0, 0.4, grain_noise=noise, **st)
+    diff = np.abs(got.astype(np.int16) - want.astype(np.int16))
+    rate = float(np.mean(diff != 0))
+    print(f"24 MP full emulation: max |diff| = {diff.max()} LSB, flip rate = {rate:.2e}")
+    assert diff.max() <= 1 and rate < 2e-3
+    x = torch.from_numpy(xyz).cuda()
+    dens = proc.render_tap(x, "density", stock, 6.0, 0.4, **st).cpu().numpy()
+    err = np.abs(dens - stages["density"])
+    print(f"24 MP density after FFT halation vs cv2 oracle: max abs err = {err.max():.2e}")
+    assert err.max() <= 1e-4
+    mtf = proc.render_tap(x, "mtf", stock, 6.0, 0.4, **st).cpu().numpy()
+    assert np.abs(mtf - stages["mtf"]).max() <= 1e-4
