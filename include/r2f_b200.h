@@ -92,6 +92,7 @@ int r2f_set_grain(r2f_ctx *ctx, const float *curve, int N, const float *kernel, 
  * 0 = auto (FFT for wide even-symmetric kernels, direct otherwise), 1 = force direct,
  * 2 = force FFT (render fails if the kernel or frame is not eligible). */
 #define R2F_OPT_CONV_PATH 1
+#define R2F_OPT_CONV_SYM 2
 int r2f_set_option(r2f_ctx *ctx, int key, int value);
 
 /* Re-seed the on-device noise stream only (no table upload, no synchronisation). */

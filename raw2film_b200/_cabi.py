@@ -20,6 +20,7 @@ EXPORTS = [
     "r2f_generate_noise", "r2f_chroma_nr", "r2f_histogram", "r2f_canvas_paste", "r2f_launch_count", "r2f_profile_enable", "r2f_profile_read",
 ]
 OPT_CONV_PATH = 1
+OPT_CONV_SYM = 2
 IN_F32, IN_U16 = 0, 1
 PROF_NAMES = ["pointwise", "expose", "halation", "density", "mtf", "noise", "grain", "burn", "finish",
               "fft_rows_fwd", "fft_cols", "fft_rows_inv"]

@@ -60,6 +60,11 @@ struct KernelSet {
     int mode[3] = {0, 0, 0};
     const float *chan[3] = {nullptr, nullptr, nullptr};
     bool set = false;
+    // y-symmetric packed layout for k_conv2d_sym (r2f_conv_sym.cu); sym_ok when every filtered layer is
+    // mirror-symmetric in y and the size is supported
+    DevBuf symbuf;
+    const float *sym[3] = {nullptr, nullptr, nullptr};
+    bool sym_ok = false;
     // FFT eligibility (r2f_fft.cu): exactly two filtered layers that share one even-symmetric base
     // kernel, K_c = alpha_c * base + beta_c * delta, third layer an exact delta.
     bool fft_ok = false;
@@ -125,6 +130,7 @@ struct r2f_ctx {
     uint64_t khat_generation = 0;
     int khat_hp = 0, khat_wp = 0;
     int conv_path = 0;  // R2F_OPT_CONV_PATH: 0 auto, 1 direct, 2 fft
+    int conv_sym = 1;   // R2F_OPT_CONV_SYM: 1 = y-symmetric kernels take the packed-FMA kernel
 
     // per-kernel profiling (r2f_profile_*)
     bool profiling = false;
@@ -190,6 +196,37 @@ int upload_kernel(KernelSet &ks, const float *kernel, int k, int channels) {
     ks.set = true;
     ks.generation += 1;
     ks.fft_ok = false;
+    // y-symmetric layout: rows dy = 0..r, (w, w) pairs, centre row halved (exact: power-of-two scaling)
+    ks.sym_ok = false;
+    for (int c = 0; c < 3; ++c) ks.sym[c] = nullptr;
+    if (conv_sym_supported(k)) {
+        const int r = k / 2, wrow = conv_sym_wrow(k);
+        const size_t sper = (size_t)(r + 1) * wrow * 2;
+        std::vector<float> sh(sper * channels, 0.0f);
+        bool sym = true;
+        float kmax = 0.f;
+        for (size_t i = 0; i < (size_t)k * k * channels; ++i) kmax = std::fmax(kmax, std::fabs(kernel[i]));
+        for (int c = 0; c < channels && sym; ++c)
+            for (int dy = 0; dy <= r && sym; ++dy)
+                for (int j = 0; j < k; ++j) {
+                    const double up = kernel[((size_t)(r - dy) * k + j) * channels + c];
+                    const double dn = kernel[((size_t)(r + dy) * k + j) * channels + c];
+                    if (std::fabs(up - dn) > 1e-7 * (double)kmax) {
+                        sym = false;
+                        break;
+                    }
+                    const float w = (float)(dy == 0 ? 0.25 * (up + dn) : 0.5 * (up + dn));
+                    sh[sper * c + ((size_t)dy * wrow + j) * 2] = w;
+                    sh[sper * c + ((size_t)dy * wrow + j) * 2 + 1] = w;
+                }
+        if (sym) {
+            rc = upload(ks.symbuf, sh.data(), sh.size() * sizeof(float));
+            if (rc != R2F_OK) return rc;
+            for (int c = 0; c < 3; ++c)
+                ks.sym[c] = static_cast<const float *>(ks.symbuf.p) + sper * (channels == 3 ? c : 0);
+            ks.sym_ok = true;
+        }
+    }
     if (channels == 3 && k >= 3) {
         int conv[3], nconv = 0;
         for (int c = 0; c < 3; ++c)
@@ -348,12 +385,21 @@ ConvArgs conv_args(const KernelSet &ks, const float *in, float *out, size_t ps, 
     a.kp = ks.kp;
     for (int c = 0; c < 3; ++c) {
         a.kern[c] = ks.chan[c];
+        a.ksym[c] = ks.sym_ok ? ks.sym[c] : nullptr;
         a.mode[c] = ks.mode[c];
         a.in_plane[c] = c;
     }
     a.epi = EPI_NONE;
     a.eps = 0.f;
     return a;
+}
+
+// direct correlation: the y-symmetric packed-FMA kernel when the kernel set allows it, else the generic one
+cudaError_t conv_dispatch(const r2f_ctx *c, const ConvArgs &a, cudaStream_t st) {
+    const bool any_conv = a.mode[0] || a.mode[1] || a.mode[2];
+    if (c->conv_sym && any_conv && a.ksym[0] && a.ksym[1] && a.ksym[2] && a.epi != EPI_GRAIN)
+        return launch_conv2d_sym(a, st);
+    return launch_conv2d(a, st);
 }
 
 ConvArgs identity_args(const float *in, float *out, size_t ps, int H, int W) {
@@ -367,6 +413,7 @@ ConvArgs identity_args(const float *in, float *out, size_t ps, int H, int W) {
     a.kp = 4;
     for (int c = 0; c < 3; ++c) {
         a.kern[c] = nullptr;
+        a.ksym[c] = nullptr;
         a.mode[c] = 0;
         a.in_plane[c] = c;
     }
@@ -499,7 +546,7 @@ int render_impl(r2f_ctx *c, const void *in, int in_format, float in_gain, int H,
         if (flags & R2F_HALATION) {
             ConvArgs a = conv_args(c->hal, P[0].base, P[1].base, ps, H, W);
             if (tap_stage == R2F_TAP_HALATION) {
-                CU(launch_conv2d(a, st));
+                CU(conv_dispatch(c, a, st));
                 c->launches += 1;
                 return export_tap(P[1]);
             }
@@ -507,7 +554,7 @@ int render_impl(r2f_ctx *c, const void *in, int in_format, float in_gain, int H,
             a.curve = cv;
             a.eps = c->eps;
             ProfScope ps_(c, st, R2F_PROF_HALATION);
-            CU(launch_conv2d(a, st));
+            CU(conv_dispatch(c, a, st));
         } else {
             if (tap_stage == R2F_TAP_HALATION) return fail(R2F_ERR_INVALID, "halation tap requested but stage is off");
             ConvArgs a = identity_args(P[0].base, P[1].base, ps, H, W);
@@ -515,7 +562,7 @@ int render_impl(r2f_ctx *c, const void *in, int in_format, float in_gain, int H,
             a.curve = cv;
             a.eps = c->eps;
             ProfScope ps_(c, st, R2F_PROF_DENSITY);
-            CU(launch_conv2d(a, st));
+            CU(conv_dispatch(c, a, st));
         }
     }
     c->launches += 1;
@@ -526,7 +573,7 @@ int render_impl(r2f_ctx *c, const void *in, int in_format, float in_gain, int H,
     if (flags & R2F_MTF) {
         ConvArgs a = conv_args(c->mtf, P[cur].base, P[1 - cur].base, ps, H, W);
         ProfScope ps_(c, st, R2F_PROF_MTF);
-        CU(launch_conv2d(a, st));
+        CU(conv_dispatch(c, a, st));
         c->launches += 1;
         cur = 1 - cur;
     }
@@ -584,7 +631,7 @@ int render_impl(r2f_ctx *c, const void *in, int in_format, float in_gain, int H,
         a.epi = EPI_GRAIN;
         a.curve = gcurve_of(c);
         ProfScope ps_(c, st, R2F_PROF_GRAIN);
-        CU(launch_conv2d(a, st));
+        CU(conv_dispatch(c, a, st));
         c->launches += 2;
         cur = 1 - cur;
     }
@@ -750,6 +797,10 @@ int r2f_set_grain(r2f_ctx *c, const float *curve, int N, const float *kernel, in
 
 int r2f_set_option(r2f_ctx *c, int key, int value) {
     if (!c) return fail(R2F_ERR_INVALID, "null context");
+    if (key == R2F_OPT_CONV_SYM && (value == 0 || value == 1)) {
+        c->conv_sym = value;
+        return R2F_OK;
+    }
     if (key == R2F_OPT_CONV_PATH && value >= 0 && value <= 2) {
         c->conv_path = value;
         return R2F_OK;
@@ -855,6 +906,7 @@ int r2f_convolve2d(r2f_ctx *c, const float *in_dev, float *out_dev, int H, int W
     if (c->conv_path == 2 && !use_fft) {
         ks.buf.release();
         ks.base.release();
+        ks.symbuf.release();
         return fail(R2F_ERR_INVALID, "FFT path forced but this kernel/frame/workspace is not eligible");
     }
     if (e == cudaSuccess && use_fft) {
@@ -870,12 +922,13 @@ int r2f_convolve2d(r2f_ctx *c, const float *in_dev, float *out_dev, int H, int W
         }
         c->khat_generation = 0;  // the cached spectrum belongs to a temporary kernel: invalidate
     } else if (e == cudaSuccess) {
-        e = launch_conv2d(conv_args(ks, a.base, b.base, ps, H, W), st);
+        e = conv_dispatch(c, conv_args(ks, a.base, b.base, ps, H, W), st);
     }
     if (e == cudaSuccess) e = launch_planar_to_interleaved(b, out_dev, npix, c->num_sms, st);
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);
     ks.buf.release();
     ks.base.release();
+    ks.symbuf.release();
     if (rc != R2F_OK) return rc;
     if (e != cudaSuccess) return fail_cuda(e, "r2f_convolve2d");
     c->launches += 3;

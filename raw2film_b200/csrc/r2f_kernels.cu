@@ -8,6 +8,7 @@
 //   k_noise       a7            white N(0,1) field (Philox4x32-10 + Box-Muller)
 //   k_burn_*      a8            low-res highlight mask
 //   k_finish      a8+a9+a10     burn apply, tetrahedral LUT, quantise
+#include "conv_tile.cuh"
 #include "r2f_kernels.h"
 
 namespace r2f {
@@ -197,25 +198,6 @@ cudaError_t launch_expose(const void *in, int fmt, float gain, Planes out, size_
 // For kernel column j the thread slides a 16-row register window down the tile column:
 // one new LDS per 16 FMAs.
 // ------------------------------------------------------------------------------------------
-// Cooperative load of a (rows x cols) tile whose top-left corner is (gy0, gx0) in a W x H plane,
-// BORDER_REFLECT_101 outside the plane.  One warp per tile row, lanes along x: no div/mod, and the
-// reflection is only evaluated for tiles that actually cross the frame border.
-__device__ __forceinline__ void fill_tile(float *__restrict__ tile, const float *__restrict__ src, int rows, int cols,
-                                          int gy0, int gx0, int H, int W, int nthreads, int pitch = 0) {
-    if (pitch == 0) pitch = cols;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = nthreads >> 5;
-    const bool inside_x = gx0 >= 0 && gx0 + cols <= W;
-    for (int ty = warp; ty < rows; ty += nwarps) {
-        const float *row = src + (size_t)reflect101(gy0 + ty, H) * W;
-        float *dst = tile + ty * pitch;
-        if (inside_x) {
-            for (int tx = lane; tx < cols; tx += 32) dst[tx] = __ldg(row + gx0 + tx);
-        } else {
-            for (int tx = lane; tx < cols; tx += 32) dst[tx] = __ldg(row + reflect101(gx0 + tx, W));
-        }
-    }
-}
-
 // One kernel row: 16 FMAs on the register window, then (unless LAST) slide the window down by
 // one tile row.  `u` is the compile-time slot of the row that leaves the window.
 template <int LAST>

@@ -30,6 +30,9 @@ struct ConvArgs {
     int H, W;
     const float *kern[3];  // device, transposed + padded: kern[c][j * kp + i] = K[i][j][c]
     int k, kp;
+    // y-symmetric layout for k_conv2d_sym, or nullptr: ksym[c][(dy * wrow + j) * 2 + {0,1}] = K[r+dy][j][c]
+    // (duplicated pair), row dy = 0 halved, wrow = conv_sym_wrow(k)
+    const float *ksym[3];
     int mode[3];      // 0 = identity (exact centre delta), 1 = correlate
     int in_plane[3];  // source plane feeding output channel c
     int epi;
@@ -53,6 +56,11 @@ cudaError_t launch_expose(const void *in, int fmt, float gain, Planes out, size_
                           cudaStream_t st);
 // direct 2-D correlation, reflect-101 borders, fused epilogue
 cudaError_t launch_conv2d(const ConvArgs &a, cudaStream_t st);
+// same contract for kernels that are mirror-symmetric in y (r2f_conv_sym.cu): packed-FMA path
+constexpr int kConvSymMaxK = 33;
+int conv_sym_wrow(int k);
+bool conv_sym_supported(int k);
+cudaError_t launch_conv2d_sym(const ConvArgs &a, cudaStream_t st);
 // planar density -> [burn] -> tetrahedral LUT -> u8 interleaved, or float32 interleaved (taps)
 
 cudaError_t launch_finish(Planes in, size_t npix, int H, int W, const Lut3D &l3, const BurnArgs &burn, uint8_t *out_u8,

@@ -93,6 +93,10 @@ class B200Processor:
         """Halation correlation path: "auto" (FFT for wide even-symmetric kernels), "direct" or "fft"."""
         _cabi.check(_cabi.lib.r2f_set_option(self._ctx, _cabi.OPT_CONV_PATH, {"auto": 0, "direct": 1, "fft": 2}[mode]))
 
+    def set_conv_sym(self, enabled: bool = True) -> None:
+        """Direct correlation with y-symmetric kernels: packed-FMA kernel (default) or the generic one."""
+        _cabi.check(_cabi.lib.r2f_set_option(self._ctx, _cabi.OPT_CONV_SYM, 1 if enabled else 0))
+
     @property
     def launch_count(self) -> int:
         return int(_cabi.lib.r2f_launch_count(self._ctx))

@@ -122,6 +122,44 @@ def test_convolve_vs_float64_truth(proc, shape, k):
     assert np.abs(got - truth).max() <= 5e-6
 
 
+@pytest.mark.parametrize("k", [3, 5, 7, 9, 11, 13, 15, 17, 19, 21, 23, 25, 27, 29, 31, 33])
+def test_symmetric_kernel_path_vs_truth_and_generic(proc, k):
+    """Kernels mirrored in y (but NOT in x: the tap orientation stays checked) take k_conv2d_sym (row-pair
+    sums + packed FMA); it must agree with the float64 truth and with the generic kernel on ragged frames,
+    frames smaller than a tile and frames smaller than the kernel radius."""
+    rng = np.random.default_rng(k)
+    for shape in ((70 + k, 131), (64, 64), (5, 9), (130, 67)):
+        img = rng.random((*shape, 3), dtype=np.float32)
+        half = rng.random((k // 2 + 1, k, 3), dtype=np.float32)
+        kern = np.concatenate([half[:0:-1], half], axis=0)
+        kern[:, :, 2] = 0.0
+        kern[k // 2, k // 2, 2] = 1.0                               # one identity layer
+        kern /= kern.sum(axis=(0, 1), keepdims=True)
+        assert np.array_equal(kern, kern[::-1])
+        proc.set_conv_sym(True)
+        sym = _gpu_convolve(proc, img, kern, "direct")
+        proc.set_conv_sym(False)
+        gen = _gpu_convolve(proc, img, kern, "direct")
+        proc.set_conv_sym(True)
+        if min(shape) > k // 2:
+            truth = fo.correlate_truth_f64(img, kern)
+            assert np.abs(sym - truth).max() <= 5e-6
+        assert np.abs(sym - gen).max() <= 5e-6
+        assert np.array_equal(sym[..., 2], img[..., 2])
+
+
+@pytest.mark.parametrize("scale,strength", [(6000 / 36, 0.0), (9504 / 36, 0.5), (1920 / 36, 0.0)])
+def test_symmetric_kernel_path_real_mtf(proc, scale, strength):
+    from raw2film_b200 import builders
+
+    rng = np.random.default_rng(7)
+    img = (rng.random((200, 333, 3), dtype=np.float32) * 3.5).astype(np.float32)
+    kern = builders.mtf_kernel(SyntheticStock().mtf, scale, strength, 1.0)
+    truth = fo.correlate_truth_f64(img, kern)
+    got = _gpu_convolve(proc, img, kern, "direct")
+    assert np.abs(got - truth).max() <= 1e-5
+
+
 def test_identity_channel_is_exact(proc):
     """A centre-delta channel (halation blue layer, effects.py:255-262 with factor 0) passes through bit-exactly."""
     rng = np.random.default_rng(1)
