@@ -9,7 +9,8 @@
 // the work from k*k to ~(k+1)/2 * k multiply-adds plus (k+7)/8 adds per (dy, output).
 //
 // Blackwell specifics: the multiply-adds are FFMA2 (fma.rn.f32x2): one issue slot per two FMAs.
-// A thread owns TWO tile rows (ty and ty+32); the packed lanes are (row ty, row ty+32), so the
+// A thread owns OW (16) adjacent outputs in each of TWO tile rows (ty and ty+32); the packed lanes are
+// (row ty, row ty+32), so the
 // window pair P[i] = (s_ty[i], s_ty+32[i]) is alignment-free for every tap offset j, and the
 // weight operand is a pre-duplicated (w, w) pair read as a shared-memory broadcast.
 // Lanes of a warp walk 32 consecutive tile rows; the row pitch is 4 (mod 8) floats, which makes
@@ -26,10 +27,10 @@ namespace r2f {
 
 namespace {
 
-template <int K>
+template <int K, int OW_>
 struct SymCfg {
     static constexpr int R = K / 2;
-    static constexpr int TW = 64, TH = 64, OW = 8, NT = 256;
+    static constexpr int TW = 64, TH = 64, OW = OW_, NT = (TW / OW_) * 32;
     static constexpr int NWIN = OW + K - 1;            // window floats per thread per row
     static constexpr int NQ = (NWIN + 3) / 4;          // ... as float4 loads
     static constexpr int COLS = (TW + K - 1 + 3) / 4 * 4;  // tile width rounded up: whole 16-byte copies
@@ -45,10 +46,10 @@ struct SymCfg {
     static constexpr int SMEM_BYTES = (TILE_FLOATS + (R + 1) * WROW * 2) * 4;
 };
 
-template <int K>
-__global__ void __launch_bounds__(256, 3)
+template <int K, int OW>
+__global__ void __launch_bounds__((64 / OW) * 32, OW == 8 ? 3 : 4)
 k_conv2d_sym(ConvArgs a) {
-    using C = SymCfg<K>;
+    using C = SymCfg<K, OW>;
     extern __shared__ __align__(16) float smem[];
     float *tile = smem;
     float *wsm = smem + C::TILE_FLOATS;
@@ -116,7 +117,7 @@ k_conv2d_sym(ConvArgs a) {
     const int gx = tx0 + col;
     if (gx >= 0 && gx < W) {
 #pragma unroll 4
-        for (int rr = rsub; rr < C::TH; rr += 4) {
+        for (int rr = rsub; rr < C::TH; rr += C::NT / 64) {
             const int gy = ty0 + rr;
             if (gy >= H) break;
             const size_t idx = (size_t)gy * W + gx;
@@ -130,8 +131,9 @@ k_conv2d_sym(ConvArgs a) {
 
 template <int K>
 cudaError_t launch_sym(const ConvArgs &a, cudaStream_t st) {
-    using C = SymCfg<K>;
-    auto kfn = k_conv2d_sym<K>;
+    constexpr int OW = 16;
+    using C = SymCfg<K, OW>;
+    auto kfn = k_conv2d_sym<K, OW>;
     cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
     if (e != cudaSuccess) return e;
     dim3 grid((a.W + C::SHIFT + C::TW - 1) / C::TW, (a.H + C::TH - 1) / C::TH, 3);
