@@ -524,6 +524,7 @@ int render_impl(r2f_ctx *c, const void *in, int in_format, float in_gain, int H,
         fa.src_xyz = in;
         fa.gain = in_gain;
         fa.lut2d = l2;
+        fa.exp_planar = P[0].base;
         fa.dst_planar = P[1].base;
         fa.curve = cv;
         fa.eps = c->eps;

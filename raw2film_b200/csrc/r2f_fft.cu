@@ -22,6 +22,8 @@
 // Inverse transforms use IFFT(x) = swap(FFT(swap(x))).
 #include "r2f_fft.h"
 
+#include "conv_tile.cuh"
+
 #include <cmath>
 #include <cstdlib>
 #include <vector>
@@ -100,6 +102,22 @@ __device__ __forceinline__ void butterfly<8>(float2 (&v)[8]) {
     v[1] = cadd(e[1], o1);   v[5] = csub(e[1], o1);
     v[2] = cadd(e[2], o2);   v[6] = csub(e[2], o2);
     v[3] = cadd(e[3], o3);   v[7] = csub(e[3], o3);
+}
+
+__device__ __forceinline__ float pick3(int c, float v0, float v1, float v2) { return c == 0 ? v0 : (c == 1 ? v1 : v2); }
+
+// Streaming global loads that do not allocate in L1 (spectrum blocks and the kernel spectrum are read once;
+// the L1 is kept for the twiddle tables).
+__device__ __forceinline__ float4 ldg_stream4(const float4 *p) {
+    float4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ float ldg_stream(const float *p) {
+    float v;
+    asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(p));
+    return v;
 }
 
 // A group of threads that cooperates on one FFT line and synchronises on its own named barrier.
@@ -190,7 +208,12 @@ __device__ __forceinline__ Lut2D stage_lut2d(const Lut2D &L, float2 *idle, int c
     const int nfloat = L.n * L.n * 3;
     if (nfloat > 2 * capacity_float2) return L;
     float *dst = reinterpret_cast<float *>(idle);
-    for (int i = g.tid; i < nfloat; i += g.size) dst[i] = __ldg(L.tab + i);
+    // asynchronous 16-byte copies that bypass L1 (.cg): the copy costs one round trip and leaves the L1
+    // to the twiddle tables
+    const int nq = (reinterpret_cast<uintptr_t>(L.tab) & 15) == 0 ? nfloat / 4 : 0;
+    for (int i = g.tid; i < nq; i += g.size) cp_async_16(dst + 4 * i, L.tab + 4 * i);
+    for (int i = 4 * nq + g.tid; i < nfloat; i += g.size) dst[i] = __ldg(L.tab + i);
+    cp_async_wait_all();
     group_sync(g);
     return Lut2D(dst, L.n);
 }
@@ -221,14 +244,32 @@ k_fft_rows_fwd(const __grid_constant__ FftConvArgs a) {
             const Lut2D l2 = stage_lut2d(a.lut2d, bufB, n, g);
             if ((W & 3) == 0) {  // row starts on a pixel-quad boundary: 128-bit frame loads
                 const size_t q0 = (size_t)y * W / 4;
-                for (int qx = g.tid; qx < W / 4; qx += g.size) {
-                    float px[4][3];
-                    load_quad<FMT>(a.src_xyz, q0 + qx, a.gain, px);
+                constexpr int U = 2;  // quads in flight per thread: the frame loads of a batch are issued together
+                for (int base = g.tid; base < W / 4; base += U * g.size) {
+                    float px[U][4][3];
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        float e0, e1, e2;
-                        lut2d_eval(l2, px[i][0], px[i][1], px[i][2], e0, e1, e2);
-                        bufA[r + 4 * qx + i] = make_float2(e0, e1);
+                    for (int u = 0; u < U; ++u) {
+                        const int qx = base + u * g.size;
+                        if (qx < W / 4) load_quad<FMT>(a.src_xyz, q0 + qx, a.gain, px[u]);
+                    }
+#pragma unroll
+                    for (int u = 0; u < U; ++u) {
+                        const int qx = base + u * g.size;
+                        if (qx < W / 4) {
+                            float e[3][4];
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) {
+                                lut2d_eval(l2, px[u][i][0], px[u][i][1], px[u][i][2], e[0][i], e[1][i], e[2][i]);
+                                bufA[r + 4 * qx + i] = make_float2(pick3(a.chan[0], e[0][i], e[1][i], e[2][i]),
+                                                                   pick3(a.chan[1], e[0][i], e[1][i], e[2][i]));
+                            }
+                            if (a.exp_planar != nullptr) {
+#pragma unroll
+                                for (int c = 0; c < 3; ++c)
+                                    __stcg(reinterpret_cast<float4 *>(a.exp_planar + c * a.plane_stride) + q0 + qx,
+                                           make_float4(e[c][0], e[c][1], e[c][2], e[c][3]));
+                            }
+                        }
                     }
                 }
             } else {
@@ -236,7 +277,13 @@ k_fft_rows_fwd(const __grid_constant__ FftConvArgs a) {
                     float X, Y, Z, e0, e1, e2;
                     load_px<FMT>(a.src_xyz, (size_t)y * W + x, a.gain, X, Y, Z);
                     lut2d_eval(l2, X, Y, Z, e0, e1, e2);
-                    bufA[r + x] = make_float2(e0, e1);
+                    bufA[r + x] = make_float2(pick3(a.chan[0], e0, e1, e2), pick3(a.chan[1], e0, e1, e2));
+                    if (a.exp_planar != nullptr) {
+                        const size_t idx = (size_t)y * W + x;
+                        a.exp_planar[idx] = e0;
+                        a.exp_planar[a.plane_stride + idx] = e1;
+                        a.exp_planar[2 * a.plane_stride + idx] = e2;
+                    }
                 }
             }
         }
@@ -278,7 +325,8 @@ k_fft_cols(const __grid_constant__ FftConvArgs a) {
     for (int y = threadIdx.x; y < H; y += blockDim.x) {  // one spectrum row (NC values) per thread
         const float2 *sp = blk + (size_t)y * NC;
         if (NC == 4) {
-            const float4 lo = *reinterpret_cast<const float4 *>(sp), hi = *reinterpret_cast<const float4 *>(sp + 2);
+            const float4 lo = ldg_stream4(reinterpret_cast<const float4 *>(sp));
+            const float4 hi = ldg_stream4(reinterpret_cast<const float4 *>(sp + 2));
             fsm[r + y] = make_float2(lo.x, lo.y);
             fsm[(size_t)pitch + r + y] = make_float2(lo.z, lo.w);
             fsm[(size_t)2 * pitch + r + y] = make_float2(hi.x, hi.y);
@@ -302,7 +350,7 @@ k_fft_cols(const __grid_constant__ FftConvArgs a) {
         const float *kh = a.khat + (size_t)(b * NC + c) * n;
         for (int u = g.tid; u < n; u += g.size) {
             const float2 z = spec[u];
-            const float w = __ldg(kh + u);
+            const float w = ldg_stream(kh + u);
             spec[u] = make_float2(z.y * w, z.x * w);
         }
         group_sync(g);
@@ -342,14 +390,14 @@ k_fft_rows_inv(const __grid_constant__ FftConvArgs a) {
             const float2 *sp = a.S + ((size_t)b * H + (y0 + row)) * NC;
             float2 *dp = fsm + (size_t)row * 2 * n + b * NC;
             if (NC == 4) {
-                const float4 lo = *reinterpret_cast<const float4 *>(sp), hi = *reinterpret_cast<const float4 *>(sp + 2);
-                *reinterpret_cast<float4 *>(dp) = lo;
-                *reinterpret_cast<float4 *>(dp + 2) = hi;
+                cp_async_16(reinterpret_cast<float *>(dp), reinterpret_cast<const float *>(sp));
+                cp_async_16(reinterpret_cast<float *>(dp + 2), reinterpret_cast<const float *>(sp + 2));
             } else {
                 for (int c = 0; c < NC; ++c) dp[c] = sp[c];
             }
         }
     }
+    cp_async_wait_all();
     __syncthreads();
     if (half >= nrows) return;
     float2 *bufA = fsm + (size_t)half * 2 * n, *bufB = bufA + n;
@@ -362,23 +410,38 @@ k_fft_rows_inv(const __grid_constant__ FftConvArgs a) {
     // out = alpha * (K (*) x) + beta * x on the two filtered layers, third layer passes through;
     // then (optionally) log10 + H-D curve
     auto finish_px = [&](const float (&src)[3], float2 zs, float (&out)[3]) {
-        out[0] = src[0]; out[1] = src[1]; out[2] = src[2];
-        out[a.chan[0]] = fmaf(a.alpha[0], zs.y, a.beta[0] * src[a.chan[0]]);   // swapped: .y = K(*)chan0
-        out[a.chan[1]] = fmaf(a.alpha[1], zs.x, a.beta[1] * src[a.chan[1]]);   //          .x = K(*)chan1
+        // compile-time register indices only (a runtime-indexed src[]/out[] would live in local memory)
+        const float x0 = pick3(a.chan[0], src[0], src[1], src[2]), x1 = pick3(a.chan[1], src[0], src[1], src[2]);
+        const float f0 = fmaf(a.alpha[0], zs.y, a.beta[0] * x0);   // swapped: .y = K(*)chan0
+        const float f1 = fmaf(a.alpha[1], zs.x, a.beta[1] * x1);   //          .x = K(*)chan1
+#pragma unroll
+        for (int c = 0; c < 3; ++c) out[c] = a.chan[0] == c ? f0 : (a.chan[1] == c ? f1 : src[c]);
         if (DENSITY) {
 #pragma unroll
             for (int c = 0; c < 3; ++c) out[c] = density_eval_fast(a.curve, c, out[c], a.eps);
         }
     };
-    if (SRC != 0 && (W & 3) == 0) {
+    if ((W & 3) == 0) {
         const size_t q0 = (size_t)y * W / 4;
         for (int qx = g.tid; qx < W / 4; qx += g.size) {
             float px[4][3], res[3][4];
-            load_quad<FMT>(a.src_xyz, q0 + qx, a.gain, px);
+            if (SRC != 0) {
+                load_quad<FMT>(a.src_xyz, q0 + qx, a.gain, px);
+            } else {
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    const float4 v = __ldcs(reinterpret_cast<const float4 *>(a.src_planar + c * ps) + q0 + qx);
+                    px[0][c] = v.x; px[1][c] = v.y; px[2][c] = v.z; px[3][c] = v.w;
+                }
+            }
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
                 float src[3], out[3];
-                lut2d_eval(l2, px[i][0], px[i][1], px[i][2], src[0], src[1], src[2]);
+                if (SRC != 0) {
+                    lut2d_eval(l2, px[i][0], px[i][1], px[i][2], src[0], src[1], src[2]);
+                } else {
+                    src[0] = px[i][0]; src[1] = px[i][1]; src[2] = px[i][2];
+                }
                 finish_px(src, buf[r + 4 * qx + i], out);
                 res[0][i] = out[0]; res[1][i] = out[1]; res[2][i] = out[2];
             }
@@ -614,8 +677,14 @@ cudaError_t launch_fft_conv(const FftConvArgs &a, int src_mode, bool density, cu
         if ((e = cudaGetLastError()) != cudaSuccess) return e;
     }
     if (stage == 0 || stage == 3) {
-        e = rows == 2 ? launch_rows_inv<2>(a, src_mode, density, row_ctas, 1024, rs, st)
-                      : launch_rows_inv<1>(a, src_mode, density, row_ctas, t1, rs, st);
+        FftConvArgs b = a;
+        int inv_mode = src_mode;
+        if (src_mode != 0 && a.exp_planar != nullptr) {  // the forward pass left the exposure planes behind
+            b.src_planar = a.exp_planar;
+            inv_mode = 0;
+        }
+        e = rows == 2 ? launch_rows_inv<2>(b, inv_mode, density, row_ctas, 1024, rs, st)
+                      : launch_rows_inv<1>(b, inv_mode, density, row_ctas, t1, rs, st);
     }
     return e;
 }

@@ -46,6 +46,9 @@ struct FftConvArgs {
     const void *src_xyz;  // interleaved frame in one of the kFmt* formats
     float gain;           // exposure gain of uint16 frames
     Lut2D lut2d;
+    // when set (and the source is an interleaved frame), k_fft_rows_fwd also stores the three exposure
+    // planes it evaluates, and k_fft_rows_inv reads them back instead of re-evaluating the 2-D LUT
+    float *exp_planar;
     size_t plane_stride;
     // destination: planar planes, optionally through log10 + H-D curve
     float *dst_planar;
