@@ -48,8 +48,9 @@ KERNEL_BYTES_PER_PX = {"pointwise": 15, "expose": 24, "halation": 24, "density":
                        "grain": 15, "burn": 4, "finish": 15,
                        # FFT halation: 12 B/px frame read + 8 B/px spectrum write | spectrum r+w + 4 B/px kernel
                        # spectrum | spectrum read + frame re-read + 12 B/px density write (padding excluded)
-                       "fft_rows_fwd": 20, "fft_cols": 20, "fft_rows_inv": 32}
-KERNEL_SASS_NAME = {"pointwise": "k_pointwise", "mtf": "k_conv2d", "halation": "k_conv2d", "grain": "k_grain_finish",
+                       # (rows_fwd also leaves the 12 B/px exposure planes behind for rows_inv)
+                       "fft_rows_fwd": 32, "fft_cols": 20, "fft_rows_inv": 32}
+KERNEL_SASS_NAME = {"pointwise": "k_pointwise", "mtf": "k_conv2d_sym", "halation": "k_conv2d_sym", "grain": "k_grain_finish",
                     "fft_rows_fwd": "k_fft_rows_fwd", "fft_cols": "k_fft_cols", "fft_rows_inv": "k_fft_rows_inv",
                     "finish": "k_finish", "expose": "k_expose", "noise": "k_noise", "density": "k_conv2d"}
 
@@ -360,7 +361,9 @@ def main():
                 if k is not None:
                     taps = sum(int(np.count_nonzero(k[..., c])) > 1 for c in range(3)) * k.shape[0] * k.shape[1]
                     roofline["fp32_tflops"] = 2.0 * taps * H * W / (kernels[dom]["ms"] * 1e-3) / 1e12
-                    roofline["note"] = "direct 2-D correlation is FP32-FMA bound, not HBM bound (SURVEY 8d)"
+                    roofline["note"] = ("direct 2-D correlation is FP32-FMA bound, not HBM bound (SURVEY 8d); fp32_tflops "
+                                        "counts the algorithmic 2*k*k flops/px/layer, the y-symmetric kernel executes "
+                                        "about half of them")
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
             from oracle import film_oracle as fo

@@ -600,6 +600,7 @@ int render_impl(r2f_ctx *c, const void *in, int in_format, float in_gain, int H,
         ga.H = H;
         ga.W = W;
         ga.gk = c->grain.chan[0];
+        ga.gk_sym = c->grain.sym_ok ? c->grain.sym[0] : nullptr;
         ga.k = c->grain.k;
         ga.kp = c->grain.kp;
         ga.bw = nch == 1;
@@ -610,7 +611,8 @@ int render_impl(r2f_ctx *c, const void *in, int in_format, float in_gain, int H,
         ga.burn = BurnArgs{};
         ga.out_u8 = out_u8;
         ProfScope ps_(c, st, R2F_PROF_GRAIN);
-        CU(launch_grain_finish(ga, st));
+        if (c->conv_sym && ga.gk_sym && grain_finish_sym_supported(ga.k)) CU(launch_grain_finish_sym(ga, st));
+        else CU(launch_grain_finish(ga, st));
         c->launches += 1;
         return R2F_OK;
     }

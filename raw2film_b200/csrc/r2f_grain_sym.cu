@@ -1,0 +1,220 @@
+// a7 + a9 + a10 fused, for grain kernels that are mirror-symmetric in y (every grain blob kernel is):
+// white noise regenerated per tile (Philox), correlated with the grain kernel by the row-pair /
+// packed-FMA scheme of r2f_conv_sym.cu, scaled by the density-dependent amplitude, added, clipped,
+// then tetrahedral LUT + quantise.  Reads 12 B/px of density, writes 3 B/px; the noise field and the
+// grained density never touch HBM.
+//
+// reference: effects.py:220-236 (apply_grain), cpu_processor.py:387-397, shaders/grain.wgsl:36-92,
+// utils.py:247-380 (tetrahedral LUT), cpu_processor.py:407 (quantise).
+//
+// Thread mapping (64x64 tile, 256 threads): warp w owns tile columns 8w..8w+7, lane l owns tile rows
+// l and l+32; the FFMA2 lanes are (row l, row l+32).  The noise tile's row pitch is 4 (mod 8) floats,
+// so the 128-bit window loads of a warp (one tile row per lane) are bank-conflict free.
+#include <cuda_runtime.h>
+
+#include "conv_tile.cuh"
+#include "noise.cuh"
+#include "r2f_kernels.h"
+
+namespace r2f {
+
+namespace {
+
+template <int K>
+struct GrainCfg {
+    static constexpr int R = K / 2;
+    static constexpr int T = 64, OW = 8, NT = 256;
+    static constexpr int NWIN = OW + K - 1;
+    static constexpr int NQ = (NWIN + 3) / 4;
+    static constexpr int COLS = T + K - 1;
+    static constexpr int NEED = (T - OW) + 4 * NQ;
+    static constexpr int P0 = ((COLS > NEED ? COLS : NEED) + 3) / 4 * 4;
+    static constexpr int PITCH = (P0 % 8 == 4) ? P0 : P0 + 4;
+    static constexpr int ROWS = T + K - 1;
+    static constexpr int WROW = (K + 1) / 2 * 2;
+    static constexpr int SPITCH = 196;  // staged output row pitch in bytes: 192 + 4, so the lanes (= rows) of a
+                                        // warp hit different banks when they store their packed words
+    static constexpr int TILE_BYTES = ROWS * PITCH * 4 > T * SPITCH ? ROWS * PITCH * 4 : T * SPITCH;
+    static constexpr int TILE_FLOATS = (TILE_BYTES + 15) / 16 * 4;
+    static constexpr int W_FLOATS = (R + 1) * WROW * 2;
+    static constexpr int PRIV_FLOATS = 3 * 2 * OW * NT;  // grained densities, thread-private slots
+    static constexpr int SMEM_BYTES = (TILE_FLOATS + W_FLOATS + PRIV_FLOATS) * 4;
+};
+
+template <int K, bool GEN>
+__global__ void __launch_bounds__(256, 3)
+k_grain_finish_sym(GrainFinishArgs a) {
+    using C = GrainCfg<K>;
+    extern __shared__ __align__(16) float smem[];
+    float *tile = smem;
+    float *wsm = smem + C::TILE_FLOATS;
+    float *priv = wsm + C::W_FLOATS;
+    const int H = a.H, W = a.W;
+    const int tx0 = blockIdx.x * C::T, ty0 = blockIdx.y * C::T;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const size_t ps = a.plane_stride;
+    for (int idx = threadIdx.x; idx < C::W_FLOATS; idx += C::NT) wsm[idx] = __ldg(a.gk_sym + idx);
+
+    const int nch = a.bw ? 1 : 3;
+    const int xs = tx0 - C::R;                                      // global x of tile column 0
+    const bool interior = xs >= 0 && xs + C::COLS <= W;             // no horizontal reflection needed
+    const int q0 = xs >> 2, nq = ((xs + C::COLS - 1) >> 2) - q0 + 1;  // aligned noise quads covering a tile row
+    const int gx0 = tx0 + C::OW * warp;                             // first of the thread's 8 columns
+    const bool vec_ok = (W & 3) == 0 && gx0 + C::OW <= W;           // whole 16-byte density loads
+
+    float2 g[C::OW];
+#pragma unroll 1
+    for (int c = 0; c < 3; ++c) {
+        if (c < nch) {
+            __syncthreads();  // the previous channel's window reads are done
+            if (GEN) {
+                if (interior) {  // one Philox call per aligned quad of four samples
+                    for (int idx = threadIdx.x; idx < C::ROWS * nq; idx += C::NT) {
+                        const int ty = idx / nq, tq = idx - ty * nq;
+                        const int gy = reflect101(ty0 - C::R + ty, H);
+                        const float4 v = noise_quad((uint32_t)(q0 + tq), gy, c, a.seed_lo, a.seed_hi);
+                        const float vals[4] = {v.x, v.y, v.z, v.w};
+                        const int tx = 4 * (q0 + tq) - xs;
+#pragma unroll
+                        for (int l = 0; l < 4; ++l)
+                            if (tx + l >= 0 && tx + l < C::COLS) tile[ty * C::PITCH + tx + l] = vals[l];
+                    }
+                } else {
+                    for (int idx = threadIdx.x; idx < C::ROWS * C::COLS; idx += C::NT) {
+                        const int ty = idx / C::COLS, tx = idx - ty * C::COLS;
+                        tile[ty * C::PITCH + tx] = noise_at(reflect101(xs + tx, W), reflect101(ty0 - C::R + ty, H), c,
+                                                            a.seed_lo, a.seed_hi);
+                    }
+                }
+            } else {
+                fill_tile(tile, a.noise + (size_t)c * ps, C::ROWS, C::COLS, ty0 - C::R, xs, H, W, C::NT, C::PITCH);
+            }
+            __syncthreads();
+#pragma unroll
+            for (int o = 0; o < C::OW; ++o) g[o] = make_float2(0.f, 0.f);
+            const float *ctr0 = tile + (lane + C::R) * C::PITCH + C::OW * warp;
+            const float *ctr1 = ctr0 + 32 * C::PITCH;
+#pragma unroll 1
+            for (int dy = 0; dy <= C::R; ++dy) {
+                const float4 *a0 = reinterpret_cast<const float4 *>(ctr0 + dy * C::PITCH);
+                const float4 *b0 = reinterpret_cast<const float4 *>(ctr0 - dy * C::PITCH);
+                const float4 *a1 = reinterpret_cast<const float4 *>(ctr1 + dy * C::PITCH);
+                const float4 *b1 = reinterpret_cast<const float4 *>(ctr1 - dy * C::PITCH);
+                float2 P[C::NQ * 4];
+#pragma unroll
+                for (int q = 0; q < C::NQ; ++q) {
+                    const float4 x = a0[q], y = b0[q], z = a1[q], w = b1[q];
+                    P[4 * q + 0] = make_float2(x.x + y.x, z.x + w.x);
+                    P[4 * q + 1] = make_float2(x.y + y.y, z.y + w.y);
+                    P[4 * q + 2] = make_float2(x.z + y.z, z.z + w.z);
+                    P[4 * q + 3] = make_float2(x.w + y.w, z.w + w.w);
+                }
+                const float4 *wr = reinterpret_cast<const float4 *>(wsm + dy * C::WROW * 2);
+#pragma unroll
+                for (int j = 0; j < K; j += 2) {
+                    const float4 w4 = wr[j >> 1];
+                    const float2 wa = make_float2(w4.x, w4.y);
+#pragma unroll
+                    for (int o = 0; o < C::OW; ++o) g[o] = __ffma2_rn(wa, P[o + j], g[o]);
+                    if (j + 1 < K) {
+                        const float2 wb = make_float2(w4.z, w4.w);
+#pragma unroll
+                        for (int o = 0; o < C::OW; ++o) g[o] = __ffma2_rn(wb, P[o + j + 1], g[o]);
+                    }
+                }
+            }
+        }
+        // grain apply on channel c (black-and-white grain reuses the single field)
+        const float *dplane = a.dens + c * ps;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int gy = ty0 + lane + 32 * h;
+            float d[C::OW];
+            if (gy < H && vec_ok) {
+                const float4 *p = reinterpret_cast<const float4 *>(dplane + (size_t)gy * W + gx0);
+                const float4 u = __ldcs(p), v = __ldcs(p + 1);
+                d[0] = u.x; d[1] = u.y; d[2] = u.z; d[3] = u.w; d[4] = v.x; d[5] = v.y; d[6] = v.z; d[7] = v.w;
+            } else {
+#pragma unroll
+                for (int o = 0; o < C::OW; ++o)
+                    d[o] = (gy < H && gx0 + o < W) ? __ldcs(dplane + (size_t)gy * W + gx0 + o) : 0.0f;
+            }
+#pragma unroll
+            for (int o = 0; o < C::OW; ++o) {
+                const float gn = h == 0 ? g[o].x : g[o].y;
+                float val = d[o] + gn * curve_eval(a.gcurve, c, d[o]);
+                val = val > 0.0f ? val : 0.0f;
+                priv[((c * 2 + h) * C::OW + o) * C::NT + threadIdx.x] = val;
+            }
+        }
+    }
+    __syncthreads();  // all noise-tile reads done: its storage becomes the output staging area
+    uint8_t *stage = reinterpret_cast<uint8_t *>(tile);
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        uint32_t b[24];
+#pragma unroll
+        for (int o = 0; o < C::OW; ++o) {
+            const float d0 = priv[((0 * 2 + h) * C::OW + o) * C::NT + threadIdx.x];
+            const float d1 = priv[((1 * 2 + h) * C::OW + o) * C::NT + threadIdx.x];
+            const float d2 = priv[((2 * 2 + h) * C::OW + o) * C::NT + threadIdx.x];
+            tetra_quant_u8(a.l3, d0, d1, d2, b[3 * o], b[3 * o + 1], b[3 * o + 2]);
+        }
+        // 8 pixels = 24 bytes = 6 packed words
+        uint32_t *sp = reinterpret_cast<uint32_t *>(stage + (lane + 32 * h) * C::SPITCH + 3 * C::OW * warp);
+#pragma unroll
+        for (int wd = 0; wd < 6; ++wd)
+            sp[wd] = b[4 * wd] | (b[4 * wd + 1] << 8) | (b[4 * wd + 2] << 16) | (b[4 * wd + 3] << 24);
+    }
+    __syncthreads();
+    const int tw = min(C::T, W - tx0), th = min(C::T, H - ty0);
+    const int row_bytes = tw * 3;
+    if (tw == C::T && ((size_t)W * 3 % 16) == 0 && (reinterpret_cast<uintptr_t>(a.out_u8) & 15) == 0) {
+        for (int idx = threadIdx.x; idx < th * 12; idx += C::NT) {  // 192 bytes = 12 x 16 per row
+            const int r = idx / 12, s16 = idx - r * 12;
+            const uint32_t *sp = reinterpret_cast<const uint32_t *>(stage + r * C::SPITCH + s16 * 16);
+            const uint4 v = make_uint4(sp[0], sp[1], sp[2], sp[3]);
+            __stcs(reinterpret_cast<uint4 *>(a.out_u8 + ((size_t)(ty0 + r) * W + tx0) * 3) + s16, v);
+        }
+    } else {
+        for (int idx = threadIdx.x; idx < th * row_bytes; idx += C::NT) {
+            const int r = idx / row_bytes, bcol = idx - r * row_bytes;
+            a.out_u8[((size_t)(ty0 + r) * W + tx0) * 3 + bcol] = stage[r * C::SPITCH + bcol];
+        }
+    }
+}
+
+template <int K>
+cudaError_t launch_gs(const GrainFinishArgs &a, cudaStream_t st) {
+    using C = GrainCfg<K>;
+    dim3 grid((a.W + C::T - 1) / C::T, (a.H + C::T - 1) / C::T);
+    cudaError_t e;
+    if (a.noise == nullptr) {
+        auto kfn = k_grain_finish_sym<K, true>;
+        if ((e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES)) != cudaSuccess)
+            return e;
+        kfn<<<grid, C::NT, C::SMEM_BYTES, st>>>(a);
+    } else {
+        auto kfn = k_grain_finish_sym<K, false>;
+        if ((e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES)) != cudaSuccess)
+            return e;
+        kfn<<<grid, C::NT, C::SMEM_BYTES, st>>>(a);
+    }
+    return cudaGetLastError();
+}
+
+}  // namespace
+
+bool grain_finish_sym_supported(int k) { return k >= 3 && k <= kGrainSymMaxK && (k & 1); }
+
+cudaError_t launch_grain_finish_sym(const GrainFinishArgs &a, cudaStream_t st) {
+    if (a.gk_sym == nullptr || a.burn.map != nullptr) return cudaErrorInvalidValue;
+    switch (a.k) {
+#define R2F_GS(KK) case KK: return launch_gs<KK>(a, st);
+        R2F_GS(3) R2F_GS(5) R2F_GS(7) R2F_GS(9) R2F_GS(11) R2F_GS(13) R2F_GS(15) R2F_GS(17) R2F_GS(19) R2F_GS(21)
+#undef R2F_GS
+        default: return cudaErrorInvalidValue;
+    }
+}
+
+}  // namespace r2f

@@ -86,6 +86,7 @@ struct GrainFinishArgs {
     size_t plane_stride;
     int H, W;
     const float *gk;     // grain kernel, transposed + padded: gk[j * kp + i]
+    const float *gk_sym; // y-symmetric packed layout (ConvArgs::ksym) or nullptr
     int k, kp;
     int bw;              // one noise field for all three layers
     uint32_t seed_lo, seed_hi;
@@ -95,6 +96,10 @@ struct GrainFinishArgs {
     uint8_t *out_u8;
 };
 cudaError_t launch_grain_finish(const GrainFinishArgs &a, cudaStream_t st);
+// same contract for y-symmetric grain kernels without burn (r2f_grain_sym.cu): row-pair sums + packed FMA
+constexpr int kGrainSymMaxK = 21;
+bool grain_finish_sym_supported(int k);
+cudaError_t launch_grain_finish_sym(const GrainFinishArgs &a, cudaStream_t st);
 // highlight-burn low-res mask: area down-sample of the green plane, max(x - d_ref, 0), 13-tap Gaussian (sigma 3)
 cudaError_t launch_burn_mask(const float *green_plane, int H, int W, int lh, int lw, float d_ref, float *tmp,
                              float *map, cudaStream_t st);

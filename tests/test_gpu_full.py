@@ -307,17 +307,24 @@ def test_fused_grain_kernel_matches_staged_kernels(proc):
     import torch
 
     stock = SyntheticStock(n3=17)
-    xyz = small_frame(200, 264, seed=77)
-    for grain_mode in (2, 1):
-        st = dict(frame_width=1.2, frame_height=0.8, grain=grain_mode, grain_seed=1234)
-        x = torch.from_numpy(xyz).cuda()
-        rgb = proc.render_tap(x, "rgb", stock, 6.0, 0.4, **st).cpu().numpy()
-        want = fo.quantise_u8(rgb)
-        got = proc.render_device(x, stock, 6.0, 0.4, **st)
-        proc.stream.synchronize()
-        got = got.cpu().numpy()
-        diff = np.abs(got.astype(np.int16) - want.astype(np.int16))
-        assert diff.max() <= 1 and np.mean(diff != 0) < 1e-3, (grain_mode, diff.max(), np.mean(diff != 0))
+    # both fused kernels (y-symmetric packed-FMA k_grain_finish_sym and the generic k_grain_finish), RGB and
+    # B/W grain, grain kernels from 5x5 to 15x15, a ragged frame (W % 4 != 0, partial tiles)
+    for shape, grain_size, sym in (((200, 264), 6.0, True), ((200, 264), 6.0, False), ((131, 203), 3.0, True),
+                                   ((131, 203), 14.0, True), ((131, 203), 14.0, False)):
+        xyz = small_frame(*shape, seed=77)
+        proc.set_conv_sym(sym)
+        for grain_mode in (2, 1):
+            st = dict(frame_width=1.2, frame_height=0.8, grain=grain_mode, grain_seed=1234)
+            x = torch.from_numpy(xyz).cuda()
+            rgb = proc.render_tap(x, "rgb", stock, grain_size, 0.4, **st).cpu().numpy()
+            want = fo.quantise_u8(rgb)
+            got = proc.render_device(x, stock, grain_size, 0.4, **st)
+            proc.stream.synchronize()
+            got = got.cpu().numpy()
+            diff = np.abs(got.astype(np.int16) - want.astype(np.int16))
+            assert diff.max() <= 1 and np.mean(diff != 0) < 1e-3, (shape, grain_size, sym, grain_mode, diff.max(),
+                                                                  np.mean(diff != 0))
+    proc.set_conv_sym(True)
 
 
 def test_process_skips_ingest_when_image_parameters_are_unchanged(proc):
