@@ -132,9 +132,12 @@ __device__ __forceinline__ void group_sync(const Group &g) {
 // Butterfly j reads src[j + t*n/R] (contiguous across lanes) and writes dst[j0 + t*Ns].
 // `tw` is this pass's twiddle table: tw[(t-1)*Ns + k] = exp(-2 pi i t k / (Ns R)), so lanes with
 // consecutive j read consecutive twiddles.
-template <int R>
+// SCALE: the outputs are multiplied by the real table scale[] and their re/im swapped on the way out
+// (the kernel-spectrum product of k_fft_cols folded into the last forward pass).
+template <int R, bool SCALE = false>
 __device__ __forceinline__ void fft_pass(const float2 *__restrict__ src, float2 *__restrict__ dst, int n, int Ns,
-                                         const float2 *__restrict__ tw, const Group &g) {
+                                         const float2 *__restrict__ tw, const Group &g,
+                                         const float *__restrict__ scale = nullptr) {
     const int nb = n / R;
     const bool pow2 = (Ns & (Ns - 1)) == 0;
 #pragma unroll 2
@@ -149,6 +152,13 @@ __device__ __forceinline__ void fft_pass(const float2 *__restrict__ src, float2 
         }
         butterfly<R>(v);
         const int j0 = (j - k) * R + k;
+        if (SCALE) {
+#pragma unroll
+            for (int t = 0; t < R; ++t) {
+                const float w = ldg_stream(scale + j0 + t * Ns);
+                v[t] = make_float2(v[t].y * w, v[t].x * w);
+            }
+        }
         if (Ns == 1 && (R & 1) == 0) {  // R consecutive outputs: 16-byte stores
             float4 *d4 = reinterpret_cast<float4 *>(dst + j0);
 #pragma unroll
@@ -163,12 +173,23 @@ __device__ __forceinline__ void fft_pass(const float2 *__restrict__ src, float2 
 
 // Forward FFT of a[0..n) using b as the ping-pong partner.  The data in `a` must already be visible
 // to the whole group.  Returns the buffer holding the result (a if the pass count is even).
-__device__ __forceinline__ float2 *fft_forward(float2 *a, float2 *b, const FftLine &L, const Group &g) {
+template <bool SCALE_LAST = false>
+__device__ __forceinline__ float2 *fft_forward(float2 *a, float2 *b, const FftLine &L, const Group &g,
+                                               const float *__restrict__ scale = nullptr) {
     float2 *src = a, *dst = b;
     int Ns = 1;
     for (int s = 0; s < L.nrad; ++s) {
         const int R = L.rad[s];
         const float2 *tw = L.tw + L.tw_off[s];
+        if (SCALE_LAST && s == L.nrad - 1) {
+            switch (R) {
+                case 2: fft_pass<2, true>(src, dst, L.n, Ns, tw, g, scale); break;
+                case 3: fft_pass<3, true>(src, dst, L.n, Ns, tw, g, scale); break;
+                case 4: fft_pass<4, true>(src, dst, L.n, Ns, tw, g, scale); break;
+                case 5: fft_pass<5, true>(src, dst, L.n, Ns, tw, g, scale); break;
+                default: fft_pass<8, true>(src, dst, L.n, Ns, tw, g, scale); break;
+            }
+        } else
         switch (R) {
             case 2: fft_pass<2>(src, dst, L.n, Ns, tw, g); break;
             case 3: fft_pass<3>(src, dst, L.n, Ns, tw, g); break;
@@ -322,16 +343,33 @@ k_fft_cols(const __grid_constant__ FftConvArgs a) {
     const int pitch = n + 2;  // even (16-byte aligned lines), de-phases the column buffers across banks
     const int b = blockIdx.x;
     float2 *blk = a.S + (size_t)b * H * NC;
-    for (int y = threadIdx.x; y < H; y += blockDim.x) {  // one spectrum row (NC values) per thread
-        const float2 *sp = blk + (size_t)y * NC;
-        if (NC == 4) {
-            const float4 lo = ldg_stream4(reinterpret_cast<const float4 *>(sp));
-            const float4 hi = ldg_stream4(reinterpret_cast<const float4 *>(sp + 2));
-            fsm[r + y] = make_float2(lo.x, lo.y);
-            fsm[(size_t)pitch + r + y] = make_float2(lo.z, lo.w);
-            fsm[(size_t)2 * pitch + r + y] = make_float2(hi.x, hi.y);
-            fsm[(size_t)3 * pitch + r + y] = make_float2(hi.z, hi.w);
-        } else {
+    if (NC == 4) {  // one spectrum row (4 values = 32 bytes) per thread; the loads of a batch are issued together
+        constexpr int U = 4;
+        for (int y0 = threadIdx.x; y0 < H; y0 += U * blockDim.x) {
+            float4 lo[U], hi[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int y = y0 + u * blockDim.x;
+                if (y < H) {
+                    const float2 *sp = blk + (size_t)y * 4;
+                    lo[u] = ldg_stream4(reinterpret_cast<const float4 *>(sp));
+                    hi[u] = ldg_stream4(reinterpret_cast<const float4 *>(sp + 2));
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int y = y0 + u * blockDim.x;
+                if (y < H) {
+                    fsm[r + y] = make_float2(lo[u].x, lo[u].y);
+                    fsm[(size_t)pitch + r + y] = make_float2(lo[u].z, lo[u].w);
+                    fsm[(size_t)2 * pitch + r + y] = make_float2(hi[u].x, hi[u].y);
+                    fsm[(size_t)3 * pitch + r + y] = make_float2(hi[u].z, hi[u].w);
+                }
+            }
+        }
+    } else {
+        for (int y = threadIdx.x; y < H; y += blockDim.x) {
+            const float2 *sp = blk + (size_t)y * NC;
             for (int c = 0; c < NC; ++c) fsm[(size_t)c * pitch + r + y] = sp[c];
         }
     }
@@ -344,16 +382,11 @@ k_fft_cols(const __grid_constant__ FftConvArgs a) {
         float2 *home = fsm + (size_t)c * pitch;
         pad_line(home, H, r, n, g);
         group_sync(g);
-        float2 *spec = fft_forward(home, tmp, a.col, g);
-        float2 *other = spec == home ? tmp : home;
-        // product with the real kernel spectrum; swap re/im so the next forward FFT is the inverse
+        // forward FFT; its last pass multiplies by the real kernel spectrum and swaps re/im, so the next
+        // forward FFT is the inverse
         const float *kh = a.khat + (size_t)(b * NC + c) * n;
-        for (int u = g.tid; u < n; u += g.size) {
-            const float2 z = spec[u];
-            const float w = ldg_stream(kh + u);
-            spec[u] = make_float2(z.y * w, z.x * w);
-        }
-        group_sync(g);
+        float2 *spec = fft_forward<true>(home, tmp, a.col, g, kh);
+        float2 *other = spec == home ? tmp : home;
         fft_forward(spec, other, a.col, g);  // 2 * nrad passes in total: the result is back in `home`
     }
     __syncthreads();
