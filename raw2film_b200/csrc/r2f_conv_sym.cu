@@ -16,8 +16,16 @@
 // Lanes of a warp walk 32 consecutive tile rows; the row pitch is 4 (mod 8) floats, which makes
 // every 128-bit window load conflict-free (8 lanes x 16 B cover all 32 banks).
 //
+// Tile staging: interior tiles are fetched by ONE TMA bulk-tensor copy (cp.async.bulk.tensor.3d over a
+// {W, H, plane} tensor map, box = PITCH x ROWS x 1, completion on an mbarrier) issued by a single thread;
+// tiles that touch the frame border need BORDER_REFLECT_101 addresses, which TMA's zero fill cannot
+// express, and use per-thread cp.async copies instead.
+//
 // Reference semantics kept: correlation (not convolution), centre anchor, BORDER_REFLECT_101
 // (cv.filter2D as called from effects.py:146-156).
+#include <cstdlib>
+
+#include <cuda.h>
 #include <cuda_runtime.h>
 
 #include "conv_tile.cuh"
@@ -46,11 +54,42 @@ struct SymCfg {
     static constexpr int SMEM_BYTES = (TILE_FLOATS + (R + 1) * WROW * 2) * 4;
 };
 
+// ---- TMA / mbarrier primitives (PTX ISA 8.x, sm_90+) ---------------------------------------------
+__device__ __forceinline__ void mbar_init(uint64_t *bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)),
+                 "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, unsigned phase) {
+    const unsigned addr = (unsigned)__cvta_generic_to_shared(bar);
+    unsigned done = 0;
+    while (!done) {
+        asm volatile(
+            "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+            : "=r"(done)
+            : "r"(addr), "r"(phase)
+            : "memory");
+    }
+}
+__device__ __forceinline__ void tma_load_3d(float *smem_dst, const CUtensorMap *map, int x, int y, int z,
+                                            uint64_t *bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+        ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(map), "r"(x), "r"(y), "r"(z),
+        "r"((unsigned)__cvta_generic_to_shared(bar))
+        : "memory");
+}
+
 template <int K, int OW>
 __global__ void __launch_bounds__((64 / OW) * 32, OW == 8 ? 3 : 4)
-k_conv2d_sym(ConvArgs a) {
+k_conv2d_sym(ConvArgs a, const __grid_constant__ CUtensorMap tmap, int use_tma) {
     using C = SymCfg<K, OW>;
-    extern __shared__ __align__(16) float smem[];
+    extern __shared__ __align__(128) float smem[];
+    __shared__ __align__(8) uint64_t tma_bar;
     float *tile = smem;
     float *wsm = smem + C::TILE_FLOATS;
     const int c = blockIdx.z;
@@ -61,10 +100,23 @@ k_conv2d_sym(ConvArgs a) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     if (a.mode[c] != 0) {
-        fill_tile_async<C::ROWS, C::COLS, C::PITCH, C::NT>(tile, src, ty0 - C::R, tx0 - C::R, H, W);
+        const int gx0 = tx0 - C::R, gy0 = ty0 - C::R;
+        // TMA when every element the windows read lies inside the frame (the box may overhang by the pitch padding)
+        const bool tma = use_tma && gx0 >= 0 && gy0 >= 0 && gx0 + C::COLS <= W && gy0 + C::ROWS <= H;
+        if (tma) {
+            if (threadIdx.x == 0) mbar_init(&tma_bar, 1);
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                mbar_expect_tx(&tma_bar, C::ROWS * C::PITCH * 4);
+                tma_load_3d(tile, &tmap, gx0, gy0, a.in_plane[c], &tma_bar);
+            }
+        } else {
+            fill_tile_async<C::ROWS, C::COLS, C::PITCH, C::NT>(tile, src, gy0, gx0, H, W);
+        }
         const float *__restrict__ wg = a.ksym[c];
         for (int idx = threadIdx.x; idx < (C::R + 1) * C::WROW * 2; idx += C::NT) wsm[idx] = __ldg(wg + idx);
-        cp_async_wait_all();
+        if (tma) mbar_wait(&tma_bar, 0);
+        else cp_async_wait_all();
         __syncthreads();
 
         float2 acc[C::OW];
@@ -129,6 +181,38 @@ k_conv2d_sym(ConvArgs a) {
     }
 }
 
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time libcuda dependency)
+using EncodeTiledFn = CUresult (*)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                   const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn encode_tiled_fn() {
+    static EncodeTiledFn fn = [] {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+            q != cudaDriverEntryPointSuccess)
+            p = nullptr;
+        return reinterpret_cast<EncodeTiledFn>(p);
+    }();
+    return fn;
+}
+
+// {W, H, 3 planes} float32 tensor map over the planar source with a box of pitch x rows x 1.
+// Returns false when the layout does not meet TMA's alignment rules (the kernel then uses cp.async).
+bool make_plane_map(const ConvArgs &a, int box_w, int box_h, CUtensorMap *map) {
+    if (getenv("R2F_NO_TMA")) return false;
+    EncodeTiledFn enc = encode_tiled_fn();
+    if (!enc || (a.W & 3) != 0 || (reinterpret_cast<uintptr_t>(a.in) & 15) != 0 || box_w > 256 || box_h > 256)
+        return false;
+    const cuuint64_t dims[3] = {(cuuint64_t)a.W, (cuuint64_t)a.H, 3};
+    const cuuint64_t strides[2] = {(cuuint64_t)a.W * 4, (cuuint64_t)a.plane_stride * 4};
+    const cuuint32_t box[3] = {(cuuint32_t)box_w, (cuuint32_t)box_h, 1};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    return enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float *>(a.in), dims, strides, box, estr,
+               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 template <int K>
 cudaError_t launch_sym(const ConvArgs &a, cudaStream_t st) {
     constexpr int OW = 16;
@@ -136,8 +220,10 @@ cudaError_t launch_sym(const ConvArgs &a, cudaStream_t st) {
     auto kfn = k_conv2d_sym<K, OW>;
     cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
     if (e != cudaSuccess) return e;
+    CUtensorMap map{};
+    const int use_tma = make_plane_map(a, C::PITCH, C::ROWS, &map) ? 1 : 0;
     dim3 grid((a.W + C::SHIFT + C::TW - 1) / C::TW, (a.H + C::TH - 1) / C::TH, 3);
-    kfn<<<grid, C::NT, C::SMEM_BYTES, st>>>(a);
+    kfn<<<grid, C::NT, C::SMEM_BYTES, st>>>(a, map, use_tma);
     return cudaGetLastError();
 }
 

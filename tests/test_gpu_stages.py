@@ -128,7 +128,7 @@ def test_symmetric_kernel_path_vs_truth_and_generic(proc, k):
     sums + packed FMA); it must agree with the float64 truth and with the generic kernel on ragged frames,
     frames smaller than a tile and frames smaller than the kernel radius."""
     rng = np.random.default_rng(k)
-    for shape in ((70 + k, 131), (64, 64), (5, 9), (130, 67)):
+    for shape in ((70 + k, 131), (64, 64), (5, 9), (130, 67), (256, 320)):   # the last one has interior (TMA) tiles
         img = rng.random((*shape, 3), dtype=np.float32)
         half = rng.random((k // 2 + 1, k, 3), dtype=np.float32)
         kern = np.concatenate([half[:0:-1], half], axis=0)
