@@ -26,6 +26,7 @@
 
 #include <cmath>
 #include <cstdlib>
+#include <initializer_list>
 #include <vector>
 
 namespace r2f {
@@ -205,6 +206,74 @@ __device__ __forceinline__ float2 *fft_forward(float2 *a, float2 *b, const FftLi
     return src;
 }
 
+// ------------------------------------------------------------------------------------------
+// Compile-time plans.  The generic passes above carry n, Ns, the radix and the group size as run-time
+// values: two thirds of their instructions are index arithmetic (multiplies, a division for non-power-
+// of-two Ns) and the five-way radix dispatch.  For the line lengths of the headline frame sizes the whole
+// plan is a template: strides and twiddle offsets become immediates, the modulo a mask or a constant
+// multiply, and every pass is fully unrolled.  Same arithmetic, same order, same tables.
+// ------------------------------------------------------------------------------------------
+template <int R, int N, int NS, int GS, bool SCALE>
+__device__ __forceinline__ void fft_pass_c(const float2 *__restrict__ src, float2 *__restrict__ dst,
+                                           const float2 *__restrict__ tw, const Group &g,
+                                           const float *__restrict__ scale) {
+    constexpr int NB = N / R;
+    constexpr int ITERS = (NB + GS - 1) / GS;
+#pragma unroll
+    for (int it = 0; it < ITERS; ++it) {
+        const int j = g.tid + it * GS;
+        if ((NB % GS) != 0 && it == ITERS - 1 && j >= NB) break;
+        const int k = (NS & (NS - 1)) == 0 ? (j & (NS - 1)) : (j % NS);
+        float2 v[R];
+#pragma unroll
+        for (int t = 0; t < R; ++t) v[t] = src[j + t * NB];
+        if (NS > 1) {
+#pragma unroll
+            for (int t = 1; t < R; ++t) v[t] = cmul(v[t], __ldg(tw + (t - 1) * NS + k));
+        }
+        butterfly<R>(v);
+        const int j0 = (j - k) * R + k;
+        if (SCALE) {
+#pragma unroll
+            for (int t = 0; t < R; ++t) {
+                const float w = ldg_stream(scale + j0 + t * NS);
+                v[t] = make_float2(v[t].y * w, v[t].x * w);
+            }
+        }
+        if (NS == 1 && (R & 1) == 0) {
+            float4 *d4 = reinterpret_cast<float4 *>(dst + j0);
+#pragma unroll
+            for (int t = 0; t < R / 2; ++t) d4[t] = make_float4(v[2 * t].x, v[2 * t].y, v[2 * t + 1].x, v[2 * t + 1].y);
+        } else {
+#pragma unroll
+            for (int t = 0; t < R; ++t) dst[j0 + t * NS] = v[t];
+        }
+    }
+    group_sync(g);
+}
+
+template <int N, int GS, bool SCALE_LAST, int NS, int TWOFF, int R, int... REST>
+__device__ __forceinline__ float2 *fft_static(float2 *src, float2 *dst, const float2 *__restrict__ tw, const Group &g,
+                                              const float *__restrict__ scale) {
+    constexpr bool last = sizeof...(REST) == 0;
+    fft_pass_c<R, N, NS, GS, SCALE_LAST && last>(src, dst, tw + TWOFF, g, scale);
+    if constexpr (last) return dst;
+    else return fft_static<N, GS, SCALE_LAST, NS * R, TWOFF + (R - 1) * NS, REST...>(dst, src, tw, g, scale);
+}
+
+// PLAN ids (kernel template parameter): 0 = run-time plan.  Keep in sync with static_plan_id() below.
+//   1: n = 6144, 512-thread group, 8 8 8 4 3   (rows, 24 MP)      2: n = 4096, 512, 8 8 8 8      (columns, 24 MP)
+//   3: n = 10240, 1024-thread group, 8 8 8 4 5 (rows, 61 MP)      4: n = 6912, 512, 8 8 4 3 3 3  (columns, 61 MP)
+template <int PLAN, bool SCALE_LAST = false>
+__device__ __forceinline__ float2 *fft_run(float2 *a, float2 *b, const FftLine &L, const Group &g,
+                                           const float *__restrict__ scale = nullptr) {
+    if constexpr (PLAN == 1) return fft_static<6144, 512, SCALE_LAST, 1, 0, 8, 8, 8, 4, 3>(a, b, L.tw, g, scale);
+    else if constexpr (PLAN == 2) return fft_static<4096, 512, SCALE_LAST, 1, 0, 8, 8, 8, 8>(a, b, L.tw, g, scale);
+    else if constexpr (PLAN == 3) return fft_static<10240, 1024, SCALE_LAST, 1, 0, 8, 8, 8, 4, 5>(a, b, L.tw, g, scale);
+    else if constexpr (PLAN == 4) return fft_static<6912, 512, SCALE_LAST, 1, 0, 8, 8, 4, 3, 3, 3>(a, b, L.tw, g, scale);
+    else return fft_forward<SCALE_LAST>(a, b, L, g, scale);
+}
+
 // reflect-101 fill of the r-wide borders of a padded line whose interior [r, r+len) is loaded,
 // and zero fill of the tail [len+2r, n).
 __device__ __forceinline__ void pad_line(float2 *buf, int len, int r, int n, const Group &g) {
@@ -242,7 +311,7 @@ __device__ __forceinline__ Lut2D stage_lut2d(const Lut2D &L, float2 *idle, int c
 // ------------------------------------------------------------------------------------------
 // rows, forward
 // ------------------------------------------------------------------------------------------
-template <int SRC, int ROWS>  // SRC 0: planar planes, 1 + FMT: interleaved frame (kFmt*) through the 2-D LUT
+template <int SRC, int ROWS, int PLAN>  // SRC 0: planar planes, 1 + FMT: interleaved frame (kFmt*) through the 2-D LUT
 __global__ void __launch_bounds__(1024, 1)
 k_fft_rows_fwd(const __grid_constant__ FftConvArgs a) {
     extern __shared__ __align__(16) float2 fsm[];
@@ -311,7 +380,7 @@ k_fft_rows_fwd(const __grid_constant__ FftConvArgs a) {
         group_sync(g);
         pad_line(bufA, W, r, n, g);
         group_sync(g);
-        fft_forward(bufA, bufB, a.row, g);
+        fft_run<PLAN>(bufA, bufB, a.row, g);
     }
     __syncthreads();
     // blocked store: S[(b*H + y)*NC + c]; the NC columns of the CTA's rows are contiguous
@@ -336,6 +405,7 @@ k_fft_rows_fwd(const __grid_constant__ FftConvArgs a) {
 // columns: forward FFT, * Khat, inverse FFT, fused.  NC columns per CTA (one contiguous block of
 // S), a.col_groups thread groups, each with its own ping-pong buffer.
 // ------------------------------------------------------------------------------------------
+template <int PLAN>
 __global__ void __launch_bounds__(1024, 1)
 k_fft_cols(const __grid_constant__ FftConvArgs a) {
     extern __shared__ __align__(16) float2 fsm[];
@@ -385,9 +455,9 @@ k_fft_cols(const __grid_constant__ FftConvArgs a) {
         // forward FFT; its last pass multiplies by the real kernel spectrum and swaps re/im, so the next
         // forward FFT is the inverse
         const float *kh = a.khat + (size_t)(b * NC + c) * n;
-        float2 *spec = fft_forward<true>(home, tmp, a.col, g, kh);
+        float2 *spec = fft_run<PLAN, true>(home, tmp, a.col, g, kh);
         float2 *other = spec == home ? tmp : home;
-        fft_forward(spec, other, a.col, g);  // 2 * nrad passes in total: the result is back in `home`
+        fft_run<PLAN>(spec, other, a.col, g);  // 2 * nrad passes in total: the result is back in `home`
     }
     __syncthreads();
     // keep the swapped form: k_fft_rows_inv consumes swap(x) directly
@@ -407,7 +477,7 @@ k_fft_cols(const __grid_constant__ FftConvArgs a) {
 // ------------------------------------------------------------------------------------------
 // rows, inverse + epilogue
 // ------------------------------------------------------------------------------------------
-template <int SRC, int DENSITY, int ROWS>
+template <int SRC, int DENSITY, int ROWS, int PLAN>
 __global__ void __launch_bounds__(1024, 1)
 k_fft_rows_inv(const __grid_constant__ FftConvArgs a) {
     extern __shared__ __align__(16) float2 fsm[];
@@ -434,7 +504,7 @@ k_fft_rows_inv(const __grid_constant__ FftConvArgs a) {
     __syncthreads();
     if (half >= nrows) return;
     float2 *bufA = fsm + (size_t)half * 2 * n, *bufB = bufA + n;
-    float2 *buf = fft_forward(bufA, bufB, a.row, g);
+    float2 *buf = fft_run<PLAN>(bufA, bufB, a.row, g);
     const size_t ps = a.plane_stride;
     const int y = y0 + half;
     constexpr int FMT = SRC > 0 ? SRC - 1 : 0;
@@ -648,14 +718,32 @@ static cudaError_t set_smem(K kfn, size_t bytes) {
     return cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
 }
 
-template <int ROWS>
+// Compile-time plan matching a line (length, radix sequence) and the thread-group size, or 0.
+static int static_plan_id(const FftLine &l, int group_threads) {
+    auto is = [&](int n, int gs, std::initializer_list<int> rad) {
+        if (l.n != n || group_threads != gs || l.nrad != (int)rad.size()) return false;
+        int i = 0;
+        for (int r : rad)
+            if (l.rad[i++] != r) return false;
+        return true;
+    };
+    static const char *off = getenv("R2F_FFT_STATIC");  // tuning knob: "0" forces the run-time plans
+    if (off && off[0] == '0') return 0;
+    if (is(6144, 512, {8, 8, 8, 4, 3})) return 1;
+    if (is(4096, 512, {8, 8, 8, 8})) return 2;
+    if (is(10240, 1024, {8, 8, 8, 4, 5})) return 3;
+    if (is(6912, 512, {8, 8, 4, 3, 3, 3})) return 4;
+    return 0;
+}
+
+template <int ROWS, int PLAN>
 static cudaError_t launch_rows_fwd(const FftConvArgs &a, int src_mode, int ctas, int threads, size_t smem,
                                    cudaStream_t st) {
     cudaError_t e;
-#define R2F_FWD(M)                                                                 \
-    do {                                                                           \
-        if ((e = set_smem(k_fft_rows_fwd<M, ROWS>, smem)) != cudaSuccess) return e; \
-        k_fft_rows_fwd<M, ROWS><<<ctas, threads, smem, st>>>(a);                   \
+#define R2F_FWD(M)                                                                       \
+    do {                                                                                 \
+        if ((e = set_smem(k_fft_rows_fwd<M, ROWS, PLAN>, smem)) != cudaSuccess) return e; \
+        k_fft_rows_fwd<M, ROWS, PLAN><<<ctas, threads, smem, st>>>(a);                   \
     } while (0)
     switch (src_mode) {
         case 0: R2F_FWD(0); break;
@@ -668,15 +756,20 @@ static cudaError_t launch_rows_fwd(const FftConvArgs &a, int src_mode, int ctas,
     return cudaGetLastError();
 }
 
-template <int ROWS>
+template <int ROWS, int PLAN>
 static cudaError_t launch_rows_inv(const FftConvArgs &a, int src_mode, bool density, int ctas, int threads,
                                    size_t smem, cudaStream_t st) {
     cudaError_t e;
-#define R2F_INV(M, D)                                                                 \
-    do {                                                                              \
-        if ((e = set_smem(k_fft_rows_inv<M, D, ROWS>, smem)) != cudaSuccess) return e; \
-        k_fft_rows_inv<M, D, ROWS><<<ctas, threads, smem, st>>>(a);                   \
+#define R2F_INV(M, D)                                                                       \
+    do {                                                                                    \
+        if ((e = set_smem(k_fft_rows_inv<M, D, ROWS, PLAN>, smem)) != cudaSuccess) return e; \
+        k_fft_rows_inv<M, D, ROWS, PLAN><<<ctas, threads, smem, st>>>(a);                   \
     } while (0)
+    if constexpr (PLAN != 0) {  // compile-time plans are only built for the planar source (the render path's hand-off)
+        if (src_mode != 0) return cudaErrorInvalidValue;
+        if (density) R2F_INV(0, 1);
+        else R2F_INV(0, 0);
+    } else
     switch (src_mode * 2 + (density ? 1 : 0)) {
         case 0: R2F_INV(0, 0); break;
         case 1: R2F_INV(0, 1); break;
@@ -693,21 +786,34 @@ static cudaError_t launch_rows_inv(const FftConvArgs &a, int src_mode, bool dens
     return cudaGetLastError();
 }
 
+template <int PLAN>
+static cudaError_t launch_cols(const FftConvArgs &a, int ctas, size_t smem, cudaStream_t st) {
+    cudaError_t e;
+    if ((e = set_smem(k_fft_cols<PLAN>, smem)) != cudaSuccess) return e;
+    k_fft_cols<PLAN><<<ctas, 1024, smem, st>>>(a);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_fft_conv(const FftConvArgs &a, int src_mode, bool density, cudaStream_t st, int stage) {
     const int rows = rows_per_cta(a.row.n);
     const size_t rs = fft_rows_smem(a.row.n), cs = fft_cols_smem(a.col.n, a.nc, a.col_groups);
     const int row_ctas = (a.H + rows - 1) / rows, col_ctas = a.row.n / a.nc;
     cudaError_t e = cudaSuccess;
     const int t1 = rs <= 100 * 1024 ? 512 : 1024;  // single-row CTAs small enough for two per SM run 512 threads
+    const int row_plan = rows == 1 ? static_plan_id(a.row, t1) : 0;
+    const int col_plan = static_plan_id(a.col, 1024 / a.col_groups);
     if (stage == 0 || stage == 1) {
-        e = rows == 2 ? launch_rows_fwd<2>(a, src_mode, row_ctas, 1024, rs, st)
-                      : launch_rows_fwd<1>(a, src_mode, row_ctas, t1, rs, st);
+        if (rows == 2) e = launch_rows_fwd<2, 0>(a, src_mode, row_ctas, 1024, rs, st);
+        else if (row_plan == 1) e = launch_rows_fwd<1, 1>(a, src_mode, row_ctas, t1, rs, st);
+        else if (row_plan == 3) e = launch_rows_fwd<1, 3>(a, src_mode, row_ctas, t1, rs, st);
+        else e = launch_rows_fwd<1, 0>(a, src_mode, row_ctas, t1, rs, st);
         if (e != cudaSuccess) return e;
     }
     if (stage == 0 || stage == 2) {
-        if ((e = set_smem(k_fft_cols, cs)) != cudaSuccess) return e;
-        k_fft_cols<<<col_ctas, 1024, cs, st>>>(a);
-        if ((e = cudaGetLastError()) != cudaSuccess) return e;
+        if (col_plan == 2) e = launch_cols<2>(a, col_ctas, cs, st);
+        else if (col_plan == 4) e = launch_cols<4>(a, col_ctas, cs, st);
+        else e = launch_cols<0>(a, col_ctas, cs, st);
+        if (e != cudaSuccess) return e;
     }
     if (stage == 0 || stage == 3) {
         FftConvArgs b = a;
@@ -716,8 +822,10 @@ cudaError_t launch_fft_conv(const FftConvArgs &a, int src_mode, bool density, cu
             b.src_planar = a.exp_planar;
             inv_mode = 0;
         }
-        e = rows == 2 ? launch_rows_inv<2>(b, inv_mode, density, row_ctas, 1024, rs, st)
-                      : launch_rows_inv<1>(b, inv_mode, density, row_ctas, t1, rs, st);
+        if (rows == 2) e = launch_rows_inv<2, 0>(b, inv_mode, density, row_ctas, 1024, rs, st);
+        else if (row_plan == 1 && inv_mode == 0) e = launch_rows_inv<1, 1>(b, inv_mode, density, row_ctas, t1, rs, st);
+        else if (row_plan == 3 && inv_mode == 0) e = launch_rows_inv<1, 3>(b, inv_mode, density, row_ctas, t1, rs, st);
+        else e = launch_rows_inv<1, 0>(b, inv_mode, density, row_ctas, t1, rs, st);
     }
     return e;
 }
