@@ -165,6 +165,14 @@ int r2f_chroma_nr(r2f_ctx *ctx, const float *in_dev, int in_channels, float *out
  * The 256-bin post-processing and rasterisation (utils.py:171-223) are host-side (hostops.histogram_image). */
 int r2f_histogram(r2f_ctx *ctx, const uint8_t *img_dev, int H, int W, uint32_t *counts_dev, void *stream);
 
+/* Reduction of calc_exposure (color_processing.py:71-99; called on every decoded frame, raw_conversion.py:51-53;
+ * SURVEY 8f-1): *mean_out (host) = mean over rows 0,2,4,.. and columns 0,2,4,.. of green ** (1 / factor), green
+ * taken from a device frame in either input format (uint16 is divided by 65535 first, raw_conversion.py:51).
+ * Each term is rounded to binary32 like the reference's float32 array; the sum is binary64 in a fixed order.
+ * The caller finishes with exp_comp = log2(ref_exposure / mean ** factor).  Synchronises the stream. */
+int r2f_calc_exposure(r2f_ctx *ctx, const void *in_dev, int in_format, int H, int W, int in_channels, double factor,
+                      double *mean_out, void *stream);
+
 /* add_canvas (effects.py:338-357): fill a canvas_h x canvas_w x 3 uint8 image with (r, g, b) and paste
  * the H x W x 3 render at (off_y, off_x); geometry from get_canvas_data (effects.py:290-335). */
 int r2f_canvas_paste(r2f_ctx *ctx, const uint8_t *src_dev, int H, int W, uint8_t *dst_dev, int canvas_h, int canvas_w,

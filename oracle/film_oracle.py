@@ -496,6 +496,24 @@ def add_canvas(image: np.ndarray, canvas_mode: str, canvas_scale: float = 1.0, c
     canvas[off[0]:off[0] + image.shape[0], off[1]:off[1] + image.shape[1]] = image
     return canvas
 
+# ---- auto exposure (reference color_processing.py:71-99; applied at raw_conversion.py:51-53) ----------
+def calc_exposure(rgb: np.ndarray, ref_exposure: float = 0.18, metadata: dict | None = None) -> float:
+    """Exposure compensation in stops: power mean (exponent 1/factor) of the green samples of every second
+    row and column, against 18 % grey.  `factor` is 3 without EXIF, else sqrt(N^2 / ISO / t) + 1 with N
+    defaulting to f/4 (color_processing.py:78-92).  Same NumPy expressions, same float32 array arithmetic."""
+    lum_mat = rgb[::2, ::2, 1]
+    factor = 3
+    if metadata is not None:
+        if "EXIF:FNumber" in metadata and metadata["EXIF:FNumber"] and metadata["EXIF:FNumber"] != "undef":
+            factor = metadata["EXIF:FNumber"] ** 2 / metadata["EXIF:ISO"] / metadata["EXIF:ExposureTime"]
+        else:
+            factor = 4 ** 2 / metadata["EXIF:ISO"] / metadata["EXIF:ExposureTime"]
+        factor = math.sqrt(factor) + 1
+    log_lum = lum_mat ** (1 / factor)
+    average_exposure = log_lum.mean() ** factor
+    return math.log2(ref_exposure / average_exposure)
+
+
 
 # --------------------------------------------------------------------------------------
 # a1  the whole hot path in the reference's order (cpu_processor.py:363-407)

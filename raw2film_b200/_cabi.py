@@ -17,7 +17,7 @@ EXPORTS = [
     "r2f_set_lut3d", "r2f_set_halation_kernel", "r2f_set_mtf_kernel", "r2f_set_grain", "r2f_set_grain_seed", "r2f_set_option",
     "r2f_set_burn",
     "r2f_workspace_bytes", "r2f_render", "r2f_render_ex", "r2f_render_tap", "r2f_render_tap_ex", "r2f_render_host", "r2f_convolve2d",
-    "r2f_generate_noise", "r2f_chroma_nr", "r2f_histogram", "r2f_canvas_paste", "r2f_launch_count", "r2f_profile_enable", "r2f_profile_read",
+    "r2f_generate_noise", "r2f_chroma_nr", "r2f_histogram", "r2f_calc_exposure", "r2f_canvas_paste", "r2f_launch_count", "r2f_profile_enable", "r2f_profile_read",
 ]
 OPT_CONV_PATH = 1
 OPT_CONV_SYM = 2
@@ -63,6 +63,7 @@ def _load():
         "r2f_generate_noise": (ci, [vp, vp, ci, ci, ci, u64, vp]),
         "r2f_chroma_nr": (ci, [vp, vp, ci, vp, ci, ci, fp, ci, vp, sz, vp]),
         "r2f_histogram": (ci, [vp, vp, ci, ci, vp, vp]),
+        "r2f_calc_exposure": (ci, [vp, vp, ci, ci, ci, ci, cd, ctypes.POINTER(cd), vp]),
         "r2f_canvas_paste": (ci, [vp, vp, ci, ci, vp, ci, ci, ci, ci, ci, ci, ci, vp]),
         "r2f_launch_count": (u64, [vp]),
         "r2f_profile_enable": (ci, [vp, ci]),

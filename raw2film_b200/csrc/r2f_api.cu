@@ -119,6 +119,7 @@ struct r2f_ctx {
     float d_ref = 0.f, burn_strength = 0.f, burn_scale = 50.f;
     DevBuf burn_buf;
     DevBuf cnr_taps;
+    DevBuf expo_buf;  // r2f_calc_exposure: per-CTA partial sums + the result
 
     // r2f_render_host staging
     DevBuf h_in, h_out, h_ws, h_noise;
@@ -991,6 +992,24 @@ int r2f_canvas_paste(r2f_ctx *c, const uint8_t *src_dev, int H, int W, uint8_t *
     CU(launch_canvas_paste(src_dev, H, W, dst_dev, canvas_h, canvas_w, off_y, off_x, r, g, b, c->num_sms,
                            static_cast<cudaStream_t>(stream)));
     c->launches += 1;
+    return R2F_OK;
+}
+
+int r2f_calc_exposure(r2f_ctx *c, const void *in_dev, int in_format, int H, int W, int in_channels, double factor,
+                      double *mean_out, void *stream) {
+    if (!c || !in_dev || !mean_out || H < 1 || W < 1 || (in_channels != 3 && in_channels != 4) || !(factor > 0.0))
+        return fail(R2F_ERR_INVALID, "r2f_calc_exposure: bad arguments");
+    if (in_format != R2F_IN_F32 && in_format != R2F_IN_U16) return fail(R2F_ERR_INVALID, "unknown input format");
+    DeviceGuard guard(c->device);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int fmt = (in_format == R2F_IN_U16 ? 2 : 0) + (in_channels == 4 ? 1 : 0);
+    const int nblocks = c->num_sms * 8;
+    CU(c->expo_buf.ensure((size_t)(nblocks + 1) * sizeof(double)));
+    double *partial = static_cast<double *>(c->expo_buf.p), *out = partial + nblocks;
+    CU(launch_exposure_mean(in_dev, fmt, H, W, 1.0 / factor, partial, nblocks, out, st));
+    c->launches += 2;
+    CU(cudaMemcpyAsync(mean_out, out, sizeof(double), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
     return R2F_OK;
 }
 

@@ -894,4 +894,62 @@ cudaError_t launch_burn_mask(const float *green_plane, int H, int W, int lh, int
     return cudaGetLastError();
 }
 
+// ------------------------------------------------------------------------------------------
+// auto exposure (next row 8f-1; reference color_processing.py:71-99, called from raw_conversion.py:51-53):
+// mean over the green samples of every second row and column of  v ** (1 / factor).
+// Each term is rounded to binary32 like the reference's float32 array power; the terms are summed in
+// binary64 in a fixed order (per-thread stride loop, warp shuffles, one partial per CTA, then one CTA
+// over the partials), so the result is deterministic and at least as accurate as numpy's float32
+// pairwise mean.
+// ------------------------------------------------------------------------------------------
+template <int FMT>
+__global__ void __launch_bounds__(kThreads)
+k_exposure_partial(const void *__restrict__ in, int H, int W, double inv_factor, double *__restrict__ partial) {
+    const int hs = (H + 1) >> 1, wsub = (W + 1) >> 1;
+    const size_t total = (size_t)hs * wsub;
+    const size_t stride = (size_t)gridDim.x * kThreads;
+    constexpr int CIN = InFmt<FMT>::cin;
+    double acc = 0.0;
+    for (size_t sidx = (size_t)blockIdx.x * kThreads + threadIdx.x; sidx < total; sidx += stride) {
+        const int ys = (int)(sidx / wsub), xs = (int)(sidx - (size_t)ys * wsub);
+        const size_t pix = (size_t)(2 * ys) * W + 2 * xs;
+        float g;
+        if (InFmt<FMT>::u16) g = u16_to_linear(static_cast<const uint16_t *>(in)[pix * CIN + 1], 1.0f);
+        else g = static_cast<const float *>(in)[pix * CIN + 1];
+        acc += (double)(float)pow((double)g, inv_factor);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
+    __shared__ double wsum[kThreads / 32];
+    if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int i = 0; i < kThreads / 32; ++i) t += wsum[i];
+        partial[blockIdx.x] = t;
+    }
+}
+
+__global__ void k_exposure_final(const double *__restrict__ partial, int n, double count, double *__restrict__ out) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        double t = 0.0;
+        for (int i = 0; i < n; ++i) t += partial[i];
+        out[0] = t / count;
+    }
+}
+
+cudaError_t launch_exposure_mean(const void *in, int fmt, int H, int W, double inv_factor, double *partial, int nblocks,
+                                 double *out, cudaStream_t st) {
+    const double count = (double)((H + 1) / 2) * (double)((W + 1) / 2);
+    switch (fmt) {
+        case 0: k_exposure_partial<0><<<nblocks, kThreads, 0, st>>>(in, H, W, inv_factor, partial); break;
+        case 1: k_exposure_partial<1><<<nblocks, kThreads, 0, st>>>(in, H, W, inv_factor, partial); break;
+        case 2: k_exposure_partial<2><<<nblocks, kThreads, 0, st>>>(in, H, W, inv_factor, partial); break;
+        case 3: k_exposure_partial<3><<<nblocks, kThreads, 0, st>>>(in, H, W, inv_factor, partial); break;
+        default: return cudaErrorInvalidValue;
+    }
+    k_exposure_final<<<1, 32, 0, st>>>(partial, nblocks, count, out);
+    return cudaGetLastError();
+}
+
 }  // namespace r2f

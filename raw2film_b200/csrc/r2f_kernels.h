@@ -70,6 +70,10 @@ cudaError_t launch_chroma_nr(const float *in, int cin, float *out, int H, int W,
                              float *ws, size_t ps, int num_sms, cudaStream_t st);
 // 3 x 256 histogram counts of a uint8 H x W x 3 image (reference utils.py:158-169)
 cudaError_t launch_histogram(const uint8_t *img, size_t npix, unsigned int *counts_dev, int num_sms, cudaStream_t st);
+// auto exposure: mean of green ** inv_factor over every second row/column (color_processing.py:71-99);
+// `partial` holds nblocks doubles of scratch, `out` one double (device)
+cudaError_t launch_exposure_mean(const void *in, int fmt, int H, int W, double inv_factor, double *partial, int nblocks,
+                                 double *out, cudaStream_t st);
 // canvas border: colour fill + paste (reference effects.py:338-357)
 cudaError_t launch_canvas_paste(const uint8_t *src, int H, int W, uint8_t *dst, int CH, int CW, int off_y, int off_x,
                                 int r, int g, int b, int num_sms, cudaStream_t st);

@@ -6,11 +6,29 @@ also run on the CPU (they belong to the reference's "CPU phase", not to the per-
   (cpu_processor.py:127-134, gpu_processor.py:751-758) and after it (cpu_processor.py:411-412).
 * `canvas_geometry` -- reference effects.py:290-335 (`get_canvas_data`): canvas size, colour and
   paste offset; the paste itself runs on the device (r2f_canvas_paste).
+* `exposure_factor` -- reference color_processing.py:78-92: the EXIF-dependent exponent of the auto-exposure
+  power mean (the reduction itself runs on the device, r2f_calc_exposure).
 """
 from __future__ import annotations
 
+import math
+
 import cv2 as cv
 import numpy as np
+
+
+def exposure_factor(metadata: dict | None) -> float:
+    """Exponent `factor` of calc_exposure (reference color_processing.py:78-92): 3 without metadata, else
+    sqrt(N^2 / ISO / t) + 1 with f-number N (f/4 when EXIF has none), ISO and exposure time t."""
+    factor = 3
+    if metadata is not None:
+        fnum = metadata.get("EXIF:FNumber")
+        if "EXIF:FNumber" in metadata and fnum and fnum != "undef":
+            factor = fnum ** 2 / metadata["EXIF:ISO"] / metadata["EXIF:ExposureTime"]
+        else:
+            factor = 4 ** 2 / metadata["EXIF:ISO"] / metadata["EXIF:ExposureTime"]
+        factor = math.sqrt(factor) + 1
+    return float(factor)
 
 
 def resolution_scaling(image: np.ndarray, resolution) -> np.ndarray:

@@ -16,6 +16,7 @@ processors run them (their "CPU phase"); canvas borders are pasted on the device
 from __future__ import annotations
 
 import ctypes
+import math
 import random
 
 import numpy as np
@@ -248,6 +249,26 @@ class B200Processor:
             result = out.cpu().numpy()
         self._ingest_stream.synchronize()
         return result
+
+    def calc_exposure(self, frame, ref_exposure: float = 0.18, metadata: dict | None = None) -> float:
+        """Exposure compensation in stops of a decoded frame (reference color_processing.py:71-99, applied
+        as `rgb *= 2 ** calc_exposure(rgb, metadata)` right after the decode, raw_conversion.py:51-53).
+
+        `frame`: (H, W, 3|4) float32 or uint16 (uint16 is read as value / 65535), NumPy or a CUDA tensor.
+        The strided power-mean reduction runs on the device; the EXIF-dependent exponent and the final
+        log2 are scalar host arithmetic, same expressions as the reference."""
+        torch = self._torch
+        factor = hostops.exposure_factor(metadata)
+        x = frame if torch.is_tensor(frame) else torch.from_numpy(np.ascontiguousarray(frame))
+        if x.dtype not in (torch.float32, torch.uint16) or x.ndim != 3 or x.shape[2] not in (3, 4):
+            raise ValueError("frame must be (H, W, 3|4) float32 or uint16")
+        with torch.cuda.stream(self.stream):
+            x = x.to(self.device, non_blocking=True).contiguous()
+            mean = ctypes.c_double(0.0)
+            _cabi.check(_cabi.lib.r2f_calc_exposure(
+                self._ctx, x.data_ptr(), _cabi.IN_U16 if x.dtype == torch.uint16 else _cabi.IN_F32, x.shape[0],
+                x.shape[1], x.shape[2], factor, ctypes.byref(mean), self.stream.cuda_stream))
+        return math.log2(ref_exposure / mean.value ** factor)
 
     def histogram_counts(self, image_dev=None):
         """(3, 256) int64 per-channel counts of a uint8 (H, W, 3) CUDA tensor (default: the last render)."""

@@ -15,6 +15,7 @@ Every array named `ref_*` was computed by a reference function:
   raw2film.utils.resolution_scaling         (utils.py:226-244)
   raw2film.effects.chroma_nr_filter         (effects.py:421-561)
   raw2film.utils.generate_histogram         (utils.py:145-223)
+  raw2film.color_processing.calc_exposure   (color_processing.py:71-99)   [`make_golden.py calc_exposure`]
 """
 from __future__ import annotations
 
@@ -155,5 +156,34 @@ def main():
     print("golden vectors written to", HERE)
 
 
+def make_calc_exposure():
+    """calc_exposure (color_processing.py:71-99) on frames ingested like raw_conversion.py:51
+    (uint16 / 65535 in float32), odd and even sizes, with and without EXIF metadata."""
+    load_reference()
+    from raw2film import color_processing  # noqa: E402
+
+    rng = np.random.default_rng(7151)
+    out = {}
+    metas = [None, {"EXIF:FNumber": 2.8, "EXIF:ISO": 400, "EXIF:ExposureTime": 1 / 250},
+             {"EXIF:FNumber": "undef", "EXIF:ISO": 100, "EXIF:ExposureTime": 1 / 30}]
+    out["meta_fnumber"] = np.array([0.0, 2.8, -1.0])       # 0: no metadata, -1: "undef"
+    out["meta_iso"] = np.array([0.0, 400.0, 100.0])
+    out["meta_time"] = np.array([0.0, 1 / 250, 1 / 30])
+    for i, shape in enumerate([(97, 131), (64, 96), (101, 150)]):
+        lum = np.exp(rng.normal(-2.5, 1.2, shape)).clip(0, 1)
+        u16 = (rng.random((*shape, 3)) * 0.5 + 0.5) * lum[..., None] * 65535
+        u16 = u16.astype(np.uint16)
+        u16[:3, :5] = 0                                                 # zeros: 0 ** (1/factor) = 0
+        u16[5, :7] = 65535
+        out[f"u16_{i}"] = u16
+        rgb = u16.astype(np.float32) / 65535.0
+        out[f"ref_exp_{i}"] = np.array([color_processing.calc_exposure(rgb, metadata=m) for m in metas], np.float64)
+    np.savez_compressed(os.path.join(HERE, "calc_exposure.npz"), **out)
+    print("calc_exposure.npz written:", {k: v for k, v in out.items() if k.startswith("ref_")})
+
+
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "calc_exposure":
+        make_calc_exposure()
+    else:
+        main()

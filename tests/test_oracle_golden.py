@@ -74,3 +74,26 @@ def test_chroma_nr_bit_exact():
         n = size * 2 + 1
         assert np.array_equal(fo.gaussian_kernel_1d(n, 0.3 * ((n - 1) * 0.5 - 1) + 0.8), g[f"ref_kernel{size}"])
         assert np.array_equal(fo.chroma_nr_filter(g["xyz"], size), g[f"ref_out{size}"])
+
+
+def _exposure_cases():
+    g = np.load(G + "calc_exposure.npz")
+    metas = []
+    for f, iso, t in zip(g["meta_fnumber"], g["meta_iso"], g["meta_time"]):
+        if iso == 0:
+            metas.append(None)
+        else:
+            metas.append({"EXIF:FNumber": "undef" if f < 0 else float(f), "EXIF:ISO": float(iso),
+                          "EXIF:ExposureTime": float(t)})
+    return g, metas
+
+
+def test_calc_exposure_matches_reference_golden():
+    """calc_exposure (color_processing.py:71-99) on frames ingested like raw_conversion.py:51; the values were
+    produced by the reference function itself.  Same NumPy expressions -> equal to the last bit on the NumPy
+    that minted them; 1e-6 stops of slack for a different libm powf."""
+    g, metas = _exposure_cases()
+    for i in range(3):
+        rgb = g[f"u16_{i}"].astype(np.float32) / np.float32(65535.0)
+        got = [fo.calc_exposure(rgb, metadata=m) for m in metas]
+        assert np.allclose(got, g[f"ref_exp_{i}"], rtol=0, atol=1e-6), (i, got, g[f"ref_exp_{i}"])
