@@ -301,8 +301,9 @@ struct FftGeometry {
 FftGeometry fft_geometry(int H, int W, int k) {
     FftGeometry g;
     const int r = k / 2;
-    g.Wp = fft_good_size(W + 2 * r, 2);
-    g.Hp = fft_good_size(H + 2 * r, 1);
+    // multiples of 16: the line buffers are addressed through a swizzle that permutes whole 16-element rows
+    g.Wp = fft_good_size(W + 2 * r, 16);
+    g.Hp = fft_good_size(H + 2 * r, 16);
     if (!g.Wp || !g.Hp) return g;
     if (fft_rows_smem(g.Wp) > 227 * 1024 || !fft_col_geometry(g.Hp, g.Wp, g.nc, g.groups)) return g;
     // the spectrum scratch must fit in one planar working image (3 planes of float32)

@@ -105,6 +105,13 @@ __device__ __forceinline__ void butterfly<8>(float2 (&v)[8]) {
     v[3] = cadd(e[3], o3);   v[7] = csub(e[3], o3);
 }
 
+// Line buffers are addressed through an XOR swizzle of the 16-byte chunk index: within every 128-byte row of a
+// line (16 float2) the chunk column is XORed with the row number.  Reads of consecutive elements stay
+// conflict-free (a row is only permuted), and the strided stores of the first Stockham passes (a thread
+// writes R consecutive outputs, then runs of Ns = 8) spread over all banks instead of 2 or 4 bank groups.
+// sw(i + m*128) == sw(i) + m*128, which the compile-time plans exploit (one swizzle per butterfly).
+__device__ __forceinline__ int sw(int i) { return i ^ ((i >> 3) & 14); }
+
 __device__ __forceinline__ float pick3(int c, float v0, float v1, float v2) { return c == 0 ? v0 : (c == 1 ? v1 : v2); }
 
 // Streaming global loads that do not allocate in L1 (spectrum blocks and the kernel spectrum are read once;
@@ -146,7 +153,7 @@ __device__ __forceinline__ void fft_pass(const float2 *__restrict__ src, float2 
         const int k = pow2 ? (j & (Ns - 1)) : (j % Ns);
         float2 v[R];
 #pragma unroll
-        for (int t = 0; t < R; ++t) v[t] = src[j + t * nb];
+        for (int t = 0; t < R; ++t) v[t] = src[sw(j + t * nb)];
         if (Ns > 1) {
 #pragma unroll
             for (int t = 1; t < R; ++t) v[t] = cmul(v[t], __ldg(tw + (t - 1) * Ns + k));
@@ -161,12 +168,13 @@ __device__ __forceinline__ void fft_pass(const float2 *__restrict__ src, float2 
             }
         }
         if (Ns == 1 && (R & 1) == 0) {  // R consecutive outputs: 16-byte stores
-            float4 *d4 = reinterpret_cast<float4 *>(dst + j0);
 #pragma unroll
-            for (int t = 0; t < R / 2; ++t) d4[t] = make_float4(v[2 * t].x, v[2 * t].y, v[2 * t + 1].x, v[2 * t + 1].y);
+            for (int t = 0; t < R / 2; ++t)
+                *reinterpret_cast<float4 *>(dst + sw(j0 + 2 * t)) =
+                    make_float4(v[2 * t].x, v[2 * t].y, v[2 * t + 1].x, v[2 * t + 1].y);
         } else {
 #pragma unroll
-            for (int t = 0; t < R; ++t) dst[j0 + t * Ns] = v[t];
+            for (int t = 0; t < R; ++t) dst[sw(j0 + t * Ns)] = v[t];
         }
     }
     group_sync(g);
@@ -226,7 +234,7 @@ __device__ __forceinline__ void fft_pass_c(const float2 *__restrict__ src, float
         const int k = (NS & (NS - 1)) == 0 ? (j & (NS - 1)) : (j % NS);
         float2 v[R];
 #pragma unroll
-        for (int t = 0; t < R; ++t) v[t] = src[j + t * NB];
+        for (int t = 0; t < R; ++t) v[t] = (NB % 128 == 0) ? src[sw(j) + t * NB] : src[sw(j + t * NB)];
         if (NS > 1) {
 #pragma unroll
             for (int t = 1; t < R; ++t) v[t] = cmul(v[t], __ldg(tw + (t - 1) * NS + k));
@@ -241,12 +249,13 @@ __device__ __forceinline__ void fft_pass_c(const float2 *__restrict__ src, float
             }
         }
         if (NS == 1 && (R & 1) == 0) {
-            float4 *d4 = reinterpret_cast<float4 *>(dst + j0);
 #pragma unroll
-            for (int t = 0; t < R / 2; ++t) d4[t] = make_float4(v[2 * t].x, v[2 * t].y, v[2 * t + 1].x, v[2 * t + 1].y);
+            for (int t = 0; t < R / 2; ++t)
+                *reinterpret_cast<float4 *>(dst + sw(j0 + 2 * t)) =
+                    make_float4(v[2 * t].x, v[2 * t].y, v[2 * t + 1].x, v[2 * t + 1].y);
         } else {
 #pragma unroll
-            for (int t = 0; t < R; ++t) dst[j0 + t * NS] = v[t];
+            for (int t = 0; t < R; ++t) dst[(NS % 128 == 0) ? sw(j0) + t * NS : sw(j0 + t * NS)] = v[t];
         }
     }
     group_sync(g);
@@ -278,10 +287,10 @@ __device__ __forceinline__ float2 *fft_run(float2 *a, float2 *b, const FftLine &
 // and zero fill of the tail [len+2r, n).
 __device__ __forceinline__ void pad_line(float2 *buf, int len, int r, int n, const Group &g) {
     for (int p = g.tid; p < r; p += g.size) {
-        buf[p] = buf[r + reflect101(p - r, len)];
-        buf[r + len + p] = buf[r + reflect101(len + p, len)];
+        buf[sw(p)] = buf[sw(r + reflect101(p - r, len))];
+        buf[sw(r + len + p)] = buf[sw(r + reflect101(len + p, len))];
     }
-    for (int p = len + 2 * r + g.tid; p < n; p += g.size) buf[p] = make_float2(0.f, 0.f);
+    for (int p = len + 2 * r + g.tid; p < n; p += g.size) buf[sw(p)] = make_float2(0.f, 0.f);
 }
 
 // Row kernels: ROWS image rows per CTA, one thread group per row (ROWS == 2: two 512-thread groups
@@ -327,7 +336,7 @@ k_fft_rows_fwd(const __grid_constant__ FftConvArgs a) {
         if (SRC == 0) {
             for (int x = g.tid; x < W; x += g.size) {
                 const size_t idx = (size_t)y * W + x;
-                bufA[r + x] = make_float2(a.src_planar[(size_t)a.chan[0] * a.plane_stride + idx],
+                bufA[sw(r + x)] = make_float2(a.src_planar[(size_t)a.chan[0] * a.plane_stride + idx],
                                           a.src_planar[(size_t)a.chan[1] * a.plane_stride + idx]);
             }
         } else {
@@ -350,7 +359,7 @@ k_fft_rows_fwd(const __grid_constant__ FftConvArgs a) {
 #pragma unroll
                             for (int i = 0; i < 4; ++i) {
                                 lut2d_eval(l2, px[u][i][0], px[u][i][1], px[u][i][2], e[0][i], e[1][i], e[2][i]);
-                                bufA[r + 4 * qx + i] = make_float2(pick3(a.chan[0], e[0][i], e[1][i], e[2][i]),
+                                bufA[sw(r + 4 * qx + i)] = make_float2(pick3(a.chan[0], e[0][i], e[1][i], e[2][i]),
                                                                    pick3(a.chan[1], e[0][i], e[1][i], e[2][i]));
                             }
                             if (a.exp_planar != nullptr) {
@@ -367,7 +376,7 @@ k_fft_rows_fwd(const __grid_constant__ FftConvArgs a) {
                     float X, Y, Z, e0, e1, e2;
                     load_px<FMT>(a.src_xyz, (size_t)y * W + x, a.gain, X, Y, Z);
                     lut2d_eval(l2, X, Y, Z, e0, e1, e2);
-                    bufA[r + x] = make_float2(pick3(a.chan[0], e0, e1, e2), pick3(a.chan[1], e0, e1, e2));
+                    bufA[sw(r + x)] = make_float2(pick3(a.chan[0], e0, e1, e2), pick3(a.chan[1], e0, e1, e2));
                     if (a.exp_planar != nullptr) {
                         const size_t idx = (size_t)y * W + x;
                         a.exp_planar[idx] = e0;
@@ -388,14 +397,15 @@ k_fft_rows_fwd(const __grid_constant__ FftConvArgs a) {
     const int nblk = n / NC;
     for (int b = threadIdx.x; b < nblk; b += blockDim.x) {  // one column block per thread: no div/mod
         for (int row = 0; row < nrows; ++row) {
-            const float2 *sp = fsm + (size_t)row * 2 * n + res_off + b * NC;
+            const float2 *line = fsm + (size_t)row * 2 * n + res_off;
             float2 *dp = a.S + ((size_t)b * H + (y0 + row)) * NC;
             if (NC == 4) {
-                const float4 lo = *reinterpret_cast<const float4 *>(sp), hi = *reinterpret_cast<const float4 *>(sp + 2);
+                const float4 lo = *reinterpret_cast<const float4 *>(line + sw(4 * b));
+                const float4 hi = *reinterpret_cast<const float4 *>(line + sw(4 * b + 2));
                 *reinterpret_cast<float4 *>(dp) = lo;
                 *reinterpret_cast<float4 *>(dp + 2) = hi;
             } else {
-                for (int c = 0; c < NC; ++c) dp[c] = sp[c];
+                for (int c = 0; c < NC; ++c) dp[c] = line[sw(b * NC + c)];
             }
         }
     }
@@ -430,17 +440,18 @@ k_fft_cols(const __grid_constant__ FftConvArgs a) {
             for (int u = 0; u < U; ++u) {
                 const int y = y0 + u * blockDim.x;
                 if (y < H) {
-                    fsm[r + y] = make_float2(lo[u].x, lo[u].y);
-                    fsm[(size_t)pitch + r + y] = make_float2(lo[u].z, lo[u].w);
-                    fsm[(size_t)2 * pitch + r + y] = make_float2(hi[u].x, hi[u].y);
-                    fsm[(size_t)3 * pitch + r + y] = make_float2(hi[u].z, hi[u].w);
+                    const int e = sw(r + y);
+                    fsm[e] = make_float2(lo[u].x, lo[u].y);
+                    fsm[(size_t)pitch + e] = make_float2(lo[u].z, lo[u].w);
+                    fsm[(size_t)2 * pitch + e] = make_float2(hi[u].x, hi[u].y);
+                    fsm[(size_t)3 * pitch + e] = make_float2(hi[u].z, hi[u].w);
                 }
             }
         }
     } else {
         for (int y = threadIdx.x; y < H; y += blockDim.x) {
             const float2 *sp = blk + (size_t)y * NC;
-            for (int c = 0; c < NC; ++c) fsm[(size_t)c * pitch + r + y] = sp[c];
+            for (int c = 0; c < NC; ++c) fsm[(size_t)c * pitch + sw(r + y)] = sp[c];
         }
     }
     __syncthreads();
@@ -464,12 +475,13 @@ k_fft_cols(const __grid_constant__ FftConvArgs a) {
     for (int y = threadIdx.x; y < H; y += blockDim.x) {
         float2 *dp = blk + (size_t)y * NC;
         if (NC == 4) {
-            const float2 c0 = fsm[r + y], c1 = fsm[(size_t)pitch + r + y];
-            const float2 c2 = fsm[(size_t)2 * pitch + r + y], c3 = fsm[(size_t)3 * pitch + r + y];
+            const int e = sw(r + y);
+            const float2 c0 = fsm[e], c1 = fsm[(size_t)pitch + e];
+            const float2 c2 = fsm[(size_t)2 * pitch + e], c3 = fsm[(size_t)3 * pitch + e];
             *reinterpret_cast<float4 *>(dp) = make_float4(c0.x, c0.y, c1.x, c1.y);
             *reinterpret_cast<float4 *>(dp + 2) = make_float4(c2.x, c2.y, c3.x, c3.y);
         } else {
-            for (int c = 0; c < NC; ++c) dp[c] = fsm[(size_t)c * pitch + r + y];
+            for (int c = 0; c < NC; ++c) dp[c] = fsm[(size_t)c * pitch + sw(r + y)];
         }
     }
 }
@@ -491,12 +503,12 @@ k_fft_rows_inv(const __grid_constant__ FftConvArgs a) {
     for (int b = threadIdx.x; b < nblk; b += blockDim.x) {
         for (int row = 0; row < nrows; ++row) {
             const float2 *sp = a.S + ((size_t)b * H + (y0 + row)) * NC;
-            float2 *dp = fsm + (size_t)row * 2 * n + b * NC;
+            float2 *line = fsm + (size_t)row * 2 * n;
             if (NC == 4) {
-                cp_async_16(reinterpret_cast<float *>(dp), reinterpret_cast<const float *>(sp));
-                cp_async_16(reinterpret_cast<float *>(dp + 2), reinterpret_cast<const float *>(sp + 2));
+                cp_async_16(reinterpret_cast<float *>(line + sw(4 * b)), reinterpret_cast<const float *>(sp));
+                cp_async_16(reinterpret_cast<float *>(line + sw(4 * b + 2)), reinterpret_cast<const float *>(sp + 2));
             } else {
-                for (int c = 0; c < NC; ++c) dp[c] = sp[c];
+                for (int c = 0; c < NC; ++c) line[sw(b * NC + c)] = sp[c];
             }
         }
     }
@@ -545,7 +557,7 @@ k_fft_rows_inv(const __grid_constant__ FftConvArgs a) {
                 } else {
                     src[0] = px[i][0]; src[1] = px[i][1]; src[2] = px[i][2];
                 }
-                finish_px(src, buf[r + 4 * qx + i], out);
+                finish_px(src, buf[sw(r + 4 * qx + i)], out);
                 res[0][i] = out[0]; res[1][i] = out[1]; res[2][i] = out[2];
             }
 #pragma unroll
@@ -565,7 +577,7 @@ k_fft_rows_inv(const __grid_constant__ FftConvArgs a) {
                 load_px<FMT>(a.src_xyz, idx, a.gain, X, Y, Z);
                 lut2d_eval(l2, X, Y, Z, src[0], src[1], src[2]);
             }
-            finish_px(src, buf[r + x], out);
+            finish_px(src, buf[sw(r + x)], out);
 #pragma unroll
             for (int c = 0; c < 3; ++c) a.dst_planar[c * ps + idx] = out[c];
         }
