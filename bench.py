@@ -356,14 +356,20 @@ def main():
                         "share_of_step": kernels[dom]["ms"] * kernels[dom]["launches_per_step"] / (ms_total / args.steps),
                         "step_alg_gbs": ALG_BYTES_PER_PX[args.config] * H * W / (ms_total / args.steps * 1e-3) / 1e9,
                         "step_frac": ALG_BYTES_PER_PX[args.config] * H * W / (ms_total / args.steps * 1e-3) / 1e9 / peak}
-            if dom in ("halation", "mtf"):
-                k = {"halation": proc.halation_kernel, "mtf": proc.mtf_kernel}.get(dom)
-                if k is not None:
+            # direct correlations are FP32 bound: report their algorithmic flop rate (2*k*k per px and filtered layer)
+            for name in ("halation", "mtf"):
+                k = {"halation": proc.halation_kernel, "mtf": proc.mtf_kernel}.get(name)
+                if name in kernels and k is not None:
                     taps = sum(int(np.count_nonzero(k[..., c])) > 1 for c in range(3)) * k.shape[0] * k.shape[1]
-                    roofline["fp32_tflops"] = 2.0 * taps * H * W / (kernels[dom]["ms"] * 1e-3) / 1e12
-                    roofline["note"] = ("direct 2-D correlation is FP32-FMA bound, not HBM bound (SURVEY 8d); fp32_tflops "
-                                        "counts the algorithmic 2*k*k flops/px/layer, the y-symmetric kernel executes "
-                                        "about half of them")
+                    kernels[name]["alg_fp32_tflops"] = 2.0 * taps * H * W / (kernels[name]["ms"] * 1e-3) / 1e12
+            if dom in ("halation", "mtf") and "alg_fp32_tflops" in kernels[dom]:
+                roofline["fp32_tflops"] = kernels[dom]["alg_fp32_tflops"]
+                roofline["note"] = ("direct 2-D correlation is FP32-FMA bound, not HBM bound (SURVEY 8d); fp32_tflops "
+                                    "counts the algorithmic 2*k*k flops/px/layer, the y-symmetric kernel executes "
+                                    "about half of them")
+            elif dom == "grain":
+                roofline["note"] = ("fused grain + tetrahedral LUT + quantise: ~470 instructions per pixel for 15 B/px, "
+                                    "bound by instruction issue and L1TEX, not HBM (profiles/)")
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
             from oracle import film_oracle as fo
