@@ -706,7 +706,8 @@ int r2f_destroy(r2f_ctx *c) {
     DeviceGuard guard(c->device);
     for (DevBuf *b : {&c->lut2d, &c->curve, &c->lut3d, &c->hal.buf, &c->mtf.buf, &c->grain.buf, &c->gcurve,
                       &c->burn_buf, &c->h_in, &c->h_out, &c->h_ws, &c->h_noise, &c->hal.base, &c->mtf.base,
-                      &c->grain.base, &c->khat, &c->khat_scratch, &c->cnr_taps})
+                      &c->grain.base, &c->khat, &c->khat_scratch, &c->cnr_taps, &c->hal.symbuf, &c->mtf.symbuf,
+                      &c->grain.symbuf, &c->expo_buf})
         b->release();
     for (auto &kv : c->fft_lines) {
         kv.second->roots.release();

@@ -69,8 +69,11 @@ k_grain_finish_sym(GrainFinishArgs a) {
             __syncthreads();  // the previous channel's window reads are done
             if (GEN) {
                 if (interior) {  // one Philox call per aligned quad of four samples
+                    // idx / nq by a reciprocal multiply (nq is CTA-uniform, idx < 2^16): exact, and ~20
+                    // instructions cheaper per quad than the generic division
+                    const unsigned magic = 0xffffffffu / (unsigned)nq + 1u;
                     for (int idx = threadIdx.x; idx < C::ROWS * nq; idx += C::NT) {
-                        const int ty = idx / nq, tq = idx - ty * nq;
+                        const int ty = (int)__umulhi((unsigned)idx, magic), tq = idx - ty * nq;
                         const int gy = reflect101(ty0 - C::R + ty, H);
                         const float4 v = noise_quad((uint32_t)(q0 + tq), gy, c, a.seed_lo, a.seed_hi);
                         const float vals[4] = {v.x, v.y, v.z, v.w};
