@@ -77,7 +77,7 @@ struct KernelSet {
 // device copies of the per-length FFT tables
 struct FftLineDev {
     FftLineHost host;
-    DevBuf roots, cosines;
+    DevBuf roots, cosines, roots_ip, perm;
     FftLine line() const {
         FftLine l{};
         l.n = host.n;
@@ -87,6 +87,7 @@ struct FftLineDev {
             l.tw_off[i] = host.tw_off[i];
         }
         l.tw = static_cast<const float2 *>(roots.p);
+        l.tw_ip = static_cast<const float2 *>(roots_ip.p);
         return l;
     }
 };
@@ -130,6 +131,7 @@ struct r2f_ctx {
     DevBuf khat, khat_scratch;
     uint64_t khat_generation = 0;
     int khat_hp = 0, khat_wp = 0;
+    bool khat_permuted = false;
     int conv_path = 0;  // R2F_OPT_CONV_PATH: 0 auto, 1 direct, 2 fft
     int conv_sym = 1;   // R2F_OPT_CONV_SYM: 1 = y-symmetric kernels take the packed-FMA kernel
 
@@ -295,6 +297,7 @@ FftLineDev *fft_line_for(r2f_ctx *c, int n);
 
 struct FftGeometry {
     int Hp = 0, Wp = 0, nc = 0, groups = 0;
+    bool inplace = false;  // in-place column kernel: four columns per CTA, one thread group each
     bool ok = false;
 };
 
@@ -305,7 +308,14 @@ FftGeometry fft_geometry(int H, int W, int k) {
     g.Wp = fft_good_size(W + 2 * r, 16);
     g.Hp = fft_good_size(H + 2 * r, 16);
     if (!g.Wp || !g.Hp) return g;
-    if (fft_rows_smem(g.Wp) > 227 * 1024 || !fft_col_geometry(g.Hp, g.Wp, g.nc, g.groups)) return g;
+    if (fft_rows_smem(g.Wp) > 227 * 1024) return g;
+    if (g.Wp % 4 == 0 && fft_cols_inplace_available(g.Hp) && fft_cols_inplace_smem(g.Hp) <= 227 * 1024) {
+        g.nc = 4;
+        g.groups = 4;
+        g.inplace = true;
+    } else if (!fft_col_geometry(g.Hp, g.Wp, g.nc, g.groups)) {
+        return g;
+    }
     // the spectrum scratch must fit in one planar working image (3 planes of float32)
     if ((size_t)g.Wp * H * sizeof(float2) > plane_stride_for(H, W) * 3 * sizeof(float)) return g;
     g.ok = true;
@@ -319,6 +329,8 @@ FftLineDev *fft_line_for(r2f_ctx *c, int n) {
     std::unique_ptr<FftLineDev> d(new FftLineDev());
     if (!fft_make_line(n, d->host)) return nullptr;
     if (upload(d->roots, d->host.roots.data(), d->host.roots.size() * sizeof(float2)) != R2F_OK) return nullptr;
+    if (upload(d->roots_ip, d->host.roots_ip.data(), d->host.roots_ip.size() * sizeof(float2)) != R2F_OK) return nullptr;
+    if (upload(d->perm, d->host.perm.data(), d->host.perm.size() * sizeof(int)) != R2F_OK) return nullptr;
     if (upload(d->cosines, d->host.cosines.data(), d->host.cosines.size() * sizeof(double)) != R2F_OK) return nullptr;
     FftLineDev *raw = d.get();
     c->fft_lines[n] = std::move(d);
@@ -329,16 +341,19 @@ FftLineDev *fft_line_for(r2f_ctx *c, int n) {
 int fft_prepare(r2f_ctx *c, const KernelSet &ks, int H, int W, const FftGeometry &g, FftConvArgs &a, cudaStream_t st) {
     FftLineDev *row = fft_line_for(c, g.Wp), *col = fft_line_for(c, g.Hp);
     if (!row || !col) return fail(R2F_ERR_INVALID, "FFT plan construction failed");
-    if (c->khat_generation != ks.generation || c->khat_hp != g.Hp || c->khat_wp != g.Wp || !c->khat.p) {
+    if (c->khat_generation != ks.generation || c->khat_hp != g.Hp || c->khat_wp != g.Wp || !c->khat.p ||
+        c->khat_permuted != g.inplace) {
         CU(c->khat.ensure((size_t)g.Hp * g.Wp * sizeof(float)));
         CU(c->khat_scratch.ensure((size_t)ks.k * g.Wp * sizeof(double)));
         CU(launch_khat(static_cast<const float *>(ks.base.p), ks.k, g.Hp, g.Wp,
                        static_cast<const double *>(col->cosines.p), static_cast<const double *>(row->cosines.p),
-                       static_cast<double *>(c->khat_scratch.p), static_cast<float *>(c->khat.p), st));
+                       static_cast<double *>(c->khat_scratch.p), static_cast<float *>(c->khat.p),
+                       g.inplace ? static_cast<const int *>(col->perm.p) : nullptr, st));
         c->launches += 2;
         c->khat_generation = ks.generation;
         c->khat_hp = g.Hp;
         c->khat_wp = g.Wp;
+        c->khat_permuted = g.inplace;
     }
     a.H = H;
     a.W = W;
@@ -347,6 +362,7 @@ int fft_prepare(r2f_ctx *c, const KernelSet &ks, int H, int W, const FftGeometry
     a.col = col->line();
     a.nc = g.nc;
     a.col_groups = g.groups;
+    a.col_inplace = g.inplace ? 1 : 0;
     a.khat = static_cast<const float *>(c->khat.p);
     for (int i = 0; i < 2; ++i) {
         a.chan[i] = ks.fft_chan[i];
@@ -711,6 +727,8 @@ int r2f_destroy(r2f_ctx *c) {
         b->release();
     for (auto &kv : c->fft_lines) {
         kv.second->roots.release();
+        kv.second->roots_ip.release();
+        kv.second->perm.release();
         kv.second->cosines.release();
     }
     if (c->host_stream) cudaStreamDestroy(c->host_stream);

@@ -283,6 +283,97 @@ __device__ __forceinline__ float2 *fft_run(float2 *a, float2 *b, const FftLine &
     else return fft_forward<SCALE_LAST>(a, b, L, g, scale);
 }
 
+// ------------------------------------------------------------------------------------------
+// In-place passes for the column kernel: forward decimation-in-frequency (natural order in, mixed-radix digit-
+// reversed order out), product with the (equally permuted) kernel spectrum, inverse as a forward decimation-in-
+// time transform of the re/im-swapped data (digit-reversed in, natural out).  No ping-pong partner: a column
+// needs n float2 of shared memory instead of 2n, so all four columns of a block are transformed concurrently by
+// four 256-thread groups.  The innermost radix of the forward transform, the product and the innermost radix of
+// the inverse touch the same R contiguous elements and are fused in registers (ip_mid).
+// ------------------------------------------------------------------------------------------
+template <int R, int N, int B, int GS, bool DIT>
+__device__ __forceinline__ void ip_pass(float2 *__restrict__ x, const float2 *__restrict__ tw, const Group &g) {
+    constexpr int S = B / R, NB = N / R;
+    constexpr int ITERS = (NB + GS - 1) / GS;
+    static_assert(S > 1, "the innermost pass is ip_mid");
+#pragma unroll 1   // one butterfly's data live at a time: the 1024-thread CTA caps a thread at 64 registers
+    for (int it = 0; it < ITERS; ++it) {
+        const int j = g.tid + it * GS;
+        if ((NB % GS) != 0 && it == ITERS - 1 && j >= NB) break;
+        const int blk = j / S, k = j - blk * S;
+        const int base = blk * B + k;
+        float2 v[R];
+#pragma unroll
+        for (int t = 0; t < R; ++t) v[t] = (S % 128 == 0) ? x[sw(base) + t * S] : x[sw(base + t * S)];
+        if (DIT) {
+#pragma unroll
+            for (int t = 1; t < R; ++t) v[t] = cmul(v[t], __ldg(tw + (t - 1) * S + k));
+        }
+        butterfly<R>(v);
+        if (!DIT) {
+#pragma unroll
+            for (int t = 1; t < R; ++t) v[t] = cmul(v[t], __ldg(tw + (t - 1) * S + k));
+        }
+#pragma unroll
+        for (int t = 0; t < R; ++t) x[(S % 128 == 0) ? sw(base) + t * S : sw(base + t * S)] = v[t];
+    }
+    group_sync(g);
+}
+
+template <int R, int N, int GS>
+__device__ __forceinline__ void ip_mid(float2 *__restrict__ x, const float *__restrict__ kh, const Group &g) {
+    constexpr int NB = N / R;
+    constexpr int ITERS = (NB + GS - 1) / GS;
+#pragma unroll 1   // one butterfly's data live at a time: the 1024-thread CTA caps a thread at 64 registers
+    for (int it = 0; it < ITERS; ++it) {
+        const int j = g.tid + it * GS;
+        if ((NB % GS) != 0 && it == ITERS - 1 && j >= NB) break;
+        const int base = j * R;
+        float2 v[R];
+        if ((R & 1) == 0) {
+#pragma unroll
+            for (int t = 0; t < R / 2; ++t) {
+                const float4 q = *reinterpret_cast<const float4 *>(x + sw(base + 2 * t));
+                v[2 * t] = make_float2(q.x, q.y);
+                v[2 * t + 1] = make_float2(q.z, q.w);
+            }
+        } else {
+#pragma unroll
+            for (int t = 0; t < R; ++t) v[t] = x[sw(base + t)];
+        }
+        butterfly<R>(v);  // innermost forward radix (stride 1: no twiddles)
+#pragma unroll
+        for (int t = 0; t < R; ++t) {  // x Khat, swap re/im: the following forward passes compute the inverse
+            const float w = ldg_stream(kh + base + t);
+            v[t] = make_float2(v[t].y * w, v[t].x * w);
+        }
+        butterfly<R>(v);  // innermost radix of the inverse
+        if ((R & 1) == 0) {
+#pragma unroll
+            for (int t = 0; t < R / 2; ++t)
+                *reinterpret_cast<float4 *>(x + sw(base + 2 * t)) =
+                    make_float4(v[2 * t].x, v[2 * t].y, v[2 * t + 1].x, v[2 * t + 1].y);
+        } else {
+#pragma unroll
+            for (int t = 0; t < R; ++t) x[sw(base + t)] = v[t];
+        }
+    }
+    group_sync(g);
+}
+
+template <int N, int B, int GS, int TWOFF, int R, int... REST>
+__device__ __forceinline__ void ip_conv(float2 *__restrict__ x, const float2 *__restrict__ tw,
+                                        const float *__restrict__ kh, const Group &g) {
+    if constexpr (sizeof...(REST) == 0) {
+        static_assert(B == R, "radices must multiply to N");
+        ip_mid<R, N, GS>(x, kh, g);
+    } else {
+        ip_pass<R, N, B, GS, false>(x, tw + TWOFF, g);
+        ip_conv<N, B / R, GS, TWOFF + (R - 1) * (B / R), REST...>(x, tw, kh, g);
+        ip_pass<R, N, B, GS, true>(x, tw + TWOFF, g);
+    }
+}
+
 // reflect-101 fill of the r-wide borders of a padded line whose interior [r, r+len) is loaded,
 // and zero fill of the tail [len+2r, n).
 __device__ __forceinline__ void pad_line(float2 *buf, int len, int r, int n, const Group &g) {
@@ -486,6 +577,63 @@ k_fft_cols(const __grid_constant__ FftConvArgs a) {
     }
 }
 
+// In-place variant (compile-time plans only): four 256-thread groups, one column each, n float2 per column.
+// IPLAN 1: n = 4096 (8 8 8 8), IPLAN 2: n = 6912 (8 8 4 3 3 3); a.khat rows are permuted by the line's perm[].
+template <int IPLAN>
+__global__ void __launch_bounds__(1024, 1)
+k_fft_cols_ip(const __grid_constant__ FftConvArgs a) {
+    extern __shared__ __align__(16) float2 fsm[];
+    constexpr int n = IPLAN == 1 ? 4096 : 6912;
+    constexpr int GS = 256;
+    const int H = a.H, r = a.r;
+    const int b = blockIdx.x;
+    float2 *blk = a.S + (size_t)b * H * 4;
+    {
+        constexpr int U = 4;
+        for (int y0 = threadIdx.x; y0 < H; y0 += U * blockDim.x) {
+            float4 lo[U], hi[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int y = y0 + u * blockDim.x;
+                if (y < H) {
+                    const float2 *sp = blk + (size_t)y * 4;
+                    lo[u] = ldg_stream4(reinterpret_cast<const float4 *>(sp));
+                    hi[u] = ldg_stream4(reinterpret_cast<const float4 *>(sp + 2));
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int y = y0 + u * blockDim.x;
+                if (y < H) {
+                    const int e = sw(r + y);
+                    fsm[e] = make_float2(lo[u].x, lo[u].y);
+                    fsm[n + e] = make_float2(lo[u].z, lo[u].w);
+                    fsm[2 * n + e] = make_float2(hi[u].x, hi[u].y);
+                    fsm[3 * n + e] = make_float2(hi[u].z, hi[u].w);
+                }
+            }
+        }
+    }
+    __syncthreads();
+    const int gi = (int)threadIdx.x / GS;
+    const Group g{(int)threadIdx.x % GS, GS, 1 + gi};
+    float2 *home = fsm + (size_t)gi * n;
+    pad_line(home, H, r, n, g);
+    group_sync(g);
+    const float *kh = a.khat + (size_t)(b * 4 + gi) * n;
+    if constexpr (IPLAN == 1) ip_conv<4096, 4096, GS, 0, 8, 8, 8, 8>(home, a.col.tw_ip, kh, g);
+    else ip_conv<6912, 6912, GS, 0, 8, 8, 4, 3, 3, 3>(home, a.col.tw_ip, kh, g);
+    __syncthreads();
+    // keep the swapped form: k_fft_rows_inv consumes swap(x) directly
+    for (int y = threadIdx.x; y < H; y += blockDim.x) {
+        float2 *dp = blk + (size_t)y * 4;
+        const int e = sw(r + y);
+        const float2 c0 = fsm[e], c1 = fsm[n + e], c2 = fsm[2 * n + e], c3 = fsm[3 * n + e];
+        *reinterpret_cast<float4 *>(dp) = make_float4(c0.x, c0.y, c1.x, c1.y);
+        *reinterpret_cast<float4 *>(dp + 2) = make_float4(c2.x, c2.y, c3.x, c3.y);
+    }
+}
+
 // ------------------------------------------------------------------------------------------
 // rows, inverse + epilogue
 // ------------------------------------------------------------------------------------------
@@ -606,7 +754,7 @@ __global__ void k_khat_stage1(const float *__restrict__ kern /* k x k base */, i
 }
 
 __global__ void k_khat_stage2(const double *__restrict__ A, int k, int Hp, int Wp, const double *__restrict__ cosH,
-                              double norm, float *__restrict__ khat /* [Wp][Hp] */) {
+                              double norm, float *__restrict__ khat /* [Wp][Hp] */, const int *__restrict__ perm) {
     const int u = blockIdx.x * blockDim.x + threadIdx.x;
     const int v = blockIdx.y;
     if (u >= Hp) return;
@@ -617,7 +765,7 @@ __global__ void k_khat_stage2(const double *__restrict__ A, int k, int Hp, int W
         const long long q = ((long long)u * (di < 0 ? -di : di)) % Hp;
         acc = fma(A[(size_t)i * Wp + v], cosH[q], acc);
     }
-    khat[(size_t)v * Hp + u] = (float)(acc * norm);
+    khat[(size_t)v * Hp + (perm ? perm[u] : u)] = (float)(acc * norm);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -681,8 +829,48 @@ bool fft_make_line(int n, FftLineHost &out) {
             }
         Ns *= R;
     }
+    // in-place passes: block B, stride S = B / R, entry (t-1)*S + k = exp(-2 pi i t k / B); the innermost pass
+    // (S = 1) has no twiddles
+    out.roots_ip.clear();
+    int B = n;
+    for (int R : rad) {
+        const int S = B / R;
+        if (S > 1)
+            for (int t = 1; t < R; ++t)
+                for (int k = 0; k < S; ++k) {
+                    const double ang = two_pi * (double)t * (double)k / (double)B;
+                    out.roots_ip.push_back(make_float2((float)std::cos(ang), (float)(-std::sin(ang))));
+                }
+        B = S;
+    }
+    if (out.roots_ip.empty()) out.roots_ip.push_back(make_float2(1.f, 0.f));
+    // X[k] with k = k1 + R1 k2 + R1 R2 k3 + ... ends at position k1 n/R1 + k2 n/(R1 R2) + ...
+    out.perm.resize(n);
+    for (int k = 0; k < n; ++k) {
+        int kk = k, pos = 0, blk = n;
+        for (int R : rad) {
+            blk /= R;
+            pos += (kk % R) * blk;
+            kk /= R;
+        }
+        out.perm[k] = pos;
+    }
     return true;
 }
+
+static int inplace_plan_id(const FftLineHost &l) {
+    static const char *off = getenv("R2F_FFT_INPLACE");  // tuning knob: "0" keeps the ping-pong column kernel
+    if (off && off[0] == '0') return 0;
+    if (l.n == 4096 && l.rad == std::vector<int>{8, 8, 8, 8}) return 1;
+    if (l.n == 6912 && l.rad == std::vector<int>{8, 8, 4, 3, 3, 3}) return 2;
+    return 0;
+}
+bool fft_cols_inplace_available(int Hp) {
+    FftLineHost l;
+    l.n = Hp;
+    return factor_235(Hp, l.rad) && inplace_plan_id(l) != 0;
+}
+size_t fft_cols_inplace_smem(int Hp) { return (size_t)4 * Hp * sizeof(float2); }
 
 constexpr size_t kFftMaxSmem = 227 * 1024;
 
@@ -717,11 +905,13 @@ bool fft_col_geometry(int Hp, int Wp, int &nc, int &groups) {
 }
 
 cudaError_t launch_khat(const float *base_kernel_dev, int k, int Hp, int Wp, const double *cosH_dev,
-                        const double *cosW_dev, double *scratchA_dev, float *khat_dev, cudaStream_t st) {
+                        const double *cosW_dev, double *scratchA_dev, float *khat_dev, const int *perm_dev,
+                        cudaStream_t st) {
     dim3 g1((Wp + 255) / 256, k);
     k_khat_stage1<<<g1, 256, 0, st>>>(base_kernel_dev, k, Wp, cosW_dev, scratchA_dev);
     dim3 g2((Hp + 255) / 256, Wp);
-    k_khat_stage2<<<g2, 256, 0, st>>>(scratchA_dev, k, Hp, Wp, cosH_dev, 1.0 / ((double)Hp * (double)Wp), khat_dev);
+    k_khat_stage2<<<g2, 256, 0, st>>>(scratchA_dev, k, Hp, Wp, cosH_dev, 1.0 / ((double)Hp * (double)Wp), khat_dev,
+                                      perm_dev);
     return cudaGetLastError();
 }
 
@@ -821,7 +1011,17 @@ cudaError_t launch_fft_conv(const FftConvArgs &a, int src_mode, bool density, cu
         else e = launch_rows_fwd<1, 0>(a, src_mode, row_ctas, t1, rs, st);
         if (e != cudaSuccess) return e;
     }
-    if (stage == 0 || stage == 2) {
+    if ((stage == 0 || stage == 2) && a.col_inplace) {
+        const size_t ips = fft_cols_inplace_smem(a.col.n);
+        if (a.col.n == 4096) {
+            if ((e = set_smem(k_fft_cols_ip<1>, ips)) != cudaSuccess) return e;
+            k_fft_cols_ip<1><<<col_ctas, 1024, ips, st>>>(a);
+        } else {
+            if ((e = set_smem(k_fft_cols_ip<2>, ips)) != cudaSuccess) return e;
+            k_fft_cols_ip<2><<<col_ctas, 1024, ips, st>>>(a);
+        }
+        if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    } else if (stage == 0 || stage == 2) {
         if (col_plan == 2) e = launch_cols<2>(a, col_ctas, cs, st);
         else if (col_plan == 4) e = launch_cols<4>(a, col_ctas, cs, st);
         else e = launch_cols<0>(a, col_ctas, cs, st);

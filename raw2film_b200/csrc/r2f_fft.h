@@ -21,6 +21,10 @@ struct FftLine {
     int rad[kFftMaxPasses];
     int tw_off[kFftMaxPasses];  // start of each pass's twiddle table inside tw
     const float2 *tw;           // per-pass tables, pass p: tw[tw_off[p] + (t-1)*Ns + k] = exp(-2 pi i t k / (Ns R))
+    // in-place decimation-in-frequency / -in-time passes (column kernel, compile-time plans): pass p works on
+    // blocks of B = n / (R_1 .. R_{p-1}) with stride S = B / R_p; tables follow each other in pass order,
+    // entry (t-1)*S + k = exp(-2 pi i t k / B)
+    const float2 *tw_ip;
 };
 
 // Host-side description of one FFT length (factorisation + double-built root / cosine tables).
@@ -29,6 +33,8 @@ struct FftLineHost {
     std::vector<int> rad;
     std::vector<int> tw_off;
     std::vector<float2> roots;
+    std::vector<float2> roots_ip;  // tables of the in-place passes (FftLine::tw_ip)
+    std::vector<int> perm;         // perm[k] = position of X[k] after the in-place forward passes
     std::vector<double> cosines;
 };
 
@@ -37,6 +43,7 @@ struct FftConvArgs {
     FftLine row, col;   // lengths Wp (>= W + 2r, multiple of kFftColsPerBlock) and Hp (>= H + 2r)
     int nc;             // columns per CTA / per block of S (2..4, divides Wp)
     int col_groups;     // thread groups per column CTA (1 or 2)
+    int col_inplace;    // 1: in-place column kernel (one 256-thread group per column, khat permuted by col perm)
     float2 *S;          // spectrum scratch, (Wp / nc) x H x nc complex
     const float *khat;  // [Wp][Hp] real kernel spectrum, 1/(Hp*Wp) folded in
     int chan[2];        // the two planes filtered together (R, G)
@@ -63,8 +70,14 @@ size_t fft_cols_smem(int Hp, int nc, int groups);
 bool fft_col_geometry(int Hp, int Wp, int &nc, int &groups);
 
 // Kernel spectrum of an even-symmetric k x k base kernel (device, row-major) -> khat [Wp][Hp].
+// `perm_dev` (Hp ints or nullptr): khat[v][perm[u]] receives the value of row frequency u (in-place column kernel).
 cudaError_t launch_khat(const float *base_kernel_dev, int k, int Hp, int Wp, const double *cosH_dev,
-                        const double *cosW_dev, double *scratchA_dev, float *khat_dev, cudaStream_t st);
+                        const double *cosW_dev, double *scratchA_dev, float *khat_dev, const int *perm_dev,
+                        cudaStream_t st);
+// True when the in-place column kernel has a compile-time plan for this line length (it always works on
+// blocks of four columns).
+bool fft_cols_inplace_available(int Hp);
+size_t fft_cols_inplace_smem(int Hp);
 
 // src_mode: 0 planar, 1 + kFmt* for an interleaved frame routed through the 2-D LUT.
 // stage: 0 = all three kernels, 1 = rows forward, 2 = columns, 3 = rows inverse (for per-kernel timing)
