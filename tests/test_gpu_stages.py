@@ -53,7 +53,11 @@ def _gpu_convolve(proc, img, kernel, path="auto"):
 
 
 @pytest.mark.parametrize("shape,scale,size", [((300, 200), 150.0, 1.0), ((211, 307), 102.0, 1.0), ((97, 130), 40.0, 1.0),
-                                              ((402, 603), 6000 / 36, 1.0), ((530, 801), 9504 / 36, 2.0)])
+                                              ((402, 603), 6000 / 36, 1.0), ((530, 801), 9504 / 36, 2.0),
+                                              # tall strip: column length 4096 -> the compile-time in-place column
+                                              # kernel (k_fft_cols_ip) of the 24 MP frame; the 6912 plan of the 61 MP
+                                              # frame is covered by the full-size test in test_gpu_full.py
+                                              ((4000, 128), 6000 / 36, 1.0)])
 def test_halation_fft_path_vs_truth_and_direct(proc, shape, scale, size):
     """The FFT path (packed R+iG, real kernel spectrum) against the float64 direct truth and against
     the direct CUDA kernel, on ragged sizes (odd H -> single-row tail CTA, W % 4 != 0) with real
