@@ -57,7 +57,9 @@ def _gpu_convolve(proc, img, kernel, path="auto"):
                                               # tall strip: column length 4096 -> the compile-time in-place column
                                               # kernel (k_fft_cols_ip) of the 24 MP frame; the 6912 plan of the 61 MP
                                               # frame is covered by the full-size test in test_gpu_full.py
-                                              ((4000, 128), 6000 / 36, 1.0)])
+                                              ((4000, 128), 6000 / 36, 1.0),
+                                              # wide strip: row length 6144 -> the compile-time row plan, ragged rows
+                                              ((130, 6000), 6000 / 36, 1.0)])
 def test_halation_fft_path_vs_truth_and_direct(proc, shape, scale, size):
     """The FFT path (packed R+iG, real kernel spectrum) against the float64 direct truth and against
     the direct CUDA kernel, on ragged sizes (odd H -> single-row tail CTA, W % 4 != 0) with real
