@@ -358,8 +358,8 @@ def main():
                         "step_frac": ALG_BYTES_PER_PX[args.config] * H * W / (ms_total / args.steps * 1e-3) / 1e9 / peak}
             # direct correlations are FP32 bound: report their algorithmic flop rate (2*k*k per px and filtered layer)
             for name in ("halation", "mtf"):
-                k = {"halation": proc.halation_kernel, "mtf": proc.mtf_kernel}.get(name)
-                if name in kernels and k is not None:
+                k = getattr(proc, name + "_kernel", None) if name in kernels else None
+                if k is not None:
                     taps = sum(int(np.count_nonzero(k[..., c])) > 1 for c in range(3)) * k.shape[0] * k.shape[1]
                     kernels[name]["alg_fp32_tflops"] = 2.0 * taps * H * W / (kernels[name]["ms"] * 1e-3) / 1e12
             if dom in ("halation", "mtf") and "alg_fp32_tflops" in kernels[dom]:

@@ -53,15 +53,19 @@ __device__ __forceinline__ void pixel_chain(const float (&xyz)[3], const Lut2D &
 // ------------------------------------------------------------------------------------------
 // K1: fused pointwise chain
 // ------------------------------------------------------------------------------------------
+// 512-thread CTAs: with the tables in shared memory (60 KB at the default sizes) three 256-thread CTAs fit an SM
+// (24 warps); two 512-thread CTAs carry 32 warps in the same register file (64 registers per thread).
+constexpr int kPwThreads = 512;
+
 template <int FMT, bool SMEM_TABLES>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kPwThreads, 2)
 k_pointwise(const void *__restrict__ in, float gain, uint8_t *__restrict__ out, size_t npix, Lut2D l2, Curve1D cv,
             float eps, Lut3D l3) {
     extern __shared__ __align__(16) float smem[];
     if (SMEM_TABLES) stage_tables(smem, l2, cv, true, true);
     const size_t nquad = npix / 4;
-    const size_t stride = (size_t)gridDim.x * kThreads;
-    for (size_t q = (size_t)blockIdx.x * kThreads + threadIdx.x; q < nquad; q += stride) {
+    const size_t stride = (size_t)gridDim.x * kPwThreads;
+    for (size_t q = (size_t)blockIdx.x * kPwThreads + threadIdx.x; q < nquad; q += stride) {
         float px[4][3];
         load_quad<FMT>(in, q, gain, px);
         uint32_t b[12];
@@ -101,7 +105,8 @@ cudaError_t launch_pointwise(const void *in, int fmt, float gain, uint8_t *out, 
                              const Curve1D &cv, float eps, const Lut3D &l3, int num_sms, cudaStream_t st) {
     const size_t sm = table_smem_bytes(l2, cv, true, true);
     const bool use_smem = sm <= kMaxTableSmem;
-    const int grid = grid_for(npix / 4 + 1, num_sms, 8);
+    int grid = (int)((npix / 4 + kPwThreads) / kPwThreads);
+    if (grid > num_sms * 2) grid = num_sms * 2;
 #define R2F_LAUNCH_PW(C, S)                                                                                \
     do {                                                                                                   \
         auto kfn = k_pointwise<C, S>;                                                                      \
@@ -109,7 +114,7 @@ cudaError_t launch_pointwise(const void *in, int fmt, float gain, uint8_t *out, 
             cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm); \
             if (e != cudaSuccess) return e;                                                                \
         }                                                                                                  \
-        kfn<<<grid, kThreads, S ? sm : 0, st>>>(in, gain, out, npix, l2, cv, eps, l3);                     \
+        kfn<<<grid, kPwThreads, S ? sm : 0, st>>>(in, gain, out, npix, l2, cv, eps, l3);                   \
     } while (0)
     switch (fmt * 2 + (use_smem ? 1 : 0)) {
         case 0: R2F_LAUNCH_PW(0, false); break;
