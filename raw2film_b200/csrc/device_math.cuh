@@ -159,6 +159,11 @@ __device__ __forceinline__ void lut2d_eval(const Lut2D &L, float X, float Y, flo
 // (tools/gen_log10_tables.py documents the tables).
 static __device__ __noinline__ float log10_slow(float c) { return (float)log10((double)c); }
 
+// Series coefficients in the constant bank: DFMA takes them as c[bank][offset] operands.  As literals the
+// compiler rebuilds each 64-bit immediate with two UMOVs per use (36 instructions per pixel in k_pointwise).
+static __constant__ double kLog10Poly[7] = {R2F_LOG10_A1, R2F_LOG10_A2, R2F_LOG10_A3, R2F_LOG10_A4,
+                                            R2F_LOG10_A5, R2F_LOG10_A6, R2F_LOG10_A7};
+
 __device__ __forceinline__ float log10_exact(float c) {
     const uint32_t ix = __float_as_uint(c);
     if (ix - 0x00800000u >= 0x7f000000u) return log10_slow(c);  // zero, subnormal, negative, inf, nan
@@ -170,13 +175,13 @@ __device__ __forceinline__ float log10_exact(float c) {
     const double z = __hiloint2double((int)((iz >> 3) + 0x38000000u), (int)(iz << 29));
     const double2 tab = __ldg(&kLog10Tab[i]);
     const double r = fma(z, tab.x, -1.0);
-    double p = R2F_LOG10_A7;
-    p = fma(p, r, R2F_LOG10_A6);
-    p = fma(p, r, R2F_LOG10_A5);
-    p = fma(p, r, R2F_LOG10_A4);
-    p = fma(p, r, R2F_LOG10_A3);
-    p = fma(p, r, R2F_LOG10_A2);
-    p = fma(p, r, R2F_LOG10_A1);
+    double p = kLog10Poly[6];
+    p = fma(p, r, kLog10Poly[5]);
+    p = fma(p, r, kLog10Poly[4]);
+    p = fma(p, r, kLog10Poly[3]);
+    p = fma(p, r, kLog10Poly[2]);
+    p = fma(p, r, kLog10Poly[1]);
+    p = fma(p, r, kLog10Poly[0]);
     const double y = fma(r, p, __ldg(&kLog10Exp[k + 160]) + tab.y);
     const uint32_t t = (uint32_t)__double2loint(y) & 0x1fffffffu;
     if ((uint32_t)(t - (0x10000000u - 64u)) < 128u) return log10_slow(c);
