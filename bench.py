@@ -41,8 +41,14 @@ CONFIGS = {
            "61MP 9504x6336 full emulation, halation_size=2 (133x133), MTF 27x27x3"),
     "C5": (1080, 1920, dict(halation=False, sharpness=False, grain=0),
            "2MP 1920x1080 simplified preview (pointwise)"),
+    # not a BASELINE config: the interactive preview with every effect left on (what the GUI renders by default)
+    "C5F": (1080, 1920, dict(halation=True, sharpness=True, grain=2, halation_green_factor=0.3),
+            "2MP 1920x1080 full-emulation preview (halation 15x15, MTF 5x5x3, RGB grain)"),
+    # half_size decode of a 24 MP camera (the GUI's default ingest), every effect on
+    "C6": (2000, 3000, dict(halation=True, sharpness=True, grain=2, halation_green_factor=0.3),
+           "6MP 3000x2000 full emulation (half-size decode)"),
 }
-ALG_BYTES_PER_PX = {"C1": 15, "C2": 63, "C3": 63, "C5": 15}
+ALG_BYTES_PER_PX = {"C1": 15, "C2": 63, "C3": 63, "C5": 15, "C5F": 63, "C6": 63}
 # per-kernel algorithmic bytes/px: own input + output tensors (SURVEY 8d "same rule per kernel")
 KERNEL_BYTES_PER_PX = {"pointwise": 15, "expose": 24, "halation": 24, "density": 24, "mtf": 24, "noise": 12,
                        "grain": 15, "burn": 4, "finish": 15,
@@ -260,7 +266,7 @@ def main():
     _cabi.check(_cabi.lib.r2f_profile_enable(proc._ctx, 0))
 
     # --- per-call latency (BASELINE config 5 asks for p50/p99): synchronous device-resident calls ----
-    lat_n = 1000 if args.config == "C5" else 50
+    lat_n = 1000 if args.config in ("C5", "C5F") else 50
     lat = []
     for i in range(lat_n):
         t0 = time.perf_counter()
