@@ -30,6 +30,7 @@
 
 #include "conv_tile.cuh"
 #include "r2f_kernels.h"
+#include "sym_conv.cuh"
 
 namespace r2f {
 
@@ -122,38 +123,10 @@ k_conv2d_sym(ConvArgs a, const __grid_constant__ CUtensorMap tmap, int use_tma) 
         float2 acc[C::OW];
 #pragma unroll
         for (int o = 0; o < C::OW; ++o) acc[o] = make_float2(0.f, 0.f);
-        // rows lane and lane+32 of the tile; window starts at tile column 8*warp
+        // rows lane and lane+32 of the tile; window starts at tile column OW*warp
         const float *ctr0 = tile + (lane + C::R) * C::PITCH + C::OW * warp;
         const float *ctr1 = ctr0 + 32 * C::PITCH;
-#pragma unroll 1
-        for (int dy = 0; dy <= C::R; ++dy) {
-            const float4 *a0 = reinterpret_cast<const float4 *>(ctr0 + dy * C::PITCH);
-            const float4 *b0 = reinterpret_cast<const float4 *>(ctr0 - dy * C::PITCH);
-            const float4 *a1 = reinterpret_cast<const float4 *>(ctr1 + dy * C::PITCH);
-            const float4 *b1 = reinterpret_cast<const float4 *>(ctr1 - dy * C::PITCH);
-            float2 P[C::NQ * 4];
-#pragma unroll
-            for (int q = 0; q < C::NQ; ++q) {
-                const float4 x = a0[q], y = b0[q], z = a1[q], w = b1[q];
-                P[4 * q + 0] = make_float2(x.x + y.x, z.x + w.x);
-                P[4 * q + 1] = make_float2(x.y + y.y, z.y + w.y);
-                P[4 * q + 2] = make_float2(x.z + y.z, z.z + w.z);
-                P[4 * q + 3] = make_float2(x.w + y.w, z.w + w.w);
-            }
-            const float4 *wr = reinterpret_cast<const float4 *>(wsm + dy * C::WROW * 2);
-#pragma unroll
-            for (int j = 0; j < K; j += 2) {
-                const float4 w4 = wr[j >> 1];
-                const float2 wa = make_float2(w4.x, w4.y);
-#pragma unroll
-                for (int o = 0; o < C::OW; ++o) acc[o] = __ffma2_rn(wa, P[o + j], acc[o]);
-                if (j + 1 < K) {
-                    const float2 wb = make_float2(w4.z, w4.w);
-#pragma unroll
-                    for (int o = 0; o < C::OW; ++o) acc[o] = __ffma2_rn(wb, P[o + j + 1], acc[o]);
-                }
-            }
-        }
+        sym_correlate<K, C::OW, C::PITCH, C::WROW>(ctr0, ctr1, wsm, acc);
         __syncthreads();  // everyone is done reading the input tile: reuse it as the output stage
 #pragma unroll
         for (int o = 0; o < C::OW; ++o) {
