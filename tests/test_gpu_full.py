@@ -152,6 +152,56 @@ def test_full_size_properties_24mp(proc):
     assert np.array_equal(got, oracle_render(fo, xyz[rows], stock, 6.0, 0.4, off))
 
 
+@pytest.mark.parametrize("which", ["halation", "mtf"])
+def test_full_size_24mp_spatial_stages_are_linear_and_shift_consistent(proc, which):
+    """The two spatial stages at the BASELINE size (6000x4000) through properties that do not need a CPU truth:
+    the correlation is linear -- K (*) (a x + b y) == a K (*) x + b K (*) y -- and translation-consistent away
+    from the borders, for the halation kernel (43x43, FFT path: compile-time row/column plans, in-place column
+    kernel) and for the MTF kernel (17x17x3, y-symmetric FFMA2 kernel with TMA-staged tiles)."""
+    import torch
+    from raw2film_b200 import _cabi, builders
+
+    h, w = 4000, 6000
+    scale = w / 36
+    if which == "halation":
+        kern = fo.compute_halation_kernel(scale, 1.0, 1.0, 0.3, 0.0, 1.0)
+        path = "fft"
+    else:
+        kern = builders.mtf_kernel(SyntheticStock().mtf, scale)
+        path = "direct"
+    kern = np.ascontiguousarray(kern, np.float32)
+    g = torch.Generator(device="cuda").manual_seed(11)
+    x = torch.rand((h, w, 3), device="cuda", generator=g)
+    y = torch.rand((h, w, 3), device="cuda", generator=g)
+    ws = torch.empty(int(_cabi.lib.r2f_workspace_bytes(h, w, 0)), dtype=torch.uint8, device="cuda")
+
+    def conv(img):
+        out = torch.empty_like(img)
+        torch.cuda.synchronize()
+        _cabi.check(_cabi.lib.r2f_convolve2d(proc._ctx, img.data_ptr(), out.data_ptr(), h, w, _cabi.f32_ptr(kern),
+                                             kern.shape[0], ws.data_ptr(), ws.numel(), None))
+        torch.cuda.synchronize()
+        return out
+
+    proc.set_conv_path(path)
+    try:
+        cx, cy = conv(x), conv(y)
+        mix = conv((0.75 * x + 0.5 * y).contiguous())
+        assert (mix - (0.75 * cx + 0.5 * cy)).abs().max().item() <= 2e-6
+        # shift by (64, 128): interior outputs must follow the input
+        r = kern.shape[0] // 2
+        xs = torch.roll(x, shifts=(64, 128), dims=(0, 1)).contiguous()
+        cs = conv(xs)
+        a = cs[64 + r:h - r, 128 + r:w - r]
+        b = cx[r:h - r - 64, r:w - r - 128]
+        assert (a - b).abs().max().item() <= 2e-6
+        # the kernel layers sum to 1: a flat field stays flat (borders included: REFLECT_101)
+        flat = torch.full((h, w, 3), 0.37, device="cuda")
+        assert (conv(flat) - 0.37).abs().max().item() <= 2e-6
+    finally:
+        proc.set_conv_path("auto")
+
+
 def test_errors_are_loud(proc):
     import torch
     from raw2film_b200 import _cabi
