@@ -578,7 +578,8 @@ k_fft_cols(const __grid_constant__ FftConvArgs a) {
 }
 
 // In-place variant (compile-time plans only): four 256-thread groups, one column each, n float2 per column.
-// IPLAN 1: n = 4096 (8 8 8 8), IPLAN 2: n = 6912 (8 8 4 3 3 3); a.khat rows are permuted by the line's perm[].
+// IPLAN 1: n = 4096 (8 8 8 8), IPLAN 2: n = 6912 (3 3 3 4 8 8: the line's radices reversed); a.khat rows are
+// permuted by the line's perm[].
 template <int IPLAN>
 __global__ void __launch_bounds__(1024, 1)
 k_fft_cols_ip(const __grid_constant__ FftConvArgs a) {
@@ -622,7 +623,7 @@ k_fft_cols_ip(const __grid_constant__ FftConvArgs a) {
     group_sync(g);
     const float *kh = a.khat + (size_t)(b * 4 + gi) * n;
     if constexpr (IPLAN == 1) ip_conv<4096, 4096, GS, 0, 8, 8, 8, 8>(home, a.col.tw_ip, kh, g);
-    else ip_conv<6912, 6912, GS, 0, 8, 8, 4, 3, 3, 3>(home, a.col.tw_ip, kh, g);
+    else ip_conv<6912, 6912, GS, 0, 3, 3, 3, 4, 8, 8>(home, a.col.tw_ip, kh, g);
     __syncthreads();
     // keep the swapped form: k_fft_rows_inv consumes swap(x) directly
     for (int y = threadIdx.x; y < H; y += blockDim.x) {
@@ -830,10 +831,13 @@ bool fft_make_line(int n, FftLineHost &out) {
         Ns *= R;
     }
     // in-place passes: block B, stride S = B / R, entry (t-1)*S + k = exp(-2 pi i t k / B); the innermost pass
-    // (S = 1) has no twiddles
+    // (S = 1) has no twiddles.  The in-place kernels run the radices in REVERSE order (odd radices first, radix 8
+    // innermost): the early passes then have strides that are multiples of 128 (one swizzle per butterfly) and the
+    // fused innermost step works on 8 contiguous elements with 16-byte accesses.
+    const std::vector<int> rad_ip(rad.rbegin(), rad.rend());
     out.roots_ip.clear();
     int B = n;
-    for (int R : rad) {
+    for (int R : rad_ip) {
         const int S = B / R;
         if (S > 1)
             for (int t = 1; t < R; ++t)
@@ -848,7 +852,7 @@ bool fft_make_line(int n, FftLineHost &out) {
     out.perm.resize(n);
     for (int k = 0; k < n; ++k) {
         int kk = k, pos = 0, blk = n;
-        for (int R : rad) {
+        for (int R : rad_ip) {
             blk /= R;
             pos += (kk % R) * blk;
             kk /= R;
