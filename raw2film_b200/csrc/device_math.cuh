@@ -118,6 +118,15 @@ __device__ __forceinline__ void load_quad(const void *__restrict__ in, size_t q,
 // ---- a2: chromaticity-indexed input LUT (reference shaders/lut_2d.wgsl:18-108) ---------
 // Branch-free; the float operations and their order are exactly those of
 // oracle/pointwise_oracle.c lut2d_pixel (index clamps and selects do not round).
+// SMEM: L.tab is known to point into shared memory (a table parked there by the caller); the nine vertex reads
+// are then explicit ld.shared instead of generic loads, which the hardware routes through the global-load queue.
+__device__ __forceinline__ float lds_f32(unsigned addr) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+    return v;
+}
+
+template <bool SMEM = false>
 __device__ __forceinline__ void lut2d_eval(const Lut2D &L, float X, float Y, float Z, float &e0, float &e1,
                                            float &e2) {
     const float S = (X + Y) + Z;
@@ -140,9 +149,21 @@ __device__ __forceinline__ void lut2d_eval(const Lut2D &L, float X, float Y, flo
     const float wa = lower ? rf : 1.0f - gf;
     const float wb = lower ? gf : 1.0f - rf;
     const float wc = lower ? 1.0f - fs : fs - 1.0f;
-    const float v0 = ((a[0] * wa + b[0] * wb) + c[0] * wc) * S;
-    const float v1 = ((a[1] * wa + b[1] * wb) + c[1] * wc) * S;
-    const float v2 = ((a[2] * wa + b[2] * wb) + c[2] * wc) * S;
+    float a0, a1, a2, b0, b1, b2, c0, c1, c2;
+    if (SMEM) {
+        const unsigned sa = (unsigned)__cvta_generic_to_shared(a), sb = (unsigned)__cvta_generic_to_shared(b);
+        const unsigned sc = (unsigned)__cvta_generic_to_shared(c);
+        a0 = lds_f32(sa); a1 = lds_f32(sa + 4); a2 = lds_f32(sa + 8);
+        b0 = lds_f32(sb); b1 = lds_f32(sb + 4); b2 = lds_f32(sb + 8);
+        c0 = lds_f32(sc); c1 = lds_f32(sc + 4); c2 = lds_f32(sc + 8);
+    } else {
+        a0 = a[0]; a1 = a[1]; a2 = a[2];
+        b0 = b[0]; b1 = b[1]; b2 = b[2];
+        c0 = c[0]; c1 = c[1]; c2 = c[2];
+    }
+    const float v0 = ((a0 * wa + b0 * wb) + c0 * wc) * S;
+    const float v1 = ((a1 * wa + b1 * wb) + c1 * wc) * S;
+    const float v2 = ((a2 * wa + b2 * wb) + c2 * wc) * S;
     e0 = dark ? 0.0f : v0;
     e1 = dark ? 0.0f : v1;
     e2 = dark ? 0.0f : v2;

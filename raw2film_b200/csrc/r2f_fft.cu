@@ -408,6 +408,58 @@ __device__ __forceinline__ Lut2D stage_lut2d(const Lut2D &L, float2 *idle, int c
     return Lut2D(dst, L.n);
 }
 
+// Interleaved frame row y -> 2-D input LUT -> (chan0 + i chan1) into `line` (offset r, swizzled) and, when asked, the
+// three exposure planes.  LUT_SMEM: l2.tab points into shared memory (parked by stage_lut2d).
+template <int FMT, bool LUT_SMEM>
+__device__ __forceinline__ void load_row_xyz(const FftConvArgs &a, const Lut2D &l2, float2 *__restrict__ line, int y,
+                                             const Group &g) {
+    const int W = a.W, r = a.r;
+    if ((W & 3) == 0) {  // row starts on a pixel-quad boundary: 128-bit frame loads
+        const size_t q0 = (size_t)y * W / 4;
+        constexpr int U = 2;  // quads in flight per thread: the frame loads of a batch are issued together
+        for (int base = g.tid; base < W / 4; base += U * g.size) {
+            float px[U][4][3];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int qx = base + u * g.size;
+                if (qx < W / 4) load_quad<FMT>(a.src_xyz, q0 + qx, a.gain, px[u]);
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int qx = base + u * g.size;
+                if (qx < W / 4) {
+                    float e[3][4];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        lut2d_eval<LUT_SMEM>(l2, px[u][i][0], px[u][i][1], px[u][i][2], e[0][i], e[1][i], e[2][i]);
+                        line[sw(r + 4 * qx + i)] = make_float2(pick3(a.chan[0], e[0][i], e[1][i], e[2][i]),
+                                                           pick3(a.chan[1], e[0][i], e[1][i], e[2][i]));
+                    }
+                    if (a.exp_planar != nullptr) {
+#pragma unroll
+                        for (int c = 0; c < 3; ++c)
+                            __stcg(reinterpret_cast<float4 *>(a.exp_planar + c * a.plane_stride) + q0 + qx,
+                                   make_float4(e[c][0], e[c][1], e[c][2], e[c][3]));
+                    }
+                }
+            }
+        }
+    } else {
+        for (int x = g.tid; x < W; x += g.size) {
+            float X, Y, Z, e0, e1, e2;
+            load_px<FMT>(a.src_xyz, (size_t)y * W + x, a.gain, X, Y, Z);
+            lut2d_eval<LUT_SMEM>(l2, X, Y, Z, e0, e1, e2);
+            line[sw(r + x)] = make_float2(pick3(a.chan[0], e0, e1, e2), pick3(a.chan[1], e0, e1, e2));
+            if (a.exp_planar != nullptr) {
+                const size_t idx = (size_t)y * W + x;
+                a.exp_planar[idx] = e0;
+                a.exp_planar[a.plane_stride + idx] = e1;
+                a.exp_planar[2 * a.plane_stride + idx] = e2;
+            }
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------
 // rows, forward
 // ------------------------------------------------------------------------------------------
@@ -432,50 +484,8 @@ k_fft_rows_fwd(const __grid_constant__ FftConvArgs a) {
             }
         } else {
             const Lut2D l2 = stage_lut2d(a.lut2d, bufB, n, g);
-            if ((W & 3) == 0) {  // row starts on a pixel-quad boundary: 128-bit frame loads
-                const size_t q0 = (size_t)y * W / 4;
-                constexpr int U = 2;  // quads in flight per thread: the frame loads of a batch are issued together
-                for (int base = g.tid; base < W / 4; base += U * g.size) {
-                    float px[U][4][3];
-#pragma unroll
-                    for (int u = 0; u < U; ++u) {
-                        const int qx = base + u * g.size;
-                        if (qx < W / 4) load_quad<FMT>(a.src_xyz, q0 + qx, a.gain, px[u]);
-                    }
-#pragma unroll
-                    for (int u = 0; u < U; ++u) {
-                        const int qx = base + u * g.size;
-                        if (qx < W / 4) {
-                            float e[3][4];
-#pragma unroll
-                            for (int i = 0; i < 4; ++i) {
-                                lut2d_eval(l2, px[u][i][0], px[u][i][1], px[u][i][2], e[0][i], e[1][i], e[2][i]);
-                                bufA[sw(r + 4 * qx + i)] = make_float2(pick3(a.chan[0], e[0][i], e[1][i], e[2][i]),
-                                                                   pick3(a.chan[1], e[0][i], e[1][i], e[2][i]));
-                            }
-                            if (a.exp_planar != nullptr) {
-#pragma unroll
-                                for (int c = 0; c < 3; ++c)
-                                    __stcg(reinterpret_cast<float4 *>(a.exp_planar + c * a.plane_stride) + q0 + qx,
-                                           make_float4(e[c][0], e[c][1], e[c][2], e[c][3]));
-                            }
-                        }
-                    }
-                }
-            } else {
-                for (int x = g.tid; x < W; x += g.size) {
-                    float X, Y, Z, e0, e1, e2;
-                    load_px<FMT>(a.src_xyz, (size_t)y * W + x, a.gain, X, Y, Z);
-                    lut2d_eval(l2, X, Y, Z, e0, e1, e2);
-                    bufA[sw(r + x)] = make_float2(pick3(a.chan[0], e0, e1, e2), pick3(a.chan[1], e0, e1, e2));
-                    if (a.exp_planar != nullptr) {
-                        const size_t idx = (size_t)y * W + x;
-                        a.exp_planar[idx] = e0;
-                        a.exp_planar[a.plane_stride + idx] = e1;
-                        a.exp_planar[2 * a.plane_stride + idx] = e2;
-                    }
-                }
-            }
+            if (l2.tab != a.lut2d.tab) load_row_xyz<FMT, true>(a, l2, bufA, y, g);   // parked in shared memory
+            else load_row_xyz<FMT, false>(a, l2, bufA, y, g);
         }
         group_sync(g);
         pad_line(bufA, W, r, n, g);
