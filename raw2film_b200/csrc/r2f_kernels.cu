@@ -25,18 +25,25 @@ __device__ __forceinline__ void store_quad_u8(uint8_t *__restrict__ out, size_t 
 
 // stage the small tables (2-D LUT, curve rows) in shared memory
 __device__ __forceinline__ void stage_tables(float *smem, Lut2D &l2, Curve1D &cv, bool want2d, bool want1d) {
+    // asynchronous 16-byte copies (all of a thread's copies in flight at once) when the table is 16-byte aligned
+    auto stage = [](float *dst, const float *src, int n) {
+        const int nq = (reinterpret_cast<uintptr_t>(src) & 15) == 0 ? n / 4 : 0;
+        for (int i = threadIdx.x; i < nq; i += blockDim.x) cp_async_16(dst + 4 * i, src + 4 * i);
+        for (int i = 4 * nq + threadIdx.x; i < n; i += blockDim.x) dst[i] = src[i];
+    };
     float *p = smem;
     if (want2d) {
         const int n = l2.n * l2.n * 3;
-        for (int i = threadIdx.x; i < n; i += blockDim.x) p[i] = l2.tab[i];
+        stage(p, l2.tab, n);
         l2.tab = p;
         p += (n + 3) / 4 * 4;
     }
     if (want1d) {
         const int n = cv.N * 3;
-        for (int i = threadIdx.x; i < n; i += blockDim.x) p[i] = cv.rows[i];
+        stage(p, cv.rows, n);
         cv.rows = p;
     }
+    cp_async_wait_all();
     __syncthreads();
 }
 
