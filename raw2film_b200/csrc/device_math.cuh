@@ -20,7 +20,9 @@ struct Lut2D {
 };
 
 struct Curve1D {
-    const float *rows;  // rows R,G,B of the (4, N) table, contiguous (3*N floats)
+    // rows R,G,B of the (4, N) table as segments: seg[ch*N + i] = (row[i], row[i+1] - row[i]) (the float32
+    // difference the interpolation would form anyway), last entry (row[N-1], 0): one 8-byte read per lookup
+    const float2 *seg;
     int N;
     float x0;         // first abscissa
     float inv_range;  // float32(1 / (x_last - x_first))
@@ -228,9 +230,8 @@ __device__ __forceinline__ float curve_eval(const Curve1D &C, int ch, float v) {
     const float p = t * (float)(C.N - 1);
     const int i = min((int)p, C.N - 2);
     const float f = p - (float)i;
-    const float *row = C.rows + ch * C.N + i;
-    const float lo = row[0], hi = row[1];
-    return lo + f * (hi - lo);
+    const float2 s = C.seg[ch * C.N + i];
+    return s.x + f * s.y;
 }
 
 __device__ __forceinline__ float density_eval(const Curve1D &C, int ch, float exposure, float eps) {

@@ -158,6 +158,21 @@ struct DeviceGuard {
     }
 };
 
+int upload(DevBuf &b, const void *host, size_t bytes);
+
+// rows 1..3 of a (4, N) curve table -> 3*N segments (value, forward difference in float32), see Curve1D
+int upload_curve_segments(DevBuf &b, const float *curve, int N) {
+    std::vector<float> seg((size_t)3 * N * 2);
+    for (int ch = 0; ch < 3; ++ch) {
+        const float *row = curve + (size_t)(ch + 1) * N;
+        for (int i = 0; i < N; ++i) {
+            seg[((size_t)ch * N + i) * 2] = row[i];
+            seg[((size_t)ch * N + i) * 2 + 1] = i + 1 < N ? row[i + 1] - row[i] : 0.0f;
+        }
+    }
+    return upload(b, seg.data(), seg.size() * sizeof(float));
+}
+
 int upload(DevBuf &b, const void *host, size_t bytes) {
     CU(b.ensure(bytes));
     CU(cudaMemcpy(b.p, host, bytes, cudaMemcpyHostToDevice));
@@ -382,10 +397,10 @@ bool want_fft(const r2f_ctx *c, const KernelSet &ks, int H, int W, FftGeometry &
 
 Lut2D lut2d_of(const r2f_ctx *c) { return Lut2D{static_cast<const float *>(c->lut2d.p), c->n2}; }
 Curve1D curve_of(const r2f_ctx *c) {
-    return Curve1D{static_cast<const float *>(c->curve.p), c->n1, c->x0, c->inv_range};
+    return Curve1D{static_cast<const float2 *>(c->curve.p), c->n1, c->x0, c->inv_range};
 }
 Curve1D gcurve_of(const r2f_ctx *c) {
-    return Curve1D{static_cast<const float *>(c->gcurve.p), c->ng, c->gx0, c->ginv};
+    return Curve1D{static_cast<const float2 *>(c->gcurve.p), c->ng, c->gx0, c->ginv};
 }
 Lut3D lut3d_of(const r2f_ctx *c) {
     return Lut3D{static_cast<const float4 *>(c->lut3d.p), c->n3, c->s3, c->s3f, c->margin3, c->fast3};
@@ -747,7 +762,7 @@ int r2f_set_lut2d(r2f_ctx *c, const float *lut, int n) {
 int r2f_set_curve1d(r2f_ctx *c, const float *curve, int N, float log_eps) {
     if (!c || !curve || N < 2) return fail(R2F_ERR_INVALID, "r2f_set_curve1d: bad arguments");
     DeviceGuard guard(c->device);
-    int rc = upload(c->curve, curve + N, (size_t)3 * N * sizeof(float));
+    int rc = upload_curve_segments(c->curve, curve, N);
     if (rc != R2F_OK) return rc;
     c->n1 = N;
     c->x0 = curve[0];
@@ -807,7 +822,7 @@ int r2f_set_mtf_kernel(r2f_ctx *c, const float *kernel, int k) {
 int r2f_set_grain(r2f_ctx *c, const float *curve, int N, const float *kernel, int k, uint64_t seed) {
     if (!c || !curve || N < 2) return fail(R2F_ERR_INVALID, "r2f_set_grain: bad arguments");
     DeviceGuard guard(c->device);
-    int rc = upload(c->gcurve, curve + N, (size_t)3 * N * sizeof(float));
+    int rc = upload_curve_segments(c->gcurve, curve, N);
     if (rc != R2F_OK) return rc;
     c->ng = N;
     c->gx0 = curve[0];

@@ -39,9 +39,9 @@ __device__ __forceinline__ void stage_tables(float *smem, Lut2D &l2, Curve1D &cv
         p += (n + 3) / 4 * 4;
     }
     if (want1d) {
-        const int n = cv.N * 3;
-        stage(p, cv.rows, n);
-        cv.rows = p;
+        const int n = cv.N * 3 * 2;
+        stage(p, reinterpret_cast<const float *>(cv.seg), n);
+        cv.seg = reinterpret_cast<const float2 *>(p);
     }
     cp_async_wait_all();
     __syncthreads();
@@ -102,7 +102,7 @@ static int grid_for(size_t work_items, int num_sms, int ctas_per_sm) {
 static size_t table_smem_bytes(const Lut2D &l2, const Curve1D &cv, bool want2d, bool want1d) {
     size_t f = 0;
     if (want2d) f += ((size_t)l2.n * l2.n * 3 + 3) / 4 * 4;
-    if (want1d) f += (size_t)cv.N * 3;
+    if (want1d) f += (size_t)cv.N * 3 * 2;
     return f * sizeof(float);
 }
 
