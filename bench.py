@@ -6,13 +6,17 @@
 One "step" = one pass of the hot path over one synthetic frame of the named config
 (default C2: 6000x4000 linear XYZ, full emulation: halation 43x43, MTF 17x17x3, RGB grain).
 Metric: megapixels/s (whole job, all ranks).  `value` is device-resident (frames already in HBM,
-inputs > L2 and rotated between steps); `e2e` goes through the public API
-`B200Processor.process_preloaded` with pinned HOST buffers (H2D + render + D2H inside the timed
-region).  Multi-GPU (torchrun, one rank per GPU): frames are independent, every rank renders its
+inputs > L2 and rotated between steps).  `e2e` is the reference's own entry point for preloaded frames,
+`B200Processor.process_preloaded` (gpu_processor.py:1643-1693), called once per frame with pinned HOST
+buffers: H2D + render + D2H inside the timed region, nothing overlapped across calls.  `e2e_pipelined` /
+`e2e_u16` are the batch-export form (`PipelinedRenderer`: copies and renders of consecutive frames overlap),
+and `c4` is BASELINE config 4 itself: 64 frames, stock = frame index % 4, frame -> rank index % world, through
+`BatchExporter`.  Multi-GPU (torchrun, one rank per GPU): frames are independent, every rank renders its
 own K frames (weak scaling), no data-path collective; timing = max over ranks of CUDA-event time.
 
 `--impl reference` times the reference's CPU algorithm (the oracle port: cv2.filter2D + OpenMP C
-restatement, all host threads) on a bounded sample of the same workload.
+restatement, all host threads) on the same config: the whole frame per step when K + W steps of it fit
+in a few minutes, else a horizontal band of it (kernels at the full frame's px/mm).
 """
 from __future__ import annotations
 
@@ -69,6 +73,7 @@ def load_traffic(config, kernel):
     except Exception:  # noqa: BLE001
         return None
 GRAIN_SIZE, GRAIN_SIGMA = 6.0, 0.4                                  # gui.py:498, 509
+FFMA_PEAK_TFLOPS = 73.0      # measured: tools/micro/ffma2_rate.cu, profiles/r01_ffma2_rate.txt
 
 
 def load_peaks():
@@ -140,22 +145,32 @@ def cpu_render_once(fo, xyz, stock, settings):
     return oracle_render(fo, xyz, stock, GRAIN_SIZE, GRAIN_SIGMA, settings)
 
 
-def cpu_sample(cfg_name, H, W, settings, frac=4):
-    """Bounded CPU sample: a horizontal band of the frame rendered with the full frame's px/mm
-    (so the halation / MTF kernels have the production size)."""
+def config_dict(name):
+    """The `config` object of the JSON line: static, identical for both arms (`--impl b200` / `reference`)."""
+    H, W, settings, desc = CONFIGS[name]
+    return {"workload": desc, "name": name, "frame": f"{W}x{H}x3 float32 linear XYZ",
+            "settings": {k: settings[k] for k in sorted(settings)},
+            "stock": "SyntheticStock variant = rank % 4 (mixed stocks across GPUs), n2/N/n3 = 64/1024/33",
+            "l2": f"inputs larger than L2: distinct {H * W * 12 / 1e6:.0f} MB frames rotated between steps"}
+
+
+def cpu_sample(cfg_name, H, W, settings, rows=None):
+    """CPU sample of the workload: the whole frame, or (`rows`) a horizontal band of it rendered with the full
+    frame's px/mm so the halation / MTF kernels keep their production size."""
     from raw2film_b200.synthetic import natural_frame
 
-    rows = H if cfg_name in ("C1", "C5") else max(256, H // frac)
+    rows = H if rows is None else max(64, min(H, int(rows)))
     scale_px_mm = max(H, W) / 36.0
     xyz = natural_frame(H, W, 0)[:rows].copy()
     st = dict(settings)
     st["frame_width"] = max(rows, W) / scale_px_mm
     st["frame_height"] = st["frame_width"] * 2 / 3
-    return xyz, st, f"{W}x{rows} band of the {W}x{H} natural frame 0, kernels at the full-frame {scale_px_mm:.1f} px/mm"
+    what = "whole frame" if rows == H else f"{W}x{rows} band"
+    return xyz, st, f"{what} of the {W}x{H} natural frame 0, kernels at the full-frame {scale_px_mm:.1f} px/mm"
 
 
 def run_reference(args, world, rank):
-    """--impl reference: the oracle port of the reference CPU path on the host cores."""
+    """--impl reference: the oracle port of the reference CPU path on the host cores, same config dict."""
     if rank != 0:
         return
     from oracle import film_oracle as fo
@@ -164,9 +179,18 @@ def run_reference(args, world, rank):
     H, W, settings, desc = CONFIGS[args.config]
     stock = SyntheticStock()
     fo.use_all_host_threads()
-    xyz, st, sample = cpu_sample(args.config, H, W, settings)
+    # calibrate on a 1/16 band, then take the whole frame if warm-up + K steps of it stay within ~3 minutes
+    xyz, st, _ = cpu_sample(args.config, H, W, settings, rows=max(128, H // 16))
+    cpu_render_once(fo, xyz[:64].copy(), stock, st)
+    t0 = time.perf_counter()
+    cpu_render_once(fo, xyz, stock, st)
+    per_row = (time.perf_counter() - t0) / xyz.shape[0]
+    warm = max(1, min(args.warmup, 1))
+    budget_s = 180.0
+    rows = H if per_row * H * (args.steps + warm) <= budget_s else int(budget_s / (per_row * (args.steps + warm)))
+    xyz, st, sample = cpu_sample(args.config, H, W, settings, rows=rows)
     mp = xyz.shape[0] * xyz.shape[1] / 1e6
-    for _ in range(max(1, min(args.warmup, 1))):
+    for _ in range(warm):
         cpu_render_once(fo, xyz, stock, st)
     t0 = time.perf_counter()
     for _ in range(args.steps):
@@ -178,7 +202,7 @@ def run_reference(args, world, rank):
         "impl": "reference", "metric": "megapixels_per_second", "value": val, "unit": "MP/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": desc, "name": args.config},
+        "config": config_dict(args.config),
         "cpu_baseline": {"value": val, "unit": "MP/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": "MP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -195,6 +219,8 @@ def main():
     ap.add_argument("--config", default="C2", choices=sorted(CONFIGS))
     ap.add_argument("--frames", type=int, default=3, help="distinct resident input frames rotated between steps")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--c4-frames", type=int, default=64, help="frames of the mixed-stock batch leg (0 = skip)")
+    ap.add_argument("--kernel-only", action="store_true", help="device-resident leg only (ncu captures)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     world, rank, local = dist_setup(args.gpus)
@@ -203,13 +229,14 @@ def main():
         run_reference(args, world, rank)
         return
 
+    import ctypes
+
     import torch
     import torch.distributed as dist
 
-    from raw2film_b200 import B200Processor, _cabi
-    from raw2film_b200.synthetic import SyntheticStock, natural_frame
-
+    from raw2film_b200 import B200Processor, BatchExporter, PipelinedRenderer, _cabi
     from raw2film_b200.affinity import bind_to_gpu
+    from raw2film_b200.synthetic import SyntheticStock, natural_frame
 
     affinity = bind_to_gpu(local)          # before any pinned allocation: first touch on the GPU's NUMA node
     torch.cuda.set_device(local)
@@ -220,14 +247,15 @@ def main():
     stock = SyntheticStock(variant=rank % 4)   # mixed stocks across ranks
     proc = B200Processor(device=local)
 
-    # --- inputs: pinned host payloads (for e2e) and their device-resident copies (for value) ----------
+    # --- inputs: frames generated straight into pinned host memory (phase 1 hands them over without a copy)
+    # and their device-resident copies (for `value`) ------------------------------------------------------
     n_frames = max(2, args.frames)
-    payloads, dev_frames = [], []
+    payloads, dev_frames, host_frames = [], [], []
     for i in range(n_frames):
-        frame = natural_frame(H, W, rank * 1000 + i)
+        frame = natural_frame(H, W, rank * 1000 + i, out=proc.pinned_frame(H, W))
+        host_frames.append(frame)
         payloads.append(proc.extract_image_data_cpu(frame, **settings))
         dev_frames.append(torch.from_numpy(payloads[-1]["image_array"]).to(proc.device))
-        del frame
     torch.cuda.synchronize()
 
     def step_device(i):
@@ -258,12 +286,16 @@ def main():
     barrier()
     ms_total = ev0.elapsed_time(ev1)
     launches = proc.launch_count - launches0
-    import ctypes
-
     prof_ms = (ctypes.c_double * len(_cabi.PROF_NAMES))()
     prof_n = (ctypes.c_uint64 * len(_cabi.PROF_NAMES))()
     _cabi.check(_cabi.lib.r2f_profile_read(proc._ctx, prof_ms, prof_n))
     _cabi.check(_cabi.lib.r2f_profile_enable(proc._ctx, 0))
+    if args.kernel_only:
+        if rank == 0:
+            sampler.stop()
+            print(json.dumps({"ms_per_step": ms_total / args.steps, "kernel_only": True, "config": args.config}))
+        proc.close()
+        return
 
     # --- per-call latency (BASELINE config 5 asks for p50/p99): synchronous device-resident calls ----
     lat_n = 1000 if args.config in ("C5", "C5F") else 50
@@ -279,23 +311,27 @@ def main():
                "what": "wall time of one synchronous B200Processor.render_device call (device-resident frame)"}
 
     # --- timed, end to end through the public API (pinned host in, host out) ---------------------
-    # (a) synchronous per-frame call, as the reference's single export makes it
-    for i in range(2):
-        proc.process_preloaded(payloads[i % n_frames], stock, GRAIN_SIZE, GRAIN_SIGMA, **settings)
-    barrier()
-    s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    s0.record(proc.stream)
-    sync_steps = max(3, min(args.steps, 10))
-    for i in range(sync_steps):
-        out = proc.process_preloaded(payloads[i % n_frames], stock, GRAIN_SIZE, GRAIN_SIGMA, **settings)
-    s1.record(proc.stream)
-    barrier()
-    ms_sync = s0.elapsed_time(s1) / sync_steps
-    # (b) batch export: PipelinedRenderer overlaps H2D / render / D2H of consecutive frames
-    from raw2film_b200 import PipelinedRenderer
-
-    pipe = PipelinedRenderer(proc, depth=3)
+    # (a) the reference's entry point for preloaded frames, one synchronous call per frame
     checksum = 0
+    for i in range(3):
+        proc.process_preloaded(payloads[i % n_frames], stock, GRAIN_SIZE, GRAIN_SIGMA, **settings)
+    own_pipe = proc._own_pipeline()
+    barrier()
+    h2d0, d2h0 = own_pipe.h2d_bytes, own_pipe.d2h_bytes
+    s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_wall = time.perf_counter()
+    s0.record(own_pipe.s_in)
+    for i in range(args.steps):
+        out = proc.process_preloaded(payloads[i % n_frames], stock, GRAIN_SIZE, GRAIN_SIGMA, **settings)
+        checksum += int(out[0, 0, 0])
+    s1.record(own_pipe.s_out)
+    barrier()
+    ms_sync = s0.elapsed_time(s1)
+    ms_sync_wall = (time.perf_counter() - t_wall) * 1e3
+    h2d_sync = (own_pipe.h2d_bytes - h2d0) // args.steps
+    d2h_sync = (own_pipe.d2h_bytes - d2h0) // args.steps
+    # (b) batch export: PipelinedRenderer overlaps H2D / render / D2H of consecutive frames
+    pipe = PipelinedRenderer(proc, depth=3)
 
     def sink(idx, img):
         nonlocal checksum
@@ -318,9 +354,9 @@ def main():
     payloads16 = []
     for p in payloads:
         f = p["image_array"]
-        u16 = np.clip(f[..., :3] * (65535.0 / gain16), 0, 65535).astype(np.uint16)
+        u16 = proc.pinned_frame(H, W, dtype=np.uint16)
+        u16[...] = np.clip(f[..., :3] * np.float32(65535.0 / gain16), 0, 65535).astype(np.uint16)
         payloads16.append(proc.extract_image_data_cpu(u16, input_gain=gain16, **settings))
-        del u16
     pipe.run((payloads16[i % n_frames] for i in range(3)), stock, GRAIN_SIZE, GRAIN_SIGMA, sink=sink, **settings)
     barrier()
     h2d1 = pipe.h2d_bytes
@@ -332,25 +368,50 @@ def main():
     barrier()
     ms_e2e16 = u0.elapsed_time(u1)
     h2d16_per_step = (pipe.h2d_bytes - h2d1) // args.steps
+    del payloads16, pipe
+
+    # (d) BASELINE config 4: a batch of `c4_frames` frames of this config, stock = frame index % 4, frame ->
+    # rank index % world, through BatchExporter (producer thread = phase 1, consumer = pipelined phase 2)
+    c4 = None
+    if args.c4_frames > 0:
+        stocks4 = [SyntheticStock(variant=v) for v in range(4)]
+        tasks = [{"src": host_frames[i % n_frames], "negative_film": stocks4[i % 4], "grain_size": GRAIN_SIZE,
+                  "grain_sigma": GRAIN_SIGMA, "settings": settings} for i in range(args.c4_frames)]
+        exporter = BatchExporter(proc, world_size=world, rank=rank)
+        exporter.run(tasks[:4 * world], sink)                       # warm every stock's table slot on every rank
+        barrier()
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        c0.record(exporter._pipe.s_in)
+        report = exporter.run(tasks, sink)
+        c1.record(exporter._pipe.s_out)
+        barrier()
+        c4 = {"ms": c0.elapsed_time(c1), "wall_s": report["seconds"], "phase1_s": report["phase1_seconds"],
+              "frames_rank": len(report["frames"])}
     clocks = sampler.stop() if rank == 0 else None
 
     if world > 1:
-        t = torch.tensor([ms_total, ms_e2e, ms_e2e16], dtype=torch.float64, device="cuda")
+        vals = [ms_total, ms_e2e, ms_e2e16, ms_sync, ms_sync_wall, c4["ms"] if c4 else 0.0,
+                c4["wall_s"] if c4 else 0.0, c4["phase1_s"] if c4 else 0.0]
+        t = torch.tensor(vals, dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_total, ms_e2e, ms_e2e16 = float(t[0]), float(t[1]), float(t[2])
-        ln = torch.tensor([launches], dtype=torch.int64, device="cuda")
+        ms_total, ms_e2e, ms_e2e16, ms_sync, ms_sync_wall = (float(t[i]) for i in range(5))
+        if c4:
+            c4["ms"], c4["wall_s"], c4["phase1_s"] = float(t[5]), float(t[6]), float(t[7])
+        ln = torch.tensor([launches, c4["frames_rank"] if c4 else 0], dtype=torch.int64, device="cuda")
         dist.all_reduce(ln)
         launches = int(ln[0])
+        if c4:
+            c4["frames_rank"] = int(ln[1])
 
     if rank == 0:
         peak, peak_src = load_peaks()
         value = world * args.steps * mp / (ms_total / 1e3)
-        e2e_value = world * args.steps * mp / (ms_e2e / 1e3)
         kernels = {}
         for name, ms, n in zip(_cabi.PROF_NAMES, prof_ms, prof_n):
             if n:
                 kernels[name] = {"ms": ms / n, "launches_per_step": n / args.steps,
                                  "gbs": KERNEL_BYTES_PER_PX[name] * H * W / (ms / n * 1e-3) / 1e9}
+                kernels[name]["hbm_frac"] = kernels[name]["gbs"] / peak
         dom = max(kernels, key=lambda k: kernels[k]["ms"] * kernels[k]["launches_per_step"]) if kernels else None
         roofline = None
         if dom:
@@ -362,26 +423,38 @@ def main():
                         "share_of_step": kernels[dom]["ms"] * kernels[dom]["launches_per_step"] / (ms_total / args.steps),
                         "step_alg_gbs": ALG_BYTES_PER_PX[args.config] * H * W / (ms_total / args.steps * 1e-3) / 1e9,
                         "step_frac": ALG_BYTES_PER_PX[args.config] * H * W / (ms_total / args.steps * 1e-3) / 1e9 / peak}
-            # direct correlations are FP32 bound: report their algorithmic flop rate (2*k*k per px and filtered layer)
+            # direct correlations are FP32 bound.  Two rates: the algorithmic 2*k*k flop per pixel and filtered layer
+            # (what the reference's filter2D would execute), and the flop the y-symmetric kernel really executes:
+            # (k+1)/2 * k multiply-adds + the row-pair additions (2 * NQ*4 per kernel row and 16-pixel strip) --
+            # the executed rate is the one to hold against the measured FFMA peak (profiles/r01_ffma2_rate.txt).
             for name in ("halation", "mtf"):
                 k = getattr(proc, name + "_kernel", None) if name in kernels else None
                 if k is not None:
-                    taps = sum(int(np.count_nonzero(k[..., c])) > 1 for c in range(3)) * k.shape[0] * k.shape[1]
-                    kernels[name]["alg_fp32_tflops"] = 2.0 * taps * H * W / (kernels[name]["ms"] * 1e-3) / 1e12
-            if dom in ("halation", "mtf") and "alg_fp32_tflops" in kernels[dom]:
-                roofline["fp32_tflops"] = kernels[dom]["alg_fp32_tflops"]
-                roofline["note"] = ("direct 2-D correlation is FP32-FMA bound, not HBM bound (SURVEY 8d); fp32_tflops "
-                                    "counts the algorithmic 2*k*k flops/px/layer, the y-symmetric kernel executes "
-                                    "about half of them")
+                    kk = k.shape[0]
+                    layers = sum(int(np.count_nonzero(k[..., c])) > 1 for c in range(3))
+                    sec = kernels[name]["ms"] * 1e-3
+                    kernels[name]["alg_fp32_tflops"] = 2.0 * layers * kk * kk * H * W / sec / 1e12
+                    r = kk // 2
+                    nq = (16 + kk - 1 + 3) // 4
+                    exec_flop_px = (2.0 * (r + 1) * kk) + (r + 1) * (nq * 4) * 2 / 32.0
+                    kernels[name]["exec_fp32_tflops"] = layers * exec_flop_px * H * W / sec / 1e12
+            if dom in ("halation", "mtf") and "exec_fp32_tflops" in kernels[dom]:
+                roofline["fp32"] = {"executed_tflops": kernels[dom]["exec_fp32_tflops"], "peak_tflops": FFMA_PEAK_TFLOPS,
+                                    "frac": kernels[dom]["exec_fp32_tflops"] / FFMA_PEAK_TFLOPS,
+                                    "algorithmic_tflops": kernels[dom]["alg_fp32_tflops"],
+                                    "peak_source": "tools/micro/ffma2_rate.cu on this pool's B200 (profiles/r01_ffma2_rate.txt)"}
+                roofline["note"] = ("direct 2-D correlation is FP32-FMA bound, not HBM bound (SURVEY 8d): `fp32.frac` = "
+                                    "executed flop rate / measured FFMA peak is the fraction that describes it; `frac` "
+                                    "is its HBM fraction as the contract defines it")
             elif dom == "grain":
-                roofline["note"] = ("fused grain + tetrahedral LUT + quantise: ~470 instructions per pixel for 15 B/px, "
-                                    "bound by instruction issue and L1TEX, not HBM (profiles/)")
+                roofline["note"] = ("fused MTF/grain + tetrahedral LUT + quantise: bound by instruction issue and the "
+                                    "FP32 pipe, not HBM (profiles/)")
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
             from oracle import film_oracle as fo
 
             fo.use_all_host_threads()
-            xyz, st, sample = cpu_sample(args.config, H, W, settings, frac=2)
+            xyz, st, sample = cpu_sample(args.config, H, W, settings, rows=H // 2 if H > 2000 else H)
             cpu_render_once(fo, xyz[:64].copy(), stock, st)          # warm caches / thread pools
             t0 = time.perf_counter()
             cpu_render_once(fo, xyz, stock, st)
@@ -392,23 +465,34 @@ def main():
             "metric": "megapixels_per_second", "value": value, "unit": "MP/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": desc, "name": args.config, "frames_per_s": value / mp,
-                       "l2": f"inputs larger than L2: {n_frames} distinct {H * W * 12 / 1e6:.0f} MB frames rotated",
-                       "stocks": "variant = rank % 4 (mixed stocks across GPUs)"},
-            "e2e": {"value": e2e_value, "unit": "MP/s", "h2d_bytes_per_step": h2d_per_step,
-                    "d2h_bytes_per_step": d2h_per_step, "ms_per_step": ms_e2e / args.steps,
-                    "api": "PipelinedRenderer.run over extract_image_data_cpu payloads (pinned host float32 in, "
-                           "host uint8 out, H2D/render/D2H of consecutive frames overlapped, depth 3)",
-                    "sync_call_ms": ms_sync,
-                    "sync_call_api": "B200Processor.process_preloaded, one frame at a time"},
+            "config": config_dict(args.config), "frames_per_s": value / mp,
+            "e2e": {"value": world * args.steps * mp / (ms_sync / 1e3), "unit": "MP/s", "h2d_bytes_per_step": h2d_sync,
+                    "d2h_bytes_per_step": d2h_sync, "ms_per_step": ms_sync / args.steps,
+                    "wall_ms_per_step": ms_sync_wall / args.steps,
+                    "api": "B200Processor.process_preloaded (the reference's entry point, gpu_processor.py:1643-1693): one "
+                           "synchronous call per frame, pinned host float32 in, host uint8 out; H2D, render and D2H of "
+                           "a frame run back to back, nothing overlaps across calls"},
+            "e2e_pipelined": {"value": world * args.steps * mp / (ms_e2e / 1e3), "unit": "MP/s",
+                              "h2d_bytes_per_step": h2d_per_step, "d2h_bytes_per_step": d2h_per_step,
+                              "ms_per_step": ms_e2e / args.steps,
+                              "api": "PipelinedRenderer.run (what BatchExporter drives): H2D / render / D2H of "
+                                     "consecutive frames overlapped, depth 3"},
             "e2e_u16": {"value": world * args.steps * mp / (ms_e2e16 / 1e3), "unit": "MP/s",
                         "h2d_bytes_per_step": h2d16_per_step, "d2h_bytes_per_step": d2h_per_step,
                         "ms_per_step": ms_e2e16 / args.steps,
-                        "note": "same batch from uint16 XYZ frames (what rawpy hands over); /65535 and exposure "
-                                "gain applied on the device (SURVEY 8f-1)"},
-            "latency": latency, "affinity": affinity, "gpu_launches": launches, "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu, "clocks": clocks,
-            "checksum": checksum,
+                        "note": "same pipelined batch from uint16 XYZ frames (what rawpy hands over); /65535 and "
+                                "exposure gain applied on the device (SURVEY 8f-1)"},
+            "latency": latency, "affinity": affinity, "gpu_launches": launches, "roofline": roofline, "kernels": kernels,
+            "cpu_baseline": cpu, "clocks": clocks, "checksum": checksum,
         }
+        if c4:
+            nf = c4["frames_rank"]
+            line["c4"] = {"frames": nf, "frames_per_s": nf / (c4["ms"] / 1e3), "mp_per_s": nf * mp / (c4["ms"] / 1e3),
+                          "ms_total": c4["ms"], "wall_s": c4["wall_s"], "phase1_s_max_rank": c4["phase1_s"],
+                          "what": "BASELINE config 4: batch of frames of this config through BatchExporter, stock = frame "
+                                  "index % 4 (4 table slots per GPU), frame -> rank index % world; source frames live "
+                                  "in pinned host memory (B200Processor.pinned_frame), so phase 1 hands them to the "
+                                  "copy engine without a host copy; device-timed, max over ranks"}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -7,7 +7,10 @@
  * pipeline src/raw2film/gpu_processor.py:1695-1890).  Plain pointers and sizes only;
  * no torch / numpy types.  All image pointers passed to the *_dev entry points are
  * CUDA device pointers on the context's device; `stream` is a cudaStream_t (NULL =
- * legacy default stream).  Table setters take HOST pointers and copy synchronously.
+ * legacy default stream).  Table setters take HOST pointers; the data is on the device when they
+ * return.  Setters are copy-on-write: they never touch a buffer that a render already issued (on any
+ * stream) may still be reading, so tables may be changed between the frames of a pipelined batch
+ * without synchronising (reference gui_objects.py:65-115 renders mixed stocks back to back).
  *
  * Every function returns R2F_OK (0) or an error code; r2f_last_error() returns a
  * thread-local message (the reference raises plain Python exceptions; the Python shim
@@ -25,7 +28,7 @@
 extern "C" {
 #endif
 
-#define R2F_ABI_VERSION 1
+#define R2F_ABI_VERSION 2
 
 /* status codes */
 #define R2F_OK 0
@@ -59,14 +62,28 @@ const char *r2f_last_error(void);
 int r2f_create(int device, r2f_ctx **out);
 int r2f_destroy(r2f_ctx *ctx);
 
+/* ---- table slots ----------------------------------------------------------------------------
+ * A context holds R2F_MAX_SLOTS independent table sets (2-D LUT, H-D curve, 3-D LUT, halation / MTF /
+ * grain kernels and curves, burn parameters, grain seed).  Setters write to, and renders read from, the
+ * selected slot (slot 0 after r2f_create).  The reference processors keep ONE set and rebuild it whenever a
+ * settings sub-dict changes (cpu_processor.py:157, 179, 229); a batch over mixed stocks
+ * (gui.py:2472-2514) would re-upload everything on every frame -- with one slot per stock it switches by
+ * index.  r2f_clear_slot drops a slot's tables (renders in flight keep theirs until they finish). */
+#define R2F_MAX_SLOTS 16
+int r2f_select_slot(r2f_ctx *ctx, int slot);
+int r2f_clear_slot(r2f_ctx *ctx, int slot);
+
 /* ---- table setters: the device-side half of the reference's load_* caches ------------- */
 
 /* 2-D chromaticity input LUT, (n, n, 3) float32, index order lut[x_idx][y_idx]
  * (load_input_lut cpu_processor.py:142-164; _ensure_lut_2d gpu_processor.py:349-376). */
 int r2f_set_lut2d(r2f_ctx *ctx, const float *lut, int n);
 
-/* H-D curve, (4, N) float32: row 0 = log10-exposure abscissa (uniform), rows 1..3 = R,G,B
- * density (load_density_curve cpu_processor.py:166-188; _ensure_lut_1d gpu_processor.py:307-347).
+/* H-D curve, (4, N) float32: row 0 = log10-exposure abscissa, rows 1..3 = R,G,B density
+ * (load_density_curve cpu_processor.py:166-188; _ensure_lut_1d gpu_processor.py:307-347).
+ * A uniform abscissa (every sample within 1e-3 step of the straight line between its ends, e.g. a
+ * float32 linspace) takes the normalised lookup of shaders/lut_1d.wgsl:43-47; any other strictly
+ * increasing abscissa is evaluated with np.interp semantics (binary search, binary64 slope).
  * log_eps is the lower clip of log_clip (cpu_processor.py:378; shaders/lut_1d.wgsl:24). */
 int r2f_set_curve1d(r2f_ctx *ctx, const float *curve, int N, float log_eps);
 
@@ -93,6 +110,12 @@ int r2f_set_grain(r2f_ctx *ctx, const float *curve, int N, const float *kernel, 
  * 2 = force FFT (render fails if the kernel or frame is not eligible). */
 #define R2F_OPT_CONV_PATH 1
 #define R2F_OPT_CONV_SYM 2
+/* R2F_OPT_FUSE_MTF: 1 (default) = the MTF correlation is fused into the grain/finish kernel when the kernels
+ * allow it, 0 = separate launches (A/B and parity tests).
+ * R2F_OPT_FAST_CHAIN: 1 (default) = per-pixel chains evaluate a guarded float32 fast path and defer the pixels
+ * whose uint8 result it cannot prove to the exact path; 0 = exact path for every pixel. */
+#define R2F_OPT_FUSE_MTF 3
+#define R2F_OPT_FAST_CHAIN 4
 int r2f_set_option(r2f_ctx *ctx, int key, int value);
 
 /* Re-seed the on-device noise stream only (no table upload, no synchronisation). */

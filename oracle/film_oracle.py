@@ -163,9 +163,42 @@ def curve_inv_range(curve: np.ndarray) -> np.float32:
     return F32(1.0 / d) if d != 0.0 else F32(0.0)
 
 
+def abscissa_uniform(xp: np.ndarray) -> bool:
+    """Row 0 of a (4, N) table counts as uniform when every sample lies within 1e-3 of a step of the straight
+    line between its ends (e.g. a float32 linspace).  Uniform tables take the reference GPU path's normalised
+    lookup (lut_1d.wgsl:43-47, gpu_processor.py:322-325); anything else is an np.interp."""
+    xp = np.asarray(xp, np.float64)
+    n = xp.shape[0]
+    step = (xp[-1] - xp[0]) / (n - 1)
+    if not step > 0.0:
+        return step == 0.0
+    return bool(np.all(np.abs(xp - (xp[0] + step * np.arange(n))) <= 1e-3 * step))
+
+
+def multi_channel_interp_nonuniform(image: np.ndarray, curve: np.ndarray) -> np.ndarray:
+    """np.interp semantics per channel on the table's own abscissa: clamped ends, bracketing samples by
+    binary search, slope and offset in binary64 (separate multiply and add), one rounding to binary32."""
+    image, curve = _c32(image), _c32(curve)
+    xp = curve[0].astype(np.float64)
+    n = xp.shape[0]
+    out = np.empty_like(image)
+    for k in range(3):
+        fp = curve[k + 1].astype(np.float64)
+        v = image[..., k].astype(np.float64)
+        j = np.clip(np.searchsorted(xp, v, side="right") - 1, 0, n - 2)
+        slope = (fp[j + 1] - fp[j]) / (xp[j + 1] - xp[j])
+        res = slope * (v - xp[j]) + fp[j]
+        res = np.where(~(v > xp[0]), fp[0], res)              # includes NaN -> first sample
+        res = np.where(v >= xp[-1], fp[-1], res)
+        out[..., k] = res.astype(F32)
+    return out
+
+
 def multi_channel_interp(image: np.ndarray, curve: np.ndarray) -> np.ndarray:
     image, curve = _c32(image), _c32(curve)
     assert curve.shape[0] == 4 and image.shape[-1] == 3
+    if not abscissa_uniform(curve[0]):
+        return multi_channel_interp_nonuniform(image, curve)
     out = np.empty_like(image)
     _c().orc_curve_interp(_fp(image), image.size // 3, _fp(curve), curve.shape[1], curve_inv_range(curve), _fp(out))
     return out

@@ -10,10 +10,11 @@ LIB_PATH = os.path.join(_PKG, "libr2f_b200.so")
 
 from .flags import BURN, GRAIN, GRAIN_BW, HALATION, MTF, SPATIAL, TAPS  # noqa: F401  (include/r2f_b200.h)
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 EXPORTS = [
-    "r2f_abi_version", "r2f_last_error", "r2f_create", "r2f_destroy", "r2f_set_lut2d", "r2f_set_curve1d",
+    "r2f_abi_version", "r2f_last_error", "r2f_create", "r2f_destroy", "r2f_select_slot", "r2f_clear_slot",
+    "r2f_set_lut2d", "r2f_set_curve1d",
     "r2f_set_lut3d", "r2f_set_halation_kernel", "r2f_set_mtf_kernel", "r2f_set_grain", "r2f_set_grain_seed", "r2f_set_option",
     "r2f_set_burn",
     "r2f_workspace_bytes", "r2f_render", "r2f_render_ex", "r2f_render_tap", "r2f_render_tap_ex", "r2f_render_host", "r2f_convolve2d",
@@ -21,6 +22,9 @@ EXPORTS = [
 ]
 OPT_CONV_PATH = 1
 OPT_CONV_SYM = 2
+OPT_FUSE_MTF = 3
+OPT_FAST_CHAIN = 4
+MAX_SLOTS = 16
 IN_F32, IN_U16 = 0, 1
 PROF_NAMES = ["pointwise", "expose", "halation", "density", "mtf", "noise", "grain", "burn", "finish",
               "fft_rows_fwd", "fft_cols", "fft_rows_inv"]
@@ -44,6 +48,8 @@ def _load():
         "r2f_last_error": (ctypes.c_char_p, []),
         "r2f_create": (ci, [ci, ctypes.POINTER(vp)]),
         "r2f_destroy": (ci, [vp]),
+        "r2f_select_slot": (ci, [vp, ci]),
+        "r2f_clear_slot": (ci, [vp, ci]),
         "r2f_set_lut2d": (ci, [vp, fp, ci]),
         "r2f_set_curve1d": (ci, [vp, fp, ci, cf]),
         "r2f_set_lut3d": (ci, [vp, fp, ci, cd]),

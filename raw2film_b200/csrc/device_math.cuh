@@ -13,10 +13,12 @@
 namespace r2f {
 
 struct Lut2D {
-    const float *tab;  // (n, n, 3) lut[x_idx][y_idx]
+    const float *tab;    // (n, n, 3) lut[x_idx][y_idx], packed (the FFT row kernels park this 48 KB copy)
+    const float4 *tab4;  // same vertices padded to float4: one 128-bit read per vertex
     int n;
-    __host__ __device__ Lut2D() : tab(nullptr), n(0) {}
-    __host__ __device__ Lut2D(const float *t, int n_) : tab(t), n(n_) {}
+    __host__ __device__ Lut2D() : tab(nullptr), tab4(nullptr), n(0) {}
+    __host__ __device__ Lut2D(const float *t, int n_) : tab(t), tab4(nullptr), n(n_) {}
+    __host__ __device__ Lut2D(const float *t, const float4 *t4, int n_) : tab(t), tab4(t4), n(n_) {}
 };
 
 struct Curve1D {
@@ -26,6 +28,9 @@ struct Curve1D {
     int N;
     float x0;         // first abscissa
     float inv_range;  // float32(1 / (x_last - x_first))
+    // row 0 of the table when its abscissa is NOT uniform (else nullptr): the lookup then follows np.interp
+    // (binary search for the bracketing samples, binary64 slope), see curve_eval
+    const float *xp;
 };
 
 struct Lut3D {
@@ -128,7 +133,15 @@ __device__ __forceinline__ float lds_f32(unsigned addr) {
     return v;
 }
 
-template <bool SMEM = false>
+__device__ __forceinline__ float4 lds_f32x4(unsigned addr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+    return v;
+}
+
+// VEC4: read the float4-padded copy (L.tab4; three 128-bit reads per pixel) instead of the packed one
+// (nine scalar reads whose stride of 3 floats makes 56 % of the shared-memory wavefronts bank conflicts).
+template <bool SMEM = false, bool VEC4 = false>
 __device__ __forceinline__ void lut2d_eval(const Lut2D &L, float X, float Y, float Z, float &e0, float &e1,
                                            float &e2) {
     const float S = (X + Y) + Z;
@@ -143,25 +156,43 @@ __device__ __forceinline__ void lut2d_eval(const Lut2D &L, float X, float Y, flo
     const float rf = r - rfl, gf = g - gfl;
     const float fs = rf + gf;
     const bool lower = fs <= 1.0f;
-    const int n3 = 3 * n;
-    const float *base = L.tab + (ri * n3 + gi * 3);
-    const float *a = base + n3;                       // lut[ri+1][gi]
-    const float *b = base + 3;                        // lut[ri][gi+1]
-    const float *c = base + (lower ? 0 : n3 + 3);     // lut[ri][gi] or lut[ri+1][gi+1]
     const float wa = lower ? rf : 1.0f - gf;
     const float wb = lower ? gf : 1.0f - rf;
     const float wc = lower ? 1.0f - fs : fs - 1.0f;
     float a0, a1, a2, b0, b1, b2, c0, c1, c2;
-    if (SMEM) {
-        const unsigned sa = (unsigned)__cvta_generic_to_shared(a), sb = (unsigned)__cvta_generic_to_shared(b);
-        const unsigned sc = (unsigned)__cvta_generic_to_shared(c);
-        a0 = lds_f32(sa); a1 = lds_f32(sa + 4); a2 = lds_f32(sa + 8);
-        b0 = lds_f32(sb); b1 = lds_f32(sb + 4); b2 = lds_f32(sb + 8);
-        c0 = lds_f32(sc); c1 = lds_f32(sc + 4); c2 = lds_f32(sc + 8);
+    if (VEC4) {
+        const float4 *base = L.tab4 + (ri * n + gi);
+        const float4 *pa = base + n;                     // lut[ri+1][gi]
+        const float4 *pb = base + 1;                     // lut[ri][gi+1]
+        const float4 *pc = base + (lower ? 0 : n + 1);   // lut[ri][gi] or lut[ri+1][gi+1]
+        float4 va, vb, vc;
+        if (SMEM) {
+            va = lds_f32x4((unsigned)__cvta_generic_to_shared(pa));
+            vb = lds_f32x4((unsigned)__cvta_generic_to_shared(pb));
+            vc = lds_f32x4((unsigned)__cvta_generic_to_shared(pc));
+        } else {
+            va = __ldg(pa); vb = __ldg(pb); vc = __ldg(pc);
+        }
+        a0 = va.x; a1 = va.y; a2 = va.z;
+        b0 = vb.x; b1 = vb.y; b2 = vb.z;
+        c0 = vc.x; c1 = vc.y; c2 = vc.z;
     } else {
-        a0 = a[0]; a1 = a[1]; a2 = a[2];
-        b0 = b[0]; b1 = b[1]; b2 = b[2];
-        c0 = c[0]; c1 = c[1]; c2 = c[2];
+        const int n3 = 3 * n;
+        const float *base = L.tab + (ri * n3 + gi * 3);
+        const float *a = base + n3;                       // lut[ri+1][gi]
+        const float *b = base + 3;                        // lut[ri][gi+1]
+        const float *c = base + (lower ? 0 : n3 + 3);     // lut[ri][gi] or lut[ri+1][gi+1]
+        if (SMEM) {
+            const unsigned sa = (unsigned)__cvta_generic_to_shared(a), sb = (unsigned)__cvta_generic_to_shared(b);
+            const unsigned sc = (unsigned)__cvta_generic_to_shared(c);
+            a0 = lds_f32(sa); a1 = lds_f32(sa + 4); a2 = lds_f32(sa + 8);
+            b0 = lds_f32(sb); b1 = lds_f32(sb + 4); b2 = lds_f32(sb + 8);
+            c0 = lds_f32(sc); c1 = lds_f32(sc + 4); c2 = lds_f32(sc + 8);
+        } else {
+            a0 = a[0]; a1 = a[1]; a2 = a[2];
+            b0 = b[0]; b1 = b[1]; b2 = b[2];
+            c0 = c[0]; c1 = c[1]; c2 = c[2];
+        }
     }
     const float v0 = ((a0 * wa + b0 * wb) + c0 * wc) * S;
     const float v1 = ((a1 * wa + b1 * wb) + c1 * wc) * S;
@@ -224,7 +255,26 @@ __device__ __forceinline__ float log10_clip_fast(float v, float eps) {
 }
 
 // ---- a5: per-channel curve, uniform abscissa, clamped ends (lut_1d.wgsl:43-47) -----------
+// Non-uniform abscissa: np.interp semantics (what a NumPy multi_channel_interp does on the CPU): clamped ends,
+// slope and offset in binary64, one rounding to binary32.  NaN -> first sample (like the uniform path).
+static __device__ __noinline__ float curve_eval_interp(const Curve1D &C, int ch, float v) {
+    const int N = C.N;
+    const float2 *seg = C.seg + ch * N;
+    if (!(v > C.xp[0])) return seg[0].x;
+    if (v >= C.xp[N - 1]) return seg[N - 1].x;
+    int lo = 0, hi = N - 1;  // xp[lo] <= v < xp[hi]
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (v >= C.xp[mid]) lo = mid;
+        else hi = mid;
+    }
+    const double x0 = C.xp[lo], x1 = C.xp[lo + 1], f0 = seg[lo].x, f1 = seg[lo + 1].x;
+    const double slope = (f1 - f0) / (x1 - x0);
+    return (float)(slope * ((double)v - x0) + f0);
+}
+
 __device__ __forceinline__ float curve_eval(const Curve1D &C, int ch, float v) {
+    if (C.xp != nullptr) return curve_eval_interp(C, ch, v);
     float t = (v - C.x0) * C.inv_range;
     t = fminf(fmaxf(t, 0.0f), 1.0f);  // clamp; NaN -> 0 (fmaxf returns the non-NaN operand)
     const float p = t * (float)(C.N - 1);

@@ -71,7 +71,7 @@ struct KernelSet {
     int fft_chan[2] = {0, 1};
     float fft_alpha[2] = {1.f, 1.f}, fft_beta[2] = {0.f, 0.f};
     DevBuf base;            // k x k base kernel, row-major, device
-    uint64_t generation = 0;  // bumped on every upload (keys the spectrum cache)
+    uint64_t base_hash = 0;  // FNV-1a of the base kernel's bytes and size (keys the spectrum cache)
 };
 
 // device copies of the per-length FFT tables
@@ -94,14 +94,13 @@ struct FftLineDev {
 
 }  // namespace
 
-struct r2f_ctx {
-    int device = 0;
-    int num_sms = 148;
-    uint64_t launches = 0;
-
-    DevBuf lut2d;
+// Everything one film stock + settings combination needs on the device (the reference's load_* caches,
+// cpu_processor.py:142-267, gpu_processor.py:792-936).  A context holds R2F_MAX_SLOTS of these so that a batch
+// over mixed stocks (gui_objects.py:65-115) switches tables by index instead of re-uploading them.
+struct TableSlot {
+    DevBuf lut2d, lut2d4;  // packed (n, n, 3) and float4-padded copies
     int n2 = 0;
-    DevBuf curve;
+    DevBuf curve, curve_xp;  // segments; abscissa row (only when it is not uniform)
     int n1 = 0;
     float x0 = 0.f, inv_range = 0.f, eps = 1e-6f;
     DevBuf lut3d;
@@ -111,29 +110,69 @@ struct r2f_ctx {
     int fast3 = 0;
 
     KernelSet hal, mtf, grain;
-    DevBuf gcurve;
+    DevBuf gcurve, gcurve_xp;
     int ng = 0;
     float gx0 = 0.f, ginv = 0.f;
     uint64_t seed = 0;
 
     bool burn_set = false;
     float d_ref = 0.f, burn_strength = 0.f, burn_scale = 50.f;
+};
+
+struct r2f_ctx {
+    int device = 0;
+    int num_sms = 148;
+    uint64_t launches = 0;
+
+    std::unique_ptr<TableSlot> slots[R2F_MAX_SLOTS];
+    TableSlot *t = nullptr;  // the selected slot
+    int cur_slot = 0;
+
+    // Copy-on-write table storage: a setter never overwrites a buffer a render in flight may still read.  It
+    // retires the old buffer tagged with the number of renders issued so far and takes a fresh one; retired
+    // buffers return to the pool once every render issued before the retirement has finished (render_done ring).
+    struct Retired {
+        void *p;
+        size_t bytes;
+        uint64_t seq;
+    };
+    std::vector<Retired> retired;
+    std::vector<std::pair<void *, size_t>> pool;
+    static constexpr int kRing = 32;
+    cudaEvent_t render_done[kRing] = {};
+    uint64_t issue_seq = 0, done_seq = 0;
+    cudaStream_t upload_stream = nullptr;
+    void *stage_host = nullptr;  // pinned staging for table uploads
+    size_t stage_bytes = 0;
+
     DevBuf burn_buf;
     DevBuf cnr_taps;
     DevBuf expo_buf;  // r2f_calc_exposure: per-CTA partial sums + the result
+    DevBuf hist_buf;  // r2f_histogram_image: counts + scalars
 
     // r2f_render_host staging
     DevBuf h_in, h_out, h_ws, h_noise;
     cudaStream_t host_stream = nullptr;
 
-    // FFT halation path: per-length tables, cached kernel spectrum
+    // FFT halation path: per-length tables, small LRU of kernel spectra keyed by kernel content + geometry
     std::map<int, std::unique_ptr<FftLineDev>> fft_lines;
-    DevBuf khat, khat_scratch;
-    uint64_t khat_generation = 0;
-    int khat_hp = 0, khat_wp = 0;
-    bool khat_permuted = false;
+    struct KhatEntry {
+        uint64_t hash = 0;
+        int k = 0, hp = 0, wp = 0;
+        bool permuted = false;
+        DevBuf buf;
+        cudaEvent_t ready = nullptr;
+        cudaStream_t stream = nullptr;
+        uint64_t last_use = 0;
+    };
+    static constexpr int kKhatEntries = 4;
+    KhatEntry khat[kKhatEntries];
+    uint64_t khat_clock = 0;
+    DevBuf khat_scratch;
     int conv_path = 0;  // R2F_OPT_CONV_PATH: 0 auto, 1 direct, 2 fft
     int conv_sym = 1;   // R2F_OPT_CONV_SYM: 1 = y-symmetric kernels take the packed-FMA kernel
+    int fuse_mtf = 1;   // R2F_OPT_FUSE_MTF: 1 = MTF fused into the grain/finish kernel when supported
+    int fast_chain = 1; // R2F_OPT_FAST_CHAIN: 1 = guarded float32 fast path of the pointwise chain
 
     // per-kernel profiling (r2f_profile_*)
     bool profiling = false;
@@ -158,10 +197,113 @@ struct DeviceGuard {
     }
 };
 
-int upload(DevBuf &b, const void *host, size_t bytes);
+// ---- copy-on-write table storage (see r2f_ctx) ---------------------------------------------------
+// Renders issued so far that have finished: advance over the completed prefix of the event ring.
+void sweep_done(r2f_ctx *c) {
+    while (c->done_seq < c->issue_seq &&
+           cudaEventQuery(c->render_done[c->done_seq % r2f_ctx::kRing]) == cudaSuccess)
+        c->done_seq += 1;
+    (void)cudaGetLastError();  // cudaErrorNotReady is not an error
+    for (size_t i = 0; i < c->retired.size();) {
+        if (c->retired[i].seq <= c->done_seq) {
+            c->pool.emplace_back(c->retired[i].p, c->retired[i].bytes);
+            c->retired[i] = c->retired.back();
+            c->retired.pop_back();
+        } else {
+            ++i;
+        }
+    }
+}
 
-// rows 1..3 of a (4, N) curve table -> 3*N segments (value, forward difference in float32), see Curve1D
-int upload_curve_segments(DevBuf &b, const float *curve, int N) {
+// Marks the end of one render call on its stream.
+cudaError_t mark_render(r2f_ctx *c, cudaStream_t st) {
+    const uint64_t seq = c->issue_seq;
+    cudaEvent_t &ev = c->render_done[seq % r2f_ctx::kRing];
+    if (!ev) {
+        cudaError_t e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
+        if (e != cudaSuccess) return e;
+    } else if (c->done_seq + r2f_ctx::kRing <= seq) {
+        // the ring slot still guards render seq - kRing: it has to finish before the event is re-recorded
+        cudaError_t e = cudaEventSynchronize(ev);
+        if (e != cudaSuccess) return e;
+        sweep_done(c);
+    }
+    cudaError_t e = cudaEventRecord(ev, st);
+    if (e == cudaSuccess) c->issue_seq = seq + 1;
+    return e;
+}
+
+void retire(r2f_ctx *c, DevBuf &b) {
+    if (b.p) c->retired.push_back({b.p, b.bytes, c->issue_seq});
+    b.p = nullptr;
+    b.bytes = 0;
+}
+
+cudaError_t acquire(r2f_ctx *c, DevBuf &b, size_t need) {
+    sweep_done(c);
+    size_t best = c->pool.size();
+    for (size_t i = 0; i < c->pool.size(); ++i)
+        if (c->pool[i].second >= need && c->pool[i].second <= 2 * need + 4096 &&
+            (best == c->pool.size() || c->pool[i].second < c->pool[best].second))
+            best = i;
+    if (best != c->pool.size()) {
+        b.p = c->pool[best].first;
+        b.bytes = c->pool[best].second;
+        c->pool[best] = c->pool.back();
+        c->pool.pop_back();
+        return cudaSuccess;
+    }
+    // keep the pool bounded: idle buffers are released before new memory is taken (cudaFree synchronises)
+    size_t pooled = 0;
+    for (auto &pb : c->pool) pooled += pb.second;
+    if (pooled > ((size_t)1 << 30)) {
+        for (auto &pb : c->pool) cudaFree(pb.first);
+        c->pool.clear();
+    }
+    b.p = nullptr;
+    b.bytes = 0;
+    cudaError_t e = cudaMalloc(&b.p, need);
+    if (e == cudaSuccess) b.bytes = need;
+    return e;
+}
+
+// Host table -> a FRESH device buffer (never the one a render in flight may be reading), complete on return:
+// pinned staging + asynchronous copy on the context's upload stream + synchronise.  (A plain cudaMemcpy from
+// pageable memory may return before the DMA has landed, and the legacy stream does not order against the
+// non-blocking streams renders run on.)
+int upload(r2f_ctx *c, DevBuf &b, const void *host, size_t bytes) {
+    retire(c, b);
+    CU(acquire(c, b, bytes));
+    if (!c->upload_stream) CU(cudaStreamCreateWithFlags(&c->upload_stream, cudaStreamNonBlocking));
+    if (c->stage_bytes < bytes) {
+        if (c->stage_host) cudaFreeHost(c->stage_host);
+        c->stage_host = nullptr;
+        c->stage_bytes = 0;
+        size_t cap = bytes < ((size_t)1 << 20) ? ((size_t)1 << 20) : bytes;
+        CU(cudaMallocHost(&c->stage_host, cap));
+        c->stage_bytes = cap;
+    }
+    std::memcpy(c->stage_host, host, bytes);
+    CU(cudaMemcpyAsync(b.p, c->stage_host, bytes, cudaMemcpyHostToDevice, c->upload_stream));
+    CU(cudaStreamSynchronize(c->upload_stream));
+    return R2F_OK;
+}
+
+// A (4, N) table's abscissa (row 0) counts as uniform when every sample lies within 1e-3 of a step of the
+// straight line between its ends -- e.g. a float32 np.linspace.  Uniform tables take the reference GPU path's
+// normalised lookup (shaders/lut_1d.wgsl:43-47, gpu_processor.py:322-325); anything else is evaluated with
+// np.interp semantics on the stored abscissa (binary search, binary64 slope), see curve_eval.
+bool abscissa_uniform(const float *xp, int N) {
+    const double a = xp[0], b = xp[N - 1], step = (b - a) / (double)(N - 1);
+    if (!(step > 0.0)) return step == 0.0;  // degenerate range: the normalised lookup returns row[0]
+    for (int i = 0; i < N; ++i)
+        if (!(std::fabs((double)xp[i] - (a + step * i)) <= 1e-3 * step)) return false;
+    return true;
+}
+
+// rows 1..3 of a (4, N) curve table -> 3*N segments (value, forward difference in float32), see Curve1D;
+// a non-uniform abscissa is stored next to them.
+int upload_curve(r2f_ctx *c, DevBuf &b, DevBuf &xp, const float *curve, int N) {
     std::vector<float> seg((size_t)3 * N * 2);
     for (int ch = 0; ch < 3; ++ch) {
         const float *row = curve + (size_t)(ch + 1) * N;
@@ -170,13 +312,24 @@ int upload_curve_segments(DevBuf &b, const float *curve, int N) {
             seg[((size_t)ch * N + i) * 2 + 1] = i + 1 < N ? row[i + 1] - row[i] : 0.0f;
         }
     }
-    return upload(b, seg.data(), seg.size() * sizeof(float));
+    int rc = upload(c, b, seg.data(), seg.size() * sizeof(float));
+    if (rc != R2F_OK) return rc;
+    if (abscissa_uniform(curve, N)) {
+        retire(c, xp);
+        return R2F_OK;
+    }
+    for (int i = 0; i + 1 < N; ++i)
+        if (!(curve[i + 1] > curve[i])) return fail(R2F_ERR_INVALID, "curve abscissa (row 0) must be strictly increasing");
+    return upload(c, xp, curve, (size_t)N * sizeof(float));
 }
 
-int upload(DevBuf &b, const void *host, size_t bytes) {
-    CU(b.ensure(bytes));
-    CU(cudaMemcpy(b.p, host, bytes, cudaMemcpyHostToDevice));
-    return R2F_OK;
+uint64_t fnv1a(const void *data, size_t bytes, uint64_t h = 1469598103934665603ull) {
+    const unsigned char *p = static_cast<const unsigned char *>(data);
+    for (size_t i = 0; i < bytes; ++i) {
+        h ^= p[i];
+        h *= 1099511628211ull;
+    }
+    return h;
 }
 
 float inv_range_of(float first, float last) {
@@ -185,7 +338,7 @@ float inv_range_of(float first, float last) {
 }
 
 // channels == 3: (k,k,3) interleaved; channels == 1: (k,k)
-int upload_kernel(KernelSet &ks, const float *kernel, int k, int channels) {
+int upload_kernel(r2f_ctx *ctx, KernelSet &ks, const float *kernel, int k, int channels) {
     if (kernel == nullptr || k < 1 || (k & 1) == 0) return fail(R2F_ERR_INVALID, "kernel must be non-null with odd size");
     const int kp = (k + 3) / 4 * 4;
     const size_t per = (size_t)k * kp;
@@ -202,7 +355,7 @@ int upload_kernel(KernelSet &ks, const float *kernel, int k, int channels) {
             }
         mode[c] = delta ? 0 : 1;
     }
-    int rc = upload(ks.buf, host.data(), host.size() * sizeof(float));
+    int rc = upload(ctx, ks.buf, host.data(), host.size() * sizeof(float));
     if (rc != R2F_OK) return rc;
     ks.k = k;
     ks.kp = kp;
@@ -212,7 +365,7 @@ int upload_kernel(KernelSet &ks, const float *kernel, int k, int channels) {
         ks.chan[c] = static_cast<const float *>(ks.buf.p) + per * src;
     }
     ks.set = true;
-    ks.generation += 1;
+    ks.base_hash = 0;
     ks.fft_ok = false;
     // y-symmetric layout: rows dy = 0..r, (w, w) pairs, centre row halved (exact: power-of-two scaling)
     ks.sym_ok = false;
@@ -238,7 +391,7 @@ int upload_kernel(KernelSet &ks, const float *kernel, int k, int channels) {
                     sh[sper * c + ((size_t)dy * wrow + j) * 2 + 1] = w;
                 }
         if (sym) {
-            rc = upload(ks.symbuf, sh.data(), sh.size() * sizeof(float));
+            rc = upload(ctx, ks.symbuf, sh.data(), sh.size() * sizeof(float));
             if (rc != R2F_OK) return rc;
             for (int c = 0; c < 3; ++c)
                 ks.sym[c] = static_cast<const float *>(ks.symbuf.p) + sper * (channels == 3 ? c : 0);
@@ -289,8 +442,9 @@ int upload_kernel(KernelSet &ks, const float *kernel, int k, int channels) {
                     }
                     base[(size_t)mid * k + mid] = (float)smooth_centre;
                     const double bc = (double)base[(size_t)mid * k + mid];
-                    rc = upload(ks.base, base.data(), base.size() * sizeof(float));
+                    rc = upload(ctx, ks.base, base.data(), base.size() * sizeof(float));
                     if (rc != R2F_OK) return rc;
+                    ks.base_hash = fnv1a(base.data(), base.size() * sizeof(float), 1469598103934665603ull ^ (uint64_t)k);
                     ks.fft_ok = true;
                     ks.fft_chan[0] = c0;
                     ks.fft_chan[1] = c1;
@@ -343,10 +497,10 @@ FftLineDev *fft_line_for(r2f_ctx *c, int n) {
     if (it != c->fft_lines.end()) return it->second.get();
     std::unique_ptr<FftLineDev> d(new FftLineDev());
     if (!fft_make_line(n, d->host)) return nullptr;
-    if (upload(d->roots, d->host.roots.data(), d->host.roots.size() * sizeof(float2)) != R2F_OK) return nullptr;
-    if (upload(d->roots_ip, d->host.roots_ip.data(), d->host.roots_ip.size() * sizeof(float2)) != R2F_OK) return nullptr;
-    if (upload(d->perm, d->host.perm.data(), d->host.perm.size() * sizeof(int)) != R2F_OK) return nullptr;
-    if (upload(d->cosines, d->host.cosines.data(), d->host.cosines.size() * sizeof(double)) != R2F_OK) return nullptr;
+    if (upload(c, d->roots, d->host.roots.data(), d->host.roots.size() * sizeof(float2)) != R2F_OK) return nullptr;
+    if (upload(c, d->roots_ip, d->host.roots_ip.data(), d->host.roots_ip.size() * sizeof(float2)) != R2F_OK) return nullptr;
+    if (upload(c, d->perm, d->host.perm.data(), d->host.perm.size() * sizeof(int)) != R2F_OK) return nullptr;
+    if (upload(c, d->cosines, d->host.cosines.data(), d->host.cosines.size() * sizeof(double)) != R2F_OK) return nullptr;
     FftLineDev *raw = d.get();
     c->fft_lines[n] = std::move(d);
     return raw;
@@ -356,20 +510,36 @@ FftLineDev *fft_line_for(r2f_ctx *c, int n) {
 int fft_prepare(r2f_ctx *c, const KernelSet &ks, int H, int W, const FftGeometry &g, FftConvArgs &a, cudaStream_t st) {
     FftLineDev *row = fft_line_for(c, g.Wp), *col = fft_line_for(c, g.Hp);
     if (!row || !col) return fail(R2F_ERR_INVALID, "FFT plan construction failed");
-    if (c->khat_generation != ks.generation || c->khat_hp != g.Hp || c->khat_wp != g.Wp || !c->khat.p ||
-        c->khat_permuted != g.inplace) {
-        CU(c->khat.ensure((size_t)g.Hp * g.Wp * sizeof(float)));
+    // kernel spectrum: small LRU keyed by the base kernel's content and the padded geometry, shared by all
+    // table slots (stocks usually share one halation kernel)
+    r2f_ctx::KhatEntry *ent = nullptr, *lru = &c->khat[0];
+    for (auto &e : c->khat) {
+        if (e.buf.p && e.hash == ks.base_hash && e.k == ks.k && e.hp == g.Hp && e.wp == g.Wp && e.permuted == g.inplace)
+            ent = &e;
+        if (!e.buf.p || (lru->buf.p && e.last_use < lru->last_use)) lru = &e;
+    }
+    if (!ent) {
+        ent = lru;
+        retire(c, ent->buf);
+        CU(acquire(c, ent->buf, (size_t)g.Hp * g.Wp * sizeof(float)));
         CU(c->khat_scratch.ensure((size_t)ks.k * g.Wp * sizeof(double)));
         CU(launch_khat(static_cast<const float *>(ks.base.p), ks.k, g.Hp, g.Wp,
                        static_cast<const double *>(col->cosines.p), static_cast<const double *>(row->cosines.p),
-                       static_cast<double *>(c->khat_scratch.p), static_cast<float *>(c->khat.p),
+                       static_cast<double *>(c->khat_scratch.p), static_cast<float *>(ent->buf.p),
                        g.inplace ? static_cast<const int *>(col->perm.p) : nullptr, st));
         c->launches += 2;
-        c->khat_generation = ks.generation;
-        c->khat_hp = g.Hp;
-        c->khat_wp = g.Wp;
-        c->khat_permuted = g.inplace;
+        if (!ent->ready) CU(cudaEventCreateWithFlags(&ent->ready, cudaEventDisableTiming));
+        CU(cudaEventRecord(ent->ready, st));
+        ent->stream = st;
+        ent->hash = ks.base_hash;
+        ent->k = ks.k;
+        ent->hp = g.Hp;
+        ent->wp = g.Wp;
+        ent->permuted = g.inplace;
+    } else if (ent->stream != st) {
+        CU(cudaStreamWaitEvent(st, ent->ready, 0));  // built on another stream: order this render after it
     }
+    ent->last_use = ++c->khat_clock;
     a.H = H;
     a.W = W;
     a.r = ks.k / 2;
@@ -378,7 +548,7 @@ int fft_prepare(r2f_ctx *c, const KernelSet &ks, int H, int W, const FftGeometry
     a.nc = g.nc;
     a.col_groups = g.groups;
     a.col_inplace = g.inplace ? 1 : 0;
-    a.khat = static_cast<const float *>(c->khat.p);
+    a.khat = static_cast<const float *>(ent->buf.p);
     for (int i = 0; i < 2; ++i) {
         a.chan[i] = ks.fft_chan[i];
         a.alpha[i] = ks.fft_alpha[i];
@@ -395,15 +565,20 @@ bool want_fft(const r2f_ctx *c, const KernelSet &ks, int H, int W, FftGeometry &
     return g.ok;
 }
 
-Lut2D lut2d_of(const r2f_ctx *c) { return Lut2D{static_cast<const float *>(c->lut2d.p), c->n2}; }
+Lut2D lut2d_of(const r2f_ctx *c) {
+    return Lut2D(static_cast<const float *>(c->t->lut2d.p), static_cast<const float4 *>(c->t->lut2d4.p), c->t->n2);
+}
 Curve1D curve_of(const r2f_ctx *c) {
-    return Curve1D{static_cast<const float2 *>(c->curve.p), c->n1, c->x0, c->inv_range};
+    return Curve1D{static_cast<const float2 *>(c->t->curve.p), c->t->n1, c->t->x0, c->t->inv_range,
+                   static_cast<const float *>(c->t->curve_xp.p)};
 }
 Curve1D gcurve_of(const r2f_ctx *c) {
-    return Curve1D{static_cast<const float2 *>(c->gcurve.p), c->ng, c->gx0, c->ginv};
+    return Curve1D{static_cast<const float2 *>(c->t->gcurve.p), c->t->ng, c->t->gx0, c->t->ginv,
+                   static_cast<const float *>(c->t->gcurve_xp.p)};
 }
 Lut3D lut3d_of(const r2f_ctx *c) {
-    return Lut3D{static_cast<const float4 *>(c->lut3d.p), c->n3, c->s3, c->s3f, c->margin3, c->fast3};
+    const TableSlot *t = c->t;
+    return Lut3D{static_cast<const float4 *>(t->lut3d.p), t->n3, t->s3, t->s3f, t->margin3, t->fast3};
 }
 
 ConvArgs conv_args(const KernelSet &ks, const float *in, float *out, size_t ps, int H, int W) {
@@ -489,18 +664,19 @@ BurnDims burn_dims(int H, int W, float burn_scale) {
 }
 
 int check_tables(const r2f_ctx *c, unsigned flags) {
-    if (!c->lut2d.p) return fail(R2F_ERR_INVALID, "2D input LUT not set (r2f_set_lut2d)");
-    if (!c->curve.p) return fail(R2F_ERR_INVALID, "density curve not set (r2f_set_curve1d)");
-    if (!c->lut3d.p) return fail(R2F_ERR_INVALID, "3D output LUT not set (r2f_set_lut3d)");
-    if ((flags & R2F_HALATION) && !c->hal.set) return fail(R2F_ERR_INVALID, "halation kernel not set");
-    if ((flags & R2F_MTF) && !c->mtf.set) return fail(R2F_ERR_INVALID, "MTF kernel not set");
-    if ((flags & R2F_GRAIN) && (!c->grain.set || !c->gcurve.p)) return fail(R2F_ERR_INVALID, "grain tables not set");
-    if ((flags & R2F_BURN) && !c->burn_set) return fail(R2F_ERR_INVALID, "burn parameters not set");
+    const TableSlot *t = c->t;
+    if (!t->lut2d.p) return fail(R2F_ERR_INVALID, "2D input LUT not set (r2f_set_lut2d)");
+    if (!t->curve.p) return fail(R2F_ERR_INVALID, "density curve not set (r2f_set_curve1d)");
+    if (!t->lut3d.p) return fail(R2F_ERR_INVALID, "3D output LUT not set (r2f_set_lut3d)");
+    if ((flags & R2F_HALATION) && !t->hal.set) return fail(R2F_ERR_INVALID, "halation kernel not set");
+    if ((flags & R2F_MTF) && !t->mtf.set) return fail(R2F_ERR_INVALID, "MTF kernel not set");
+    if ((flags & R2F_GRAIN) && (!t->grain.set || !t->gcurve.p)) return fail(R2F_ERR_INVALID, "grain tables not set");
+    if ((flags & R2F_BURN) && !t->burn_set) return fail(R2F_ERR_INVALID, "burn parameters not set");
     return R2F_OK;
 }
 
 // The whole pipeline.  tap_stage == 0: normal render to out_u8.
-int render_impl(r2f_ctx *c, const void *in, int in_format, float in_gain, int H, int W, int cin, uint8_t *out_u8,
+int render_body(r2f_ctx *c, const void *in, int in_format, float in_gain, int H, int W, int cin, uint8_t *out_u8,
                 unsigned flags, const float *noise, int noise_ch, void *ws, size_t ws_bytes, int tap_stage,
                 float *tap, cudaStream_t st) {
     if (!c) return fail(R2F_ERR_INVALID, "null context");
@@ -525,7 +701,7 @@ int render_impl(r2f_ctx *c, const void *in, int in_format, float in_gain, int H,
 
     if (tap_stage == 0 && spatial == 0) {  // configs C1 / C5: one fused pass
         ProfScope ps_(c, st, R2F_PROF_POINTWISE);
-        CU(launch_pointwise(in, fmt, in_gain, out_u8, npix, l2, cv, c->eps, l3, c->num_sms, st));
+        CU(launch_pointwise(in, fmt, in_gain, out_u8, npix, l2, cv, c->t->eps, l3, c->num_sms, st));
         c->launches += 1;
         return R2F_OK;
     }
@@ -544,13 +720,13 @@ int render_impl(r2f_ctx *c, const void *in, int in_format, float in_gain, int H,
 
     // a2 (+ a3 + a4 + a5): exposure, halation, density
     FftGeometry geo;
-    const bool hal_fft = (flags & R2F_HALATION) && want_fft(c, c->hal, H, W, geo);
+    const bool hal_fft = (flags & R2F_HALATION) && want_fft(c, c->t->hal, H, W, geo);
     if (c->conv_path == 2 && (flags & R2F_HALATION) && !hal_fft)
         return fail(R2F_ERR_INVALID, "FFT path forced (R2F_OPT_CONV_PATH=2) but this kernel/frame is not eligible");
     if (hal_fft && tap_stage != R2F_TAP_EXPOSURE) {
         // XYZ -> 2-D LUT is fused into the row transforms; the exposure image is never materialised
         FftConvArgs fa{};
-        rc = fft_prepare(c, c->hal, H, W, geo, fa, st);
+        rc = fft_prepare(c, c->t->hal, H, W, geo, fa, st);
         if (rc != R2F_OK) return rc;
         fa.S = reinterpret_cast<float2 *>(P[2].base);
         fa.src_planar = nullptr;
@@ -560,7 +736,7 @@ int render_impl(r2f_ctx *c, const void *in, int in_format, float in_gain, int H,
         fa.exp_planar = P[0].base;
         fa.dst_planar = P[1].base;
         fa.curve = cv;
-        fa.eps = c->eps;
+        fa.eps = c->t->eps;
         for (int stage = 1; stage <= 3; ++stage) {
             ProfScope ps_(c, st, R2F_PROF_FFT_ROWS_FWD + stage - 1);
             CU(launch_fft_conv(fa, 1 + fmt, tap_stage != R2F_TAP_HALATION, st, stage));
@@ -578,7 +754,7 @@ int render_impl(r2f_ctx *c, const void *in, int in_format, float in_gain, int H,
         c->launches += 1;
         if (tap_stage == R2F_TAP_EXPOSURE) return export_tap(P[0]);
         if (flags & R2F_HALATION) {
-            ConvArgs a = conv_args(c->hal, P[0].base, P[1].base, ps, H, W);
+            ConvArgs a = conv_args(c->t->hal, P[0].base, P[1].base, ps, H, W);
             if (tap_stage == R2F_TAP_HALATION) {
                 CU(conv_dispatch(c, a, st));
                 c->launches += 1;
@@ -586,7 +762,7 @@ int render_impl(r2f_ctx *c, const void *in, int in_format, float in_gain, int H,
             }
             a.epi = EPI_DENSITY_FAST;
             a.curve = cv;
-            a.eps = c->eps;
+            a.eps = c->t->eps;
             ProfScope ps_(c, st, R2F_PROF_HALATION);
             CU(conv_dispatch(c, a, st));
         } else {
@@ -594,7 +770,7 @@ int render_impl(r2f_ctx *c, const void *in, int in_format, float in_gain, int H,
             ConvArgs a = identity_args(P[0].base, P[1].base, ps, H, W);
             a.epi = EPI_DENSITY;
             a.curve = cv;
-            a.eps = c->eps;
+            a.eps = c->t->eps;
             ProfScope ps_(c, st, R2F_PROF_DENSITY);
             CU(conv_dispatch(c, a, st));
         }
@@ -605,7 +781,7 @@ int render_impl(r2f_ctx *c, const void *in, int in_format, float in_gain, int H,
 
     // a6: MTF
     if (flags & R2F_MTF) {
-        ConvArgs a = conv_args(c->mtf, P[cur].base, P[1 - cur].base, ps, H, W);
+        ConvArgs a = conv_args(c->t->mtf, P[cur].base, P[1 - cur].base, ps, H, W);
         ProfScope ps_(c, st, R2F_PROF_MTF);
         CU(conv_dispatch(c, a, st));
         c->launches += 1;
@@ -616,7 +792,7 @@ int render_impl(r2f_ctx *c, const void *in, int in_format, float in_gain, int H,
     // a7 + a8 + a9 + a10 fused (normal render): noise regenerated per tile, nothing but the density
     // read and the uint8 write touches HBM.  Taps keep the staged kernels below.
     if (tap_stage == 0 && (flags & R2F_GRAIN) && !(flags & R2F_BURN) &&
-        (size_t)(64 + c->grain.k - 1) * (64 + c->grain.k - 1) * 4 + (size_t)c->grain.k * c->grain.kp * 4 + 16384 <=
+        (size_t)(64 + c->t->grain.k - 1) * (64 + c->t->grain.k - 1) * 4 + (size_t)c->t->grain.k * c->t->grain.kp * 4 + 16384 <=
             200 * 1024) {
         const int nch = (flags & R2F_GRAIN_BW) ? 1 : 3;
         GrainFinishArgs ga{};
@@ -632,13 +808,13 @@ int render_impl(r2f_ctx *c, const void *in, int in_format, float in_gain, int H,
         ga.plane_stride = ps;
         ga.H = H;
         ga.W = W;
-        ga.gk = c->grain.chan[0];
-        ga.gk_sym = c->grain.sym_ok ? c->grain.sym[0] : nullptr;
-        ga.k = c->grain.k;
-        ga.kp = c->grain.kp;
+        ga.gk = c->t->grain.chan[0];
+        ga.gk_sym = c->t->grain.sym_ok ? c->t->grain.sym[0] : nullptr;
+        ga.k = c->t->grain.k;
+        ga.kp = c->t->grain.kp;
         ga.bw = nch == 1;
-        ga.seed_lo = (uint32_t)c->seed;
-        ga.seed_hi = (uint32_t)(c->seed >> 32);
+        ga.seed_lo = (uint32_t)c->t->seed;
+        ga.seed_hi = (uint32_t)(c->t->seed >> 32);
         ga.gcurve = gcurve_of(c);
         ga.l3 = l3;
         ga.burn = BurnArgs{};
@@ -659,9 +835,9 @@ int render_impl(r2f_ctx *c, const void *in, int in_format, float in_gain, int H,
             CU(launch_interleaved_to_planar(noise, nch, nch, P[2], npix, c->num_sms, st));
         } else {
             ProfScope ps_(c, st, R2F_PROF_NOISE);
-            CU(launch_noise(P[2], nch, H, W, c->seed, c->num_sms, st));
+            CU(launch_noise(P[2], nch, H, W, c->t->seed, c->num_sms, st));
         }
-        ConvArgs a = conv_args(c->grain, P[2].base, P[1 - cur].base, ps, H, W);
+        ConvArgs a = conv_args(c->t->grain, P[2].base, P[1 - cur].base, ps, H, W);
         for (int ch = 0; ch < 3; ++ch) a.in_plane[ch] = nch == 1 ? 0 : ch;
         a.aux = P[cur].base;
         a.epi = EPI_GRAIN;
@@ -676,20 +852,20 @@ int render_impl(r2f_ctx *c, const void *in, int in_format, float in_gain, int H,
     // a8: burn mask
     BurnArgs burn{};
     if (flags & R2F_BURN) {
-        const BurnDims bd = burn_dims(H, W, c->burn_scale);
+        const BurnDims bd = burn_dims(H, W, c->t->burn_scale);
         if (bd.lh < 1 || bd.lw < 1) return fail(R2F_ERR_INVALID, "burn_scale too small for this frame");
         const size_t n = (size_t)bd.lh * bd.lw;
         CU(c->burn_buf.ensure(2 * n * sizeof(float)));
         float *map = static_cast<float *>(c->burn_buf.p), *tmp = map + n;
         ProfScope ps_(c, st, R2F_PROF_BURN);
-        CU(launch_burn_mask(P[cur].base + ps, H, W, bd.lh, bd.lw, c->d_ref, tmp, map, st));
+        CU(launch_burn_mask(P[cur].base + ps, H, W, bd.lh, bd.lw, c->t->d_ref, tmp, map, st));
         c->launches += 3;
         burn.map = map;
         burn.lh = bd.lh;
         burn.lw = bd.lw;
         burn.zh = bd.zh;
         burn.zw = bd.zw;
-        burn.strength = c->burn_strength;
+        burn.strength = c->t->burn_strength;
     }
     if (tap_stage == R2F_TAP_BURN) {
         CU(launch_finish(P[cur], npix, H, W, l3, burn, nullptr, tap, 0, c->num_sms, st));
@@ -705,6 +881,22 @@ int render_impl(r2f_ctx *c, const void *in, int in_format, float in_gain, int H,
         CU(launch_finish(P[cur], npix, H, W, l3, burn, out_u8, nullptr, 1, c->num_sms, st));
     c->launches += 1;
     return R2F_OK;
+}
+
+
+// Every render call ends with an event on its stream: the copy-on-write table storage uses it to know when
+// a replaced buffer is no longer read (mark_render / sweep_done).
+int render_impl(r2f_ctx *c, const void *in, int in_format, float in_gain, int H, int W, int cin, uint8_t *out_u8,
+                unsigned flags, const float *noise, int noise_ch, void *ws, size_t ws_bytes, int tap_stage,
+                float *tap, cudaStream_t st) {
+    const int rc = render_body(c, in, in_format, in_gain, H, W, cin, out_u8, flags, noise, noise_ch, ws, ws_bytes,
+                               tap_stage, tap, st);
+    if (c) {
+        DeviceGuard guard(c->device);
+        cudaError_t e = mark_render(c, st);
+        if (e != cudaSuccess && rc == R2F_OK) return fail_cuda(e, "mark_render");
+    }
+    return rc;
 }
 
 }  // namespace
@@ -728,52 +920,114 @@ int r2f_create(int device, r2f_ctx **out) {
     if (!c) return fail(R2F_ERR_NOMEM, "out of host memory");
     c->device = device;
     c->num_sms = prop.multiProcessorCount;
+    c->slots[0].reset(new TableSlot());
+    c->t = c->slots[0].get();
     *out = c;
     return R2F_OK;
 }
 
+namespace {
+void release_kernel_set(KernelSet &k) {
+    k.buf.release();
+    k.symbuf.release();
+    k.base.release();
+}
+void retire_slot(r2f_ctx *c, TableSlot &t) {
+    for (DevBuf *b : {&t.lut2d, &t.lut2d4, &t.curve, &t.curve_xp, &t.lut3d, &t.gcurve, &t.gcurve_xp, &t.hal.buf, &t.hal.symbuf,
+                      &t.hal.base, &t.mtf.buf, &t.mtf.symbuf, &t.mtf.base, &t.grain.buf, &t.grain.symbuf,
+                      &t.grain.base})
+        retire(c, *b);
+}
+}  // namespace
+
 int r2f_destroy(r2f_ctx *c) {
     if (!c) return R2F_OK;
     DeviceGuard guard(c->device);
-    for (DevBuf *b : {&c->lut2d, &c->curve, &c->lut3d, &c->hal.buf, &c->mtf.buf, &c->grain.buf, &c->gcurve,
-                      &c->burn_buf, &c->h_in, &c->h_out, &c->h_ws, &c->h_noise, &c->hal.base, &c->mtf.base,
-                      &c->grain.base, &c->khat, &c->khat_scratch, &c->cnr_taps, &c->hal.symbuf, &c->mtf.symbuf,
-                      &c->grain.symbuf, &c->expo_buf})
+    cudaDeviceSynchronize();
+    for (auto &sp : c->slots) {
+        if (!sp) continue;
+        for (DevBuf *b : {&sp->lut2d, &sp->lut2d4, &sp->curve, &sp->curve_xp, &sp->lut3d, &sp->gcurve, &sp->gcurve_xp}) b->release();
+        release_kernel_set(sp->hal);
+        release_kernel_set(sp->mtf);
+        release_kernel_set(sp->grain);
+    }
+    for (DevBuf *b : {&c->burn_buf, &c->h_in, &c->h_out, &c->h_ws, &c->h_noise, &c->khat_scratch, &c->cnr_taps,
+                      &c->expo_buf, &c->hist_buf})
         b->release();
+    for (auto &e : c->khat) {
+        e.buf.release();
+        if (e.ready) cudaEventDestroy(e.ready);
+    }
+    for (auto &r : c->retired) cudaFree(r.p);
+    for (auto &pb : c->pool) cudaFree(pb.first);
+    for (auto &ev : c->render_done)
+        if (ev) cudaEventDestroy(ev);
     for (auto &kv : c->fft_lines) {
         kv.second->roots.release();
         kv.second->roots_ip.release();
         kv.second->perm.release();
         kv.second->cosines.release();
     }
+    if (c->stage_host) cudaFreeHost(c->stage_host);
+    if (c->upload_stream) cudaStreamDestroy(c->upload_stream);
     if (c->host_stream) cudaStreamDestroy(c->host_stream);
     delete c;
+    return R2F_OK;
+}
+
+int r2f_select_slot(r2f_ctx *c, int slot) {
+    if (!c || slot < 0 || slot >= R2F_MAX_SLOTS) return fail(R2F_ERR_INVALID, "r2f_select_slot: slot out of range");
+    if (!c->slots[slot]) c->slots[slot].reset(new (std::nothrow) TableSlot());
+    if (!c->slots[slot]) return fail(R2F_ERR_NOMEM, "out of host memory");
+    c->t = c->slots[slot].get();
+    c->cur_slot = slot;
+    return R2F_OK;
+}
+
+int r2f_clear_slot(r2f_ctx *c, int slot) {
+    if (!c || slot < 0 || slot >= R2F_MAX_SLOTS) return fail(R2F_ERR_INVALID, "r2f_clear_slot: slot out of range");
+    if (!c->slots[slot]) return R2F_OK;
+    DeviceGuard guard(c->device);
+    retire_slot(c, *c->slots[slot]);  // renders in flight keep their tables until they finish
+    *c->slots[slot] = TableSlot();
     return R2F_OK;
 }
 
 int r2f_set_lut2d(r2f_ctx *c, const float *lut, int n) {
     if (!c || !lut || n < 2) return fail(R2F_ERR_INVALID, "r2f_set_lut2d: bad arguments");
     DeviceGuard guard(c->device);
-    int rc = upload(c->lut2d, lut, (size_t)n * n * 3 * sizeof(float));
-    if (rc == R2F_OK) c->n2 = n;
+    // vertices padded to float4: one 128-bit read per vertex (three per pixel instead of nine scalar reads)
+    const size_t verts = (size_t)n * n;
+    std::vector<float> padded(verts * 4);
+    for (size_t v = 0; v < verts; ++v) {
+        padded[4 * v + 0] = lut[3 * v + 0];
+        padded[4 * v + 1] = lut[3 * v + 1];
+        padded[4 * v + 2] = lut[3 * v + 2];
+        padded[4 * v + 3] = 0.0f;
+    }
+    int rc = upload(c, c->t->lut2d4, padded.data(), padded.size() * sizeof(float));
+    if (rc == R2F_OK) rc = upload(c, c->t->lut2d, lut, verts * 3 * sizeof(float));
+    if (rc == R2F_OK) c->t->n2 = n;
     return rc;
 }
 
 int r2f_set_curve1d(r2f_ctx *c, const float *curve, int N, float log_eps) {
     if (!c || !curve || N < 2) return fail(R2F_ERR_INVALID, "r2f_set_curve1d: bad arguments");
     DeviceGuard guard(c->device);
-    int rc = upload_curve_segments(c->curve, curve, N);
+    TableSlot *t = c->t;
+    int rc = upload_curve(c, t->curve, t->curve_xp, curve, N);
     if (rc != R2F_OK) return rc;
-    c->n1 = N;
-    c->x0 = curve[0];
-    c->inv_range = inv_range_of(curve[0], curve[N - 1]);
-    c->eps = log_eps;
+    t->n1 = N;
+    t->x0 = curve[0];
+    t->inv_range = inv_range_of(curve[0], curve[N - 1]);
+    t->eps = log_eps;
     return R2F_OK;
 }
 
 int r2f_set_lut3d(r2f_ctx *c, const float *lut, int n, double scale) {
     if (!c || !lut || n < 2) return fail(R2F_ERR_INVALID, "r2f_set_lut3d: bad arguments");
     DeviceGuard guard(c->device);
+    TableSlot *t = c->t;
     const size_t verts = (size_t)n * n * n;
     std::vector<float> padded(verts * 4);
     for (size_t v = 0; v < verts; ++v) {
@@ -782,10 +1036,10 @@ int r2f_set_lut3d(r2f_ctx *c, const float *lut, int n, double scale) {
         padded[4 * v + 2] = lut[3 * v + 2];
         padded[4 * v + 3] = 0.0f;
     }
-    int rc = upload(c->lut3d, padded.data(), padded.size() * sizeof(float));
+    int rc = upload(c, t->lut3d, padded.data(), padded.size() * sizeof(float));
     if (rc != R2F_OK) return rc;
-    c->n3 = n;
-    c->s3 = scale * (double)(n - 1);  // utils.py:258
+    t->n3 = n;
+    t->s3 = scale * (double)(n - 1);  // utils.py:258
     // Error bound of the float32 fast path (device_math.cuh tetra_quant_u8), in units of the
     // quantised output: three fused roundings of partial sums bounded by 1 + 2*range, the final
     // binary32 rounding of the exact path, the float32 product with 255, and -- when s is not a
@@ -797,40 +1051,41 @@ int r2f_set_lut3d(r2f_ctx *c, const float *lut, int n, double scale) {
     // the three fused roundings (and the exact path's final rounding) is at most u * absmax
     double err = 3.0 * u * absmax + u * absmax + 1e-30;
     int e2 = 0;
-    const bool pow2 = std::frexp(c->s3, &e2) == 0.5 && c->s3 > 0.0;
+    const bool pow2 = std::frexp(t->s3, &e2) == 0.5 && t->s3 > 0.0;
     if (!pow2) err += 3.0 * (2.0 * absmax) * (2.0 * u * (double)n);  // coordinate rounding x slopes
     double margin = 255.0 * err + 2.0 * u * 255.0 * std::fmax(1.0, absmax);
     margin *= 1.5;                                          // safety factor
-    c->s3f = (float)c->s3;
-    c->margin3 = (float)margin;
-    c->fast3 = (margin < 0.2 && (double)c->s3f == c->s3 && std::isfinite(absmax)) ? 1 : 0;
+    t->s3f = (float)t->s3;
+    t->margin3 = (float)margin;
+    t->fast3 = (margin < 0.2 && (double)t->s3f == t->s3 && std::isfinite(absmax)) ? 1 : 0;
     return R2F_OK;
 }
 
 int r2f_set_halation_kernel(r2f_ctx *c, const float *kernel, int k) {
     if (!c) return fail(R2F_ERR_INVALID, "null context");
     DeviceGuard guard(c->device);
-    return upload_kernel(c->hal, kernel, k, 3);
+    return upload_kernel(c, c->t->hal, kernel, k, 3);
 }
 
 int r2f_set_mtf_kernel(r2f_ctx *c, const float *kernel, int k) {
     if (!c) return fail(R2F_ERR_INVALID, "null context");
     DeviceGuard guard(c->device);
-    return upload_kernel(c->mtf, kernel, k, 3);
+    return upload_kernel(c, c->t->mtf, kernel, k, 3);
 }
 
 int r2f_set_grain(r2f_ctx *c, const float *curve, int N, const float *kernel, int k, uint64_t seed) {
     if (!c || !curve || N < 2) return fail(R2F_ERR_INVALID, "r2f_set_grain: bad arguments");
     DeviceGuard guard(c->device);
-    int rc = upload_curve_segments(c->gcurve, curve, N);
+    TableSlot *t = c->t;
+    int rc = upload_curve(c, t->gcurve, t->gcurve_xp, curve, N);
     if (rc != R2F_OK) return rc;
-    c->ng = N;
-    c->gx0 = curve[0];
-    c->ginv = inv_range_of(curve[0], curve[N - 1]);
+    t->ng = N;
+    t->gx0 = curve[0];
+    t->ginv = inv_range_of(curve[0], curve[N - 1]);
     const float one = 1.0f;  // gpu_processor.py:931-932: missing kernel -> 1x1 ones
-    rc = kernel ? upload_kernel(c->grain, kernel, k, 1) : upload_kernel(c->grain, &one, 1, 1);
+    rc = kernel ? upload_kernel(c, t->grain, kernel, k, 1) : upload_kernel(c, t->grain, &one, 1, 1);
     if (rc != R2F_OK) return rc;
-    c->seed = seed;
+    t->seed = seed;
     return R2F_OK;
 }
 
@@ -844,21 +1099,29 @@ int r2f_set_option(r2f_ctx *c, int key, int value) {
         c->conv_path = value;
         return R2F_OK;
     }
+    if (key == R2F_OPT_FUSE_MTF && (value == 0 || value == 1)) {
+        c->fuse_mtf = value;
+        return R2F_OK;
+    }
+    if (key == R2F_OPT_FAST_CHAIN && (value == 0 || value == 1)) {
+        c->fast_chain = value;
+        return R2F_OK;
+    }
     return fail(R2F_ERR_INVALID, "r2f_set_option: unknown key or value");
 }
 
 int r2f_set_grain_seed(r2f_ctx *c, uint64_t seed) {
     if (!c) return fail(R2F_ERR_INVALID, "null context");
-    c->seed = seed;
+    c->t->seed = seed;
     return R2F_OK;
 }
 
 int r2f_set_burn(r2f_ctx *c, float d_ref, float highlight_burn, float burn_scale) {
     if (!c || !(burn_scale > 0.f)) return fail(R2F_ERR_INVALID, "r2f_set_burn: bad arguments");
-    c->d_ref = d_ref;
-    c->burn_strength = highlight_burn;
-    c->burn_scale = burn_scale;
-    c->burn_set = true;
+    c->t->d_ref = d_ref;
+    c->t->burn_strength = highlight_burn;
+    c->t->burn_scale = burn_scale;
+    c->t->burn_set = true;
     return R2F_OK;
 }
 
@@ -935,7 +1198,7 @@ int r2f_convolve2d(r2f_ctx *c, const float *in_dev, float *out_dev, int H, int W
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     KernelSet ks;
     CU(cudaStreamSynchronize(st));
-    int rc = upload_kernel(ks, kernel, k, 3);
+    int rc = upload_kernel(c, ks, kernel, k, 3);
     if (rc != R2F_OK) return rc;
     Planes a{static_cast<float *>(workspace_dev), ps}, b{static_cast<float *>(workspace_dev) + 3 * ps, ps};
     const size_t npix = (size_t)H * W;
@@ -943,15 +1206,13 @@ int r2f_convolve2d(r2f_ctx *c, const float *in_dev, float *out_dev, int H, int W
     FftGeometry geo;
     const bool use_fft = want_fft(c, ks, H, W, geo) && workspace_bytes >= ps * 9 * sizeof(float);
     if (c->conv_path == 2 && !use_fft) {
-        ks.buf.release();
-        ks.base.release();
-        ks.symbuf.release();
+        retire(c, ks.buf);
+        retire(c, ks.base);
+        retire(c, ks.symbuf);
         return fail(R2F_ERR_INVALID, "FFT path forced but this kernel/frame/workspace is not eligible");
     }
     if (e == cudaSuccess && use_fft) {
         FftConvArgs fa{};
-        ks.generation = ~0ull - (c->launches & 0xffff);  // never collides with a cached halation spectrum
-        c->khat_generation = 0;
         rc = fft_prepare(c, ks, H, W, geo, fa, st);
         if (rc == R2F_OK) {
             fa.S = reinterpret_cast<float2 *>(static_cast<float *>(workspace_dev) + 6 * ps);
@@ -959,15 +1220,23 @@ int r2f_convolve2d(r2f_ctx *c, const float *in_dev, float *out_dev, int H, int W
             fa.dst_planar = b.base;
             e = launch_fft_conv(fa, 0, false, st);
         }
-        c->khat_generation = 0;  // the cached spectrum belongs to a temporary kernel: invalidate
     } else if (e == cudaSuccess) {
         e = conv_dispatch(c, conv_args(ks, a.base, b.base, ps, H, W), st);
     }
     if (e == cudaSuccess) e = launch_planar_to_interleaved(b, out_dev, npix, c->num_sms, st);
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);
-    ks.buf.release();
-    ks.base.release();
-    ks.symbuf.release();
+    if (e == cudaSuccess) {  // the temporary kernel's buffers are idle again: straight back to the pool
+        for (DevBuf *b : {&ks.buf, &ks.base, &ks.symbuf})
+            if (b->p) {
+                c->pool.emplace_back(b->p, b->bytes);
+                b->p = nullptr;
+                b->bytes = 0;
+            }
+    } else {
+        ks.buf.release();
+        ks.base.release();
+        ks.symbuf.release();
+    }
     if (rc != R2F_OK) return rc;
     if (e != cudaSuccess) return fail_cuda(e, "r2f_convolve2d");
     c->launches += 3;

@@ -32,11 +32,11 @@ __device__ __forceinline__ void stage_tables(float *smem, Lut2D &l2, Curve1D &cv
         for (int i = 4 * nq + threadIdx.x; i < n; i += blockDim.x) dst[i] = src[i];
     };
     float *p = smem;
-    if (want2d) {
-        const int n = l2.n * l2.n * 3;
-        stage(p, l2.tab, n);
-        l2.tab = p;
-        p += (n + 3) / 4 * 4;
+    if (want2d) {  // the float4-padded copy
+        const int n = l2.n * l2.n * 4;
+        stage(p, reinterpret_cast<const float *>(l2.tab4), n);
+        l2.tab4 = reinterpret_cast<const float4 *>(p);
+        p += n;
     }
     if (want1d) {
         const int n = cv.N * 3 * 2;
@@ -47,10 +47,11 @@ __device__ __forceinline__ void stage_tables(float *smem, Lut2D &l2, Curve1D &cv
     __syncthreads();
 }
 
+template <bool SMEM>
 __device__ __forceinline__ void pixel_chain(const float (&xyz)[3], const Lut2D &l2, const Curve1D &cv, float eps,
                                             const Lut3D &l3, uint32_t &r, uint32_t &g, uint32_t &b) {
     float e0, e1, e2;
-    lut2d_eval(l2, xyz[0], xyz[1], xyz[2], e0, e1, e2);
+    lut2d_eval<SMEM, true>(l2, xyz[0], xyz[1], xyz[2], e0, e1, e2);
     const float d0 = density_eval(cv, 0, e0, eps);
     const float d1 = density_eval(cv, 1, e1, eps);
     const float d2 = density_eval(cv, 2, e2, eps);
@@ -77,7 +78,8 @@ k_pointwise(const void *__restrict__ in, float gain, uint8_t *__restrict__ out, 
         load_quad<FMT>(in, q, gain, px);
         uint32_t b[12];
 #pragma unroll
-        for (int p = 0; p < 4; ++p) pixel_chain(px[p], l2, cv, eps, l3, b[3 * p], b[3 * p + 1], b[3 * p + 2]);
+        for (int p = 0; p < 4; ++p)
+            pixel_chain<SMEM_TABLES>(px[p], l2, cv, eps, l3, b[3 * p], b[3 * p + 1], b[3 * p + 2]);
         store_quad_u8(out, q, b);
     }
     if (blockIdx.x == 0 && threadIdx.x < (npix & 3)) {
@@ -85,7 +87,7 @@ k_pointwise(const void *__restrict__ in, float gain, uint8_t *__restrict__ out, 
         float xyz[3];
         load_px<FMT>(in, p, gain, xyz[0], xyz[1], xyz[2]);
         uint32_t r, g, b;
-        pixel_chain(xyz, l2, cv, eps, l3, r, g, b);
+        pixel_chain<SMEM_TABLES>(xyz, l2, cv, eps, l3, r, g, b);
         out[p * 3] = (uint8_t)r;
         out[p * 3 + 1] = (uint8_t)g;
         out[p * 3 + 2] = (uint8_t)b;
@@ -101,7 +103,7 @@ static int grid_for(size_t work_items, int num_sms, int ctas_per_sm) {
 
 static size_t table_smem_bytes(const Lut2D &l2, const Curve1D &cv, bool want2d, bool want1d) {
     size_t f = 0;
-    if (want2d) f += ((size_t)l2.n * l2.n * 3 + 3) / 4 * 4;
+    if (want2d) f += (size_t)l2.n * l2.n * 4;
     if (want1d) f += (size_t)cv.N * 3 * 2;
     return f * sizeof(float);
 }
@@ -155,7 +157,8 @@ k_expose(const void *__restrict__ in, float gain, float *__restrict__ out, size_
         load_quad<FMT>(in, q, gain, px);
         float e[3][4];
 #pragma unroll
-        for (int p = 0; p < 4; ++p) lut2d_eval(l2, px[p][0], px[p][1], px[p][2], e[0][p], e[1][p], e[2][p]);
+        for (int p = 0; p < 4; ++p)
+            lut2d_eval<SMEM_TABLES, true>(l2, px[p][0], px[p][1], px[p][2], e[0][p], e[1][p], e[2][p]);
 #pragma unroll
         for (int c = 0; c < 3; ++c)
             reinterpret_cast<float4 *>(out + c * plane_stride)[q] = make_float4(e[c][0], e[c][1], e[c][2], e[c][3]);
@@ -164,7 +167,7 @@ k_expose(const void *__restrict__ in, float gain, float *__restrict__ out, size_
         const size_t p = nquad * 4 + threadIdx.x;
         float X, Y, Z, e0, e1, e2;
         load_px<FMT>(in, p, gain, X, Y, Z);
-        lut2d_eval(l2, X, Y, Z, e0, e1, e2);
+        lut2d_eval<SMEM_TABLES, true>(l2, X, Y, Z, e0, e1, e2);
         out[p] = e0;
         out[plane_stride + p] = e1;
         out[2 * plane_stride + p] = e2;

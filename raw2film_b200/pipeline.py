@@ -5,10 +5,18 @@ This is the B200 form of the reference's batch export loop (`GpuWorker.run_tasks
 src/raw2film/gui_objects.py:65-115: the CPU phase of frame i+1 overlaps the GPU phase of
 frame i through a 1-deep queue): here the overlap is pushed down to the copy engines, so that a
 batch is bound by max(PCIe H2D, render, PCIe D2H) per frame instead of their sum.
+
+Consecutive frames may use different film stocks and settings (BASELINE config 4, "mixed stocks"):
+the processor keeps one device table slot per stock and every table upload is copy-on-write
+(include/r2f_b200.h), so a frame in flight never sees tables that a later submit changed.
+
+`B200Processor.process_preloaded` is one submit + result on a three-slot instance of this class.
 """
 from __future__ import annotations
 
 import numpy as np
+
+from . import _cabi, hostops
 
 
 class PipelinedRenderer:
@@ -26,60 +34,91 @@ class PipelinedRenderer:
         self.s_in = torch.cuda.Stream(device=dev)
         self.s_out = torch.cuda.Stream(device=dev)
         self.s_compute = processor.stream
-        self._slots = [dict(dev_in=None, dev_out=None, host_out=None, h2d=None, done=None, d2h=None)
+        self._slots = [dict(dev_in=None, dev_out=None, host_out=None, canvas_dev=None, used=False)
                        for _ in range(self.depth)]
         self._count = 0
+        self._last_slot = None
         self.h2d_bytes = 0
         self.d2h_bytes = 0
 
-    def _slot_buffers(self, slot, shape_in, tdtype):
+    def _slot_buffers(self, slot, shape_in, tdtype, out_shape):
         torch = self._torch
         h, w, ch = shape_in
+        dev = self.proc.device
         if slot["dev_in"] is None or tuple(slot["dev_in"].shape) != (h, w, ch) or slot["dev_in"].dtype != tdtype:
-            slot["dev_in"] = torch.empty((h, w, ch), dtype=tdtype, device=self.proc.device)
-            slot["dev_out"] = torch.empty((h, w, 3), dtype=torch.uint8, device=self.proc.device)
-            slot["host_out"] = torch.empty((h, w, 3), dtype=torch.uint8, pin_memory=True)
+            slot["dev_in"] = torch.empty((h, w, ch), dtype=tdtype, device=dev)
+            slot["dev_out"] = torch.empty((h, w, 3), dtype=torch.uint8, device=dev)
+        if slot["host_out"] is None or tuple(slot["host_out"].shape) != tuple(out_shape):
+            slot["host_out"] = torch.empty(tuple(out_shape), dtype=torch.uint8, pin_memory=True)
+            slot["canvas_dev"] = None
+        if "h2d" not in slot:
             for k in ("h2d", "done", "d2h"):
                 slot[k] = torch.cuda.Event()
-            slot["used"] = False
 
-    def submit(self, cpu_payload, negative_film, grain_size, grain_sigma, **settings) -> int:
+    def submit(self, cpu_payload, negative_film, grain_size, grain_sigma, upload: bool = True, **settings) -> int:
+        """Enqueue one frame.  `upload=False` renders the frame that the previous submit left on the device
+        again (interactive re-render with changed settings: no host -> device copy)."""
         torch = self._torch
-        if cpu_payload.get("_canvas") is not None or (
-                cpu_payload.get("_orig_resolution") is not None
-                and tuple(cpu_payload["_orig_resolution"]) != tuple(cpu_payload["image_array"].shape[:2])):
-            raise NotImplementedError("canvas / post-resize frames go through B200Processor.process_preloaded")
+        proc = self.proc
         arr = cpu_payload["image_array"]
-        host = cpu_payload.get("_pinned")
         tdtype = torch.uint16 if arr.dtype == np.uint16 else torch.float32
-        if host is None:  # foreign payload: stage through pinned memory (extra host copy)
-            host = torch.empty(arr.shape, dtype=tdtype, pin_memory=True)
-            host.numpy()[...] = arr
+        h, w = arr.shape[:2]
+        canvas = cpu_payload.get("_canvas")
+        out_shape = (h, w, 3) if canvas is None else (canvas["size"][0], canvas["size"][1], 3)
         ticket = self._count
         slot = self._slots[ticket % self.depth]
-        self._slot_buffers(slot, arr.shape, tdtype)
         if slot["used"]:
             slot["d2h"].synchronize()          # the slot's previous result has left the device
-        with torch.cuda.stream(self.s_in):
-            if slot["used"]:
-                self.s_in.wait_event(slot["done"])   # previous render of this slot finished reading dev_in
-            slot["dev_in"].copy_(host, non_blocking=True)
-            slot["h2d"].record(self.s_in)
-        self.s_compute.wait_event(slot["h2d"])
+        if upload:
+            host = cpu_payload.get("_pinned")
+            if host is None:  # foreign payload: stage through pinned memory (extra host copy)
+                host = torch.empty(arr.shape, dtype=tdtype, pin_memory=True)
+                host.numpy()[...] = arr
+            self._slot_buffers(slot, arr.shape, tdtype, out_shape)
+            with torch.cuda.stream(self.s_in):
+                if slot.get("last_read") is not None:
+                    self.s_in.wait_event(slot["last_read"])   # the last render that read this dev_in has finished
+                slot["dev_in"].copy_(host, non_blocking=True)
+                slot["h2d"].record(self.s_in)
+            self.s_compute.wait_event(slot["h2d"])
+            slot["keep"] = host                       # keep the pinned source alive until the copy ran
+            self.h2d_bytes += host.numel() * host.element_size()
+            dev_in = slot["dev_in"]
+            reader = slot
+        else:
+            prev = self._last_slot
+            if prev is None or prev["dev_in"] is None or tuple(prev["dev_in"].shape) != tuple(arr.shape):
+                raise RuntimeError("upload=False needs the same frame to be on the device from the previous submit")
+            dev_in = prev["dev_in"]                   # same compute stream: ordered after the previous render
+            reader = prev
+            self._slot_buffers(slot, arr.shape, tdtype, out_shape)
         if slot["used"]:
             self.s_compute.wait_event(slot["d2h"])
-        self.proc.render_device(slot["dev_in"], negative_film, grain_size, grain_sigma, out=slot["dev_out"],
-                                stream=self.s_compute, sync_caller=False,
-                                input_gain=cpu_payload.get("input_gain", 1.0), **settings)
+        proc.output_resolution = cpu_payload.get("output_resolution")
+        proc.canvas_resolution = cpu_payload.get("canvas_resolution")
+        proc.pipeline_resolution = cpu_payload.get("pipeline_resolution")
+        out_dev = proc.render_device(dev_in, negative_film, grain_size, grain_sigma, out=slot["dev_out"],
+                                     stream=self.s_compute, sync_caller=False,
+                                     input_gain=cpu_payload.get("input_gain", 1.0), **settings)
+        if canvas is not None:                        # add_canvas (cpu_processor.py:409) on the device
+            ch_, cw_ = canvas["size"]
+            if slot["canvas_dev"] is None or tuple(slot["canvas_dev"].shape) != (ch_, cw_, 3):
+                slot["canvas_dev"] = torch.empty((ch_, cw_, 3), dtype=torch.uint8, device=proc.device)
+            r, g, b = canvas["colour"]
+            _cabi.check(_cabi.lib.r2f_canvas_paste(proc._ctx, out_dev.data_ptr(), h, w, slot["canvas_dev"].data_ptr(),
+                                                   ch_, cw_, int(canvas["offset"][0]), int(canvas["offset"][1]),
+                                                   r, g, b, self.s_compute.cuda_stream))
+            out_dev = slot["canvas_dev"]
         slot["done"].record(self.s_compute)
+        reader["last_read"] = slot["done"]
         with torch.cuda.stream(self.s_out):
             self.s_out.wait_event(slot["done"])
-            slot["host_out"].copy_(slot["dev_out"], non_blocking=True)
+            slot["host_out"].copy_(out_dev, non_blocking=True)
             slot["d2h"].record(self.s_out)
         slot["used"] = True
-        slot["keep"] = host                       # keep the pinned source alive until the copy ran
+        slot["orig_resolution"] = cpu_payload.get("_orig_resolution")
+        self._last_slot = slot if upload else self._last_slot
         self._count += 1
-        self.h2d_bytes += host.numel() * host.element_size()
         self.d2h_bytes += slot["host_out"].numel()
         return ticket
 
@@ -88,7 +127,11 @@ class PipelinedRenderer:
             raise ValueError("ticket is not in flight any more")
         slot = self._slots[ticket % self.depth]
         slot["d2h"].synchronize()
-        return slot["host_out"].numpy()
+        image = slot["host_out"].numpy()
+        orig = slot.get("orig_resolution")
+        if orig is not None:                          # post-step of cpu_processor.py:411-412
+            image = hostops.resolution_scaling(image, orig)
+        return image
 
     def run(self, payloads, negative_film, grain_size, grain_sigma, sink=None, **settings):
         """Render an iterable of payloads in order; `sink(index, image)` is called as results land."""

@@ -18,6 +18,7 @@ from __future__ import annotations
 import ctypes
 import math
 import random
+from collections import OrderedDict
 
 import numpy as np
 
@@ -40,10 +41,44 @@ def _resolve_create_lut(explicit):
         return None
 
 
-class B200Processor:
-    """Drop-in for the reference processors on one B200 (one instance per GPU / stream)."""
+_SLOT_DICTS = ("input_param_dict", "curve_param_dict", "output_param_dict", "mtf_param_dict", "halation_param_dict",
+               "grain_param_dict", "highlight_burn_param_dict")
+_SLOT_ARRAYS = ("tex_lut_2d", "tex_lut_1d", "tex_lut_3d", "halation_kernel", "mtf_kernel", "_grain_curve",
+                "_grain_kernel")
 
-    def __init__(self, cameras=None, lenses=None, device: int | None = None, ingest=None, create_lut=None):
+
+class _TableSlot:
+    """Host-side mirror of one device table slot (r2f_select_slot): the comparison dicts of
+    cpu_processor.py:41-45 / gpu_processor.py:213-221 and the host copies of the tables, per film stock."""
+
+    def __init__(self, index: int, key=None):
+        self.index, self.key = index, key
+        for name in _SLOT_DICTS + _SLOT_ARRAYS:
+            setattr(self, name, None)
+
+
+def _slot_property(name):
+    def get(self):
+        return getattr(self._cur, name)
+
+    def put(self, value):
+        setattr(self._cur, name, value)
+
+    return property(get, put)
+
+
+class B200Processor:
+    """Drop-in for the reference processors on one B200 (one instance per GPU / stream).
+
+    The reference keeps one set of LUTs and rebuilds it whenever a settings sub-dict changes
+    (cpu_processor.py:157, 179, 229).  Here every film stock (keyed by `.name`, like the reference's cache keys)
+    owns a device table slot with its own comparison dicts, up to `table_slots` stocks (least recently used
+    evicted): a batch that alternates stocks switches slots by index and uploads nothing.  Within a slot the
+    reference's rule holds -- a table is rebuilt only when its settings sub-dict changes -- and the upload is
+    copy-on-write on the device, so frames still in flight keep the tables they were submitted with."""
+
+    def __init__(self, cameras=None, lenses=None, device: int | None = None, ingest=None, create_lut=None,
+                 table_slots: int = 8):
         import torch
 
         if not torch.cuda.is_available():
@@ -59,15 +94,15 @@ class B200Processor:
         self._ingest = ingest
         self._create_lut = _resolve_create_lut(create_lut)
 
-        # comparison dicts, as in cpu_processor.py:41-45 / gpu_processor.py:213-221
+        # comparison dicts, as in cpu_processor.py:41-45 / gpu_processor.py:213-221: the image dict lives on
+        # the processor, the table dicts in the selected stock's slot (properties below)
         self.image_param_dict = None
-        self.input_param_dict = None
-        self.curve_param_dict = None
-        self.output_param_dict = None
-        self.mtf_param_dict = None
-        self.halation_param_dict = None
-        self.grain_param_dict = None
-        self.highlight_burn_param_dict = None
+        self._max_slots = max(1, min(int(table_slots), _cabi.MAX_SLOTS))
+        self._slots: OrderedDict = OrderedDict()
+        self._cur = _TableSlot(0)
+        self._pinned_frames = {}          # host address -> pinned tensor (pinned_frame)
+        self._pipe = None                 # two-slot PipelinedRenderer behind process_preloaded
+        self._last_out = None             # device tensor of the most recent render
 
         self.pipeline_resolution = None   # (w, h) like gpu_processor.py:222
         self.output_resolution = None
@@ -78,6 +113,30 @@ class B200Processor:
         self._dev_noise = None
         self._cached_payload = None
         self._in_channels = 3
+
+    def _select_slot(self, negative_film):
+        """Make the table slot of `negative_film` current (allocate / evict as needed)."""
+        key = negative_film.name
+        if self._cur.key == key:
+            return self._cur
+        slot = self._slots.get(key)
+        if slot is not None:
+            self._slots.move_to_end(key)
+        elif self._cur.key is None and not self._slots:
+            slot = self._cur                                  # first stock adopts slot 0
+            slot.key = key
+            self._slots[key] = slot
+        elif len(self._slots) < self._max_slots:
+            slot = _TableSlot(len(self._slots), key)
+            self._slots[key] = slot
+        else:
+            _, old = self._slots.popitem(last=False)          # least recently used
+            _cabi.check(_cabi.lib.r2f_clear_slot(self._ctx, old.index))
+            slot = _TableSlot(old.index, key)
+            self._slots[key] = slot
+        _cabi.check(_cabi.lib.r2f_select_slot(self._ctx, slot.index))
+        self._cur = slot
+        return slot
 
     def close(self):
         if getattr(self, "_ctx", None):
@@ -107,6 +166,7 @@ class B200Processor:
     # ------------------------------------------------------------------------------------------
     def load_input_lut(self, negative_film, exp_kelvin, tint, exp_comp):
         """2-D input LUT (cpu_processor.py:142-164)."""
+        self._select_slot(negative_film)
         new = {"negative_film": negative_film.name, "exp_kelvin": exp_kelvin, "tint": tint, "exp_comp": exp_comp}
         if new == self.input_param_dict:
             return
@@ -118,7 +178,9 @@ class B200Processor:
         self.input_param_dict = new
 
     def load_density_curve(self, negative_film, push_pull, color_masking=None, log_eps: float = 1e-6):
-        """(4, N) H-D curve (cpu_processor.py:166-188)."""
+        """(4, N) H-D curve (cpu_processor.py:166-188).  A non-uniform abscissa (row 0) is honoured with
+        np.interp semantics on the device (see r2f_set_curve1d)."""
+        self._select_slot(negative_film)
         new = {"negative_film": negative_film.name, "push_pull": push_pull, "color_masking": color_masking,
                "log_eps": log_eps}
         if new == self.curve_param_dict:
@@ -136,6 +198,7 @@ class B200Processor:
                         inversion_gamma=4.0, idealized_curve=False, inversion=False, white_balance=False,
                         white_clip=False, icc_transform=None, color_masking=None):
         """Output 3-D LUT (cpu_processor.py:190-267), ICC baked in through 8-bit PIL as the reference does."""
+        self._select_slot(negative_film)
         new = {"negative_film": negative_film.name, "print_film": print_film.name if print_film is not None else None,
                "red_light": red_light, "green_light": green_light, "blue_light": blue_light,
                "projector_kelvin": projector_kelvin, "shadow_comp": shadow_comp, "sat_adjust": sat_adjust,
@@ -187,6 +250,7 @@ class B200Processor:
 
     def load_mtf_kernel(self, negative_film, scale, sharpening_strength, sharpening_sigma):
         """gpu_processor.py:815-838 / effects.py:165-185."""
+        self._select_slot(negative_film)
         new = {"negative_film": negative_film.name, "scale": scale, "sharpening_strength": sharpening_strength,
                "sharpening_sigma": sharpening_sigma}
         if new == self.mtf_param_dict:
@@ -200,6 +264,7 @@ class B200Processor:
     def load_grain(self, negative_film, scale, grain_size_mm=0.01, grain_sigma=0.4, bw_grain=False, seed=None):
         """gpu_processor.py:904-936: grain amplitude curve + smoothing kernel (+ a fresh seed per frame,
         gpu_processor.py:586-592)."""
+        self._select_slot(negative_film)
         if seed is None:
             seed = random.randint(0, 2 ** 63 - 1)
         new = {"negative_film": negative_film.name, "scale": scale, "grain_size_mm": grain_size_mm,
@@ -222,6 +287,7 @@ class B200Processor:
 
     def load_highlight_burn(self, negative_film, highlight_burn, burn_scale):
         """gpu_processor.py:856-878 / effects.py:392-418."""
+        self._select_slot(negative_film)
         d_ref = negative_film.d_ref[1 if len(negative_film.d_ref) > 1 else 0]
         new = {"d_ref": d_ref, "highlight_burn": highlight_burn, "burn_scale": burn_scale}
         if new == self.highlight_burn_param_dict:
@@ -273,7 +339,7 @@ class B200Processor:
     def histogram_counts(self, image_dev=None):
         """(3, 256) int64 per-channel counts of a uint8 (H, W, 3) CUDA tensor (default: the last render)."""
         torch = self._torch
-        img = self._dev_out if image_dev is None else image_dev
+        img = self._last_out if image_dev is None else image_dev
         if img is None:
             raise RuntimeError("nothing rendered yet")
         h, w = img.shape[:2]
@@ -350,11 +416,17 @@ class B200Processor:
             canvas_res = (out_size[1], out_size[0])
         channels = 4 if alpha else 3
         is_u16 = image.dtype == np.uint16
-        pinned = torch.empty((h, w, channels), dtype=torch.uint16 if is_u16 else torch.float32, pin_memory=True)
-        arr = pinned.numpy()
-        arr[..., :3] = image[..., :3]
-        if alpha:
-            arr[..., 3] = 65535 if is_u16 else 1.0
+        pinned = self._pinned_frames.get(image.ctypes.data) if image.flags.c_contiguous else None
+        if pinned is not None and tuple(pinned.shape) == (h, w, channels) and image.dtype in (np.uint16, F32):
+            arr = image                                   # already page-locked (pinned_frame): no host copy
+        else:
+            if image.dtype not in (np.uint16, F32):
+                image = image.astype(F32)
+            pinned = torch.empty((h, w, channels), dtype=torch.uint16 if is_u16 else torch.float32, pin_memory=True)
+            arr = pinned.numpy()
+            arr[..., :3] = image[..., :3]
+            if alpha:
+                arr[..., 3] = 65535 if is_u16 else 1.0
         return {"image_array": arr, "output_resolution": (output_res[1], output_res[0]),
                 "canvas_resolution": canvas_res, "pipeline_resolution": (w, h), "_pinned": pinned,
                 "input_gain": float(np.float32(input_gain)), "_canvas": canvas, "_orig_resolution": orig_resolution}
@@ -393,6 +465,7 @@ class B200Processor:
 
     def _load_tables(self, negative_film, grain_size, grain_sigma, s, h, w):
         """Loaders + stage gating of cpu_processor.py:342-403.  Returns (flags, scale)."""
+        self._select_slot(negative_film)
         self.load_input_lut(negative_film, s["exp_kelvin"], s["tint"], s["exp_comp"])
         self.load_density_curve(negative_film, s["push_pull"], s["color_masking"])
         self.load_output_lut(negative_film, s["print_film"], s["red_light"], s["green_light"], s["blue_light"],
@@ -459,6 +532,7 @@ class B200Processor:
                                             stream.cuda_stream))
         if sync_caller:  # order later work on the caller's stream after the render (asynchronous, no host sync)
             torch.cuda.current_stream(self.device).wait_stream(stream)
+        self._last_out = out
         return out
 
     def render_tap(self, xyz_dev, stage: str, negative_film, grain_size, grain_sigma, input_gain=1.0, **settings):
@@ -481,38 +555,41 @@ class B200Processor:
         return tap
 
     def process_preloaded(self, cpu_payload, negative_film, grain_size, grain_sigma, dst_texture=None,
-                          histogram_texture=None, _upload=True, **settings):
+                          histogram_texture=None, _upload=True, own_result=False, **settings):
         """gpu_processor.py:1643-1693: upload the preloaded frame, render, read back.
-        Returns an owned uint8 (H, W, 3) host array."""
+
+        Runs as one submit + result on the processor's own three-slot `PipelinedRenderer`: device frame,
+        device result and pinned host result buffers are allocated once per frame size and reused.  Like the
+        reference's GPU path, which hands back a view of its mapped read-back buffer
+        (gpu_processor.py:1350-1357), the returned uint8 (H, W, 3) array is a view of a pinned buffer that
+        stays valid for the next two calls; `own_result=True` returns a private copy instead."""
         if dst_texture is not None or histogram_texture is not None:
             raise NotImplementedError("presenting into a wgpu texture / histogram is UI plumbing (out of scope)")
-        torch = self._torch
         if _upload:
             self.image_param_dict = None      # the device frame changes: process() re-validates its cache
-            self.prepare_gpu_textures(cpu_payload)
-        out_dev = self.render_device(self._dev_in, negative_film, grain_size, grain_sigma,
-                                     input_gain=self._in_gain, **settings)
-        canvas = cpu_payload.get("_canvas")
-        if canvas is not None:                       # add_canvas (cpu_processor.py:409) on the device
-            h, w = out_dev.shape[:2]
-            ch, cw = canvas["size"]
-            canvas_dev = torch.empty((ch, cw, 3), dtype=torch.uint8, device=self.device)
-            r, g, b = canvas["colour"]
-            _cabi.check(_cabi.lib.r2f_canvas_paste(self._ctx, out_dev.data_ptr(), h, w, canvas_dev.data_ptr(), ch, cw,
-                                                   int(canvas["offset"][0]), int(canvas["offset"][1]), r, g, b,
-                                                   self.stream.cuda_stream))
-            out_dev = canvas_dev
-        h, w = out_dev.shape[:2]
-        host = torch.empty((h, w, 3), dtype=torch.uint8, pin_memory=True)
-        with torch.cuda.stream(self.stream):
-            host.copy_(out_dev, non_blocking=True)
-        self.stream.synchronize()
-        self._d2h_bytes = host.numel()
-        image = host.numpy()
-        orig = cpu_payload.get("_orig_resolution")
-        if orig is not None:                         # post-step of cpu_processor.py:411-412 (host cv2)
-            image = hostops.resolution_scaling(image, orig)
-        return image
+        pipe = self._own_pipeline()
+        ticket = pipe.submit(cpu_payload, negative_film, grain_size, grain_sigma, upload=_upload, **settings)
+        image = pipe.result(ticket)
+        return np.array(image) if own_result else image
+
+    def _own_pipeline(self):
+        if getattr(self, "_pipe", None) is None:
+            from .pipeline import PipelinedRenderer
+
+            self._pipe = PipelinedRenderer(self, depth=3)
+        return self._pipe
+
+    def pinned_frame(self, h: int, w: int, channels: int = 3, dtype=np.float32) -> np.ndarray:
+        """A (h, w, channels) array in page-locked host memory.  A decoder that writes its frame straight into it
+        spares phase 1 (`extract_image_data_cpu`) its host copy: such an array is handed to the DMA engine as is."""
+        torch = self._torch
+        t = torch.empty((h, w, channels), dtype=torch.uint16 if np.dtype(dtype) == np.uint16 else torch.float32,
+                        pin_memory=True)
+        arr = t.numpy()
+        self._pinned_frames[arr.ctypes.data] = t
+        if len(self._pinned_frames) > 64:                 # forget the oldest registrations
+            self._pinned_frames.pop(next(iter(self._pinned_frames)))
+        return arr
 
     def process(self, src, negative_film, grain_size, grain_sigma, **settings):
         """cpu_processor.py:269-414: the reference's render entry point.
@@ -538,7 +615,15 @@ class B200Processor:
         else:
             payload = self.extract_image_data_cpu(src, **ingest_args)
             upload = True
+        # like CpuProcessor.process the result is a fresh array the caller owns (process_preloaded, the GPU-style
+        # entry point, returns a view of its read-back buffer like gpu_processor.py:1350-1357 does)
+        settings.setdefault("own_result", True)
         out = self.process_preloaded(payload, negative_film, grain_size, grain_sigma, _upload=upload, **settings)
         self._cached_payload = payload
         self.image_param_dict = new_param_dict
         return out
+
+
+for _name in _SLOT_DICTS + _SLOT_ARRAYS:      # per-stock comparison dicts / host tables live in the selected slot
+    setattr(B200Processor, _name, _slot_property(_name))
+del _name

@@ -32,16 +32,21 @@ class SyntheticStock:
     mixed-stock batch config (BASELINE config 4)."""
 
     def __init__(self, name: str | None = None, variant: int = 0, n2: int = 64, n1: int = 1024, n3: int = 33,
-                 density_measure: str = "status_m", with_mtf: bool = True, with_grain: bool = True):
+                 density_measure: str = "status_m", with_mtf: bool = True, with_grain: bool = True,
+                 warped_curve: bool = False):
         # The processors key their LUT caches on `.name` (reference cpu_processor.py:151, 174, 211), so two
         # stocks with different tables must not share a name: the default name encodes every parameter.
         if name is None:
             name = (f"Synthetic {100 * (int(variant) + 1)} [{n2}/{n1}/{n3} {density_measure}"
-                    f"{'' if with_mtf else ' no-mtf'}{'' if with_grain else ' no-grain'}]")
+                    f"{'' if with_mtf else ' no-mtf'}{'' if with_grain else ' no-grain'}"
+                    f"{' warped' if warped_curve else ''}]")
         self.name = name
         self.variant = int(variant)
         self.n2, self.n1, self.n3 = int(n2), int(n1), int(n3)
         self.density_measure = density_measure
+        # warped_curve: the H-D and grain curves are sampled on a NON-uniform abscissa (denser around the
+        # mid-tones), which the real package is free to do (SURVEY 8c(ii)); lookups are then np.interp
+        self.warped_curve = bool(warped_curve)
         v = self.variant
         self.d_ref = (0.50 + 0.03 * v, 0.60 + 0.02 * v, 0.70 + 0.01 * v)
         self.rms_density = (0.012 + 0.002 * v) if with_grain else None
@@ -61,7 +66,7 @@ class SyntheticStock:
     # hashable + comparable by identity of its parameters (used as a cache key like FilmSpectral)
     def _key(self):
         return (self.name, self.variant, self.n2, self.n1, self.n3, self.density_measure, self.mtf is None,
-                self.rms_density is None)
+                self.rms_density is None, self.warped_curve)
 
     def __hash__(self):
         return hash(self._key())
@@ -84,6 +89,9 @@ class SyntheticStock:
     # ---- (4, N) H-D curve: row 0 log10 exposure (uniform), rows 1..3 density --------------------
     def get_density_curve(self, push_pull=0.0, color_masking=None) -> np.ndarray:
         loge = np.linspace(-4.0, 2.0, self.n1)
+        if self.warped_curve:
+            u = np.linspace(-1.0, 1.0, self.n1)
+            loge = -1.0 + 3.0 * (0.35 * u + 0.65 * u ** 3)
         mask = 1.0 if color_masking is None else float(color_masking)
         rows = [loge]
         for c in range(3):
@@ -97,6 +105,8 @@ class SyntheticStock:
     # ---- (4, N) grain amplitude over density -----------------------------------------------------
     def get_grain_curve(self, scale, adx=False, bw_grain=False) -> np.ndarray:
         dens = np.linspace(0.0, 4.0, self.n1)
+        if self.warped_curve:
+            dens = 4.0 * np.linspace(0.0, 1.0, self.n1) ** 1.7
         rms = self.rms_density or 0.0
         # Selwyn: rms over a 48 um aperture -> per-pixel sigma grows with sampling density
         amp = rms * math.sqrt(max(scale, 1.0) * 0.048 * math.sqrt(math.pi) / 2.0)

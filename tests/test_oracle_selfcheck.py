@@ -123,3 +123,26 @@ def test_grain_field_statistics():
         assert field.shape == (256, 256, 3) and abs(field.std() - 1.0) < 0.05 and abs(field.mean()) < 0.02
     bw = fo.generate_grain((64, 64, 3), 166.0, 0.006, True, 0.4, seed=1)
     assert np.array_equal(bw[..., 0], bw[..., 1]) and np.array_equal(bw[..., 1], bw[..., 2])
+
+
+def test_nonuniform_curve_is_np_interp_and_uniform_detection():
+    """SURVEY 8c(ii): a (4, N) table with a non-uniform abscissa is evaluated like np.interp (bit for bit);
+    a float32 linspace counts as uniform and keeps the reference GPU path's normalised lookup."""
+    from raw2film_b200.synthetic import SyntheticStock
+
+    rng = np.random.default_rng(3)
+    warped = SyntheticStock(warped_curve=True)
+    curve = warped.get_density_curve()
+    assert not fo.abscissa_uniform(curve[0]) and np.all(np.diff(curve[0]) > 0)
+    assert fo.abscissa_uniform(SyntheticStock().get_density_curve()[0])
+    assert fo.abscissa_uniform(np.linspace(0, 4, 4096).astype(np.float32))
+    img = rng.uniform(-6.5, 2.5, (64, 80, 3)).astype(np.float32)
+    got = fo.multi_channel_interp(img, curve)
+    want = np.stack([np.interp(img[..., k].astype(np.float64), curve[0].astype(np.float64),
+                               curve[k + 1].astype(np.float64)).astype(np.float32) for k in range(3)], axis=-1)
+    assert np.array_equal(got, want)
+    # on a uniform table both rules agree to rounding
+    uni = SyntheticStock().get_density_curve()
+    a = fo.multi_channel_interp(img, uni)
+    b = fo.multi_channel_interp_nonuniform(img, uni)
+    assert np.abs(a - b).max() < 2e-6
