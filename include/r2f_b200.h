@@ -204,6 +204,11 @@ int r2f_canvas_paste(r2f_ctx *ctx, const uint8_t *src_dev, int H, int W, uint8_t
 /* Number of kernel launches issued by this context since creation (bench.py gpu_launches). */
 uint64_t r2f_launch_count(const r2f_ctx *ctx);
 
+/* Guarded fast chain statistics (R2F_OPT_FAST_CHAIN): pixels that the float32 fast path could not decide and the
+ * exact chain evaluated since the last call (the counter is reset), and the selected slot's proven bound on
+ * |255 * (fast - exact)| (-1 when its tables do not qualify for the fast path).  Synchronises the device. */
+int r2f_fast_chain_stats(r2f_ctx *ctx, uint64_t *deferred_pixels, float *margin);
+
 /* Per-kernel device timing (bench.py roofline): when enabled, every launch of the render
  * pipeline is bracketed by CUDA events on the launching stream.  r2f_profile_read waits for the
  * recorded events, ACCUMULATES milliseconds and launch counts per kernel id into the caller's

@@ -273,8 +273,9 @@ static __device__ __noinline__ float curve_eval_interp(const Curve1D &C, int ch,
     return (float)(slope * ((double)v - x0) + f0);
 }
 
+// Uniform abscissa only (C.xp == nullptr): the hot kernels call this one and the C ABI routes tables with a
+// non-uniform abscissa to the generic kernels, which call curve_eval_any.
 __device__ __forceinline__ float curve_eval(const Curve1D &C, int ch, float v) {
-    if (C.xp != nullptr) return curve_eval_interp(C, ch, v);
     float t = (v - C.x0) * C.inv_range;
     t = fminf(fmaxf(t, 0.0f), 1.0f);  // clamp; NaN -> 0 (fmaxf returns the non-NaN operand)
     const float p = t * (float)(C.N - 1);
@@ -284,11 +285,21 @@ __device__ __forceinline__ float curve_eval(const Curve1D &C, int ch, float v) {
     return s.x + f * s.y;
 }
 
-__device__ __forceinline__ float density_eval(const Curve1D &C, int ch, float exposure, float eps) {
-    return curve_eval(C, ch, log10_clip(exposure, eps));
+__device__ __forceinline__ float curve_eval_any(const Curve1D &C, int ch, float v) {
+    if (C.xp != nullptr) return curve_eval_interp(C, ch, v);
+    return curve_eval(C, ch, v);
 }
+
+// ANY: honour a non-uniform abscissa (generic kernels); otherwise the table is known to be uniform
+template <bool ANY = false>
+__device__ __forceinline__ float density_eval(const Curve1D &C, int ch, float exposure, float eps) {
+    const float l = log10_clip(exposure, eps);
+    return ANY ? curve_eval_any(C, ch, l) : curve_eval(C, ch, l);
+}
+template <bool ANY = false>
 __device__ __forceinline__ float density_eval_fast(const Curve1D &C, int ch, float exposure, float eps) {
-    return curve_eval(C, ch, log10_clip_fast(exposure, eps));
+    const float l = log10_clip_fast(exposure, eps);
+    return ANY ? curve_eval_any(C, ch, l) : curve_eval(C, ch, l);
 }
 
 // ---- a9: tetrahedral 3-D LUT (reference utils.py:247-380) -----------------------------------

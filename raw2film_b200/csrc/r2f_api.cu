@@ -117,6 +117,14 @@ struct TableSlot {
 
     bool burn_set = false;
     float d_ref = 0.f, burn_strength = 0.f, burn_scale = 50.f;
+
+    // guarded float32 fast chain (fast_chain.cuh): host copies of what its error bound needs, derived tables
+    std::vector<float> curve_host;     // the (4, N) H-D table as set
+    double lut_lip[3][3] = {};         // [k][c]: largest step of output channel k between lattice neighbours along axis c
+    double lut_absmax = 0.0, lut_min = 0.0, lut_max = 0.0;
+    DevBuf lut255, fseg;
+    FastChain fast{};
+    bool fast_valid = false;           // `fast` matches the current curve + 3-D LUT
 };
 
 struct r2f_ctx {
@@ -149,6 +157,7 @@ struct r2f_ctx {
     DevBuf cnr_taps;
     DevBuf expo_buf;  // r2f_calc_exposure: per-CTA partial sums + the result
     DevBuf hist_buf;  // r2f_histogram_image: counts + scalars
+    DevBuf stats_buf; // fast-chain statistics (deferred pixel count)
 
     // r2f_render_host staging
     DevBuf h_in, h_out, h_ws, h_noise;
@@ -605,7 +614,8 @@ ConvArgs conv_args(const KernelSet &ks, const float *in, float *out, size_t ps, 
 // direct correlation: the y-symmetric packed-FMA kernel when the kernel set allows it, else the generic one
 cudaError_t conv_dispatch(const r2f_ctx *c, const ConvArgs &a, cudaStream_t st) {
     const bool any_conv = a.mode[0] || a.mode[1] || a.mode[2];
-    if (c->conv_sym && any_conv && a.ksym[0] && a.ksym[1] && a.ksym[2] && a.epi != EPI_GRAIN)
+    const bool nonuniform = a.epi != EPI_NONE && a.curve.xp != nullptr;  // only the generic kernel runs np.interp
+    if (c->conv_sym && any_conv && a.ksym[0] && a.ksym[1] && a.ksym[2] && a.epi != EPI_GRAIN && !nonuniform)
         return launch_conv2d_sym(a, st);
     return launch_conv2d(a, st);
 }
@@ -663,6 +673,78 @@ BurnDims burn_dims(int H, int W, float burn_scale) {
     return d;
 }
 
+// Derives the fast chain's tables and its error bound from the slot's H-D curve and 3-D LUT (see fast_chain.cuh
+// for the argument).  u = 2^-24; every term is a worst case over the whole table, so the bound holds for any pixel.
+int fast_chain_build(r2f_ctx *c) {
+    TableSlot *t = c->t;
+    if (t->fast_valid) return R2F_OK;
+    t->fast = FastChain{};
+    t->fast_valid = true;
+    const int N = t->n1, n = t->n3;
+    if (t->curve_xp.p != nullptr || t->curve_host.size() != (size_t)4 * N || N < 2 || n < 2) return R2F_OK;
+    const float *cv = t->curve_host.data();
+    const double x0 = cv[0], xN = cv[N - 1], R = xN - x0;
+    if (!(R > 0.0) || !(t->eps >= 1e-30f) || !(t->s3 > 0.0)) return R2F_OK;
+    if (!(t->lut_min >= 0.0) || !(t->lut_max <= 1.0)) return R2F_OK;  // quantisation without clamps needs [0, 1]
+    const double u = std::ldexp(1.0, -24), s3 = t->s3;
+    double dmin = 1e300, dmax = -1e300, maxseg[3] = {0, 0, 0}, dabs[3] = {0, 0, 0};
+    for (int ch = 0; ch < 3; ++ch) {
+        const float *row = cv + (size_t)(ch + 1) * N;
+        for (int i = 0; i < N; ++i) {
+            if (!std::isfinite(row[i])) return R2F_OK;
+            dmin = std::fmin(dmin, row[i]);
+            dmax = std::fmax(dmax, row[i]);
+            dabs[ch] = std::fmax(dabs[ch], std::fabs((double)row[i]));
+            if (i + 1 < N) maxseg[ch] = std::fmax(maxseg[ch], std::fabs((double)row[i + 1] - (double)row[i]));
+        }
+    }
+    if (!(dmin >= 0.0) || !(dmax * s3 <= (double)(n - 1) - 0.01)) return R2F_OK;  // stay inside the lattice: no clamps
+    // abscissa coordinate p: exact chain vs fast chain (both against the true value)
+    const double Lm = std::fmax(std::fabs(x0), std::fabs(xN)) + 1.0, log10_2 = 0.30102999566398119521;
+    const double et_exact = (u * Lm + u * (R + 2.0)) / R + 3.0 * u;
+    const double e_l2 = std::ldexp(1.0, -22) + 2.0 * u * (Lm / log10_2);
+    const double cA = log10_2 / R, cB = -x0 / R;
+    const double et_fast = e_l2 * cA + u * (Lm / R + std::fabs(x0) / R + 1.5);
+    const double ep = (N - 1) * (et_exact + et_fast) + 4.0 * u * (N - 1);
+    double dv[3];
+    for (int ch = 0; ch < 3; ++ch)
+        dv[ch] = s3 * (ep * maxseg[ch] + 2.0 * u * dabs[ch]) + 3.0 * u * (dabs[ch] * s3);
+    double margin = 0.0, lipmax = 0.0;
+    for (int k = 0; k < 3; ++k)
+        for (int ch = 0; ch < 3; ++ch) lipmax = std::fmax(lipmax, t->lut_lip[k][ch]);
+    for (int k = 0; k < 3; ++k) {
+        double e = 0.0;
+        for (int ch = 0; ch < 3; ++ch) e += dv[ch] * t->lut_lip[k][ch];
+        e = 255.0 * (e + u * t->lut_absmax + 3.0 * u * lipmax) + 10.0 * u * 255.0 * t->lut_absmax + u * 255.0;
+        margin = std::fmax(margin, e);
+    }
+    margin *= 1.25;  // safety factor
+    if (!(margin < 0.2)) return R2F_OK;  // most pixels would be deferred: not worth it
+    // scaled segments
+    std::vector<float> fs((size_t)3 * N * 2);
+    for (int ch = 0; ch < 3; ++ch) {
+        const float *row = cv + (size_t)(ch + 1) * N;
+        for (int i = 0; i < N; ++i) {
+            fs[((size_t)ch * N + i) * 2] = (float)((double)row[i] * s3);
+            fs[((size_t)ch * N + i) * 2 + 1] = i + 1 < N ? (float)(((double)row[i + 1] - (double)row[i]) * s3) : 0.0f;
+        }
+    }
+    int rc = upload(c, t->fseg, fs.data(), fs.size() * sizeof(float));
+    if (rc != R2F_OK) return rc;
+    FastChain f{};
+    f.cA = (float)cA;
+    f.cB = (float)cB;
+    f.pscale = std::nextafterf((float)(N - 1), 0.0f);
+    f.margin = (float)margin;
+    f.fseg = static_cast<const float2 *>(t->fseg.p);
+    f.lut255 = static_cast<const float4 *>(t->lut255.p);
+    f.N = N;
+    f.n3 = n;
+    f.ok = t->lut255.p != nullptr ? 1 : 0;
+    t->fast = f;
+    return R2F_OK;
+}
+
 int check_tables(const r2f_ctx *c, unsigned flags) {
     const TableSlot *t = c->t;
     if (!t->lut2d.p) return fail(R2F_ERR_INVALID, "2D input LUT not set (r2f_set_lut2d)");
@@ -700,8 +782,22 @@ int render_body(r2f_ctx *c, const void *in, int in_format, float in_gain, int H,
     const Lut3D l3 = lut3d_of(c);
 
     if (tap_stage == 0 && spatial == 0) {  // configs C1 / C5: one fused pass
+        if (c->fast_chain) {
+            rc = fast_chain_build(c);
+            if (rc != R2F_OK) return rc;
+        }
+        const FastChain &fc = c->t->fast;
         ProfScope ps_(c, st, R2F_PROF_POINTWISE);
-        CU(launch_pointwise(in, fmt, in_gain, out_u8, npix, l2, cv, c->t->eps, l3, c->num_sms, st));
+        if (c->fast_chain && fc.ok && pointwise_fast_smem(l2, fc) <= 100 * 1024 && npix < ((size_t)1 << 32)) {
+            if (!c->stats_buf.p) {
+                CU(c->stats_buf.ensure(sizeof(unsigned long long)));
+                CU(cudaMemsetAsync(c->stats_buf.p, 0, sizeof(unsigned long long), st));
+            }
+            CU(launch_pointwise_fast(in, fmt, in_gain, out_u8, npix, l2, cv, c->t->eps, l3, fc,
+                                     static_cast<unsigned long long *>(c->stats_buf.p), c->num_sms, st));
+        } else {
+            CU(launch_pointwise(in, fmt, in_gain, out_u8, npix, l2, cv, c->t->eps, l3, c->num_sms, st));
+        }
         c->launches += 1;
         return R2F_OK;
     }
@@ -737,14 +833,26 @@ int render_body(r2f_ctx *c, const void *in, int in_format, float in_gain, int H,
         fa.dst_planar = P[1].base;
         fa.curve = cv;
         fa.eps = c->t->eps;
+        // the row-inverse kernel's fused log10 + curve epilogue knows uniform tables only
+        const bool fuse_density = tap_stage != R2F_TAP_HALATION && cv.xp == nullptr;
         for (int stage = 1; stage <= 3; ++stage) {
             ProfScope ps_(c, st, R2F_PROF_FFT_ROWS_FWD + stage - 1);
-            CU(launch_fft_conv(fa, 1 + fmt, tap_stage != R2F_TAP_HALATION, st, stage));
+            CU(launch_fft_conv(fa, 1 + fmt, fuse_density, st, stage));
         }
         c->launches += 2;  // + the one counted below
         if (tap_stage == R2F_TAP_HALATION) {
             c->launches += 1;
             return export_tap(P[1]);
+        }
+        if (!fuse_density) {  // separate density pass (generic kernel, np.interp lookup): P[1] -> P[0] -> P[1]
+            ConvArgs a = identity_args(P[1].base, P[0].base, ps, H, W);
+            a.epi = EPI_DENSITY_FAST;
+            a.curve = cv;
+            a.eps = c->t->eps;
+            ProfScope ps_(c, st, R2F_PROF_DENSITY);
+            CU(launch_conv2d(a, st));
+            CU(cudaMemcpyAsync(P[1].base, P[0].base, ps * 3 * sizeof(float), cudaMemcpyDeviceToDevice, st));
+            c->launches += 1;
         }
     } else {
         {
@@ -820,7 +928,8 @@ int render_body(r2f_ctx *c, const void *in, int in_format, float in_gain, int H,
         ga.burn = BurnArgs{};
         ga.out_u8 = out_u8;
         ProfScope ps_(c, st, R2F_PROF_GRAIN);
-        if (c->conv_sym && ga.gk_sym && grain_finish_sym_supported(ga.k)) CU(launch_grain_finish_sym(ga, st));
+        if (c->conv_sym && ga.gk_sym && grain_finish_sym_supported(ga.k) && ga.gcurve.xp == nullptr)
+            CU(launch_grain_finish_sym(ga, st));
         else CU(launch_grain_finish(ga, st));
         c->launches += 1;
         return R2F_OK;
@@ -933,7 +1042,7 @@ void release_kernel_set(KernelSet &k) {
     k.base.release();
 }
 void retire_slot(r2f_ctx *c, TableSlot &t) {
-    for (DevBuf *b : {&t.lut2d, &t.lut2d4, &t.curve, &t.curve_xp, &t.lut3d, &t.gcurve, &t.gcurve_xp, &t.hal.buf, &t.hal.symbuf,
+    for (DevBuf *b : {&t.lut255, &t.fseg, &t.lut2d, &t.lut2d4, &t.curve, &t.curve_xp, &t.lut3d, &t.gcurve, &t.gcurve_xp, &t.hal.buf, &t.hal.symbuf,
                       &t.hal.base, &t.mtf.buf, &t.mtf.symbuf, &t.mtf.base, &t.grain.buf, &t.grain.symbuf,
                       &t.grain.base})
         retire(c, *b);
@@ -946,13 +1055,13 @@ int r2f_destroy(r2f_ctx *c) {
     cudaDeviceSynchronize();
     for (auto &sp : c->slots) {
         if (!sp) continue;
-        for (DevBuf *b : {&sp->lut2d, &sp->lut2d4, &sp->curve, &sp->curve_xp, &sp->lut3d, &sp->gcurve, &sp->gcurve_xp}) b->release();
+        for (DevBuf *b : {&sp->lut255, &sp->fseg, &sp->lut2d, &sp->lut2d4, &sp->curve, &sp->curve_xp, &sp->lut3d, &sp->gcurve, &sp->gcurve_xp}) b->release();
         release_kernel_set(sp->hal);
         release_kernel_set(sp->mtf);
         release_kernel_set(sp->grain);
     }
     for (DevBuf *b : {&c->burn_buf, &c->h_in, &c->h_out, &c->h_ws, &c->h_noise, &c->khat_scratch, &c->cnr_taps,
-                      &c->expo_buf, &c->hist_buf})
+                      &c->expo_buf, &c->hist_buf, &c->stats_buf})
         b->release();
     for (auto &e : c->khat) {
         e.buf.release();
@@ -1021,6 +1130,8 @@ int r2f_set_curve1d(r2f_ctx *c, const float *curve, int N, float log_eps) {
     t->x0 = curve[0];
     t->inv_range = inv_range_of(curve[0], curve[N - 1]);
     t->eps = log_eps;
+    t->curve_host.assign(curve, curve + (size_t)4 * N);
+    t->fast_valid = false;
     return R2F_OK;
 }
 
@@ -1038,6 +1149,28 @@ int r2f_set_lut3d(r2f_ctx *c, const float *lut, int n, double scale) {
     }
     int rc = upload(c, t->lut3d, padded.data(), padded.size() * sizeof(float));
     if (rc != R2F_OK) return rc;
+    // fast chain: a copy pre-multiplied by 255 and the table's largest steps between lattice neighbours
+    t->lut_min = 1e300;
+    t->lut_max = -1e300;
+    for (int k = 0; k < 3; ++k)
+        for (int a = 0; a < 3; ++a) t->lut_lip[k][a] = 0.0;
+    const size_t strides[3] = {(size_t)n * n, (size_t)n, 1};
+    for (size_t v = 0; v < verts; ++v) {
+        const size_t idx[3] = {v / strides[0], (v / strides[1]) % n, v % n};
+        for (int k = 0; k < 3; ++k) {
+            const double x = lut[3 * v + k];
+            t->lut_min = std::fmin(t->lut_min, x);
+            t->lut_max = std::fmax(t->lut_max, x);
+            if (!(x == x)) t->lut_min = -1e300;  // NaN disqualifies the fast chain
+            for (int a = 0; a < 3; ++a)
+                if (idx[a] + 1 < (size_t)n)
+                    t->lut_lip[k][a] = std::fmax(t->lut_lip[k][a], std::fabs((double)lut[3 * (v + strides[a]) + k] - x));
+            padded[4 * v + k] = (float)(x * 255.0);
+        }
+    }
+    rc = upload(c, t->lut255, padded.data(), padded.size() * sizeof(float));
+    if (rc != R2F_OK) return rc;
+    t->fast_valid = false;
     t->n3 = n;
     t->s3 = scale * (double)(n - 1);  // utils.py:258
     // Error bound of the float32 fast path (device_math.cuh tetra_quant_u8), in units of the
@@ -1051,6 +1184,7 @@ int r2f_set_lut3d(r2f_ctx *c, const float *lut, int n, double scale) {
     // the three fused roundings (and the exact path's final rounding) is at most u * absmax
     double err = 3.0 * u * absmax + u * absmax + 1e-30;
     int e2 = 0;
+    t->lut_absmax = absmax;
     const bool pow2 = std::frexp(t->s3, &e2) == 0.5 && t->s3 > 0.0;
     if (!pow2) err += 3.0 * (2.0 * absmax) * (2.0 * u * (double)n);  // coordinate rounding x slopes
     double margin = 255.0 * err + 2.0 * u * 255.0 * std::fmax(1.0, absmax);
@@ -1318,6 +1452,20 @@ int r2f_calc_exposure(r2f_ctx *c, const void *in_dev, int in_format, int H, int 
 }
 
 uint64_t r2f_launch_count(const r2f_ctx *c) { return c ? c->launches : 0; }
+
+int r2f_fast_chain_stats(r2f_ctx *c, uint64_t *deferred_pixels, float *margin) {
+    if (!c) return fail(R2F_ERR_INVALID, "null context");
+    DeviceGuard guard(c->device);
+    unsigned long long n = 0;
+    if (c->stats_buf.p) {
+        CU(cudaDeviceSynchronize());
+        CU(cudaMemcpy(&n, c->stats_buf.p, sizeof(n), cudaMemcpyDeviceToHost));
+        CU(cudaMemset(c->stats_buf.p, 0, sizeof(n)));
+    }
+    if (deferred_pixels) *deferred_pixels = (uint64_t)n;
+    if (margin) *margin = (c->t->fast_valid && c->t->fast.ok) ? c->t->fast.margin : -1.0f;
+    return R2F_OK;
+}
 
 int r2f_profile_enable(r2f_ctx *c, int on) {
     if (!c) return fail(R2F_ERR_INVALID, "null context");

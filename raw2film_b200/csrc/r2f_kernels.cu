@@ -8,7 +8,10 @@
 //   k_noise       a7            white N(0,1) field (Philox4x32-10 + Box-Muller)
 //   k_burn_*      a8            low-res highlight mask
 //   k_finish      a8+a9+a10     burn apply, tetrahedral LUT, quantise
+#include <cstdlib>
+
 #include "conv_tile.cuh"
+#include "fast_chain.cuh"
 #include "noise.cuh"
 #include "r2f_kernels.h"
 
@@ -52,9 +55,11 @@ __device__ __forceinline__ void pixel_chain(const float (&xyz)[3], const Lut2D &
                                             const Lut3D &l3, uint32_t &r, uint32_t &g, uint32_t &b) {
     float e0, e1, e2;
     lut2d_eval<SMEM, true>(l2, xyz[0], xyz[1], xyz[2], e0, e1, e2);
-    const float d0 = density_eval(cv, 0, e0, eps);
-    const float d1 = density_eval(cv, 1, e1, eps);
-    const float d2 = density_eval(cv, 2, e2, eps);
+    // tables parked in shared memory are uniform by construction (launch_pointwise); the global-memory variant
+    // also serves curves with a non-uniform abscissa
+    const float d0 = density_eval<!SMEM>(cv, 0, e0, eps);
+    const float d1 = density_eval<!SMEM>(cv, 1, e1, eps);
+    const float d2 = density_eval<!SMEM>(cv, 2, e2, eps);
     tetra_quant_u8(l3, d0, d1, d2, r, g, b);
 }
 
@@ -64,6 +69,7 @@ __device__ __forceinline__ void pixel_chain(const float (&xyz)[3], const Lut2D &
 // 512-thread CTAs: with the tables in shared memory (60 KB at the default sizes) three 256-thread CTAs fit an SM
 // (24 warps); two 512-thread CTAs carry 32 warps in the same register file (64 registers per thread).
 constexpr int kPwThreads = 512;
+constexpr size_t kMaxTableSmem = 96 * 1024;  // keep >= 2 CTAs/SM resident
 
 template <int FMT, bool SMEM_TABLES>
 __global__ void __launch_bounds__(kPwThreads, 2)
@@ -94,6 +100,158 @@ k_pointwise(const void *__restrict__ in, float gain, uint8_t *__restrict__ out, 
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// K1 fast: the same chain through the guarded float32 fast path (fast_chain.cuh).  Pixels the fast path cannot
+// prove are queued per warp and evaluated 32 at a time by the exact chain, which overwrites their bytes.
+// No CTA-wide synchronisation after the table staging: ballots, the queue and the drain are warp-local.
+// ------------------------------------------------------------------------------------------
+constexpr int kPwQueue = 64;  // per-warp queue capacity: < 32 left over + at most 32 pushed per ballot
+
+template <int FMT>
+static __device__ __noinline__ void pw_exact_pixel(const void *__restrict__ in, float gain, uint8_t *__restrict__ out,
+                                                   unsigned pix, Lut2D l2, Curve1D cv, float eps, Lut3D l3) {
+    float xyz[3];
+    load_px<FMT>(in, pix, gain, xyz[0], xyz[1], xyz[2]);
+    float e0, e1, e2;
+    lut2d_eval<true, true>(l2, xyz[0], xyz[1], xyz[2], e0, e1, e2);
+    const float d0 = density_eval(cv, 0, e0, eps), d1 = density_eval(cv, 1, e1, eps), d2 = density_eval(cv, 2, e2, eps);
+    float o0, o1, o2;
+    tetra_eval(l3, d0, d1, d2, o0, o1, o2);
+    uint8_t *o = out + (size_t)pix * 3;
+    o[0] = (uint8_t)quantise_u8(o0);
+    o[1] = (uint8_t)quantise_u8(o1);
+    o[2] = (uint8_t)quantise_u8(o2);
+}
+
+template <int FMT, int NT>
+__global__ void __launch_bounds__(NT, NT >= 512 ? 2 : (NT >= 384 ? 2 : 3))
+k_pointwise_fast(const void *__restrict__ in, float gain, uint8_t *__restrict__ out, size_t npix, Lut2D l2, Curve1D cv,
+                 float eps, Lut3D l3, FastChain F, unsigned long long *__restrict__ stats) {
+    extern __shared__ __align__(16) float smem[];
+    // shared memory: float4-padded 2-D LUT | scaled curve segments | per-warp queues
+    {
+        const int n2f = l2.n * l2.n * 4, n1f = F.N * 3 * 2;
+        const float *src2 = reinterpret_cast<const float *>(l2.tab4), *src1 = reinterpret_cast<const float *>(F.fseg);
+        for (int i = threadIdx.x; i < n2f / 4; i += NT) cp_async_16(smem + 4 * i, src2 + 4 * i);
+        for (int i = threadIdx.x; i < n1f / 4; i += NT) cp_async_16(smem + n2f + 4 * i, src1 + 4 * i);
+        for (int i = (n1f / 4) * 4 + threadIdx.x; i < n1f; i += NT) smem[n2f + i] = src1[i];
+        l2.tab4 = reinterpret_cast<const float4 *>(smem);
+        F.fseg = reinterpret_cast<const float2 *>(smem + n2f);
+        cp_async_wait_all();
+        __syncthreads();
+    }
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    FastChainS S;
+    S.lut2d = (unsigned)__cvta_generic_to_shared(smem);
+    S.fseg = S.lut2d + (unsigned)(l2.n * l2.n * 16);
+    S.seg_stride = (unsigned)F.N * 8u;
+    S.n2 = l2.n;
+    S.row16 = (unsigned)l2.n * 16u;
+    S.n2m1 = (float)(l2.n - 1);
+    S.hi2 = (float)(l2.n - 2);
+    S.eps = eps;
+    S.cA = F.cA;
+    S.cB = F.cB;
+    S.pscale = F.pscale;
+    S.margin = F.margin;
+    S.lut255 = F.lut255;
+    S.n3 = F.n3;
+    S.sg16 = F.n3 * 16;
+    S.sr16 = F.n3 * F.n3 * 16;
+    S.o111_16 = S.sr16 + S.sg16 + 16;
+    unsigned *wq = reinterpret_cast<unsigned *>(smem + l2.n * l2.n * 4 + ((F.N * 3 * 2 + 3) & ~3)) + warp * kPwQueue;
+    int wq_count = 0;       // warp-uniform
+    unsigned deferred = 0;  // lane 0 counts for the statistics
+    const size_t nquad = npix / 4;
+    const size_t stride = (size_t)gridDim.x * NT;
+    for (size_t qb = (size_t)blockIdx.x * NT + warp * 32; qb < nquad; qb += stride) {
+        const size_t q = qb + lane;
+        const bool active = q < nquad;
+        unsigned bad = 0;  // bit p: pixel p of the quad is undecided
+        if (active) {
+            float px[4][3];
+            load_quad<FMT>(in, q, gain, px);
+            uint32_t b[12];
+#pragma unroll
+            for (int p = 0; p < 4; ++p)
+                if (!chain_fast_s(px[p], S, b[3 * p], b[3 * p + 1], b[3 * p + 2])) bad |= 1u << p;
+            store_quad_u8(out, q, b);
+        }
+        // the stores above are ordered before any overwrite by another lane of this warp: __syncwarp in the drain
+        if (__any_sync(0xffffffffu, bad != 0)) {
+#pragma unroll 1
+            for (int p = 0; p < 4; ++p) {
+                const bool u = (bad >> p) & 1u;
+                const unsigned bal = __ballot_sync(0xffffffffu, u);
+                if (bal == 0) continue;
+                if (u) wq[wq_count + __popc(bal & ((1u << lane) - 1u))] = (unsigned)(q * 4 + p);
+                wq_count += __popc(bal);
+                __syncwarp();
+                if (wq_count >= 32) {
+                    wq_count -= 32;
+                    pw_exact_pixel<FMT>(in, gain, out, wq[wq_count + lane], l2, cv, eps, l3);
+                    deferred += 32;
+                    __syncwarp();
+                }
+            }
+        }
+    }
+    __syncwarp();
+    if (lane < wq_count) pw_exact_pixel<FMT>(in, gain, out, wq[lane], l2, cv, eps, l3);
+    deferred += wq_count;
+    if (stats != nullptr && lane == 0 && deferred) atomicAdd(stats, (unsigned long long)deferred);
+    if (blockIdx.x == 0 && threadIdx.x < (npix & 3))
+        pw_exact_pixel<FMT>(in, gain, out, (unsigned)(nquad * 4 + threadIdx.x), l2, cv, eps, l3);
+}
+
+size_t pointwise_fast_smem(const Lut2D &l2, const FastChain &F) {
+    return ((size_t)l2.n * l2.n * 4 + (((size_t)F.N * 3 * 2 + 3) & ~(size_t)3)) * sizeof(float) +
+           (size_t)(512 / 32) * kPwQueue * sizeof(unsigned);
+}
+
+static int pw_fast_threads() {  // A/B knob: R2F_PW_THREADS = 512 (default) | 384 | 256
+    static const int v = [] {
+        const char *e = getenv("R2F_PW_THREADS");
+        const int t = e ? atoi(e) : 512;
+        return (t == 384 || t == 256) ? t : 512;
+    }();
+    return v;
+}
+
+cudaError_t launch_pointwise_fast(const void *in, int fmt, float gain, uint8_t *out, size_t npix, const Lut2D &l2,
+                                  const Curve1D &cv, float eps, const Lut3D &l3, const FastChain &F,
+                                  unsigned long long *stats, int num_sms, cudaStream_t st) {
+    const size_t sm = pointwise_fast_smem(l2, F);
+    if (!F.ok || sm > kMaxTableSmem + 8192 || cv.xp != nullptr || npix >= ((size_t)1 << 32))
+        return cudaErrorInvalidValue;
+    const int nt = pw_fast_threads(), per_sm = nt == 256 ? 3 : 2;
+    int grid = (int)((npix / 4 + nt) / nt);
+    if (grid > num_sms * per_sm) grid = num_sms * per_sm;
+#define R2F_LAUNCH_PWF2(C, T)                                                                                   \
+    do {                                                                                                        \
+        auto kfn = k_pointwise_fast<C, T>;                                                                      \
+        cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);        \
+        if (e != cudaSuccess) return e;                                                                         \
+        kfn<<<grid, T, sm, st>>>(in, gain, out, npix, l2, cv, eps, l3, F, stats);                               \
+    } while (0)
+#define R2F_LAUNCH_PWF(C)                                                                                       \
+    do {                                                                                                        \
+        if (nt == 384) R2F_LAUNCH_PWF2(C, 384);                                                                 \
+        else if (nt == 256) R2F_LAUNCH_PWF2(C, 256);                                                            \
+        else R2F_LAUNCH_PWF2(C, 512);                                                                           \
+    } while (0)
+    switch (fmt) {
+        case 0: R2F_LAUNCH_PWF(0); break;
+        case 1: R2F_LAUNCH_PWF(1); break;
+        case 2: R2F_LAUNCH_PWF(2); break;
+        case 3: R2F_LAUNCH_PWF(3); break;
+        default: return cudaErrorInvalidValue;
+    }
+#undef R2F_LAUNCH_PWF2
+#undef R2F_LAUNCH_PWF
+    return cudaGetLastError();
+}
+
 static int grid_for(size_t work_items, int num_sms, int ctas_per_sm) {
     size_t want = (work_items + kThreads - 1) / kThreads;
     size_t cap = (size_t)num_sms * ctas_per_sm;
@@ -108,12 +266,11 @@ static size_t table_smem_bytes(const Lut2D &l2, const Curve1D &cv, bool want2d, 
     return f * sizeof(float);
 }
 
-constexpr size_t kMaxTableSmem = 96 * 1024;  // keep >= 2 CTAs/SM resident
 
 cudaError_t launch_pointwise(const void *in, int fmt, float gain, uint8_t *out, size_t npix, const Lut2D &l2,
                              const Curve1D &cv, float eps, const Lut3D &l3, int num_sms, cudaStream_t st) {
     const size_t sm = table_smem_bytes(l2, cv, true, true);
-    const bool use_smem = sm <= kMaxTableSmem;
+    const bool use_smem = sm <= kMaxTableSmem && cv.xp == nullptr;
     int grid = (int)((npix / 4 + kPwThreads) / kPwThreads);
     if (grid > num_sms * 2) grid = num_sms * 2;
 #define R2F_LAUNCH_PW(C, S)                                                                                \
@@ -318,12 +475,12 @@ k_conv2d(ConvArgs a) {
             const size_t idx = (size_t)gy * W + gx;
             float val = acc[o];
             if (a.epi == EPI_DENSITY) {
-                val = density_eval(a.curve, c, val, a.eps);
+                val = density_eval<true>(a.curve, c, val, a.eps);
             } else if (a.epi == EPI_DENSITY_FAST) {
-                val = density_eval_fast(a.curve, c, val, a.eps);
+                val = density_eval_fast<true>(a.curve, c, val, a.eps);
             } else if (a.epi == EPI_GRAIN) {
                 const float d = a.aux[c * ps + idx];
-                const float g = val * curve_eval(a.curve, c, d);
+                const float g = val * curve_eval_any(a.curve, c, d);
                 val = d + g;
                 val = val > 0.0f ? val : 0.0f;
             }
@@ -768,7 +925,7 @@ k_grain_finish(GrainFinishArgs a) {
 #pragma unroll
         for (int o = 0; o < 16; ++o) {
             const float d = dval[o];
-            float val = d + g[o] * curve_eval(a.gcurve, c, d);
+            float val = d + g[o] * curve_eval_any(a.gcurve, c, d);
             val = val > 0.0f ? val : 0.0f;
             priv[(c * 16 + o) * 256 + threadIdx.x] = val;
         }

@@ -6,6 +6,7 @@
 #include <cuda_runtime.h>
 
 #include "device_math.cuh"
+#include "fast_chain.cuh"
 
 namespace r2f {
 
@@ -51,6 +52,12 @@ struct BurnArgs {
 // `fmt` = kFmt* (device_math.cuh); `gain` is the exposure gain applied to uint16 input only.
 cudaError_t launch_pointwise(const void *in, int fmt, float gain, uint8_t *out, size_t npix, const Lut2D &l2,
                              const Curve1D &cv, float eps, const Lut3D &l3, int num_sms, cudaStream_t st);
+// K1 through the guarded float32 fast path (fast_chain.cuh); `stats` (device, optional) accumulates the number of
+// pixels that were deferred to the exact chain.  Fails with cudaErrorInvalidValue when the tables do not qualify.
+size_t pointwise_fast_smem(const Lut2D &l2, const FastChain &F);
+cudaError_t launch_pointwise_fast(const void *in, int fmt, float gain, uint8_t *out, size_t npix, const Lut2D &l2,
+                                  const Curve1D &cv, float eps, const Lut3D &l3, const FastChain &F,
+                                  unsigned long long *stats, int num_sms, cudaStream_t st);
 // XYZ (interleaved, 3 or 4 channels) -> planar exposure
 cudaError_t launch_expose(const void *in, int fmt, float gain, Planes out, size_t npix, const Lut2D &l2, int num_sms,
                           cudaStream_t st);

@@ -157,6 +157,22 @@ class B200Processor:
         """Direct correlation with y-symmetric kernels: packed-FMA kernel (default) or the generic one."""
         _cabi.check(_cabi.lib.r2f_set_option(self._ctx, _cabi.OPT_CONV_SYM, 1 if enabled else 0))
 
+    def set_fast_chain(self, enabled: bool = True) -> None:
+        """Per-pixel chains: guarded float32 fast path with exact fallback per pixel (default) or the exact chain
+        for every pixel.  Both produce the same bytes; the switch exists for A/B timing and the parity tests."""
+        _cabi.check(_cabi.lib.r2f_set_option(self._ctx, _cabi.OPT_FAST_CHAIN, 1 if enabled else 0))
+
+    def set_fuse_mtf(self, enabled: bool = True) -> None:
+        """MTF fused into the grain / finish kernel (default) or run as its own correlation pass."""
+        _cabi.check(_cabi.lib.r2f_set_option(self._ctx, _cabi.OPT_FUSE_MTF, 1 if enabled else 0))
+
+    def fast_chain_stats(self):
+        """(pixels the fast chain handed to the exact chain since the last call, proven |255 * error| bound of the
+        selected stock's tables or -1 if they do not qualify)."""
+        n, m = ctypes.c_uint64(0), ctypes.c_float(0.0)
+        _cabi.check(_cabi.lib.r2f_fast_chain_stats(self._ctx, ctypes.byref(n), ctypes.byref(m)))
+        return int(n.value), float(m.value)
+
     @property
     def launch_count(self) -> int:
         return int(_cabi.lib.r2f_launch_count(self._ctx))

@@ -93,3 +93,40 @@ def test_pointwise_24mp_bit_exact(proc, kind):
     got, want = _gpu_u8(proc, xyz, stock, **OFF), _oracle_u8(xyz, stock, **OFF)
     bad = np.count_nonzero(got != want)
     assert bad == 0, f"{bad} of {got.size} bytes differ (max |d| = {np.abs(got.astype(int) - want).max()})"
+
+
+@pytest.mark.parametrize("kind", ["natural", "adversarial"])
+def test_fast_chain_equals_exact_chain_and_defers_few_pixels(proc, kind):
+    """The guarded float32 fast path (csrc/fast_chain.cuh) must give the bytes of the exact chain for every pixel,
+    and only a small share of the pixels may need the exact fallback (otherwise it is not a fast path)."""
+    stock = SyntheticStock()
+    h, w = 2000, 3000
+    xyz = natural_frame(h, w, 5) if kind == "natural" else adversarial_frame(h, w, 5)
+    proc.fast_chain_stats()                              # reset the counter
+    fast = _gpu_u8(proc, xyz, stock, **OFF)
+    deferred, margin = proc.fast_chain_stats()
+    assert 0 < margin < 0.05, margin                     # the default tables qualify, with a tight bound
+    proc.set_fast_chain(False)
+    try:
+        exact = _gpu_u8(proc, xyz, stock, **OFF)
+        assert proc.fast_chain_stats()[0] == 0
+    finally:
+        proc.set_fast_chain(True)
+    assert np.array_equal(fast, exact)
+    assert np.array_equal(exact, _oracle_u8(xyz, stock, **OFF))
+    assert 0 < deferred < 0.15 * h * w, (deferred, h * w)
+    print(f"fast chain [{kind}]: margin {margin:.2e}, deferred {deferred / (h * w):.3%} of the pixels")
+
+
+def test_fast_chain_disqualified_tables_take_the_exact_chain(proc):
+    """Tables outside the fast path's preconditions (3-D LUT values outside [0, 1]) silently use the exact chain."""
+
+    class Hot(SyntheticStock):
+        def create_lut(self, *a, **k):
+            return (super().create_lut(*a, **k) * np.float32(1.5) - np.float32(0.2)).astype(np.float32)
+
+    stock = Hot(name="lut outside unit range")
+    xyz = small_frame(150, 210, seed=9)
+    got = _gpu_u8(proc, xyz, stock, **OFF)
+    assert proc.fast_chain_stats()[1] == -1.0
+    assert np.array_equal(got, _oracle_u8(xyz, stock, **OFF))
