@@ -699,6 +699,7 @@ int fast_chain_build(r2f_ctx *c) {
         }
     }
     if (!(dmin >= 0.0) || !(dmax * s3 <= (double)(n - 1) - 0.01)) return R2F_OK;  // stay inside the lattice: no clamps
+    if (n > 129 || N > (1 << 20) || t->n2 > 1024) return R2F_OK;              // index arithmetic of the fast chain
     // abscissa coordinate p: exact chain vs fast chain (both against the true value)
     const double Lm = std::fmax(std::fabs(x0), std::fabs(xN)) + 1.0, log10_2 = 0.30102999566398119521;
     const double et_exact = (u * Lm + u * (R + 2.0)) / R + 3.0 * u;
@@ -725,8 +726,10 @@ int fast_chain_build(r2f_ctx *c) {
     for (int ch = 0; ch < 3; ++ch) {
         const float *row = cv + (size_t)(ch + 1) * N;
         for (int i = 0; i < N; ++i) {
-            fs[((size_t)ch * N + i) * 2] = (float)((double)row[i] * s3);
-            fs[((size_t)ch * N + i) * 2 + 1] = i + 1 < N ? (float)(((double)row[i + 1] - (double)row[i]) * s3) : 0.0f;
+            // (midpoint of the segment in lattice units - 0.5, its forward difference): see fast_chain.cuh
+            const double d = i + 1 < N ? (double)row[i + 1] - (double)row[i] : 0.0;
+            fs[((size_t)ch * N + i) * 2] = (float)(((double)row[i] + 0.5 * d) * s3 - 0.5);
+            fs[((size_t)ch * N + i) * 2 + 1] = (float)(d * s3);
         }
     }
     int rc = upload(c, t->fseg, fs.data(), fs.size() * sizeof(float));
@@ -788,7 +791,7 @@ int render_body(r2f_ctx *c, const void *in, int in_format, float in_gain, int H,
         }
         const FastChain &fc = c->t->fast;
         ProfScope ps_(c, st, R2F_PROF_POINTWISE);
-        if (c->fast_chain && fc.ok && pointwise_fast_smem(l2, fc) <= 100 * 1024 && npix < ((size_t)1 << 32)) {
+        if (c->fast_chain && fc.ok && pointwise_fast_smem(l2, fc) <= 104 * 1024 && npix < ((size_t)1 << 32)) {
             if (!c->stats_buf.p) {
                 CU(c->stats_buf.ensure(sizeof(unsigned long long)));
                 CU(cudaMemsetAsync(c->stats_buf.p, 0, sizeof(unsigned long long), st));
@@ -1165,7 +1168,7 @@ int r2f_set_lut3d(r2f_ctx *c, const float *lut, int n, double scale) {
             for (int a = 0; a < 3; ++a)
                 if (idx[a] + 1 < (size_t)n)
                     t->lut_lip[k][a] = std::fmax(t->lut_lip[k][a], std::fabs((double)lut[3 * (v + strides[a]) + k] - x));
-            padded[4 * v + k] = (float)(x * 255.0);
+            padded[4 * v + k] = (float)(x * 255.0 - 0.5);
         }
     }
     rc = upload(c, t->lut255, padded.data(), padded.size() * sizeof(float));

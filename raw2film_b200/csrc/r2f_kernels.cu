@@ -124,7 +124,7 @@ static __device__ __noinline__ void pw_exact_pixel(const void *__restrict__ in, 
 }
 
 template <int FMT, int NT>
-__global__ void __launch_bounds__(NT, NT >= 512 ? 2 : (NT >= 384 ? 2 : 3))
+__global__ void __launch_bounds__(NT, NT >= 768 ? 1 : 2)
 k_pointwise_fast(const void *__restrict__ in, float gain, uint8_t *__restrict__ out, size_t npix, Lut2D l2, Curve1D cv,
                  float eps, Lut3D l3, FastChain F, unsigned long long *__restrict__ stats) {
     extern __shared__ __align__(16) float smem[];
@@ -143,22 +143,21 @@ k_pointwise_fast(const void *__restrict__ in, float gain, uint8_t *__restrict__ 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     FastChainS S;
     S.lut2d = (unsigned)__cvta_generic_to_shared(smem);
-    S.fseg = S.lut2d + (unsigned)(l2.n * l2.n * 16);
-    S.seg_stride = (unsigned)F.N * 8u;
-    S.n2 = l2.n;
     S.row16 = (unsigned)l2.n * 16u;
+    S.n2 = l2.n;
     S.n2m1 = (float)(l2.n - 1);
     S.hi2 = (float)(l2.n - 2);
     S.eps = eps;
     S.cA = F.cA;
     S.cB = F.cB;
     S.pscale = F.pscale;
-    S.margin = F.margin;
-    S.lut255 = F.lut255;
+    S.half_m = 0.5f - F.margin;
+    for (int ch = 0; ch < 3; ++ch)
+        S.seg_w[ch] = S.lut2d + (unsigned)(l2.n * l2.n * 16) + (unsigned)(ch * F.N) * 8u - (kMagicBits << 3);
+    S.lut = F.lut255;
     S.n3 = F.n3;
-    S.sg16 = F.n3 * 16;
-    S.sr16 = F.n3 * F.n3 * 16;
-    S.o111_16 = S.sr16 + S.sg16 + 16;
+    S.o111 = F.n3 * F.n3 + F.n3 + 1;
+    S.neg_k = 0u - kMagicBits * (unsigned)S.o111;
     unsigned *wq = reinterpret_cast<unsigned *>(smem + l2.n * l2.n * 4 + ((F.N * 3 * 2 + 3) & ~3)) + warp * kPwQueue;
     int wq_count = 0;       // warp-uniform
     unsigned deferred = 0;  // lane 0 counts for the statistics
@@ -206,14 +205,17 @@ k_pointwise_fast(const void *__restrict__ in, float gain, uint8_t *__restrict__ 
 
 size_t pointwise_fast_smem(const Lut2D &l2, const FastChain &F) {
     return ((size_t)l2.n * l2.n * 4 + (((size_t)F.N * 3 * 2 + 3) & ~(size_t)3)) * sizeof(float) +
-           (size_t)(512 / 32) * kPwQueue * sizeof(unsigned);
+           (size_t)(1024 / 32) * kPwQueue * sizeof(unsigned);
 }
 
-static int pw_fast_threads() {  // A/B knob: R2F_PW_THREADS = 512 (default) | 384 | 256
+// CTA shape.  One 1024-thread CTA per SM parks ONE copy of the tables (96 KB), which leaves ~156 KB of the SM's
+// unified L1 to the 3-D LUT gathers; two 512-thread CTAs park two copies and measure 0.27 ms at 24 MP against
+// 0.173 ms (profiles/r02_*).  A/B knob: R2F_PW_THREADS = 1024 (default) | 768 | 512 | 384 | 256.
+static int pw_fast_threads() {
     static const int v = [] {
         const char *e = getenv("R2F_PW_THREADS");
-        const int t = e ? atoi(e) : 512;
-        return (t == 384 || t == 256) ? t : 512;
+        const int t = e ? atoi(e) : 1024;
+        return (t == 256 || t == 384 || t == 512 || t == 768) ? t : 1024;
     }();
     return v;
 }
@@ -222,9 +224,9 @@ cudaError_t launch_pointwise_fast(const void *in, int fmt, float gain, uint8_t *
                                   const Curve1D &cv, float eps, const Lut3D &l3, const FastChain &F,
                                   unsigned long long *stats, int num_sms, cudaStream_t st) {
     const size_t sm = pointwise_fast_smem(l2, F);
-    if (!F.ok || sm > kMaxTableSmem + 8192 || cv.xp != nullptr || npix >= ((size_t)1 << 32))
+    if (!F.ok || sm > kMaxTableSmem + 12288 || cv.xp != nullptr || npix >= ((size_t)1 << 32))
         return cudaErrorInvalidValue;
-    const int nt = pw_fast_threads(), per_sm = nt == 256 ? 3 : 2;
+    const int nt = pw_fast_threads(), per_sm = nt >= 768 ? 1 : 2;
     int grid = (int)((npix / 4 + nt) / nt);
     if (grid > num_sms * per_sm) grid = num_sms * per_sm;
 #define R2F_LAUNCH_PWF2(C, T)                                                                                   \
@@ -238,6 +240,8 @@ cudaError_t launch_pointwise_fast(const void *in, int fmt, float gain, uint8_t *
     do {                                                                                                        \
         if (nt == 384) R2F_LAUNCH_PWF2(C, 384);                                                                 \
         else if (nt == 256) R2F_LAUNCH_PWF2(C, 256);                                                            \
+        else if (nt == 768) R2F_LAUNCH_PWF2(C, 768);                                                            \
+        else if (nt == 1024) R2F_LAUNCH_PWF2(C, 1024);                                                          \
         else R2F_LAUNCH_PWF2(C, 512);                                                                           \
     } while (0)
     switch (fmt) {
