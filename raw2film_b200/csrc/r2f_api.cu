@@ -122,7 +122,9 @@ struct TableSlot {
     std::vector<float> curve_host;     // the (4, N) H-D table as set
     double lut_lip[3][3] = {};         // [k][c]: largest step of output channel k between lattice neighbours along axis c
     double lut_absmax = 0.0, lut_min = 0.0, lut_max = 0.0;
-    DevBuf lut255, fseg;
+    DevBuf lut255, fseg, gfseg;
+    FastTetra ft{};                    // guarded float32 tetrahedral LUT of the grain / finish tails
+    FastCurve gfast{};                 // conversion-free grain amplitude curve (uniform abscissa only)
     FastChain fast{};
     bool fast_valid = false;           // `fast` matches the current curve + 3-D LUT
 };
@@ -927,7 +929,10 @@ int render_body(r2f_ctx *c, const void *in, int in_format, float in_gain, int H,
         ga.seed_lo = (uint32_t)c->t->seed;
         ga.seed_hi = (uint32_t)(c->t->seed >> 32);
         ga.gcurve = gcurve_of(c);
+        ga.gfast = c->fast_chain ? c->t->gfast : FastCurve{};
         ga.l3 = l3;
+        ga.ft = c->t->ft;
+        if (!c->fast_chain) ga.ft.ok = 0;
         ga.burn = BurnArgs{};
         ga.out_u8 = out_u8;
         ProfScope ps_(c, st, R2F_PROF_GRAIN);
@@ -1045,7 +1050,7 @@ void release_kernel_set(KernelSet &k) {
     k.base.release();
 }
 void retire_slot(r2f_ctx *c, TableSlot &t) {
-    for (DevBuf *b : {&t.lut255, &t.fseg, &t.lut2d, &t.lut2d4, &t.curve, &t.curve_xp, &t.lut3d, &t.gcurve, &t.gcurve_xp, &t.hal.buf, &t.hal.symbuf,
+    for (DevBuf *b : {&t.lut255, &t.fseg, &t.gfseg, &t.lut2d, &t.lut2d4, &t.curve, &t.curve_xp, &t.lut3d, &t.gcurve, &t.gcurve_xp, &t.hal.buf, &t.hal.symbuf,
                       &t.hal.base, &t.mtf.buf, &t.mtf.symbuf, &t.mtf.base, &t.grain.buf, &t.grain.symbuf,
                       &t.grain.base})
         retire(c, *b);
@@ -1058,7 +1063,7 @@ int r2f_destroy(r2f_ctx *c) {
     cudaDeviceSynchronize();
     for (auto &sp : c->slots) {
         if (!sp) continue;
-        for (DevBuf *b : {&sp->lut255, &sp->fseg, &sp->lut2d, &sp->lut2d4, &sp->curve, &sp->curve_xp, &sp->lut3d, &sp->gcurve, &sp->gcurve_xp}) b->release();
+        for (DevBuf *b : {&sp->lut255, &sp->fseg, &sp->gfseg, &sp->lut2d, &sp->lut2d4, &sp->curve, &sp->curve_xp, &sp->lut3d, &sp->gcurve, &sp->gcurve_xp}) b->release();
         release_kernel_set(sp->hal);
         release_kernel_set(sp->mtf);
         release_kernel_set(sp->grain);
@@ -1195,6 +1200,27 @@ int r2f_set_lut3d(r2f_ctx *c, const float *lut, int n, double scale) {
     t->s3f = (float)t->s3;
     t->margin3 = (float)margin;
     t->fast3 = (margin < 0.2 && (double)t->s3f == t->s3 && std::isfinite(absmax)) ? 1 : 0;
+    // FastTetra (fast_chain.cuh): the fraction is exact, so only arithmetic roundings, the clamp just below the last
+    // lattice plane and -- when s is not a power of two -- the rounding of v = d * s enter the bound
+    double lipmax = 0.0;
+    for (int k = 0; k < 3; ++k)
+        for (int a = 0; a < 3; ++a) lipmax = std::fmax(lipmax, t->lut_lip[k][a]);
+    const float vtop = std::nextafterf((float)(n - 1), 0.0f);
+    double mt = 255.0 * (u * absmax + 3.0 * u * lipmax) + 10.0 * u * 255.0 * absmax + u * 255.0;
+    mt += 255.0 * 3.0 * lipmax * ((double)(n - 1) - (double)vtop);
+    if (!pow2) mt += 255.0 * 3.0 * lipmax * (2.0 * u * (double)n);
+    mt *= 1.25;
+    FastTetra ft{};
+    ft.lut = static_cast<const float4 *>(t->lut255.p);
+    ft.s3f = t->s3f;
+    ft.vtop = vtop;
+    ft.half_m = (float)(0.5 - mt);
+    ft.n = n;
+    ft.o111 = n * n + n + 1;
+    ft.neg_k = 0u - kMagicBits * (unsigned)ft.o111;
+    ft.ok = (mt < 0.2 && (double)t->s3f == t->s3 && t->lut_min >= 0.0 && t->lut_max <= 1.0 && n <= 129 &&
+             std::isfinite(absmax)) ? 1 : 0;
+    t->ft = ft;
     return R2F_OK;
 }
 
@@ -1219,6 +1245,26 @@ int r2f_set_grain(r2f_ctx *c, const float *curve, int N, const float *kernel, in
     t->ng = N;
     t->gx0 = curve[0];
     t->ginv = inv_range_of(curve[0], curve[N - 1]);
+    t->gfast = FastCurve{};
+    if (t->gcurve_xp.p == nullptr && curve[N - 1] > curve[0] && N <= (1 << 20)) {  // uniform: conversion-free form
+        std::vector<float> fs((size_t)3 * N * 2);
+        for (int ch = 0; ch < 3; ++ch) {
+            const float *row = curve + (size_t)(ch + 1) * N;
+            for (int i = 0; i < N; ++i) {
+                const double d = i + 1 < N ? (double)row[i + 1] - (double)row[i] : 0.0;
+                fs[((size_t)ch * N + i) * 2] = (float)((double)row[i] + 0.5 * d);
+                fs[((size_t)ch * N + i) * 2 + 1] = (float)d;
+            }
+        }
+        rc = upload(c, t->gfseg, fs.data(), fs.size() * sizeof(float));
+        if (rc != R2F_OK) return rc;
+        const double R = (double)curve[N - 1] - (double)curve[0];
+        t->gfast.seg = static_cast<const float2 *>(t->gfseg.p);
+        t->gfast.cA = (float)(1.0 / R);
+        t->gfast.cB = (float)(-(double)curve[0] / R);
+        t->gfast.pscale = std::nextafterf((float)(N - 1), 0.0f);
+        t->gfast.N = N;
+    }
     const float one = 1.0f;  // gpu_processor.py:931-932: missing kernel -> 1x1 ones
     rc = kernel ? upload_kernel(c, t->grain, kernel, k, 1) : upload_kernel(c, t->grain, &one, 1, 1);
     if (rc != R2F_OK) return rc;

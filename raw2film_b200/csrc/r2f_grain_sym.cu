@@ -42,9 +42,9 @@ struct GrainCfg {
     static constexpr int SMEM_BYTES = (TILE_FLOATS + W_FLOATS + PRIV_FLOATS) * 4;
 };
 
-template <int K, bool GEN>
+template <int K, bool GEN, bool FASTC>
 __global__ void __launch_bounds__(256, 3)
-k_grain_finish_sym(GrainFinishArgs a) {
+k_grain_finish_sym(const __grid_constant__ GrainFinishArgs a) {
     using C = GrainCfg<K>;
     extern __shared__ __align__(16) float smem[];
     float *tile = smem;
@@ -118,7 +118,8 @@ k_grain_finish_sym(GrainFinishArgs a) {
 #pragma unroll
             for (int o = 0; o < C::OW; ++o) {
                 const float gn = h == 0 ? g[o].x : g[o].y;
-                float val = d[o] + gn * curve_eval(a.gcurve, c, d[o]);
+                const float amp = FASTC ? fast_curve_eval(a.gfast, c, d[o]) : curve_eval(a.gcurve, c, d[o]);
+                float val = d[o] + gn * amp;
                 val = val > 0.0f ? val : 0.0f;
                 priv[((c * 2 + h) * C::OW + o) * C::NT + threadIdx.x] = val;
             }
@@ -128,19 +129,23 @@ k_grain_finish_sym(GrainFinishArgs a) {
     uint8_t *stage = reinterpret_cast<uint8_t *>(tile);
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
-        uint32_t b[24];
+        uint32_t px[C::OW];  // 0x00BBGGRR per pixel
 #pragma unroll
         for (int o = 0; o < C::OW; ++o) {
             const float d0 = priv[((0 * 2 + h) * C::OW + o) * C::NT + threadIdx.x];
             const float d1 = priv[((1 * 2 + h) * C::OW + o) * C::NT + threadIdx.x];
             const float d2 = priv[((2 * 2 + h) * C::OW + o) * C::NT + threadIdx.x];
-            tetra_quant_u8(a.l3, d0, d1, d2, b[3 * o], b[3 * o + 1], b[3 * o + 2]);
+            px[o] = tetra_u8<true>(a.ft, a.l3, d0, d1, d2);  // the grain stage clipped: densities are >= 0
         }
         // 8 pixels = 24 bytes = 6 packed words
         uint32_t *sp = reinterpret_cast<uint32_t *>(stage + (lane + 32 * h) * C::SPITCH + 3 * C::OW * warp);
 #pragma unroll
-        for (int wd = 0; wd < 6; ++wd)
-            sp[wd] = b[4 * wd] | (b[4 * wd + 1] << 8) | (b[4 * wd + 2] << 16) | (b[4 * wd + 3] << 24);
+        for (int q4 = 0; q4 < C::OW / 4; ++q4) {
+            const uint32_t p0 = px[4 * q4], p1 = px[4 * q4 + 1], p2 = px[4 * q4 + 2], p3 = px[4 * q4 + 3];
+            sp[3 * q4 + 0] = p0 | (p1 << 24);
+            sp[3 * q4 + 1] = (p1 >> 8) | (p2 << 16);
+            sp[3 * q4 + 2] = (p2 >> 16) | (p3 << 8);
+        }
     }
     __syncthreads();
     const int tw = min(C::T, W - tx0), th = min(C::T, H - ty0);
@@ -165,17 +170,23 @@ cudaError_t launch_gs(const GrainFinishArgs &a, cudaStream_t st) {
     using C = GrainCfg<K>;
     dim3 grid((a.W + C::T - 1) / C::T, (a.H + C::T - 1) / C::T);
     cudaError_t e;
+#define R2F_GS_LAUNCH(GEN_, FC_)                                                                                   \
+    do {                                                                                                          \
+        auto kfn = k_grain_finish_sym<K, GEN_, FC_>;                                                              \
+        if ((e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES)) !=        \
+            cudaSuccess)                                                                                          \
+            return e;                                                                                             \
+        kfn<<<grid, C::NT, C::SMEM_BYTES, st>>>(a);                                                               \
+    } while (0)
+    const bool fc = a.gfast.seg != nullptr;
     if (a.noise == nullptr) {
-        auto kfn = k_grain_finish_sym<K, true>;
-        if ((e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES)) != cudaSuccess)
-            return e;
-        kfn<<<grid, C::NT, C::SMEM_BYTES, st>>>(a);
+        if (fc) R2F_GS_LAUNCH(true, true);
+        else R2F_GS_LAUNCH(true, false);
     } else {
-        auto kfn = k_grain_finish_sym<K, false>;
-        if ((e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES)) != cudaSuccess)
-            return e;
-        kfn<<<grid, C::NT, C::SMEM_BYTES, st>>>(a);
+        if (fc) R2F_GS_LAUNCH(false, true);
+        else R2F_GS_LAUNCH(false, false);
     }
+#undef R2F_GS_LAUNCH
     return cudaGetLastError();
 }
 

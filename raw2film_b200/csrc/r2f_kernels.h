@@ -102,7 +102,9 @@ struct GrainFinishArgs {
     int bw;              // one noise field for all three layers
     uint32_t seed_lo, seed_hi;
     Curve1D gcurve;
+    FastCurve gfast;     // conversion-free form of gcurve (uniform abscissa), seg == nullptr: use gcurve
     Lut3D l3;
+    FastTetra ft;        // guarded float32 tetrahedral LUT + quantise (ok == 0: exact path only)
     BurnArgs burn;
     uint8_t *out_u8;
 };
