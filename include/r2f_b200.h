@@ -188,6 +188,12 @@ int r2f_chroma_nr(r2f_ctx *ctx, const float *in_dev, int in_channels, float *out
  * The 256-bin post-processing and rasterisation (utils.py:171-223) are host-side (hostops.histogram_image). */
 int r2f_histogram(r2f_ctx *ctx, const uint8_t *img_dev, int H, int W, uint32_t *counts_dev, void *stream);
 
+/* All three passes of generate_histogram (utils.py:145-223; shaders/histogram.wgsl:35-158) on the device: counts,
+ * float32 log1p / smoothing / scaling, and the rasterised (height, 256, 4) uint8 widget image written to out_dev.
+ * mix_table: HOST, the (2, 2, 2, 4) uint8 colour-mix table (32 bytes, utils.py:95-142). */
+int r2f_histogram_image(r2f_ctx *ctx, const uint8_t *img_dev, int H, int W, const uint8_t *mix_table, int height,
+                        uint8_t *out_dev, void *stream);
+
 /* Reduction of calc_exposure (color_processing.py:71-99; called on every decoded frame, raw_conversion.py:51-53;
  * SURVEY 8f-1): *mean_out (host) = mean over rows 0,2,4,.. and columns 0,2,4,.. of green ** (1 / factor), green
  * taken from a device frame in either input format (uint16 is divided by 65535 first, raw_conversion.py:51).
@@ -200,6 +206,19 @@ int r2f_calc_exposure(r2f_ctx *ctx, const void *in_dev, int in_format, int H, in
  * the H x W x 3 render at (off_y, off_x); geometry from get_canvas_data (effects.py:290-335). */
 int r2f_canvas_paste(r2f_ctx *ctx, const uint8_t *src_dev, int H, int W, uint8_t *dst_dev, int canvas_h, int canvas_w,
                      int off_y, int off_x, int r, int g, int b, void *stream);
+
+/* resolution_scaling (utils.py:226-244): cv2.resize on the device.  INTER_AREA is what the reference
+ * uses when shrinking (the float32 frame before the path, cpu_processor.py:122-134 / gpu_processor.py:748-758),
+ * INTER_LANCZOS4 when enlarging (the uint8 image after it, cpu_processor.py:411-412).  in_dev: H x W x in_channels
+ * float32 (3 or 4 channels) or uint8 (3 channels); out_dev: out_h x out_w x 3 of the same type.  OpenCV's
+ * arithmetic in its operation order: INTER_AREA (both types) and uint8 INTER_LANCZOS4 are bit-identical to cv2;
+ * float32 INTER_LANCZOS4 agrees to a few ulp (cv2's vertical pass is host-SIMD dependent). */
+#define R2F_PIX_F32 0
+#define R2F_PIX_U8 2
+#define R2F_INTER_AREA 0
+#define R2F_INTER_LANCZOS4 1
+int r2f_resize(r2f_ctx *ctx, const void *in_dev, int pix_format, int H, int W, int in_channels, void *out_dev,
+               int out_h, int out_w, int interpolation, void *stream);
 
 /* Number of kernel launches issued by this context since creation (bench.py gpu_launches). */
 uint64_t r2f_launch_count(const r2f_ctx *ctx);

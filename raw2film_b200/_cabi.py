@@ -18,13 +18,15 @@ EXPORTS = [
     "r2f_set_lut3d", "r2f_set_halation_kernel", "r2f_set_mtf_kernel", "r2f_set_grain", "r2f_set_grain_seed", "r2f_set_option",
     "r2f_set_burn",
     "r2f_workspace_bytes", "r2f_render", "r2f_render_ex", "r2f_render_tap", "r2f_render_tap_ex", "r2f_render_host", "r2f_convolve2d",
-    "r2f_generate_noise", "r2f_chroma_nr", "r2f_histogram", "r2f_calc_exposure", "r2f_canvas_paste", "r2f_launch_count", "r2f_fast_chain_stats", "r2f_profile_enable", "r2f_profile_read",
+    "r2f_generate_noise", "r2f_chroma_nr", "r2f_histogram", "r2f_histogram_image", "r2f_calc_exposure", "r2f_canvas_paste", "r2f_resize", "r2f_launch_count", "r2f_fast_chain_stats", "r2f_profile_enable", "r2f_profile_read",
 ]
 OPT_CONV_PATH = 1
 OPT_CONV_SYM = 2
 OPT_FUSE_MTF = 3
 OPT_FAST_CHAIN = 4
 MAX_SLOTS = 16
+PIX_F32, PIX_U8 = 0, 2
+INTER_AREA, INTER_LANCZOS4 = 0, 1
 IN_F32, IN_U16 = 0, 1
 PROF_NAMES = ["pointwise", "expose", "halation", "density", "mtf", "noise", "grain", "burn", "finish",
               "fft_rows_fwd", "fft_cols", "fft_rows_inv"]
@@ -69,8 +71,10 @@ def _load():
         "r2f_generate_noise": (ci, [vp, vp, ci, ci, ci, u64, vp]),
         "r2f_chroma_nr": (ci, [vp, vp, ci, vp, ci, ci, fp, ci, vp, sz, vp]),
         "r2f_histogram": (ci, [vp, vp, ci, ci, vp, vp]),
+        "r2f_histogram_image": (ci, [vp, vp, ci, ci, vp, ci, vp, vp]),
         "r2f_calc_exposure": (ci, [vp, vp, ci, ci, ci, ci, cd, ctypes.POINTER(cd), vp]),
         "r2f_canvas_paste": (ci, [vp, vp, ci, ci, vp, ci, ci, ci, ci, ci, ci, ci, vp]),
+        "r2f_resize": (ci, [vp, vp, ci, ci, ci, ci, vp, ci, ci, ci, vp]),
         "r2f_launch_count": (u64, [vp]),
         "r2f_fast_chain_stats": (ci, [vp, ctypes.POINTER(u64), ctypes.POINTER(cf)]),
         "r2f_profile_enable": (ci, [vp, ci]),

@@ -11,8 +11,8 @@ import subprocess
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG_DIR, "csrc")
 LIB_PATH = os.path.join(PKG_DIR, "libr2f_b200.so")
-SOURCES = ["r2f_api.cu", "r2f_kernels.cu", "r2f_fft.cu", "r2f_conv_sym.cu", "r2f_grain_sym.cu"]
-HEADERS = ["device_math.cuh", "conv_tile.cuh", "noise.cuh", "sym_conv.cuh", "r2f_kernels.h", "r2f_fft.h", os.path.join("..", "..", "include", "r2f_b200.h")]
+SOURCES = ["r2f_api.cu", "r2f_kernels.cu", "r2f_fft.cu", "r2f_conv_sym.cu", "r2f_grain_sym.cu", "r2f_resize.cu"]
+HEADERS = ["device_math.cuh", "fast_chain.cuh", "conv_tile.cuh", "noise.cuh", "sym_conv.cuh", "r2f_kernels.h", "r2f_fft.h", "r2f_resize.h", os.path.join("..", "..", "include", "r2f_b200.h")]
 
 NVCC_FLAGS = [
     "-O3", "-std=c++17",

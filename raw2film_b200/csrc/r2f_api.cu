@@ -9,7 +9,9 @@
 #include "../../include/r2f_b200.h"
 #include "r2f_fft.h"
 #include "r2f_kernels.h"
+#include "r2f_resize.h"
 #include <map>
+#include <tuple>
 #include <memory>
 
 using namespace r2f;
@@ -160,6 +162,13 @@ struct r2f_ctx {
     DevBuf expo_buf;  // r2f_calc_exposure: per-CTA partial sums + the result
     DevBuf hist_buf;  // r2f_histogram_image: counts + scalars
     DevBuf stats_buf; // fast-chain statistics (deferred pixel count)
+    // r2f_resize tap tables per (kind, source size, destination size); kind 0 = area, 1 = lanczos4
+    struct ResizeTab {
+        DevBuf a, b, c;
+        uint64_t last_use = 0;
+    };
+    std::map<std::tuple<int, int, int>, ResizeTab> resize_tabs;
+    uint64_t resize_clock = 0;
 
     // r2f_render_host staging
     DevBuf h_in, h_out, h_ws, h_noise;
@@ -1075,6 +1084,11 @@ int r2f_destroy(r2f_ctx *c) {
         e.buf.release();
         if (e.ready) cudaEventDestroy(e.ready);
     }
+    for (auto &kv : c->resize_tabs) {
+        kv.second.a.release();
+        kv.second.b.release();
+        kv.second.c.release();
+    }
     for (auto &r : c->retired) cudaFree(r.p);
     for (auto &pb : c->pool) cudaFree(pb.first);
     for (auto &ev : c->render_done)
@@ -1471,6 +1485,22 @@ int r2f_histogram(r2f_ctx *c, const uint8_t *img_dev, int H, int W, uint32_t *co
     return R2F_OK;
 }
 
+int r2f_histogram_image(r2f_ctx *c, const uint8_t *img_dev, int H, int W, const uint8_t *mix_table, int height,
+                        uint8_t *out_dev, void *stream) {
+    if (!c || !img_dev || !mix_table || !out_dev || H < 1 || W < 1 || height < 1)
+        return fail(R2F_ERR_INVALID, "r2f_histogram_image: bad arguments");
+    if ((reinterpret_cast<uintptr_t>(img_dev) & 3) != 0 || (reinterpret_cast<uintptr_t>(out_dev) & 3) != 0)
+        return fail(R2F_ERR_INVALID, "image and output must be 4-byte aligned");
+    DeviceGuard guard(c->device);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    CU(c->hist_buf.ensure(768 * sizeof(unsigned int)));
+    unsigned int *counts = static_cast<unsigned int *>(c->hist_buf.p);
+    CU(launch_histogram(img_dev, (size_t)H * W, counts, c->num_sms, st));
+    CU(launch_histogram_image(counts, height, mix_table, out_dev, st));
+    c->launches += 2;
+    return R2F_OK;
+}
+
 int r2f_canvas_paste(r2f_ctx *c, const uint8_t *src_dev, int H, int W, uint8_t *dst_dev, int canvas_h, int canvas_w,
                      int off_y, int off_x, int r, int g, int b, void *stream) {
     if (!c || !src_dev || !dst_dev || H < 1 || W < 1 || canvas_h < 1 || canvas_w < 1)
@@ -1497,6 +1527,84 @@ int r2f_calc_exposure(r2f_ctx *c, const void *in_dev, int in_format, int H, int 
     c->launches += 2;
     CU(cudaMemcpyAsync(mean_out, out, sizeof(double), cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
+    return R2F_OK;
+}
+
+namespace {
+// tap tables of one axis on the device, cached per (kind, source size, destination size)
+int resize_axis_tab(r2f_ctx *c, int kind, int ssize, int dsize, r2f_ctx::ResizeTab **out) {
+    auto key = std::make_tuple(kind, ssize, dsize);
+    auto it = c->resize_tabs.find(key);
+    if (it == c->resize_tabs.end()) {
+        if (c->resize_tabs.size() >= 16) {  // drop the least recently used entry (its buffers may still be read)
+            auto lru = c->resize_tabs.begin();
+            for (auto jt = c->resize_tabs.begin(); jt != c->resize_tabs.end(); ++jt)
+                if (jt->second.last_use < lru->second.last_use) lru = jt;
+            retire(c, lru->second.a);
+            retire(c, lru->second.b);
+            retire(c, lru->second.c);
+            c->resize_tabs.erase(lru);
+        }
+        r2f_ctx::ResizeTab t;
+        int rc;
+        if (kind == 0) {
+            AreaTabHost h;
+            resize_area_tab(ssize, dsize, h);
+            if ((rc = upload(c, t.a, h.start.data(), h.start.size() * sizeof(int))) != R2F_OK) return rc;
+            if ((rc = upload(c, t.b, h.si.data(), h.si.size() * sizeof(int))) != R2F_OK) return rc;
+            if ((rc = upload(c, t.c, h.alpha.data(), h.alpha.size() * sizeof(float))) != R2F_OK) return rc;
+        } else {
+            LanczosTabHost h;
+            resize_lanczos4_tab(ssize, dsize, h);
+            if ((rc = upload(c, t.a, h.ofs.data(), h.ofs.size() * sizeof(int))) != R2F_OK) return rc;
+            if ((rc = upload(c, t.b, h.coef.data(), h.coef.size() * sizeof(float))) != R2F_OK) return rc;
+            if ((rc = upload(c, t.c, h.icoef.data(), h.icoef.size() * sizeof(int))) != R2F_OK) return rc;
+        }
+        it = c->resize_tabs.emplace(key, t).first;
+    }
+    it->second.last_use = ++c->resize_clock;
+    *out = &it->second;
+    return R2F_OK;
+}
+}  // namespace
+
+int r2f_resize(r2f_ctx *c, const void *in_dev, int pix_format, int H, int W, int in_channels, void *out_dev, int out_h,
+               int out_w, int interpolation, void *stream) {
+    if (!c || !in_dev || !out_dev || H < 1 || W < 1 || out_h < 1 || out_w < 1)
+        return fail(R2F_ERR_INVALID, "r2f_resize: bad arguments");
+    if (pix_format != R2F_PIX_F32 && pix_format != R2F_PIX_U8) return fail(R2F_ERR_INVALID, "r2f_resize: unknown pixel format");
+    if (in_channels != 3 && !(in_channels == 4 && pix_format == R2F_PIX_F32))
+        return fail(R2F_ERR_INVALID, "r2f_resize: in_channels must be 3 (or 4 for float32 frames)");
+    if (interpolation != R2F_INTER_AREA && interpolation != R2F_INTER_LANCZOS4)
+        return fail(R2F_ERR_INVALID, "r2f_resize: unknown interpolation");
+    DeviceGuard guard(c->device);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const bool u8 = pix_format == R2F_PIX_U8;
+    if (interpolation == R2F_INTER_AREA) {
+        if (out_h > H || out_w > W) return fail(R2F_ERR_INVALID, "r2f_resize: INTER_AREA is the shrinking filter");
+        int ix = 1, iy = 1;
+        if (resize_area_is_fast(W, out_w, ix) && resize_area_is_fast(H, out_h, iy)) {
+            CU(launch_resize_area_int(in_dev, u8, in_channels, H, W, out_dev, out_h, out_w, ix, iy, c->num_sms, st));
+        } else {
+            r2f_ctx::ResizeTab *tx = nullptr, *ty = nullptr;
+            int rc = resize_axis_tab(c, 0, W, out_w, &tx);
+            if (rc == R2F_OK) rc = resize_axis_tab(c, 0, H, out_h, &ty);
+            if (rc != R2F_OK) return rc;
+            AreaTabDev xt{static_cast<const int *>(tx->a.p), static_cast<const int *>(tx->b.p), static_cast<const float *>(tx->c.p)};
+            AreaTabDev yt{static_cast<const int *>(ty->a.p), static_cast<const int *>(ty->b.p), static_cast<const float *>(ty->c.p)};
+            CU(launch_resize_area(in_dev, u8, in_channels, H, W, out_dev, out_h, out_w, xt, yt, c->num_sms, st));
+        }
+    } else {
+        r2f_ctx::ResizeTab *tx = nullptr, *ty = nullptr;
+        int rc = resize_axis_tab(c, 1, W, out_w, &tx);
+        if (rc == R2F_OK) rc = resize_axis_tab(c, 1, H, out_h, &ty);
+        if (rc != R2F_OK) return rc;
+        LanczosTabDev xt{static_cast<const int *>(tx->a.p), static_cast<const float *>(tx->b.p), static_cast<const int *>(tx->c.p)};
+        LanczosTabDev yt{static_cast<const int *>(ty->a.p), static_cast<const float *>(ty->b.p), static_cast<const int *>(ty->c.p)};
+        CU(launch_resize_lanczos4(in_dev, u8, in_channels, H, W, out_dev, out_h, out_w, xt, yt, c->num_sms, st));
+    }
+    c->launches += 1;
+    CU(mark_render(c, st));  // the tap tables are copy-on-write storage like the LUTs
     return R2F_OK;
 }
 

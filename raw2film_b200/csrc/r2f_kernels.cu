@@ -761,6 +761,59 @@ cudaError_t launch_histogram(const uint8_t *img, size_t npix, unsigned int *coun
     return cudaGetLastError();
 }
 
+// Passes 2 and 3 of the histogram widget (reference utils.py:171-223; shaders/histogram.wgsl:63-158), one CTA:
+// float32 log1p(count / peak), 3-tap moving average with replicated ends, scaling to `height`, truncation, then the
+// (2,2,2,4) colour-mix lookup per widget pixel.  Same float32 operations as the NumPy code (log1p evaluated in
+// binary64 and rounded once, i.e. a correctly rounded log1pf).
+__global__ void __launch_bounds__(768)
+k_histogram_image(const unsigned int *__restrict__ counts, int height, uint32_t mix0, uint32_t mix1, uint32_t mix2,
+                  uint32_t mix3, uint32_t mix4, uint32_t mix5, uint32_t mix6, uint32_t mix7,
+                  uint8_t *__restrict__ out /* height x 256 x 4 */) {
+    __shared__ float f[768];
+    __shared__ float red[24];
+    __shared__ int hts[768];
+    const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+    auto block_max = [&](float v) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+        __syncthreads();
+        if (lane == 0) red[warp] = v;
+        __syncthreads();
+        float m = red[0];
+        for (int i = 1; i < 24; ++i) m = fmaxf(m, red[i]);
+        return m;
+    };
+    const float c = (float)counts[t];
+    float peak = fmaxf(block_max(c), 0.0f);
+    if (peak == 0.0f) peak = 1.0f;
+    f[t] = (float)log1p((double)__fdiv_rn(c, peak));
+    __syncthreads();
+    const int ch = t >> 8, bin = t & 255;
+    const float left = f[ch * 256 + max(bin - 1, 0)], right = f[ch * 256 + min(bin + 1, 255)];
+    const float smooth = __fdiv_rn((left + f[t]) + right, 3.0f);
+    float top = fmaxf(block_max(smooth), 0.0f);
+    if (top == 0.0f) top = 1.0f;
+    hts[t] = (int)__fdiv_rn(smooth * (float)height, top);
+    __syncthreads();
+    const uint32_t mix[8] = {mix0, mix1, mix2, mix3, mix4, mix5, mix6, mix7};
+    uint32_t *o32 = reinterpret_cast<uint32_t *>(out);
+    for (int p = t; p < height * 256; p += 768) {
+        const int y = p >> 8, x = p & 255;
+        const int a0 = y >= height - hts[x], a1 = y >= height - hts[256 + x], a2 = y >= height - hts[512 + x];
+        o32[p] = mix[a0 * 4 + a1 * 2 + a2];
+    }
+}
+
+cudaError_t launch_histogram_image(const unsigned int *counts_dev, int height, const uint8_t *mix_host, uint8_t *out,
+                                   cudaStream_t st) {
+    uint32_t m[8];
+    for (int i = 0; i < 8; ++i)
+        m[i] = (uint32_t)mix_host[4 * i] | ((uint32_t)mix_host[4 * i + 1] << 8) | ((uint32_t)mix_host[4 * i + 2] << 16) |
+               ((uint32_t)mix_host[4 * i + 3] << 24);
+    k_histogram_image<<<1, 768, 0, st>>>(counts_dev, height, m[0], m[1], m[2], m[3], m[4], m[5], m[6], m[7], out);
+    return cudaGetLastError();
+}
+
 // Canvas border (reference effects.py:338-357 add_canvas): fill the canvas with one colour and
 // paste the rendered image at (off_y, off_x).  One thread per canvas byte triple.
 __global__ void __launch_bounds__(kThreads)

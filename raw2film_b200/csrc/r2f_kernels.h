@@ -77,6 +77,9 @@ cudaError_t launch_chroma_nr(const float *in, int cin, float *out, int H, int W,
                              float *ws, size_t ps, int num_sms, cudaStream_t st);
 // 3 x 256 histogram counts of a uint8 H x W x 3 image (reference utils.py:158-169)
 cudaError_t launch_histogram(const uint8_t *img, size_t npix, unsigned int *counts_dev, int num_sms, cudaStream_t st);
+// passes 2-3 of the histogram widget: counts -> (height, 256, 4) image through the 32-byte colour-mix table (host)
+cudaError_t launch_histogram_image(const unsigned int *counts_dev, int height, const uint8_t *mix_host, uint8_t *out,
+                                   cudaStream_t st);
 // auto exposure: mean of green ** inv_factor over every second row/column (color_processing.py:71-99);
 // `partial` holds nblocks doubles of scratch, `out` one double (device)
 cudaError_t launch_exposure_mean(const void *in, int fmt, int H, int W, double inv_factor, double *partial, int nblocks,

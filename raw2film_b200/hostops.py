@@ -31,6 +31,16 @@ def exposure_factor(metadata: dict | None) -> float:
     return float(factor)
 
 
+def target_size(shape, resolution):
+    """(rows, cols) that `resolution_scaling` (reference utils.py:226-244) resizes an image of `shape` to, or None
+    when it leaves the image alone (factor exactly 1)."""
+    rows, cols = shape[:2]
+    factor = min(resolution[0] / rows, resolution[1] / cols)
+    if factor == 1:
+        return None
+    return round(rows * factor), round(cols * factor)
+
+
 def resolution_scaling(image: np.ndarray, resolution) -> np.ndarray:
     rows, cols = image.shape[:2]
     factor = min(resolution[0] / rows, resolution[1] / cols)

@@ -41,13 +41,14 @@ class PipelinedRenderer:
         self.h2d_bytes = 0
         self.d2h_bytes = 0
 
-    def _slot_buffers(self, slot, shape_in, tdtype, out_shape):
+    def _slot_buffers(self, slot, shape_in, tdtype, out_shape, render_hw):
         torch = self._torch
         h, w, ch = shape_in
         dev = self.proc.device
         if slot["dev_in"] is None or tuple(slot["dev_in"].shape) != (h, w, ch) or slot["dev_in"].dtype != tdtype:
             slot["dev_in"] = torch.empty((h, w, ch), dtype=tdtype, device=dev)
-            slot["dev_out"] = torch.empty((h, w, 3), dtype=torch.uint8, device=dev)
+        if slot["dev_out"] is None or tuple(slot["dev_out"].shape[:2]) != tuple(render_hw):
+            slot["dev_out"] = torch.empty((render_hw[0], render_hw[1], 3), dtype=torch.uint8, device=dev)
         if slot["host_out"] is None or tuple(slot["host_out"].shape) != tuple(out_shape):
             slot["host_out"] = torch.empty(tuple(out_shape), dtype=torch.uint8, pin_memory=True)
             slot["canvas_dev"] = None
@@ -62,9 +63,14 @@ class PipelinedRenderer:
         proc = self.proc
         arr = cpu_payload["image_array"]
         tdtype = torch.uint16 if arr.dtype == np.uint16 else torch.float32
-        h, w = arr.shape[:2]
+        pre = cpu_payload.get("_pre_resize")          # device resolution_scaling before the path
+        h, w = arr.shape[:2] if pre is None else pre
         canvas = cpu_payload.get("_canvas")
         out_shape = (h, w, 3) if canvas is None else (canvas["size"][0], canvas["size"][1], 3)
+        orig = cpu_payload.get("_orig_resolution")
+        post = None if orig is None else hostops.target_size(out_shape, orig)   # ... and after it
+        if post is not None:
+            out_shape = (post[0], post[1], 3)
         ticket = self._count
         slot = self._slots[ticket % self.depth]
         if slot["used"]:
@@ -74,7 +80,7 @@ class PipelinedRenderer:
             if host is None:  # foreign payload: stage through pinned memory (extra host copy)
                 host = torch.empty(arr.shape, dtype=tdtype, pin_memory=True)
                 host.numpy()[...] = arr
-            self._slot_buffers(slot, arr.shape, tdtype, out_shape)
+            self._slot_buffers(slot, arr.shape, tdtype, out_shape, (h, w))
             with torch.cuda.stream(self.s_in):
                 if slot.get("last_read") is not None:
                     self.s_in.wait_event(slot["last_read"])   # the last render that read this dev_in has finished
@@ -91,12 +97,17 @@ class PipelinedRenderer:
                 raise RuntimeError("upload=False needs the same frame to be on the device from the previous submit")
             dev_in = prev["dev_in"]                   # same compute stream: ordered after the previous render
             reader = prev
-            self._slot_buffers(slot, arr.shape, tdtype, out_shape)
+            self._slot_buffers(slot, arr.shape, tdtype, out_shape, (h, w))
         if slot["used"]:
             self.s_compute.wait_event(slot["d2h"])
         proc.output_resolution = cpu_payload.get("output_resolution")
         proc.canvas_resolution = cpu_payload.get("canvas_resolution")
         proc.pipeline_resolution = cpu_payload.get("pipeline_resolution")
+        if pre is not None:                           # resolution_scaling of the float frame, on the device
+            if tdtype != torch.float32:
+                raise ValueError("a frame that is resized before the path must be float32")
+            slot["dev_pre"] = proc.resize_device(dev_in, pre, out=slot.get("dev_pre"), stream=self.s_compute)
+            dev_in = slot["dev_pre"]
         out_dev = proc.render_device(dev_in, negative_film, grain_size, grain_sigma, out=slot["dev_out"],
                                      stream=self.s_compute, sync_caller=False,
                                      input_gain=cpu_payload.get("input_gain", 1.0), **settings)
@@ -109,6 +120,9 @@ class PipelinedRenderer:
                                                    ch_, cw_, int(canvas["offset"][0]), int(canvas["offset"][1]),
                                                    r, g, b, self.s_compute.cuda_stream))
             out_dev = slot["canvas_dev"]
+        if post is not None:                          # post-step of cpu_processor.py:411-412, on the device
+            slot["dev_post"] = proc.resize_device(out_dev, post, out=slot.get("dev_post"), stream=self.s_compute)
+            out_dev = slot["dev_post"]
         slot["done"].record(self.s_compute)
         reader["last_read"] = slot["done"]
         with torch.cuda.stream(self.s_out):
@@ -116,7 +130,6 @@ class PipelinedRenderer:
             slot["host_out"].copy_(out_dev, non_blocking=True)
             slot["d2h"].record(self.s_out)
         slot["used"] = True
-        slot["orig_resolution"] = cpu_payload.get("_orig_resolution")
         self._last_slot = slot if upload else self._last_slot
         self._count += 1
         self.d2h_bytes += slot["host_out"].numel()
@@ -127,11 +140,7 @@ class PipelinedRenderer:
             raise ValueError("ticket is not in flight any more")
         slot = self._slots[ticket % self.depth]
         slot["d2h"].synchronize()
-        image = slot["host_out"].numpy()
-        orig = slot.get("orig_resolution")
-        if orig is not None:                          # post-step of cpu_processor.py:411-412
-            image = hostops.resolution_scaling(image, orig)
-        return image
+        return slot["host_out"].numpy()
 
     def run(self, payloads, negative_film, grain_size, grain_sigma, sink=None, **settings):
         """Render an iterable of payloads in order; `sink(index, image)` is called as results land."""

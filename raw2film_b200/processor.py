@@ -365,10 +365,26 @@ class B200Processor:
         self.stream.synchronize()
         return counts.cpu().numpy().astype(np.int64).reshape(3, 256)
 
-    def generate_histogram(self, mix_table, height: int = 100, image_dev=None) -> np.ndarray:
-        """The reference's RGB histogram widget image (utils.py:145-223): counts on the device, the 256-bin
-        post-processing on the host."""
-        return hostops.histogram_image(self.histogram_counts(image_dev), np.asarray(mix_table, np.uint8), height)
+    def generate_histogram(self, mix_table, height: int = 100, image_dev=None, on_device: bool = True) -> np.ndarray:
+        """The reference's RGB histogram widget image (utils.py:145-223; shaders/histogram.wgsl passes 1-3), (height,
+        256, 4) uint8.  All three passes run on the device (r2f_histogram_image) and only the 100 KB widget image
+        comes back; `on_device=False` keeps passes 2-3 on the host (hostops.histogram_image)."""
+        mix = np.ascontiguousarray(np.asarray(mix_table, np.uint8).reshape(2, 2, 2, 4))
+        if not on_device:
+            return hostops.histogram_image(self.histogram_counts(image_dev), mix, height)
+        torch = self._torch
+        img = self._last_out if image_dev is None else image_dev
+        if img is None:
+            raise RuntimeError("nothing rendered yet")
+        h, w = img.shape[:2]
+        out = torch.empty((int(height), 256, 4), dtype=torch.uint8, device=self.device)
+        self.stream.wait_stream(torch.cuda.current_stream(self.device))
+        _cabi.check(_cabi.lib.r2f_histogram_image(self._ctx, img.data_ptr(), h, w, mix.ctypes.data_as(ctypes.c_void_p),
+                                                  int(height), out.data_ptr(), self.stream.cuda_stream))
+        with torch.cuda.stream(self.stream):
+            host = out.cpu()
+        self.stream.synchronize()
+        return host.numpy()
 
     # ------------------------------------------------------------------------------------------
     # phase 1 (CPU, state-free): gpu_processor.py:715-783
@@ -376,7 +392,8 @@ class B200Processor:
     def extract_image_data_cpu(self, src, cam=None, lens=None, lens_correction=True, frame_width=36,
                                frame_height=24, rotation=0.0, zoom=1.0, rotate_times=0, flip=False, resolution=None,
                                half_size=True, cache=True, chroma_nr=0, max_scale=400.0, canvas_mode="No",
-                               canvas_scale=1.0, canvas_ratio=1.0, alpha=False, input_gain=1.0, **kwargs):
+                               canvas_scale=1.0, canvas_ratio=1.0, alpha=False, input_gain=1.0, device_resize=True,
+                               **kwargs):
         """Returns the same payload dict as the reference.  `image_array` lives in pinned host
         memory so phase 2 can DMA it; 3 channels unless `alpha=True` (reference layout, XYZ + ones).
 
@@ -404,24 +421,31 @@ class B200Processor:
             image = self.chroma_nr_filter(image, chroma_nr)
         h, w = image.shape[:2]
         # resolution / max_scale handling of the reference's CPU phase (gpu_processor.py:748-760,
-        # cpu_processor.py:122-134): host cv2, exactly where both reference processors do it
+        # cpu_processor.py:122-134).  The resize itself (cv2 INTER_AREA / INTER_LANCZOS4, utils.py:226-244) runs on
+        # the device in phase 2 (r2f_resize, bit-identical to cv2 for INTER_AREA): the payload keeps the frame at
+        # its source size and records the target.  `device_resize=False` resizes here with cv2 like the reference.
         if resolution is None and max_scale is not None:
             resolution = (h, w)
         orig_resolution = None if resolution is None else tuple(resolution)
         scale_factor = 1.0
+        pre_resize = None
         if resolution is not None:
             resolution = list(resolution)
             scale = max(resolution) / max(frame_width, frame_height)
             if max_scale is not None and scale > max_scale:
                 scale_factor = max_scale / scale
                 resolution = [round(x * scale_factor) for x in resolution]
-            if min(resolution[0] / h, resolution[1] / w) != 1:
+            target = hostops.target_size((h, w), resolution)
+            if target is not None:
                 if image.dtype == np.uint16:      # the reference resizes the float frame (after ingest)
                     image = image[..., :3].astype(F32) / F32(65535.0)
                     image *= F32(input_gain)
                     input_gain = 1.0
-                image = hostops.resolution_scaling(np.ascontiguousarray(image[..., :3]), resolution)
-                h, w = image.shape[:2]
+                if device_resize:
+                    pre_resize = target
+                else:
+                    image = hostops.resolution_scaling(np.ascontiguousarray(image[..., :3]), resolution)
+                h, w = target
         output_res = tuple(round(x / scale_factor) for x in (h, w))
         canvas = None
         canvas_res = None
@@ -432,20 +456,23 @@ class B200Processor:
             canvas_res = (out_size[1], out_size[0])
         channels = 4 if alpha else 3
         is_u16 = image.dtype == np.uint16
+        sh_, sw_ = image.shape[:2]                            # source size (== (h, w) unless the device resizes)
         pinned = self._pinned_frames.get(image.ctypes.data) if image.flags.c_contiguous else None
-        if pinned is not None and tuple(pinned.shape) == (h, w, channels) and image.dtype in (np.uint16, F32):
+        if pinned is not None and tuple(pinned.shape) == (sh_, sw_, channels) and image.dtype in (np.uint16, F32):
             arr = image                                   # already page-locked (pinned_frame): no host copy
         else:
             if image.dtype not in (np.uint16, F32):
                 image = image.astype(F32)
-            pinned = torch.empty((h, w, channels), dtype=torch.uint16 if is_u16 else torch.float32, pin_memory=True)
+            pinned = torch.empty((sh_, sw_, channels), dtype=torch.uint16 if is_u16 else torch.float32,
+                                 pin_memory=True)
             arr = pinned.numpy()
             arr[..., :3] = image[..., :3]
             if alpha:
                 arr[..., 3] = 65535 if is_u16 else 1.0
         return {"image_array": arr, "output_resolution": (output_res[1], output_res[0]),
                 "canvas_resolution": canvas_res, "pipeline_resolution": (w, h), "_pinned": pinned,
-                "input_gain": float(np.float32(input_gain)), "_canvas": canvas, "_orig_resolution": orig_resolution}
+                "input_gain": float(np.float32(input_gain)), "_canvas": canvas, "_orig_resolution": orig_resolution,
+                "_pre_resize": pre_resize}
 
     # ------------------------------------------------------------------------------------------
     # phase 2: upload + render
@@ -595,6 +622,26 @@ class B200Processor:
             self._pipe = PipelinedRenderer(self, depth=3)
         return self._pipe
 
+    def resize_device(self, x_dev, size, out=None, stream=None):
+        """cv2.resize on the device the way `resolution_scaling` (reference utils.py:226-244) picks the filter:
+        INTER_AREA when `size` = (rows, cols) is smaller than the image, INTER_LANCZOS4 when larger.  `x_dev`: float32
+        (H, W, 3|4) or uint8 (H, W, 3) CUDA tensor; returns (rows, cols, 3) of the same dtype."""
+        torch = self._torch
+        h, w, ch = x_dev.shape
+        rows, cols = int(size[0]), int(size[1])
+        if x_dev.dtype not in (torch.float32, torch.uint8) or not x_dev.is_contiguous():
+            raise ValueError("resize_device takes a contiguous float32 or uint8 CUDA tensor")
+        shrink = rows <= h and cols <= w
+        if not shrink and (rows < h or cols < w):
+            raise ValueError("resize_device keeps the aspect ratio: both sides shrink or both grow")
+        if out is None or tuple(out.shape) != (rows, cols, 3) or out.dtype != x_dev.dtype:
+            out = torch.empty((rows, cols, 3), dtype=x_dev.dtype, device=self.device)
+        stream = self.stream if stream is None else stream
+        _cabi.check(_cabi.lib.r2f_resize(
+            self._ctx, x_dev.data_ptr(), _cabi.PIX_U8 if x_dev.dtype == torch.uint8 else _cabi.PIX_F32, h, w, ch,
+            out.data_ptr(), rows, cols, _cabi.INTER_AREA if shrink else _cabi.INTER_LANCZOS4, stream.cuda_stream))
+        return out
+
     def pinned_frame(self, h: int, w: int, channels: int = 3, dtype=np.float32) -> np.ndarray:
         """A (h, w, channels) array in page-locked host memory.  A decoder that writes its frame straight into it
         spares phase 1 (`extract_image_data_cpu`) its host copy: such an array is handed to the DMA engine as is."""
@@ -619,8 +666,9 @@ class B200Processor:
                 "flip", "resolution", "half_size", "cache", "chroma_nr", "max_scale", "canvas_mode", "canvas_scale",
                 "canvas_ratio")
         ingest_args = {k: s[k] for k in keys}
-        if "input_gain" in settings:
-            ingest_args["input_gain"] = settings["input_gain"]
+        for opt in ("input_gain", "device_resize"):
+            if opt in settings:
+                ingest_args[opt] = settings[opt]
         src_key = src if isinstance(src, str) else ("array", id(src), getattr(src, "shape", None),
                                                     str(getattr(src, "dtype", "")))
         new_param_dict = {"src": src_key, **{k: (tuple(v) if isinstance(v, list) else v)

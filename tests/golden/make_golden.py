@@ -16,6 +16,7 @@ Every array named `ref_*` was computed by a reference function:
   raw2film.effects.chroma_nr_filter         (effects.py:421-561)
   raw2film.utils.generate_histogram         (utils.py:145-223)
   raw2film.color_processing.calc_exposure   (color_processing.py:71-99)   [`make_golden.py calc_exposure`]
+  raw2film.utils.resolution_scaling         (utils.py:226-244), float32 + uint8 battery [`make_golden.py resize`]
 """
 from __future__ import annotations
 
@@ -182,8 +183,33 @@ def make_calc_exposure():
     print("calc_exposure.npz written:", {k: v for k, v in out.items() if k.startswith("ref_")})
 
 
+def make_resize():
+    """resolution_scaling (utils.py:226-244) -- i.e. cv2.resize INTER_AREA / INTER_LANCZOS4 -- on float32 frames
+    (pre-path use, cpu_processor.py:122-134) and uint8 images (post-path use, :411-412): integer and non-integer
+    shrink factors, enlargements, 3- and 4-channel float frames."""
+    _, utils = load_reference()
+    rng = np.random.default_rng(41017)
+    out = {}
+    f = (rng.random((72, 96, 3), dtype=np.float32) * np.float32(2.5)).astype(np.float32)
+    f[5:9, 7:12] = 40.0                                   # a highlight: large dynamic range
+    u = rng.integers(0, 256, (72, 96, 3), dtype=np.uint8)
+    out["f32"], out["u8"] = f, u
+    # (rows, cols) boxes handed to resolution_scaling; the aspect-preserving fit decides the real size
+    boxes = {"half": (36, 48), "third": (24, 32), "quarter": (18, 24), "sixth": (12, 16), "odd": (29, 41),
+             "near": (71, 95), "tiny": (5, 9), "tall": (50, 400), "up15": (108, 144), "up2": (144, 192),
+             "up_odd": (173, 240), "up_one": (73, 98)}
+    for name, box in boxes.items():
+        out[f"box_{name}"] = np.asarray(box)
+        out[f"ref_f32_{name}"] = utils.resolution_scaling(f.copy(), box)
+        out[f"ref_u8_{name}"] = utils.resolution_scaling(u.copy(), box)
+    np.savez_compressed(os.path.join(HERE, "resize.npz"), **out)
+    print("resize.npz written:", {k: v.shape for k, v in out.items() if k.startswith("ref_f32")})
+
+
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "calc_exposure":
         make_calc_exposure()
+    elif len(sys.argv) > 1 and sys.argv[1] == "resize":
+        make_resize()
     else:
         main()

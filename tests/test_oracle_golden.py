@@ -97,3 +97,25 @@ def test_calc_exposure_matches_reference_golden():
         rgb = g[f"u16_{i}"].astype(np.float32) / np.float32(65535.0)
         got = [fo.calc_exposure(rgb, metadata=m) for m in metas]
         assert np.allclose(got, g[f"ref_exp_{i}"], rtol=0, atol=1e-6), (i, got, g[f"ref_exp_{i}"])
+
+
+def test_resize_oracle_matches_reference_resolution_scaling():
+    """oracle/resize_oracle.py against the reference's own resolution_scaling (cv2.resize) outputs: INTER_AREA
+    (float32 and uint8, integer and fractional factors) and uint8 INTER_LANCZOS4 bit for bit; float32 INTER_LANCZOS4
+    to 1e-6 of the data range (cv2's vertical pass is host-SIMD dependent, see the oracle's header)."""
+    from oracle import resize_oracle as ro
+
+    g = np.load(G + "resize.npz")
+    names = [k[4:] for k in g.files if k.startswith("box_")]
+    assert len(names) >= 12
+    for name in names:
+        box = tuple(int(v) for v in g["box_" + name])
+        for kind in ("f32", "u8"):
+            src, want = g[kind], g[f"ref_{kind}_{name}"]
+            got = ro.resolution_scaling(src, box)
+            assert got.shape == want.shape and got.dtype == want.dtype, (name, kind)
+            shrink = want.shape[0] < src.shape[0]
+            if shrink or kind == "u8":
+                assert np.array_equal(got, want), (name, kind, np.abs(got.astype(np.float64) - want).max())
+            else:
+                assert np.abs(got - want).max() <= 1e-6 * float(src.max()), (name, kind)
