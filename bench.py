@@ -321,6 +321,34 @@ def main():
     latency = {"p50_ms": float(lat[len(lat) // 2]), "p99_ms": float(lat[min(len(lat) - 1, int(len(lat) * 0.99))]),
                "min_ms": float(lat[0]), "calls": lat_n,
                "what": "wall time of one synchronous B200Processor.render_device call (device-resident frame)"}
+    if args.config == "C5":
+        # (i) the same call replayed as a CUDA graph, (ii) the preview as the GUI drives it: a 24 MP frame resident
+        # on the device, shrunk to the widget size (INTER_AREA, utils.py:226-244) and rendered, per call
+        from raw2film_b200 import PreviewGraph
+
+        pg = PreviewGraph(proc, dev_frames[0], stock, GRAIN_SIZE, GRAIN_SIGMA, **settings)
+        lat = []
+        for i in range(lat_n):
+            t0 = time.perf_counter()
+            pg.replay()
+            proc.stream.synchronize()
+            lat.append((time.perf_counter() - t0) * 1e3)
+        lat = np.sort(np.asarray(lat))
+        latency["graph"] = {"p50_ms": float(lat[len(lat) // 2]), "p99_ms": float(lat[int(len(lat) * 0.99)]),
+                            "min_ms": float(lat[0]), "what": "PreviewGraph.replay() + stream synchronize"}
+        big = torch.from_numpy(natural_frame(4000, 6000, 77)).to(proc.device)
+        small = None
+        lat = []
+        for i in range(200):
+            t0 = time.perf_counter()
+            small = proc.resize_device(big, (H, 1620), out=small)
+            proc.render_device(small, stock, GRAIN_SIZE, GRAIN_SIGMA, sync_caller=False, **settings)
+            proc.stream.synchronize()
+            lat.append((time.perf_counter() - t0) * 1e3)
+        lat = np.sort(np.asarray(lat))
+        latency["from_24mp"] = {"p50_ms": float(lat[len(lat) // 2]), "p99_ms": float(lat[int(len(lat) * 0.99)]),
+                                "what": "device INTER_AREA 6000x4000 -> 1620x1080 + pointwise render, per call"}
+        del big, small
 
     # --- timed, end to end through the public API (pinned host in, host out) ---------------------
     # (a) the reference's entry point for preloaded frames, one synchronous call per frame

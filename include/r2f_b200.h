@@ -223,6 +223,11 @@ int r2f_resize(r2f_ctx *ctx, const void *in_dev, int pix_format, int H, int W, i
 /* Number of kernel launches issued by this context since creation (bench.py gpu_launches). */
 uint64_t r2f_launch_count(const r2f_ctx *ctx);
 
+/* Renders captured into a CUDA graph (cudaStreamBeginCapture on the stream handed to r2f_render) are not visible to
+ * the copy-on-write table storage when the graph is replayed: call this right after every cudaGraphLaunch on the
+ * stream the graph was launched on, so that tables the replay reads are not recycled under it. */
+int r2f_stream_mark(r2f_ctx *ctx, void *stream);
+
 /* Guarded fast chain statistics (R2F_OPT_FAST_CHAIN): pixels that the float32 fast path could not decide and the
  * exact chain evaluated since the last call (the counter is reset), and the selected slot's proven bound on
  * |255 * (fast - exact)| (-1 when its tables do not qualify for the fast path).  Synchronises the device. */

@@ -2,7 +2,7 @@
 render path behind the reference's processor API.  See DESIGN.md."""
 from __future__ import annotations
 
-__all__ = ["B200Processor", "SyntheticStock", "BatchExporter", "PipelinedRenderer"]
+__all__ = ["B200Processor", "SyntheticStock", "BatchExporter", "PipelinedRenderer", "PreviewGraph"]
 
 
 def __getattr__(name):  # lazy: importing the package does not need CUDA, using the processor does
@@ -22,4 +22,8 @@ def __getattr__(name):  # lazy: importing the package does not need CUDA, using 
         from .pipeline import PipelinedRenderer
 
         return PipelinedRenderer
+    if name == "PreviewGraph":
+        from .pipeline import PreviewGraph
+
+        return PreviewGraph
     raise AttributeError(name)

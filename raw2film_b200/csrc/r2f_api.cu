@@ -1019,8 +1019,13 @@ int render_impl(r2f_ctx *c, const void *in, int in_format, float in_gain, int H,
                                tap_stage, tap, st);
     if (c) {
         DeviceGuard guard(c->device);
-        cudaError_t e = mark_render(c, st);
-        if (e != cudaSuccess && rc == R2F_OK) return fail_cuda(e, "mark_render");
+        // a render that is being captured into a CUDA graph is marked when the graph is replayed (r2f_stream_mark)
+        cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+        if (cudaStreamIsCapturing(st, &cap) != cudaSuccess) (void)cudaGetLastError();
+        if (cap == cudaStreamCaptureStatusNone) {
+            cudaError_t e = mark_render(c, st);
+            if (e != cudaSuccess && rc == R2F_OK) return fail_cuda(e, "mark_render");
+        }
     }
     return rc;
 }
@@ -1609,6 +1614,13 @@ int r2f_resize(r2f_ctx *c, const void *in_dev, int pix_format, int H, int W, int
 }
 
 uint64_t r2f_launch_count(const r2f_ctx *c) { return c ? c->launches : 0; }
+
+int r2f_stream_mark(r2f_ctx *c, void *stream) {
+    if (!c) return fail(R2F_ERR_INVALID, "null context");
+    DeviceGuard guard(c->device);
+    CU(mark_render(c, static_cast<cudaStream_t>(stream)));
+    return R2F_OK;
+}
 
 int r2f_fast_chain_stats(r2f_ctx *c, uint64_t *deferred_pixels, float *margin) {
     if (!c) return fail(R2F_ERR_INVALID, "null context");

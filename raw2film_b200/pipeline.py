@@ -159,3 +159,40 @@ class PipelinedRenderer:
             if sink is not None:
                 sink(t, img)
         return n
+
+
+class PreviewGraph:
+    """One render of a fixed frame buffer, stock and settings captured as a CUDA graph: `replay()` costs one
+    cudaGraphLaunch instead of the Python walk through the loaders and the kernel launches (interactive preview,
+    BASELINE config 5: the 2 MP pointwise kernel takes ~35 us, comparable to the host work of a normal call).
+
+    The caller writes new frames into `frame` (a device tensor of the captured shape) and calls `replay()`; the
+    result lands in `out`.  A graph bakes the table pointers in: after any settings / stock change through the
+    processor it refuses to replay -- capture a new one.  The grain seed is baked in as well (the same noise field
+    on every replay), so the intended use is the simplified preview (halation / sharpness / grain off, gui.py:2206-2209)."""
+
+    def __init__(self, processor, frame_dev, negative_film, grain_size, grain_sigma, **settings):
+        import torch
+
+        self._torch = torch
+        self.proc = processor
+        self.frame = frame_dev
+        h, w = frame_dev.shape[:2]
+        self.out = torch.empty((h, w, 3), dtype=torch.uint8, device=processor.device)
+        args = (frame_dev, negative_film, grain_size, grain_sigma)
+        kw = dict(out=self.out, stream=processor.stream, sync_caller=False, **settings)
+        processor.render_device(*args, **kw)            # warm-up: tables, scratch, kernel attributes
+        processor.stream.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph, stream=processor.stream, capture_error_mode="thread_local"):
+            processor.render_device(*args, **kw)
+        self._version = processor.table_version
+        self._stream = processor.stream
+
+    def replay(self):
+        if self.proc.table_version != self._version:
+            raise RuntimeError("tables changed since this graph was captured: capture a new PreviewGraph")
+        with self._torch.cuda.stream(self._stream):
+            self.graph.replay()
+        _cabi.check(_cabi.lib.r2f_stream_mark(self.proc._ctx, self._stream.cuda_stream))
+        return self.out

@@ -103,6 +103,8 @@ class B200Processor:
         self._pinned_frames = {}          # host address -> pinned tensor (pinned_frame)
         self._pipe = None                 # two-slot PipelinedRenderer behind process_preloaded
         self._last_out = None             # device tensor of the most recent render
+        self._last_call = None            # (stock, sizes, settings, merged, flags) of the previous render_device
+        self.table_version = 0            # bumped whenever a table is uploaded or another stock's slot is selected
 
         self.pipeline_resolution = None   # (w, h) like gpu_processor.py:222
         self.output_resolution = None
@@ -136,7 +138,15 @@ class B200Processor:
             self._slots[key] = slot
         _cabi.check(_cabi.lib.r2f_select_slot(self._ctx, slot.index))
         self._cur = slot
+        self._last_call = None
+        self.table_version += 1
         return slot
+
+    def _tables_changed(self):
+        """A loader uploaded something: the next render_device call must walk the loaders again, and CUDA graphs
+        captured with the old tables (PreviewGraph) are stale."""
+        self._last_call = None
+        self.table_version += 1
 
     def close(self):
         if getattr(self, "_ctx", None):
@@ -192,6 +202,7 @@ class B200Processor:
         _cabi.check(_cabi.lib.r2f_set_lut2d(self._ctx, _cabi.f32_ptr(lut), lut.shape[0]))
         self.tex_lut_2d = lut
         self.input_param_dict = new
+        self._tables_changed()
 
     def load_density_curve(self, negative_film, push_pull, color_masking=None, log_eps: float = 1e-6):
         """(4, N) H-D curve (cpu_processor.py:166-188).  A non-uniform abscissa (row 0) is honoured with
@@ -208,6 +219,7 @@ class B200Processor:
         _cabi.check(_cabi.lib.r2f_set_curve1d(self._ctx, _cabi.f32_ptr(curve), curve.shape[1], log_eps))
         self.tex_lut_1d = curve
         self.curve_param_dict = new
+        self._tables_changed()
 
     def load_output_lut(self, negative_film, print_film=None, red_light=0.0, green_light=0.0, blue_light=0.0,
                         projector_kelvin=6500, shadow_comp=0.0, sat_adjust=1.0, gamma_func="sRGB",
@@ -249,6 +261,7 @@ class B200Processor:
         _cabi.check(_cabi.lib.r2f_set_lut3d(self._ctx, _cabi.f32_ptr(lut), lut.shape[0], 0.25))  # :405
         self.tex_lut_3d = lut
         self.output_param_dict = new
+        self._tables_changed()
 
     def load_halation_kernel(self, scale, halation_size=1.0, halation_red_factor=1.0, halation_green_factor=0.4,
                              halation_blue_factor=0.0, halation_intensity=1.0, bw=False):
@@ -263,6 +276,7 @@ class B200Processor:
         _cabi.check(_cabi.lib.r2f_set_halation_kernel(self._ctx, _cabi.f32_ptr(kern), kern.shape[0]))
         self.halation_kernel = kern
         self.halation_param_dict = new
+        self._tables_changed()
 
     def load_mtf_kernel(self, negative_film, scale, sharpening_strength, sharpening_sigma):
         """gpu_processor.py:815-838 / effects.py:165-185."""
@@ -276,6 +290,7 @@ class B200Processor:
         _cabi.check(_cabi.lib.r2f_set_mtf_kernel(self._ctx, _cabi.f32_ptr(kern), kern.shape[0]))
         self.mtf_kernel = kern
         self.mtf_param_dict = new
+        self._tables_changed()
 
     def load_grain(self, negative_film, scale, grain_size_mm=0.01, grain_sigma=0.4, bw_grain=False, seed=None):
         """gpu_processor.py:904-936: grain amplitude curve + smoothing kernel (+ a fresh seed per frame,
@@ -298,6 +313,7 @@ class B200Processor:
                 0 if kern is None else kern.shape[0], int(seed)))
             self._grain_curve, self._grain_kernel = curve, kern
             self.grain_param_dict = new
+            self._tables_changed()
         else:
             _cabi.check(_cabi.lib.r2f_set_grain_seed(self._ctx, int(seed)))
 
@@ -310,6 +326,7 @@ class B200Processor:
             return
         _cabi.check(_cabi.lib.r2f_set_burn(self._ctx, float(d_ref), float(highlight_burn), float(burn_scale)))
         self.highlight_burn_param_dict = new
+        self._tables_changed()
 
     def chroma_nr_filter(self, image: np.ndarray, chroma_nr: int) -> np.ndarray:
         """Chroma noise reduction (reference effects.py:547-561) on the device: XYZ -> xyY, Gaussian
@@ -552,13 +569,26 @@ class B200Processor:
         CUDA tensor, result a uint8 (H, W, 3) CUDA tensor.  No host copies; enqueued on `stream`
         (default: self.stream)."""
         torch = self._torch
-        s = self._merged(settings)
         h, w, ch = xyz_dev.shape
         if xyz_dev.dtype not in (torch.float32, torch.uint16) or not xyz_dev.is_contiguous() \
                 or xyz_dev.device != self.device:
             raise ValueError("xyz_dev must be a contiguous float32 / uint16 tensor on this processor's device")
         in_fmt = _cabi.IN_U16 if xyz_dev.dtype == torch.uint16 else _cabi.IN_F32
-        flags, _ = self._load_tables(negative_film, grain_size, grain_sigma, s, h, w)
+        # Repeat of the previous call (same stock object, frame size and settings): the loaders' dict compares
+        # would all say "unchanged" (cpu_processor.py:157, 179, 229), so skip them -- the interactive preview and
+        # a batch re-render the same configuration frame after frame.  A fresh grain seed is still drawn per frame.
+        last = self._last_call
+        if (last is not None and last[0] is negative_film and last[1] == (grain_size, grain_sigma, h, w)
+                and self._cur.key == negative_film.name and last[2] == settings):
+            s, flags = last[3], last[4]
+            if flags & _cabi.GRAIN and s.get("grain_seed") is None:
+                _cabi.check(_cabi.lib.r2f_set_grain_seed(self._ctx, random.randint(0, 2 ** 63 - 1)))
+        else:
+            s = self._merged(settings)
+            flags, _ = self._load_tables(negative_film, grain_size, grain_sigma, s, h, w)
+            cacheable = s.get("grain_noise") is None
+            self._last_call = (negative_film, (grain_size, grain_sigma, h, w), dict(settings), s, flags) \
+                if cacheable else None
         self._ensure_device_buffers(h, w, ch, flags)
         if out is None:
             out = self._dev_out

@@ -92,3 +92,25 @@ def test_max_scale_round_trip_bit_exact(proc):
     want = cv.resize(inner, (450, 300), interpolation=cv.INTER_LANCZOS4)
     got = proc.process(xyz, stock, 6.0, 0.4, **st)
     assert got.shape == (300, 450, 3) and np.array_equal(got, want)
+
+
+def test_preview_graph_replay_matches_direct_call_and_detects_stale_tables(proc):
+    """PreviewGraph: a captured render replays bit-identically on new frame contents, and refuses to replay once the
+    processor's tables changed (the graph holds the old table pointers)."""
+    import torch
+    from raw2film_b200 import PreviewGraph
+
+    stock = SyntheticStock()
+    st = dict(halation=False, sharpness=False, grain=0)
+    a, b = small_frame(270, 480, seed=1), small_frame(270, 480, seed=2)
+    frame = torch.from_numpy(a).cuda()
+    pg = PreviewGraph(proc, frame, stock, 6.0, 0.4, **st)
+    got_a = pg.replay().cpu().numpy()
+    frame.copy_(torch.from_numpy(b).cuda())
+    torch.cuda.synchronize()
+    got_b = pg.replay().cpu().numpy()
+    assert np.array_equal(got_a, oracle_render(fo, a, stock, 6.0, 0.4, st))
+    assert np.array_equal(got_b, oracle_render(fo, b, stock, 6.0, 0.4, st))
+    proc.render_device(frame, stock, 6.0, 0.4, **dict(st, exp_comp=0.5))      # uploads a new 2-D LUT
+    with pytest.raises(RuntimeError, match="tables changed"):
+        pg.replay()
