@@ -60,7 +60,7 @@ KERNEL_BYTES_PER_PX = {"pointwise": 15, "expose": 24, "halation": 24, "density":
                        # spectrum | spectrum read + frame re-read + 12 B/px density write (padding excluded)
                        # (rows_fwd also leaves the 12 B/px exposure planes behind for rows_inv)
                        "fft_rows_fwd": 32, "fft_cols": 20, "fft_rows_inv": 32}
-KERNEL_SASS_NAME = {"pointwise": "k_pointwise", "mtf": "k_conv2d_sym", "halation": "k_conv2d_sym", "grain": "k_grain_finish",
+KERNEL_SASS_NAME = {"pointwise": "k_pointwise_fast", "mtf": "k_conv2d_sym", "halation": "k_conv2d_sym", "grain": "k_grain_finish_sym",
                     "fft_rows_fwd": "k_fft_rows_fwd", "fft_cols": "k_fft_cols", "fft_rows_inv": "k_fft_rows_inv",
                     "finish": "k_finish", "expose": "k_expose", "noise": "k_noise", "density": "k_conv2d"}
 

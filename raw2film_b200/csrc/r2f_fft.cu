@@ -566,7 +566,10 @@ k_fft_cols(const __grid_constant__ FftConvArgs a) {
         group_sync(g);
         // forward FFT; its last pass multiplies by the real kernel spectrum and swaps re/im, so the next
         // forward FFT is the inverse
-        const float *kh = a.khat + (size_t)(b * NC + c) * n;
+        // the spectrum of an even kernel is mirror-symmetric in the column frequency: columns v and Wp - v read the
+        // same row of khat, which halves its DRAM footprint (100 -> 50 MB at 24 MP; the second reader hits L2)
+        const int vcol = b * NC + c, vm = vcol <= a.row.n - vcol ? vcol : a.row.n - vcol;
+        const float *kh = a.khat + (size_t)vm * n;
         float2 *spec = fft_run<PLAN, true>(home, tmp, a.col, g, kh);
         float2 *other = spec == home ? tmp : home;
         fft_run<PLAN>(spec, other, a.col, g);  // 2 * nrad passes in total: the result is back in `home`
@@ -631,7 +634,8 @@ k_fft_cols_ip(const __grid_constant__ FftConvArgs a) {
     float2 *home = fsm + (size_t)gi * n;
     pad_line(home, H, r, n, g);
     group_sync(g);
-    const float *kh = a.khat + (size_t)(b * 4 + gi) * n;
+    const int vcol = b * 4 + gi, vm = vcol <= a.row.n - vcol ? vcol : a.row.n - vcol;  // khat[v] == khat[Wp - v]
+    const float *kh = a.khat + (size_t)vm * n;
     if constexpr (IPLAN == 1) ip_conv<4096, 4096, GS, 0, 8, 8, 8, 8>(home, a.col.tw_ip, kh, g);
     else ip_conv<6912, 6912, GS, 0, 3, 3, 3, 4, 8, 8>(home, a.col.tw_ip, kh, g);
     __syncthreads();

@@ -206,8 +206,51 @@ def make_resize():
     print("resize.npz written:", {k: v.shape for k, v in out.items() if k.startswith("ref_f32")})
 
 
+def make_third_party():
+    """Known-answer vectors of the third-party stages from the REAL spectral_film_lut (only when it is installed):
+    the day this runs, tests/test_oracle_golden.py::test_third_party_goldens pins the WGSL restatements."""
+    from oracle import third_party
+
+    fns = third_party.load()
+    if not fns:
+        print("spectral_film_lut is not installed: nothing minted (the stages stay PARITY UNPINNED)")
+        return
+    rng = np.random.default_rng(808)
+    out = {}
+    xyz = (rng.random((64, 96, 3), dtype=np.float32) * np.float32(2.0)).astype(np.float32)
+    xyz[0, :4] = 0.0
+    lut2d = rng.random((64, 64, 3), dtype=np.float32)
+    out["xyz"], out["lut2d"] = xyz, lut2d
+    if "apply_2d_lut" in fns:
+        out["ref_apply_2d_lut"] = np.asarray(fns["apply_2d_lut"](xyz.copy(), lut2d))
+    expo = (rng.random((64, 96, 3), dtype=np.float32) * np.float32(4.0)).astype(np.float32)
+    expo[1, :4] = 0.0
+    out["exposure"] = expo
+    if "log_clip" in fns:
+        img = expo.copy()
+        res = fns["log_clip"](img)
+        out["ref_log_clip"] = np.asarray(img if res is None else res)
+    curve = np.stack([np.linspace(-4, 2, 256)] + [np.cumsum(rng.random(256) * 0.02) for _ in range(3)]).astype(np.float32)
+    warped = curve.copy()
+    warped[0] = (-1 + 3 * (0.35 * np.linspace(-1, 1, 256) + 0.65 * np.linspace(-1, 1, 256) ** 3)).astype(np.float32)
+    logs = (rng.random((64, 96, 3), dtype=np.float32) * np.float32(7.0) - np.float32(4.5)).astype(np.float32)
+    out["curve"], out["curve_warped"], out["logs"] = curve, warped, logs
+    if "multi_channel_interp" in fns:
+        out["ref_interp"] = np.asarray(fns["multi_channel_interp"](logs.copy(), curve))
+        out["ref_interp_warped"] = np.asarray(fns["multi_channel_interp"](logs.copy(), warped))
+    if "grain_kernel" in fns:
+        for i, (px, size, sigma) in enumerate([(1 / 166.67, 0.006, 0.4), (1 / 264.0, 0.006, 0.4), (1 / 53.3, 0.01, 0.3)]):
+            k = fns["grain_kernel"](px, grain_size_mm=size, grain_sigma=sigma)
+            out[f"grain_args_{i}"] = np.array([px, size, sigma])
+            out[f"ref_grain_kernel_{i}"] = np.zeros((0, 0), np.float32) if k is None else np.asarray(k, np.float32)
+    np.savez_compressed(os.path.join(HERE, "third_party.npz"), **out)
+    print("third_party.npz written:", sorted(k for k in out if k.startswith("ref_")))
+
+
 if __name__ == "__main__":
-    if len(sys.argv) > 1 and sys.argv[1] == "calc_exposure":
+    if len(sys.argv) > 1 and sys.argv[1] == "third_party":
+        make_third_party()
+    elif len(sys.argv) > 1 and sys.argv[1] == "calc_exposure":
         make_calc_exposure()
     elif len(sys.argv) > 1 and sys.argv[1] == "resize":
         make_resize()

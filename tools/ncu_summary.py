@@ -31,6 +31,14 @@ METRICS = [
     ("launch__block_size", "block"),
     ("l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "smem wavefronts"),
     ("l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "smem bank conflicts"),
+    ("sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active", "XU pipe busy %"),
+    ("sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active", "ALU pipe busy %"),
+    ("l1tex__t_sector_hit_rate.pct", "L1 hit rate %"),
+    ("smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio", "stall: long scoreboard / issue"),
+    ("smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio", "stall: short scoreboard / issue"),
+    ("smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio", "stall: math pipe throttle / issue"),
+    ("smsp__average_warps_issue_stalled_mio_throttle_per_issue_active.ratio", "stall: MIO throttle / issue"),
+    ("smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio", "stall: barrier / issue"),
 ]
 
 # SASS/demangled kernel name -> bench.py kernel key
