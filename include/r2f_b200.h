@@ -220,6 +220,14 @@ int r2f_canvas_paste(r2f_ctx *ctx, const uint8_t *src_dev, int H, int W, uint8_t
 int r2f_resize(r2f_ctx *ctx, const void *in_dev, int pix_format, int H, int W, int in_channels, void *out_dev,
                int out_h, int out_w, int interpolation, void *stream);
 
+/* Presentation blit (shaders/copy_to_int.wgsl:18-51; geometry _bind_copy_to_dst gpu_processor.py:1416-1539): scale
+ * the rendered uint8 H x W x 3 image into a dst_h x dst_w x 4 RGBA8 buffer (the preview widget), letterboxed, with
+ * the canvas rectangle filled in (r, g, b) and everything else transparent.  transform: HOST, the eight floats of
+ * the shader's uniform block {scale_x, scale_y, offset_x, offset_y, canvas_min_x, canvas_min_y, canvas_max_x,
+ * canvas_max_y}.  Bilinear sampling with texel centres at +0.5 and clamp-to-edge, as a WebGPU linear sampler. */
+int r2f_present(r2f_ctx *ctx, const uint8_t *src_dev, int H, int W, uint8_t *dst_rgba_dev, int dst_h, int dst_w,
+                const float *transform, int r, int g, int b, void *stream);
+
 /* Number of kernel launches issued by this context since creation (bench.py gpu_launches). */
 uint64_t r2f_launch_count(const r2f_ctx *ctx);
 

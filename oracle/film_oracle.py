@@ -589,3 +589,38 @@ def render(xyz: np.ndarray, luts: dict, *, frame_width=36, frame_height=24, hala
     tap("rgb", image)
     out = quantise_u8(image)                                                  # :407
     return add_canvas(out, canvas_mode, canvas_scale, canvas_ratio)           # :409
+
+
+# --------------------------------------------------------------------------------------
+# presentation blit (shaders/copy_to_int.wgsl:18-51)  -- "next" row, PARITY UNPINNED: the
+# reference samples with a hardware linear sampler whose weight precision is implementation-defined;
+# restated with exact float32 bilinear weights, texel centres at +0.5, clamp to edge, round to nearest.
+# --------------------------------------------------------------------------------------
+def present(image: np.ndarray, dst_hw, transform, colour=(255, 255, 255)) -> np.ndarray:
+    h, w = image.shape[:2]
+    dh, dw = dst_hw
+    sx, sy, ox, oy, cx0, cy0, cx1, cy1 = (F32(v) for v in transform)
+    dx = (np.arange(dw, dtype=F32) + F32(0.5))[None, :]
+    dy = (np.arange(dh, dtype=F32) + F32(0.5))[:, None]
+    su = ((dx - ox) * sx).astype(F32) + np.zeros((dh, 1), F32)
+    sv = ((dy - oy) * sy).astype(F32) + np.zeros((1, dw), F32)
+    inside = (su >= 0) & (su <= 1) & (sv >= 0) & (sv <= 1)
+    fx = (su * F32(w) - F32(0.5)).astype(F32)
+    fy = (sv * F32(h) - F32(0.5)).astype(F32)
+    x0f, y0f = np.floor(fx), np.floor(fy)
+    ax, ay = (fx - x0f).astype(F32)[..., None], (fy - y0f).astype(F32)[..., None]
+    x0 = np.clip(x0f.astype(np.int64), 0, w - 1)
+    x1 = np.clip(x0f.astype(np.int64) + 1, 0, w - 1)
+    y0 = np.clip(y0f.astype(np.int64), 0, h - 1)
+    y1 = np.clip(y0f.astype(np.int64) + 1, 0, h - 1)
+    img = image.astype(F32)
+    one = F32(1.0)
+    top = (img[y0, x0] * (one - ax) + img[y0, x1] * ax).astype(F32)
+    bot = (img[y1, x0] * (one - ax) + img[y1, x1] * ax).astype(F32)
+    val = np.clip(np.rint((top * (one - ay) + bot * ay).astype(F32)), 0, 255).astype(np.uint8)
+    out = np.zeros((dh, dw, 4), np.uint8)
+    canvas = (~inside) & (dx >= cx0) & (dx <= cx1) & (dy >= cy0) & (dy <= cy1)
+    out[canvas] = (*colour, 255)
+    out[inside, :3] = val[inside]
+    out[inside, 3] = 255
+    return out

@@ -18,7 +18,7 @@ EXPORTS = [
     "r2f_set_lut3d", "r2f_set_halation_kernel", "r2f_set_mtf_kernel", "r2f_set_grain", "r2f_set_grain_seed", "r2f_set_option",
     "r2f_set_burn",
     "r2f_workspace_bytes", "r2f_render", "r2f_render_ex", "r2f_render_tap", "r2f_render_tap_ex", "r2f_render_host", "r2f_convolve2d",
-    "r2f_generate_noise", "r2f_chroma_nr", "r2f_histogram", "r2f_histogram_image", "r2f_calc_exposure", "r2f_canvas_paste", "r2f_resize", "r2f_launch_count", "r2f_stream_mark", "r2f_fast_chain_stats", "r2f_profile_enable", "r2f_profile_read",
+    "r2f_generate_noise", "r2f_chroma_nr", "r2f_histogram", "r2f_histogram_image", "r2f_calc_exposure", "r2f_canvas_paste", "r2f_resize", "r2f_present", "r2f_launch_count", "r2f_stream_mark", "r2f_fast_chain_stats", "r2f_profile_enable", "r2f_profile_read",
 ]
 OPT_CONV_PATH = 1
 OPT_CONV_SYM = 2
@@ -75,6 +75,7 @@ def _load():
         "r2f_calc_exposure": (ci, [vp, vp, ci, ci, ci, ci, cd, ctypes.POINTER(cd), vp]),
         "r2f_canvas_paste": (ci, [vp, vp, ci, ci, vp, ci, ci, ci, ci, ci, ci, ci, vp]),
         "r2f_resize": (ci, [vp, vp, ci, ci, ci, ci, vp, ci, ci, ci, vp]),
+        "r2f_present": (ci, [vp, vp, ci, ci, vp, ci, ci, fp, ci, ci, ci, vp]),
         "r2f_launch_count": (u64, [vp]),
         "r2f_stream_mark": (ci, [vp, vp]),
         "r2f_fast_chain_stats": (ci, [vp, ctypes.POINTER(u64), ctypes.POINTER(cf)]),

@@ -1517,6 +1517,19 @@ int r2f_canvas_paste(r2f_ctx *c, const uint8_t *src_dev, int H, int W, uint8_t *
     return R2F_OK;
 }
 
+int r2f_present(r2f_ctx *c, const uint8_t *src_dev, int H, int W, uint8_t *dst_rgba_dev, int dst_h, int dst_w,
+                const float *transform, int r, int g, int b, void *stream) {
+    if (!c || !src_dev || !dst_rgba_dev || !transform || H < 1 || W < 1 || dst_h < 1 || dst_w < 1)
+        return fail(R2F_ERR_INVALID, "r2f_present: bad arguments");
+    if ((reinterpret_cast<uintptr_t>(dst_rgba_dev) & 3) != 0) return fail(R2F_ERR_INVALID, "destination must be 4-byte aligned");
+    DeviceGuard guard(c->device);
+    PresentArgs u{transform[0], transform[1], transform[2], transform[3], transform[4], transform[5], transform[6],
+                  transform[7], r & 255, g & 255, b & 255};
+    CU(launch_present(src_dev, H, W, dst_rgba_dev, dst_h, dst_w, u, c->num_sms, static_cast<cudaStream_t>(stream)));
+    c->launches += 1;
+    return R2F_OK;
+}
+
 int r2f_calc_exposure(r2f_ctx *c, const void *in_dev, int in_format, int H, int W, int in_channels, double factor,
                       double *mean_out, void *stream) {
     if (!c || !in_dev || !mean_out || H < 1 || W < 1 || (in_channels != 3 && in_channels != 4) || !(factor > 0.0))

@@ -123,7 +123,7 @@ static __device__ __noinline__ void pw_exact_pixel(const void *__restrict__ in, 
     o[2] = (uint8_t)quantise_u8(o2);
 }
 
-template <int FMT, int NT>
+template <int FMT, int NT, bool PAIR>
 __global__ void __launch_bounds__(NT, NT >= 768 ? 1 : 2)
 k_pointwise_fast(const void *__restrict__ in, float gain, uint8_t *__restrict__ out, size_t npix, Lut2D l2, Curve1D cv,
                  float eps, Lut3D l3, FastChain F, unsigned long long *__restrict__ stats) {
@@ -171,9 +171,22 @@ k_pointwise_fast(const void *__restrict__ in, float gain, uint8_t *__restrict__ 
             float px[4][3];
             load_quad<FMT>(in, q, gain, px);
             uint32_t b[12];
+            if (PAIR) {
 #pragma unroll
-            for (int p = 0; p < 4; ++p)
-                if (!chain_fast_s(px[p], S, b[3 * p], b[3 * p + 1], b[3 * p + 2])) bad |= 1u << p;
+                for (int p = 0; p < 4; p += 2) {
+                    uint32_t qa[3], qb[3];
+                    bad |= chain_fast_pair(px[p], px[p + 1], S, qa, qb) << p;
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) {
+                        b[3 * p + c] = qa[c];
+                        b[3 * p + 3 + c] = qb[c];
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int p = 0; p < 4; ++p)
+                    if (!chain_fast_s(px[p], S, b[3 * p], b[3 * p + 1], b[3 * p + 2])) bad |= 1u << p;
+            }
             store_quad_u8(out, q, b);
         }
         // the stores above are ordered before any overwrite by another lane of this warp: __syncwarp in the drain
@@ -210,12 +223,21 @@ size_t pointwise_fast_smem(const Lut2D &l2, const FastChain &F) {
 
 // CTA shape.  One 1024-thread CTA per SM parks ONE copy of the tables (96 KB), which leaves ~156 KB of the SM's
 // unified L1 to the 3-D LUT gathers; two 512-thread CTAs park two copies and measure 0.27 ms at 24 MP against
-// 0.173 ms (profiles/r02_*).  A/B knob: R2F_PW_THREADS = 1024 (default) | 768 | 512 | 384 | 256.
+// 0.173 ms (profiles/r02_*).  A/B knob: R2F_PW_THREADS = 1024 (default) | 768 | 384.
 static int pw_fast_threads() {
     static const int v = [] {
         const char *e = getenv("R2F_PW_THREADS");
         const int t = e ? atoi(e) : 1024;
-        return (t == 256 || t == 384 || t == 512 || t == 768) ? t : 1024;
+        return (t == 384 || t == 768) ? t : 1024;
+    }();
+    return v;
+}
+
+// R2F_PW_PAIR=0: scalar fast chain (chain_fast_s) instead of the packed two-pixel form (chain_fast_pair)
+static bool pw_fast_pair() {
+    static const bool v = [] {
+        const char *e = getenv("R2F_PW_PAIR");
+        return !(e && e[0] == '0');
     }();
     return v;
 }
@@ -227,22 +249,26 @@ cudaError_t launch_pointwise_fast(const void *in, int fmt, float gain, uint8_t *
     if (!F.ok || sm > kMaxTableSmem + 12288 || cv.xp != nullptr || npix >= ((size_t)1 << 32))
         return cudaErrorInvalidValue;
     const int nt = pw_fast_threads(), per_sm = nt >= 768 ? 1 : 2;
+    const bool pair = pw_fast_pair();
     int grid = (int)((npix / 4 + nt) / nt);
     if (grid > num_sms * per_sm) grid = num_sms * per_sm;
-#define R2F_LAUNCH_PWF2(C, T)                                                                                   \
+#define R2F_LAUNCH_PWF3(C, T, P)                                                                                \
     do {                                                                                                        \
-        auto kfn = k_pointwise_fast<C, T>;                                                                      \
+        auto kfn = k_pointwise_fast<C, T, P>;                                                                   \
         cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);        \
         if (e != cudaSuccess) return e;                                                                         \
         kfn<<<grid, T, sm, st>>>(in, gain, out, npix, l2, cv, eps, l3, F, stats);                               \
     } while (0)
+#define R2F_LAUNCH_PWF2(C, T)                                                                                   \
+    do {                                                                                                        \
+        if (pair) R2F_LAUNCH_PWF3(C, T, true);                                                                  \
+        else R2F_LAUNCH_PWF3(C, T, false);                                                                      \
+    } while (0)
 #define R2F_LAUNCH_PWF(C)                                                                                       \
     do {                                                                                                        \
         if (nt == 384) R2F_LAUNCH_PWF2(C, 384);                                                                 \
-        else if (nt == 256) R2F_LAUNCH_PWF2(C, 256);                                                            \
         else if (nt == 768) R2F_LAUNCH_PWF2(C, 768);                                                            \
-        else if (nt == 1024) R2F_LAUNCH_PWF2(C, 1024);                                                          \
-        else R2F_LAUNCH_PWF2(C, 512);                                                                           \
+        else R2F_LAUNCH_PWF2(C, 1024);                                                                          \
     } while (0)
     switch (fmt) {
         case 0: R2F_LAUNCH_PWF(0); break;
@@ -251,6 +277,7 @@ cudaError_t launch_pointwise_fast(const void *in, int fmt, float gain, uint8_t *
         case 3: R2F_LAUNCH_PWF(3); break;
         default: return cudaErrorInvalidValue;
     }
+#undef R2F_LAUNCH_PWF3
 #undef R2F_LAUNCH_PWF2
 #undef R2F_LAUNCH_PWF
     return cudaGetLastError();
@@ -838,6 +865,47 @@ cudaError_t launch_canvas_paste(const uint8_t *src, int H, int W, uint8_t *dst, 
                                 int r, int g, int b, int num_sms, cudaStream_t st) {
     k_canvas_paste<<<grid_for((size_t)CH * CW, num_sms, 8), kThreads, 0, st>>>(
         src, H, W, dst, CH, CW, off_y, off_x, make_uchar3((unsigned char)r, (unsigned char)g, (unsigned char)b));
+    return cudaGetLastError();
+}
+
+// Presentation blit (reference shaders/copy_to_int.wgsl:18-51, geometry gpu_processor.py:1416-1539): the rendered
+// image scaled into a widget-sized RGBA8 buffer with letterbox / canvas areas.  Destination pixel centre ->
+// normalised source uv; inside [0,1]^2: bilinear sample (texel centres at +0.5, clamp to edge), alpha 255; else
+// inside the canvas rectangle: canvas colour, alpha 255; else transparent black.
+__global__ void __launch_bounds__(kThreads)
+k_present(const uint8_t *__restrict__ src, int H, int W, uint8_t *__restrict__ dst, int DH, int DW, PresentArgs u) {
+    const size_t total = (size_t)DH * DW, stride = (size_t)gridDim.x * kThreads;
+    uint32_t *o32 = reinterpret_cast<uint32_t *>(dst);
+    for (size_t p = (size_t)blockIdx.x * kThreads + threadIdx.x; p < total; p += stride) {
+        const int y = (int)(p / DW), x = (int)(p - (size_t)y * DW);
+        const float dx = (float)x + 0.5f, dy = (float)y + 0.5f;
+        const float su = (dx - u.offset_x) * u.scale_x, sv = (dy - u.offset_y) * u.scale_y;
+        uint32_t px = 0u;
+        if (su >= 0.0f && su <= 1.0f && sv >= 0.0f && sv <= 1.0f) {
+            const float fx = su * (float)W - 0.5f, fy = sv * (float)H - 0.5f;
+            const float x0f = floorf(fx), y0f = floorf(fy);
+            const float ax = fx - x0f, ay = fy - y0f;
+            const int x0 = min(max((int)x0f, 0), W - 1), x1 = min(max((int)x0f + 1, 0), W - 1);
+            const int y0 = min(max((int)y0f, 0), H - 1), y1 = min(max((int)y0f + 1, 0), H - 1);
+            const uint8_t *r0 = src + (size_t)y0 * W * 3, *r1 = src + (size_t)y1 * W * 3;
+            px = 0xff000000u;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                const float top = (float)r0[x0 * 3 + c] * (1.0f - ax) + (float)r0[x1 * 3 + c] * ax;
+                const float bot = (float)r1[x0 * 3 + c] * (1.0f - ax) + (float)r1[x1 * 3 + c] * ax;
+                const int v = __float2int_rn(top * (1.0f - ay) + bot * ay);
+                px |= (uint32_t)min(max(v, 0), 255) << (8 * c);
+            }
+        } else if (dx >= u.canvas_min_x && dx <= u.canvas_max_x && dy >= u.canvas_min_y && dy <= u.canvas_max_y) {
+            px = 0xff000000u | (uint32_t)u.r | ((uint32_t)u.g << 8) | ((uint32_t)u.b << 16);
+        }
+        o32[p] = px;
+    }
+}
+
+cudaError_t launch_present(const uint8_t *src, int H, int W, uint8_t *dst, int DH, int DW, const PresentArgs &u,
+                           int num_sms, cudaStream_t st) {
+    k_present<<<grid_for((size_t)DH * DW, num_sms, 8), kThreads, 0, st>>>(src, H, W, dst, DH, DW, u);
     return cudaGetLastError();
 }
 

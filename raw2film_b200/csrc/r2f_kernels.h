@@ -87,6 +87,14 @@ cudaError_t launch_exposure_mean(const void *in, int fmt, int H, int W, double i
 // canvas border: colour fill + paste (reference effects.py:338-357)
 cudaError_t launch_canvas_paste(const uint8_t *src, int H, int W, uint8_t *dst, int CH, int CW, int off_y, int off_x,
                                 int r, int g, int b, int num_sms, cudaStream_t st);
+// presentation blit into a widget-sized RGBA8 buffer (reference shaders/copy_to_int.wgsl)
+struct PresentArgs {
+    float scale_x, scale_y, offset_x, offset_y;                       // destination pixel -> normalised source uv
+    float canvas_min_x, canvas_min_y, canvas_max_x, canvas_max_y;      // canvas rectangle in destination pixels
+    int r, g, b;                                                       // canvas colour
+};
+cudaError_t launch_present(const uint8_t *src, int H, int W, uint8_t *dst, int DH, int DW, const PresentArgs &u,
+                           int num_sms, cudaStream_t st);
 // layout shuffles
 cudaError_t launch_planar_to_interleaved(Planes in, float *out, size_t npix, int num_sms, cudaStream_t st);
 cudaError_t launch_interleaved_to_planar(const float *in, int cin, int nch, Planes out, size_t npix, int num_sms,

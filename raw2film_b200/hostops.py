@@ -74,6 +74,34 @@ def canvas_geometry(shape, canvas_mode: str, canvas_scale: float = 1.0, canvas_r
     return size, colour, offset
 
 
+def present_geometry(src_size, dst_size, pipeline_resolution=None, output_resolution=None, canvas_resolution=None):
+    """The uniform block of the presentation blit, restating `_bind_copy_to_dst` (reference
+    gpu_processor.py:1416-1512): (scale_x, scale_y, offset_x, offset_y, canvas_min_x, canvas_min_y, canvas_max_x,
+    canvas_max_y).  All sizes are (width, height) like the reference's attributes."""
+    src_w, src_h = src_size
+    dst_w, dst_h = dst_size
+    has_canvas = canvas_resolution is not None and canvas_resolution[0] > 0
+    if has_canvas:
+        content_w, content_h = canvas_resolution
+    elif output_resolution is not None and output_resolution[0] > 0:
+        content_w, content_h = output_resolution
+    else:
+        content_w, content_h = pipeline_resolution if pipeline_resolution is not None else (src_w, src_h)
+    src_aspect, dst_aspect = content_w / content_h, dst_w / dst_h
+    if src_aspect > dst_aspect:
+        cw, ch, cx, cy = dst_w, dst_w / src_aspect, 0.0, (dst_h - dst_w / src_aspect) / 2.0
+    else:
+        cw, ch, cx, cy = dst_h * src_aspect, dst_h, (dst_w - dst_h * src_aspect) / 2.0, 0.0
+    canvas = (cx, cy, cx + cw, cy + ch) if has_canvas else (0.0, 0.0, 0.0, 0.0)
+    if canvas_resolution is not None and output_resolution is not None:
+        target_w, target_h = output_resolution
+        rw, rh = cw * (target_w / content_w), ch * (target_h / content_h)
+        ox, oy = cx + (cw - rw) / 2.0, cy + (ch - rh) / 2.0
+    else:
+        rw, rh, ox, oy = cw, ch, cx, cy
+    return (1.0 / rw, 1.0 / rh, ox, oy) + canvas
+
+
 def histogram_image(counts: np.ndarray, mix_table: np.ndarray, height: int = 100) -> np.ndarray:
     """RGB histogram widget image (height, 256, 4) uint8 from per-channel 256-bin counts.
 

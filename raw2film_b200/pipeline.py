@@ -56,7 +56,8 @@ class PipelinedRenderer:
             for k in ("h2d", "done", "d2h"):
                 slot[k] = torch.cuda.Event()
 
-    def submit(self, cpu_payload, negative_film, grain_size, grain_sigma, upload: bool = True, **settings) -> int:
+    def submit(self, cpu_payload, negative_film, grain_size, grain_sigma, upload: bool = True, readback: bool = True,
+               **settings) -> int:
         """Enqueue one frame.  `upload=False` renders the frame that the previous submit left on the device
         again (interactive re-render with changed settings: no host -> device copy)."""
         torch = self._torch
@@ -125,15 +126,23 @@ class PipelinedRenderer:
             out_dev = slot["dev_post"]
         slot["done"].record(self.s_compute)
         reader["last_read"] = slot["done"]
+        slot["result_dev"] = out_dev
         with torch.cuda.stream(self.s_out):
             self.s_out.wait_event(slot["done"])
-            slot["host_out"].copy_(out_dev, non_blocking=True)
+            if readback:
+                slot["host_out"].copy_(out_dev, non_blocking=True)
             slot["d2h"].record(self.s_out)
         slot["used"] = True
         self._last_slot = slot if upload else self._last_slot
         self._count += 1
         self.d2h_bytes += slot["host_out"].numel()
         return ticket
+
+    def device_result(self, ticket: int):
+        """The frame's uint8 result as a CUDA tensor (valid until the slot is reused), ordered on the compute stream."""
+        if not (self._count - self.depth <= ticket < self._count):
+            raise ValueError("ticket is not in flight any more")
+        return self._slots[ticket % self.depth]["result_dev"]
 
     def result(self, ticket: int) -> np.ndarray:
         if not (self._count - self.depth <= ticket < self._count):

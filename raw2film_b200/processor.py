@@ -636,8 +636,22 @@ class B200Processor:
         reference's GPU path, which hands back a view of its mapped read-back buffer
         (gpu_processor.py:1350-1357), the returned uint8 (H, W, 3) array is a view of a pinned buffer that
         stays valid for the next two calls; `own_result=True` returns a private copy instead."""
-        if dst_texture is not None or histogram_texture is not None:
-            raise NotImplementedError("presenting into a wgpu texture / histogram is UI plumbing (out of scope)")
+        if histogram_texture is not None:
+            raise NotImplementedError("presenting the histogram into a wgpu texture is UI plumbing (out of scope); "
+                                      "generate_histogram() returns the widget image")
+        if dst_texture is not None:
+            # gpu_processor.py:1866-1890: present into the widget texture and return None.  Here the "texture" is a
+            # uint8 (h, w, 4) CUDA tensor; nothing is copied to the host.
+            if _upload:
+                self.image_param_dict = None
+            pipe = self._own_pipeline()
+            ticket = pipe.submit(cpu_payload, negative_film, grain_size, grain_sigma, upload=_upload, readback=False,
+                                 **settings)
+            canvas = cpu_payload.get("_canvas")
+            self.present(pipe.device_result(ticket), dst_texture,
+                         canvas_colour=canvas["colour"] if canvas else (255, 255, 255))
+            self.stream.synchronize()
+            return None
         if _upload:
             self.image_param_dict = None      # the device frame changes: process() re-validates its cache
         pipe = self._own_pipeline()
@@ -671,6 +685,24 @@ class B200Processor:
             self._ctx, x_dev.data_ptr(), _cabi.PIX_U8 if x_dev.dtype == torch.uint8 else _cabi.PIX_F32, h, w, ch,
             out.data_ptr(), rows, cols, _cabi.INTER_AREA if shrink else _cabi.INTER_LANCZOS4, stream.cuda_stream))
         return out
+
+    def present(self, image_dev, dst, canvas_colour=(255, 255, 255), stream=None):
+        """Blit a rendered uint8 (H, W, 3) CUDA tensor into `dst`, a uint8 (dst_h, dst_w, 4) CUDA tensor standing for
+        the preview widget's texture: scaled to fit, letterboxed, canvas area filled (the reference's last GPU
+        pass, shaders/copy_to_int.wgsl; geometry from the processor's pipeline / output / canvas resolutions like
+        gpu_processor.py:1416-1512).  Returns `dst`."""
+        torch = self._torch
+        h, w = image_dev.shape[:2]
+        dh, dw = dst.shape[:2]
+        if dst.dtype != torch.uint8 or dst.shape[2] != 4 or not dst.is_contiguous():
+            raise ValueError("dst must be a contiguous uint8 (h, w, 4) CUDA tensor")
+        t = np.asarray(hostops.present_geometry((w, h), (dw, dh), self.pipeline_resolution, self.output_resolution,
+                                                self.canvas_resolution), dtype=F32)
+        stream = self.stream if stream is None else stream
+        r, g, b = (int(v) for v in canvas_colour)
+        _cabi.check(_cabi.lib.r2f_present(self._ctx, image_dev.data_ptr(), h, w, dst.data_ptr(), dh, dw,
+                                          _cabi.f32_ptr(t), r, g, b, stream.cuda_stream))
+        return dst
 
     def pinned_frame(self, h: int, w: int, channels: int = 3, dtype=np.float32) -> np.ndarray:
         """A (h, w, channels) array in page-locked host memory.  A decoder that writes its frame straight into it

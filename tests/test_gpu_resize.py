@@ -114,3 +114,45 @@ def test_preview_graph_replay_matches_direct_call_and_detects_stale_tables(proc)
     proc.render_device(frame, stock, 6.0, 0.4, **dict(st, exp_comp=0.5))      # uploads a new 2-D LUT
     with pytest.raises(RuntimeError, match="tables changed"):
         pg.replay()
+
+
+@pytest.mark.parametrize("dst,canvas", [((300, 500), False), ((500, 300), False), ((360, 640), True)])
+def test_present_blit_matches_wgsl_restatement(proc, dst, canvas):
+    """shaders/copy_to_int.wgsl: letterboxed bilinear blit into the widget's RGBA8 buffer (canvas area filled,
+    rest transparent), geometry as _bind_copy_to_dst builds it."""
+    import torch
+    from raw2film_b200 import hostops
+
+    rng = np.random.default_rng(7)
+    img = rng.integers(0, 256, (200, 300, 3), dtype=np.uint8)
+    proc.pipeline_resolution, proc.output_resolution = (300, 200), (300, 200)
+    proc.canvas_resolution = (360, 260) if canvas else None
+    dst_t = torch.zeros((dst[0], dst[1], 4), dtype=torch.uint8, device="cuda")
+    proc.present(torch.from_numpy(img).cuda(), dst_t, canvas_colour=(10, 128, 250))
+    proc.stream.synchronize()
+    t = hostops.present_geometry((300, 200), (dst[1], dst[0]), (300, 200), (300, 200), proc.canvas_resolution)
+    want = fo.present(img, dst, t, (10, 128, 250))
+    got = dst_t.cpu().numpy()
+    assert np.array_equal(got, want)
+    assert (got[..., 3] == 255).any() and ((got[..., 3] == 0).any() or canvas)
+    if canvas:
+        assert (got[..., :3] == np.array([10, 128, 250], np.uint8)).all(axis=-1).any()
+
+
+def test_process_preloaded_presents_into_a_device_texture(proc):
+    """gpu_processor.py:1866-1890: with a destination texture the result is presented and None is returned."""
+    import torch
+
+    stock = SyntheticStock()
+    xyz = small_frame(120, 180, seed=3)
+    st = dict(halation=False, sharpness=False, grain=0)
+    payload = proc.extract_image_data_cpu(xyz, **st)
+    tex = torch.zeros((240, 240, 4), dtype=torch.uint8, device="cuda")
+    assert proc.process_preloaded(payload, stock, 6.0, 0.4, dst_texture=tex, **st) is None
+    got = tex.cpu().numpy()
+    want_img = oracle_render(fo, xyz, stock, 6.0, 0.4, st)
+    from raw2film_b200 import hostops
+
+    t = hostops.present_geometry((180, 120), (240, 240), (180, 120), (180, 120), None)
+    assert np.array_equal(got, fo.present(want_img, (240, 240), t))
+    assert got[0, 0, 3] == 0 and got[120, 120, 3] == 255          # letterbox bars above / below a 3:2 image

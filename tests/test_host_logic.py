@@ -104,3 +104,16 @@ def test_histogram_postprocessing_matches_reference_golden():
     for h in (100, 64):
         assert np.array_equal(hostops.histogram_image(counts, g["mix"], h), g[f"ref_hist{h}"])
     assert hostops.histogram_image(np.zeros((3, 256), np.int64), g["mix"], 10).shape == (10, 256, 4)
+
+
+def test_present_geometry_letterbox_and_canvas():
+    """_bind_copy_to_dst (reference gpu_processor.py:1416-1512) restated in hostops.present_geometry."""
+    from raw2film_b200 import hostops
+
+    # 3:2 image into a square widget: full width, centred vertically, no canvas rectangle
+    sx, sy, ox, oy, *canvas = hostops.present_geometry((300, 200), (240, 240), (300, 200), (300, 200), None)
+    assert (round(1 / sx), round(1 / sy), ox, oy) == (240, 160, 0.0, 40.0) and canvas == [0.0, 0.0, 0.0, 0.0]
+    # tall widget, wide image with a canvas 20 % larger: the canvas fills the width, the image is inset
+    sx, sy, ox, oy, x0, y0, x1, y1 = hostops.present_geometry((300, 200), (600, 900), (300, 200), (300, 200), (360, 240))
+    assert (x0, x1) == (0.0, 600.0) and abs((y1 - y0) - 400.0) < 1e-9 and abs(y0 - 250.0) < 1e-9
+    assert abs(1 / sx - 500.0) < 1e-9 and abs(ox - 50.0) < 1e-9 and abs(1 / sy - 400.0 * 200 / 240) < 1e-9
