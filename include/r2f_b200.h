@@ -152,6 +152,19 @@ int r2f_render_ex(r2f_ctx *ctx, const void *in_dev, int in_format, float in_gain
                   uint8_t *out_dev, unsigned flags, const float *noise_dev, int noise_channels,
                   void *workspace_dev, size_t workspace_bytes, void *stream);
 
+/* Streaming variant for callers that copy the frame in and the result out around the call (what
+ * GpuProcessor.process_preloaded does, gpu_processor.py:1643-1693: upload, pipeline, read back).  The frame arrives
+ * in `nbands` horizontal bands, band i = rows [r2f_band_row(H, nbands, i), r2f_band_row(H, nbands, i + 1)):
+ * in_ready[i] is a cudaEvent_t the CALLER records on its copy stream once band i is on the device; out_done[i] is a
+ * cudaEvent_t the LIBRARY records on `stream` once the output rows of band i are final.  The first kernel of the
+ * pipeline runs per band as its rows arrive and the last one per band, so host <-> device copies overlap the
+ * render inside one call.  Results are identical to r2f_render_ex. */
+int r2f_band_row(int H, int nbands, int i);
+int r2f_render_banded(r2f_ctx *ctx, const void *in_dev, int in_format, float in_gain, int H, int W, int in_channels,
+                      uint8_t *out_dev, unsigned flags, const float *noise_dev, int noise_channels,
+                      void *workspace_dev, size_t workspace_bytes, int nbands, void *const *in_ready,
+                      void *const *out_done, void *stream);
+
 /* Same pipeline, stopped after `tap_stage`; writes the float32 H x W x 3 working image. */
 int r2f_render_tap(r2f_ctx *ctx, const float *in_dev, int H, int W, int in_channels, unsigned flags,
                    const float *noise_dev, int noise_channels, void *workspace_dev, size_t workspace_bytes,

@@ -17,7 +17,7 @@ EXPORTS = [
     "r2f_set_lut2d", "r2f_set_curve1d",
     "r2f_set_lut3d", "r2f_set_halation_kernel", "r2f_set_mtf_kernel", "r2f_set_grain", "r2f_set_grain_seed", "r2f_set_option",
     "r2f_set_burn",
-    "r2f_workspace_bytes", "r2f_render", "r2f_render_ex", "r2f_render_tap", "r2f_render_tap_ex", "r2f_render_host", "r2f_convolve2d",
+    "r2f_workspace_bytes", "r2f_render", "r2f_render_ex", "r2f_band_row", "r2f_render_banded", "r2f_render_tap", "r2f_render_tap_ex", "r2f_render_host", "r2f_convolve2d",
     "r2f_generate_noise", "r2f_chroma_nr", "r2f_histogram", "r2f_histogram_image", "r2f_calc_exposure", "r2f_canvas_paste", "r2f_resize", "r2f_present", "r2f_launch_count", "r2f_stream_mark", "r2f_fast_chain_stats", "r2f_profile_enable", "r2f_profile_read",
 ]
 OPT_CONV_PATH = 1
@@ -64,6 +64,9 @@ def _load():
         "r2f_workspace_bytes": (sz, [ci, ci, cu]),
         "r2f_render": (ci, [vp, vp, ci, ci, ci, u8p, cu, vp, ci, vp, sz, vp]),
         "r2f_render_ex": (ci, [vp, vp, ci, cf, ci, ci, ci, u8p, cu, vp, ci, vp, sz, vp]),
+        "r2f_band_row": (ci, [ci, ci, ci]),
+        "r2f_render_banded": (ci, [vp, vp, ci, cf, ci, ci, ci, u8p, cu, vp, ci, vp, sz, ci, ctypes.POINTER(vp),
+                                  ctypes.POINTER(vp), vp]),
         "r2f_render_tap": (ci, [vp, vp, ci, ci, ci, cu, vp, ci, vp, sz, ci, vp, vp]),
         "r2f_render_tap_ex": (ci, [vp, vp, ci, cf, ci, ci, ci, cu, vp, ci, vp, sz, ci, vp, vp]),
         "r2f_render_host": (ci, [vp, vp, ci, ci, ci, vp, cu, vp, ci]),

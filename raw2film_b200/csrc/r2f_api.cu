@@ -771,10 +771,28 @@ int check_tables(const r2f_ctx *c, unsigned flags) {
     return R2F_OK;
 }
 
+// Banded streaming (r2f_render_banded): the frame arrives and the result leaves in `n` horizontal bands.  The first
+// kernel of the pipeline is launched per band as soon as that band's rows are on the device (in_ready[i]), and
+// the last one per band with an event after each (out_done[i]) so that the caller can start copying the result
+// out while later bands are still being computed.  Band i covers rows [band_row(i), band_row(i + 1)).
+struct Bands {
+    int n = 0;
+    cudaEvent_t const *in_ready = nullptr;
+    cudaEvent_t const *out_done = nullptr;
+    int waited = 0, recorded = 0;  // progress, so that fallbacks can wait for / record "the rest"
+};
+
+int band_row(int H, int n, int i) {  // multiples of 64 (tile height), 0 and H at the ends
+    if (i <= 0) return 0;
+    if (i >= n) return H;
+    const long long r = ((long long)i * H / n + 63) / 64 * 64;
+    return (int)(r < H ? r : H);
+}
+
 // The whole pipeline.  tap_stage == 0: normal render to out_u8.
 int render_body(r2f_ctx *c, const void *in, int in_format, float in_gain, int H, int W, int cin, uint8_t *out_u8,
                 unsigned flags, const float *noise, int noise_ch, void *ws, size_t ws_bytes, int tap_stage,
-                float *tap, cudaStream_t st) {
+                float *tap, cudaStream_t st, Bands *bands) {
     if (!c) return fail(R2F_ERR_INVALID, "null context");
     if (!in || H < 1 || W < 1 || (cin != 3 && cin != 4)) return fail(R2F_ERR_INVALID, "bad input image arguments");
     if (in_format != R2F_IN_F32 && in_format != R2F_IN_U16) return fail(R2F_ERR_INVALID, "unknown input format");
@@ -789,6 +807,24 @@ int render_body(r2f_ctx *c, const void *in, int in_format, float in_gain, int H,
     if (rc != R2F_OK) return rc;
     DeviceGuard guard(c->device);
 
+    const int nb = bands ? bands->n : 1;
+    auto wait_in = [&](int upto) -> cudaError_t {  // the rows of bands [0, upto) are needed
+        for (; bands && bands->waited < upto && bands->waited < nb; ++bands->waited) {
+            cudaError_t e = cudaStreamWaitEvent(st, bands->in_ready[bands->waited], 0);
+            if (e != cudaSuccess) return e;
+        }
+        return cudaSuccess;
+    };
+    auto done_out = [&](int upto) -> cudaError_t {  // the output rows of bands [0, upto) are final
+        for (; bands && bands->recorded < upto && bands->recorded < nb; ++bands->recorded) {
+            cudaError_t e = cudaEventRecord(bands->out_done[bands->recorded], st);
+            if (e != cudaSuccess) return e;
+        }
+        return cudaSuccess;
+    };
+    const size_t in_px_bytes = (size_t)cin * (in_format == R2F_IN_U16 ? 2 : 4);
+    if (tap_stage != 0) CU(wait_in(nb));  // the tap paths are not banded
+
     const size_t npix = (size_t)H * W;
     const unsigned spatial = flags & (R2F_HALATION | R2F_MTF | R2F_GRAIN | R2F_BURN);
     const Lut2D l2 = lut2d_of(c);
@@ -802,17 +838,26 @@ int render_body(r2f_ctx *c, const void *in, int in_format, float in_gain, int H,
         }
         const FastChain &fc = c->t->fast;
         ProfScope ps_(c, st, R2F_PROF_POINTWISE);
-        if (c->fast_chain && fc.ok && pointwise_fast_smem(l2, fc) <= 104 * 1024 && npix < ((size_t)1 << 32)) {
-            if (!c->stats_buf.p) {
-                CU(c->stats_buf.ensure(sizeof(unsigned long long)));
-                CU(cudaMemsetAsync(c->stats_buf.p, 0, sizeof(unsigned long long), st));
-            }
-            CU(launch_pointwise_fast(in, fmt, in_gain, out_u8, npix, l2, cv, c->t->eps, l3, fc,
-                                     static_cast<unsigned long long *>(c->stats_buf.p), c->num_sms, st));
-        } else {
-            CU(launch_pointwise(in, fmt, in_gain, out_u8, npix, l2, cv, c->t->eps, l3, c->num_sms, st));
+        const bool fast = c->fast_chain && fc.ok && pointwise_fast_smem(l2, fc) <= 104 * 1024 && npix < ((size_t)1 << 32);
+        if (fast && !c->stats_buf.p) {
+            CU(c->stats_buf.ensure(sizeof(unsigned long long)));
+            CU(cudaMemsetAsync(c->stats_buf.p, 0, sizeof(unsigned long long), st));
         }
-        c->launches += 1;
+        for (int b = 0; b < nb; ++b) {  // one launch per band (one launch in all when the call is not banded)
+            const int r0 = band_row(H, nb, b), r1 = band_row(H, nb, b + 1);
+            if (r1 <= r0) continue;
+            CU(wait_in(b + 1));
+            const void *bin = static_cast<const char *>(in) + (size_t)r0 * W * in_px_bytes;
+            uint8_t *bout = out_u8 + (size_t)r0 * W * 3;
+            const size_t bpix = (size_t)(r1 - r0) * W;
+            if (fast)
+                CU(launch_pointwise_fast(bin, fmt, in_gain, bout, bpix, l2, cv, c->t->eps, l3, fc,
+                                         static_cast<unsigned long long *>(c->stats_buf.p), c->num_sms, st));
+            else
+                CU(launch_pointwise(bin, fmt, in_gain, bout, bpix, l2, cv, c->t->eps, l3, c->num_sms, st));
+            c->launches += 1;
+            CU(done_out(b + 1));
+        }
         return R2F_OK;
     }
 
@@ -849,7 +894,19 @@ int render_body(r2f_ctx *c, const void *in, int in_format, float in_gain, int H,
         fa.eps = c->t->eps;
         // the row-inverse kernel's fused log10 + curve epilogue knows uniform tables only
         const bool fuse_density = tap_stage != R2F_TAP_HALATION && cv.xp == nullptr;
-        for (int stage = 1; stage <= 3; ++stage) {
+        {
+            ProfScope ps_(c, st, R2F_PROF_FFT_ROWS_FWD);
+            for (int b = 0; b < nb; ++b) {  // the row transforms of a band start as soon as its rows have arrived
+                const int r0 = band_row(H, nb, b), r1 = band_row(H, nb, b + 1);
+                if (r1 <= r0) continue;
+                CU(wait_in(b + 1));
+                fa.row0 = r0;
+                fa.row_count = r1 - r0;
+                CU(launch_fft_conv(fa, 1 + fmt, fuse_density, st, 1));
+            }
+            fa.row0 = fa.row_count = 0;
+        }
+        for (int stage = 2; stage <= 3; ++stage) {
             ProfScope ps_(c, st, R2F_PROF_FFT_ROWS_FWD + stage - 1);
             CU(launch_fft_conv(fa, 1 + fmt, fuse_density, st, stage));
         }
@@ -871,7 +928,13 @@ int render_body(r2f_ctx *c, const void *in, int in_format, float in_gain, int H,
     } else {
         {
             ProfScope ps_(c, st, R2F_PROF_EXPOSE);
-            CU(launch_expose(in, fmt, in_gain, P[0], npix, l2, c->num_sms, st));
+            for (int b = 0; b < nb; ++b) {
+                const int r0 = band_row(H, nb, b), r1 = band_row(H, nb, b + 1);
+                if (r1 <= r0) continue;
+                CU(wait_in(b + 1));
+                CU(launch_expose(static_cast<const char *>(in) + (size_t)r0 * W * in_px_bytes, fmt, in_gain,
+                                 Planes{P[0].base + (size_t)r0 * W, ps}, (size_t)(r1 - r0) * W, l2, c->num_sms, st));
+            }
         }
         c->launches += 1;
         if (tap_stage == R2F_TAP_EXPOSURE) return export_tap(P[0]);
@@ -945,9 +1008,16 @@ int render_body(r2f_ctx *c, const void *in, int in_format, float in_gain, int H,
         ga.burn = BurnArgs{};
         ga.out_u8 = out_u8;
         ProfScope ps_(c, st, R2F_PROF_GRAIN);
-        if (c->conv_sym && ga.gk_sym && grain_finish_sym_supported(ga.k) && ga.gcurve.xp == nullptr)
-            CU(launch_grain_finish_sym(ga, st));
-        else CU(launch_grain_finish(ga, st));
+        const bool gsym = c->conv_sym && ga.gk_sym && grain_finish_sym_supported(ga.k) && ga.gcurve.xp == nullptr;
+        for (int b = 0; b < nb; ++b) {  // the result of a band can leave while the next one is computed
+            const int r0 = band_row(H, nb, b), r1 = band_row(H, nb, b + 1);
+            if (r1 <= r0) continue;
+            ga.tile_y0 = nb > 1 ? r0 / 64 : 0;
+            ga.tile_rows = nb > 1 ? (r1 - r0 + 63) / 64 : 0;
+            if (gsym) CU(launch_grain_finish_sym(ga, st));
+            else CU(launch_grain_finish(ga, st));
+            CU(done_out(b + 1));
+        }
         c->launches += 1;
         return R2F_OK;
     }
@@ -1003,8 +1073,16 @@ int render_body(r2f_ctx *c, const void *in, int in_format, float in_gain, int H,
     ProfScope ps_(c, st, R2F_PROF_FINISH);
     if (tap_stage == R2F_TAP_RGB)
         CU(launch_finish(P[cur], npix, H, W, l3, burn, nullptr, tap, 1, c->num_sms, st));
-    else
+    else if (burn.map != nullptr || nb == 1)
         CU(launch_finish(P[cur], npix, H, W, l3, burn, out_u8, nullptr, 1, c->num_sms, st));
+    else
+        for (int b = 0; b < nb; ++b) {
+            const int r0 = band_row(H, nb, b), r1 = band_row(H, nb, b + 1);
+            if (r1 <= r0) continue;
+            CU(launch_finish(Planes{P[cur].base + (size_t)r0 * W, ps}, (size_t)(r1 - r0) * W, r1 - r0, W, l3, burn,
+                             out_u8 + (size_t)r0 * W * 3, nullptr, 1, c->num_sms, st));
+            CU(done_out(b + 1));
+        }
     c->launches += 1;
     return R2F_OK;
 }
@@ -1014,9 +1092,17 @@ int render_body(r2f_ctx *c, const void *in, int in_format, float in_gain, int H,
 // a replaced buffer is no longer read (mark_render / sweep_done).
 int render_impl(r2f_ctx *c, const void *in, int in_format, float in_gain, int H, int W, int cin, uint8_t *out_u8,
                 unsigned flags, const float *noise, int noise_ch, void *ws, size_t ws_bytes, int tap_stage,
-                float *tap, cudaStream_t st) {
-    const int rc = render_body(c, in, in_format, in_gain, H, W, cin, out_u8, flags, noise, noise_ch, ws, ws_bytes,
-                               tap_stage, tap, st);
+                float *tap, cudaStream_t st, Bands *bands = nullptr) {
+    int rc = render_body(c, in, in_format, in_gain, H, W, cin, out_u8, flags, noise, noise_ch, ws, ws_bytes,
+                         tap_stage, tap, st, bands);
+    if (c && bands && rc == R2F_OK) {  // whatever was not banded: everything is final once the stream gets here
+        DeviceGuard guard(c->device);
+        for (; bands->recorded < bands->n; ++bands->recorded)
+            if (cudaEventRecord(bands->out_done[bands->recorded], st) != cudaSuccess) {
+                rc = fail(R2F_ERR_CUDA, "cudaEventRecord (band)");
+                break;
+            }
+    }
     if (c) {
         DeviceGuard guard(c->device);
         // a render that is being captured into a CUDA graph is marked when the graph is replayed (r2f_stream_mark)
@@ -1344,6 +1430,23 @@ int r2f_render_ex(r2f_ctx *c, const void *in_dev, int in_format, float in_gain, 
                   size_t workspace_bytes, void *stream) {
     return render_impl(c, in_dev, in_format, in_gain, H, W, in_channels, out_dev, flags, noise_dev, noise_channels,
                        workspace_dev, workspace_bytes, 0, nullptr, static_cast<cudaStream_t>(stream));
+}
+
+int r2f_band_row(int H, int nbands, int i) { return band_row(H, nbands < 1 ? 1 : nbands, i); }
+
+int r2f_render_banded(r2f_ctx *c, const void *in_dev, int in_format, float in_gain, int H, int W, int in_channels,
+                      uint8_t *out_dev, unsigned flags, const float *noise_dev, int noise_channels, void *workspace_dev,
+                      size_t workspace_bytes, int nbands, void *const *in_ready, void *const *out_done, void *stream) {
+    if (nbands < 1 || nbands > 64 || !in_ready || !out_done)
+        return fail(R2F_ERR_INVALID, "r2f_render_banded: 1..64 bands with their event arrays");
+    for (int i = 0; i < nbands; ++i)
+        if (!in_ready[i] || !out_done[i]) return fail(R2F_ERR_INVALID, "r2f_render_banded: null event");
+    Bands b;
+    b.n = nbands;
+    b.in_ready = reinterpret_cast<cudaEvent_t const *>(in_ready);
+    b.out_done = reinterpret_cast<cudaEvent_t const *>(out_done);
+    return render_impl(c, in_dev, in_format, in_gain, H, W, in_channels, out_dev, flags, noise_dev, noise_channels,
+                       workspace_dev, workspace_bytes, 0, nullptr, static_cast<cudaStream_t>(stream), &b);
 }
 
 int r2f_render_tap(r2f_ctx *c, const float *in_dev, int H, int W, int in_channels, unsigned flags,

@@ -470,8 +470,9 @@ k_fft_rows_fwd(const __grid_constant__ FftConvArgs a) {
     const int W = a.W, H = a.H, r = a.r, n = a.row.n, NC = a.nc;
     const Group g = row_group<ROWS>();
     const int half = ROWS == 2 ? (int)(threadIdx.x >> 9) : 0;
-    const int y0 = blockIdx.x * ROWS;
-    const int nrows = min(ROWS, H - y0);
+    const int y0 = a.row0 + blockIdx.x * ROWS;                              // a.row0 is a multiple of ROWS
+    const int yend = a.row_count > 0 ? min(H, a.row0 + a.row_count) : H;
+    const int nrows = min(ROWS, yend - y0);
     float2 *bufA = fsm + (size_t)half * 2 * n, *bufB = bufA + n;
     const int y = y0 + half;
     if (half < nrows) {
@@ -1023,10 +1024,13 @@ cudaError_t launch_fft_conv(const FftConvArgs &a, int src_mode, bool density, cu
     const int row_plan = rows == 1 ? static_plan_id(a.row, t1) : 0;
     const int col_plan = static_plan_id(a.col, 1024 / a.col_groups);
     if (stage == 0 || stage == 1) {
-        if (rows == 2) e = launch_rows_fwd<2, 0>(a, src_mode, row_ctas, 1024, rs, st);
-        else if (row_plan == 1) e = launch_rows_fwd<1, 1>(a, src_mode, row_ctas, t1, rs, st);
-        else if (row_plan == 3) e = launch_rows_fwd<1, 3>(a, src_mode, row_ctas, t1, rs, st);
-        else e = launch_rows_fwd<1, 0>(a, src_mode, row_ctas, t1, rs, st);
+        const int fwd_rows = a.row_count > 0 ? a.row_count : a.H;
+        const int fwd_ctas = (fwd_rows + rows - 1) / rows;
+        if (a.row0 % rows != 0) return cudaErrorInvalidValue;
+        if (rows == 2) e = launch_rows_fwd<2, 0>(a, src_mode, fwd_ctas, 1024, rs, st);
+        else if (row_plan == 1) e = launch_rows_fwd<1, 1>(a, src_mode, fwd_ctas, t1, rs, st);
+        else if (row_plan == 3) e = launch_rows_fwd<1, 3>(a, src_mode, fwd_ctas, t1, rs, st);
+        else e = launch_rows_fwd<1, 0>(a, src_mode, fwd_ctas, t1, rs, st);
         if (e != cudaSuccess) return e;
     }
     if ((stage == 0 || stage == 2) && a.col_inplace) {

@@ -61,6 +61,9 @@ struct FftConvArgs {
     float *dst_planar;
     Curve1D curve;
     float eps;
+    // forward row kernel only: first row and row count of this launch (0, 0 = the whole frame); lets a caller
+    // start transforming the rows of a frame that is still arriving (r2f_render_banded)
+    int row0, row_count;
 };
 
 int fft_good_size(int min_n, int multiple_of);

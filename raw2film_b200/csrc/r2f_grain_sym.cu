@@ -51,7 +51,7 @@ k_grain_finish_sym(const __grid_constant__ GrainFinishArgs a) {
     float *wsm = smem + C::TILE_FLOATS;
     float *priv = wsm + C::W_FLOATS;
     const int H = a.H, W = a.W;
-    const int tx0 = blockIdx.x * C::T, ty0 = blockIdx.y * C::T;
+    const int tx0 = blockIdx.x * C::T, ty0 = (blockIdx.y + a.tile_y0) * C::T;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const size_t ps = a.plane_stride;
     for (int idx = threadIdx.x; idx < C::W_FLOATS; idx += C::NT) wsm[idx] = __ldg(a.gk_sym + idx);
@@ -168,7 +168,7 @@ k_grain_finish_sym(const __grid_constant__ GrainFinishArgs a) {
 template <int K>
 cudaError_t launch_gs(const GrainFinishArgs &a, cudaStream_t st) {
     using C = GrainCfg<K>;
-    dim3 grid((a.W + C::T - 1) / C::T, (a.H + C::T - 1) / C::T);
+    dim3 grid((a.W + C::T - 1) / C::T, a.tile_rows > 0 ? a.tile_rows : (a.H + C::T - 1) / C::T);
     cudaError_t e;
 #define R2F_GS_LAUNCH(GEN_, FC_)                                                                                   \
     do {                                                                                                          \

@@ -969,7 +969,7 @@ k_grain_finish(GrainFinishArgs a) {
     float *tile = smem;                                   // noise tile; later the byte staging area
     float *wsm = smem + ((rows * cols + 3) / 4) * 4;      // grain kernel
     float *priv = wsm + k * kp;                           // [3][16][256] grained densities, thread-private slots
-    const int tx0 = blockIdx.x * kGfTile, ty0 = blockIdx.y * kGfTile;
+    const int tx0 = blockIdx.x * kGfTile, ty0 = (blockIdx.y + a.tile_y0) * kGfTile;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int lx = (warp & 1) * 32 + lane, ly0 = (warp >> 1) * 16;
     const int gx = tx0 + lx;
@@ -1097,7 +1097,7 @@ cudaError_t launch_grain_finish(const GrainFinishArgs &a, cudaStream_t st) {
     if (tile_f < (size_t)kGfTile * kGfTile * 3 / 4) tile_f = (size_t)kGfTile * kGfTile * 3 / 4;
     const size_t smem = (tile_f + (size_t)a.k * a.kp + 3 * 16 * 256) * sizeof(float);
     if (smem > kMaxDynSmem) return cudaErrorInvalidValue;
-    dim3 grid((a.W + kGfTile - 1) / kGfTile, (a.H + kGfTile - 1) / kGfTile);
+    dim3 grid((a.W + kGfTile - 1) / kGfTile, a.tile_rows > 0 ? a.tile_rows : (a.H + kGfTile - 1) / kGfTile);
     cudaError_t e;
     if (a.noise == nullptr) {
         if ((e = cudaFuncSetAttribute(k_grain_finish<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) !=

@@ -118,6 +118,7 @@ struct GrainFinishArgs {
     FastTetra ft;        // guarded float32 tetrahedral LUT + quantise (ok == 0: exact path only)
     BurnArgs burn;
     uint8_t *out_u8;
+    int tile_y0, tile_rows;  // first tile row and tile-row count of this launch (0, 0 = all): banded output
 };
 cudaError_t launch_grain_finish(const GrainFinishArgs &a, cudaStream_t st);
 // same contract for y-symmetric grain kernels without burn (r2f_grain_sym.cu): row-pair sums + packed FMA

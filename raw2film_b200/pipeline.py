@@ -24,12 +24,17 @@ class PipelinedRenderer:
     frame's uint8 image is in host memory.  At most `depth` frames are in flight; the host array
     returned for ticket t stays valid until ticket t + depth is submitted."""
 
-    def __init__(self, processor, depth: int = 3):
+    def __init__(self, processor, depth: int = 3, bands: int = 1):
+        """`bands` > 1: every frame is copied in and out in that many horizontal bands, the first kernel of the
+        render starts on a band as soon as it has arrived and the result of a band leaves while the next one is
+        computed (r2f_render_banded).  That shortens a frame's own latency -- what a synchronous caller sees
+        (`process_preloaded`) -- and is pointless for throughput, where neighbouring frames already overlap."""
         import torch
 
         self._torch = torch
         self.proc = processor
         self.depth = max(2, int(depth))
+        self.bands = max(1, min(int(bands), 16))
         dev = processor.device
         self.s_in = torch.cuda.Stream(device=dev)
         self.s_out = torch.cuda.Stream(device=dev)
@@ -74,6 +79,7 @@ class PipelinedRenderer:
             out_shape = (post[0], post[1], 3)
         ticket = self._count
         slot = self._slots[ticket % self.depth]
+        band_events, rows, nb = None, None, 1
         if slot["used"]:
             slot["d2h"].synchronize()          # the slot's previous result has left the device
         if upload:
@@ -82,12 +88,27 @@ class PipelinedRenderer:
                 host = torch.empty(arr.shape, dtype=tdtype, pin_memory=True)
                 host.numpy()[...] = arr
             self._slot_buffers(slot, arr.shape, tdtype, out_shape, (h, w))
+            nb = self.bands if (pre is None and canvas is None and post is None and readback and h >= 256) else 1
+            rows = [int(_cabi.lib.r2f_band_row(h, nb, i)) for i in range(nb + 1)]
+            if nb > 1 and len(slot.get("in_ev", ())) != nb:
+                slot["in_ev"] = [torch.cuda.Event() for _ in range(nb)]
+                slot["out_ev"] = [torch.cuda.Event() for _ in range(nb)]
+                for e in slot["in_ev"] + slot["out_ev"]:
+                    e.record(self.s_in)               # creates the underlying cudaEvent_t
             with torch.cuda.stream(self.s_in):
                 if slot.get("last_read") is not None:
                     self.s_in.wait_event(slot["last_read"])   # the last render that read this dev_in has finished
-                slot["dev_in"].copy_(host, non_blocking=True)
+                if nb > 1:
+                    for i in range(nb):
+                        slot["dev_in"][rows[i]:rows[i + 1]].copy_(host[rows[i]:rows[i + 1]], non_blocking=True)
+                        slot["in_ev"][i].record(self.s_in)
+                else:
+                    slot["dev_in"].copy_(host, non_blocking=True)
                 slot["h2d"].record(self.s_in)
-            self.s_compute.wait_event(slot["h2d"])
+            if nb > 1:
+                band_events = (slot["in_ev"], slot["out_ev"])  # the render waits per band
+            else:
+                self.s_compute.wait_event(slot["h2d"])
             slot["keep"] = host                       # keep the pinned source alive until the copy ran
             self.h2d_bytes += host.numel() * host.element_size()
             dev_in = slot["dev_in"]
@@ -111,7 +132,7 @@ class PipelinedRenderer:
             dev_in = slot["dev_pre"]
         out_dev = proc.render_device(dev_in, negative_film, grain_size, grain_sigma, out=slot["dev_out"],
                                      stream=self.s_compute, sync_caller=False,
-                                     input_gain=cpu_payload.get("input_gain", 1.0), **settings)
+                                     input_gain=cpu_payload.get("input_gain", 1.0), bands=band_events, **settings)
         if canvas is not None:                        # add_canvas (cpu_processor.py:409) on the device
             ch_, cw_ = canvas["size"]
             if slot["canvas_dev"] is None or tuple(slot["canvas_dev"].shape) != (ch_, cw_, 3):
@@ -128,9 +149,14 @@ class PipelinedRenderer:
         reader["last_read"] = slot["done"]
         slot["result_dev"] = out_dev
         with torch.cuda.stream(self.s_out):
-            self.s_out.wait_event(slot["done"])
-            if readback:
-                slot["host_out"].copy_(out_dev, non_blocking=True)
+            if band_events is not None:               # copy each band out as soon as its rows are final
+                for i in range(nb):
+                    self.s_out.wait_event(slot["out_ev"][i])
+                    slot["host_out"][rows[i]:rows[i + 1]].copy_(out_dev[rows[i]:rows[i + 1]], non_blocking=True)
+            else:
+                self.s_out.wait_event(slot["done"])
+                if readback:
+                    slot["host_out"].copy_(out_dev, non_blocking=True)
             slot["d2h"].record(self.s_out)
         slot["used"] = True
         self._last_slot = slot if upload else self._last_slot

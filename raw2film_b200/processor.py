@@ -564,10 +564,11 @@ class B200Processor:
         return self._dev_noise.data_ptr(), nch
 
     def render_device(self, xyz_dev, negative_film, grain_size, grain_sigma, out=None, stream=None,
-                      sync_caller=True, input_gain=1.0, **settings):
+                      sync_caller=True, input_gain=1.0, bands=None, **settings):
         """Device-resident render: `xyz_dev` is a float32 -- or uint16 with `input_gain` -- (H, W, 3|4)
         CUDA tensor, result a uint8 (H, W, 3) CUDA tensor.  No host copies; enqueued on `stream`
-        (default: self.stream)."""
+        (default: self.stream).  `bands` = (in_events, out_events), two equally long lists of recorded
+        torch.cuda.Event: the frame is still arriving band by band (r2f_render_banded, include/r2f_b200.h)."""
         torch = self._torch
         h, w, ch = xyz_dev.shape
         if xyz_dev.dtype not in (torch.float32, torch.uint16) or not xyz_dev.is_contiguous() \
@@ -600,9 +601,17 @@ class B200Processor:
         ws_bytes = self._dev_ws.numel() if (flags & _SPATIAL) else 0
         if out is None or tuple(out.shape) != (h, w, 3):
             out = self._dev_out = torch.empty((h, w, 3), dtype=torch.uint8, device=self.device)
-        _cabi.check(_cabi.lib.r2f_render_ex(self._ctx, xyz_dev.data_ptr(), in_fmt, float(input_gain), h, w, ch,
-                                            out.data_ptr(), flags, noise_ptr, nch, ws_ptr, ws_bytes,
-                                            stream.cuda_stream))
+        if bands is None:
+            _cabi.check(_cabi.lib.r2f_render_ex(self._ctx, xyz_dev.data_ptr(), in_fmt, float(input_gain), h, w, ch,
+                                                out.data_ptr(), flags, noise_ptr, nch, ws_ptr, ws_bytes,
+                                                stream.cuda_stream))
+        else:
+            ins, outs = bands
+            arr_t = ctypes.c_void_p * len(ins)
+            _cabi.check(_cabi.lib.r2f_render_banded(
+                self._ctx, xyz_dev.data_ptr(), in_fmt, float(input_gain), h, w, ch, out.data_ptr(), flags, noise_ptr,
+                nch, ws_ptr, ws_bytes, len(ins), arr_t(*[e.cuda_event for e in ins]),
+                arr_t(*[e.cuda_event for e in outs]), stream.cuda_stream))
         if sync_caller:  # order later work on the caller's stream after the render (asynchronous, no host sync)
             torch.cuda.current_stream(self.device).wait_stream(stream)
         self._last_out = out
@@ -663,7 +672,9 @@ class B200Processor:
         if getattr(self, "_pipe", None) is None:
             from .pipeline import PipelinedRenderer
 
-            self._pipe = PipelinedRenderer(self, depth=3)
+            # a synchronous call has no neighbouring frames to overlap with: stream the frame in and the result out
+            # in bands around the first and last kernel instead (r2f_render_banded)
+            self._pipe = PipelinedRenderer(self, depth=3, bands=4)
         return self._pipe
 
     def resize_device(self, x_dev, size, out=None, stream=None):

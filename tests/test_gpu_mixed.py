@@ -248,3 +248,27 @@ def test_c3_61mp_full_emulation_vs_cv2_oracle(proc):
     assert proc.halation_kernel.shape[0] == 133 and proc.mtf_kernel.shape[0] == 27
     mx, rate = _lsb(got, want)
     assert mx <= 1 and rate < 2e-3, (mx, rate)
+
+
+@pytest.mark.parametrize("st", [
+    dict(halation=False, sharpness=False, grain=0),                                            # k_pointwise_fast per band
+    dict(halation=True, sharpness=True, grain=2, grain_seed=11, halation_green_factor=0.3),    # FFT rows + fused grain
+    dict(halation=True, sharpness=True, grain=0, frame_width=360.0, frame_height=240.0),       # k_expose, k_finish
+    dict(halation=True, sharpness=False, grain=2, grain_seed=5, highlight_burn=0.5),           # burn: unbanded tail
+])
+def test_banded_streaming_call_equals_plain_render(proc, st):
+    """process_preloaded streams the frame in and the result out in four bands around the first / last kernel
+    (r2f_render_banded); the bytes must be those of the plain device-resident render."""
+    import torch
+
+    stock = SyntheticStock()
+    xyz = natural_frame(1100, 1500, 21)            # 1100 rows: bands of 320 / 256 / 256 / 268 rows
+    want = proc.render_device(torch.from_numpy(xyz).cuda(), stock, 6.0, 0.4, **st).cpu().numpy()
+    payload = proc.extract_image_data_cpu(xyz, **st)
+    got = proc.process_preloaded(payload, stock, 6.0, 0.4, **st)
+    assert proc._own_pipeline().bands == 4
+    assert np.array_equal(got, want)
+    u16 = np.clip(xyz * (65535.0 / 32.0), 0, 65535).astype(np.uint16)
+    want16 = proc.render_device(torch.from_numpy(u16).cuda(), stock, 6.0, 0.4, input_gain=32.0, **st).cpu().numpy()
+    got16 = proc.process_preloaded(proc.extract_image_data_cpu(u16, input_gain=32.0, **st), stock, 6.0, 0.4, **st)
+    assert np.array_equal(got16, want16)
