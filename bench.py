@@ -210,6 +210,73 @@ def run_reference(args, world, rank):
     print(json.dumps(line))
 
 
+def run_aux(args, local):
+    """CUDA-event times of the entry points either side of the path on a device-resident frame."""
+    import ctypes
+
+    import torch
+
+    from raw2film_b200 import B200Processor, _cabi, builders, hostops
+    from raw2film_b200.synthetic import SyntheticStock, natural_frame
+
+    torch.cuda.set_device(local)
+    proc = B200Processor(device=local)
+    H, W = 4000, 6000
+    st = proc.stream
+    frame = torch.from_numpy(natural_frame(H, W, 0)).to(proc.device)
+    u16 = (frame.clamp(0, 1) * 65535).to(torch.int32).to(torch.uint16)
+    out8 = proc.render_device(frame, SyntheticStock(), GRAIN_SIZE, GRAIN_SIGMA, halation=False, sharpness=False,
+                              grain=0).clone()
+    ws = torch.empty(int(_cabi.lib.r2f_workspace_bytes(H, W, 0)), dtype=torch.uint8, device=proc.device)
+    res = {}
+
+    def timed(name, fn, bytes_moved, reps=10):
+        fn()
+        st.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(st)
+        for _ in range(reps):
+            fn()
+        b.record(st)
+        st.synchronize()
+        ms = a.elapsed_time(b) / reps
+        res[name] = {"ms": round(ms, 4), "gbs": round(bytes_moved / ms / 1e6, 1)}
+
+    mp = H * W
+    small = torch.empty((1080, 1620, 3), dtype=torch.float32, device=proc.device)
+    timed("resize_area_f32_24mp_to_1620x1080", lambda: proc.resize_device(frame, (1080, 1620), out=small), mp * 12)
+    half = torch.empty((2000, 3000, 3), dtype=torch.float32, device=proc.device)
+    timed("resize_area_f32_24mp_to_half", lambda: proc.resize_device(frame, (2000, 3000), out=half), mp * 15)
+    src8 = out8[:2667, :4000].contiguous()
+    up8 = torch.empty((H, W, 3), dtype=torch.uint8, device=proc.device)
+    timed("resize_lanczos4_u8_10.7mp_to_24mp", lambda: proc.resize_device(src8, (H, 6000), out=up8), mp * 3 + src8.numel())
+    taps = builders.chroma_nr_taps(3)
+    cn_out = torch.empty_like(frame)
+    timed("chroma_nr_size3_24mp", lambda: _cabi.check(_cabi.lib.r2f_chroma_nr(
+        proc._ctx, frame.data_ptr(), 3, cn_out.data_ptr(), H, W, _cabi.f32_ptr(taps), taps.shape[0], ws.data_ptr(),
+        ws.numel(), st.cuda_stream)), mp * 24)
+    mean = ctypes.c_double(0)
+    timed("calc_exposure_u16_24mp", lambda: _cabi.check(_cabi.lib.r2f_calc_exposure(
+        proc._ctx, u16.data_ptr(), _cabi.IN_U16, H, W, 3, 3.0, ctypes.byref(mean), st.cuda_stream)), mp * 6 / 4)
+    size, colour, off = hostops.canvas_geometry((H, W), "Proportional white", 1.1, 1.0)
+    canvas = torch.empty((size[0], size[1], 3), dtype=torch.uint8, device=proc.device)
+    timed("canvas_paste_24mp", lambda: _cabi.check(_cabi.lib.r2f_canvas_paste(
+        proc._ctx, out8.data_ptr(), H, W, canvas.data_ptr(), size[0], size[1], int(off[0]), int(off[1]), 255, 255,
+        255, st.cuda_stream)), mp * 3 + canvas.numel())
+    mix = np.arange(32, dtype=np.uint8)
+    hist = torch.empty((100, 256, 4), dtype=torch.uint8, device=proc.device)
+    timed("histogram_image_24mp", lambda: _cabi.check(_cabi.lib.r2f_histogram_image(
+        proc._ctx, out8.data_ptr(), H, W, mix.ctypes.data_as(ctypes.c_void_p), 100, hist.data_ptr(),
+        st.cuda_stream)), mp * 3)
+    widget = torch.empty((1080, 1920, 4), dtype=torch.uint8, device=proc.device)
+    proc.pipeline_resolution = proc.output_resolution = (W, H)
+    proc.canvas_resolution = None
+    timed("present_24mp_to_1920x1080", lambda: proc.present(out8, widget), widget.numel() + 1920 * 1080 * 12)
+    print(json.dumps({"aux": True, "frame": f"{W}x{H}", "what": "CUDA-event time per call, device-resident operands; gbs = "
+                      "bytes the call has to move / time", "steps": res}))
+    proc.close()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -221,12 +288,17 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--c4-frames", type=int, default=64, help="frames of the mixed-stock batch leg (0 = skip)")
     ap.add_argument("--kernel-only", action="store_true", help="device-resident leg only (ncu captures)")
+    ap.add_argument("--aux", action="store_true",
+                    help="time the steps either side of the path (SURVEY 8f) on a device-resident 24 MP frame instead")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     world, rank, local = dist_setup(args.gpus)
 
     if args.impl == "reference":
         run_reference(args, world, rank)
+        return
+    if args.aux:
+        run_aux(args, local)
         return
 
     import ctypes

@@ -751,7 +751,7 @@ int fast_chain_build(r2f_ctx *c) {
     f.pscale = std::nextafterf((float)(N - 1), 0.0f);
     f.margin = (float)margin;
     f.fseg = static_cast<const float2 *>(t->fseg.p);
-    f.lut255 = static_cast<const float4 *>(t->lut255.p);
+    f.lut255 = static_cast<const float4 *>(t->lut255.p) + ((size_t)n * n + n + 1);  // past the guard cells
     f.N = N;
     f.n3 = n;
     f.ok = t->lut255.p != nullptr ? 1 : 0;
@@ -1281,7 +1281,15 @@ int r2f_set_lut3d(r2f_ctx *c, const float *lut, int n, double scale) {
             padded[4 * v + k] = (float)(x * 255.0 - 0.5);
         }
     }
-    rc = upload(c, t->lut255, padded.data(), padded.size() * sizeof(float));
+    // Guard cells in front: a lattice coordinate within rounding distance below 0 (a density of exactly 0 after the
+    // fast chain's roundings) selects cell -1 with a fraction of ~1; its vertices get a weight of ~1e-7, they only
+    // have to be readable.  n*n + n + 1 vertices cover index -1 on all three axes.
+    const size_t nguard = (size_t)n * n + n + 1;
+    {
+        std::vector<float> with_guard((nguard + verts) * 4, -0.5f);
+        std::memcpy(with_guard.data() + nguard * 4, padded.data(), padded.size() * sizeof(float));
+        rc = upload(c, t->lut255, with_guard.data(), with_guard.size() * sizeof(float));
+    }
     if (rc != R2F_OK) return rc;
     t->fast_valid = false;
     t->n3 = n;
@@ -1316,7 +1324,7 @@ int r2f_set_lut3d(r2f_ctx *c, const float *lut, int n, double scale) {
     if (!pow2) mt += 255.0 * 3.0 * lipmax * (2.0 * u * (double)n);
     mt *= 1.25;
     FastTetra ft{};
-    ft.lut = static_cast<const float4 *>(t->lut255.p);
+    ft.lut = static_cast<const float4 *>(t->lut255.p) + nguard;
     ft.s3f = t->s3f;
     ft.vtop = vtop;
     ft.half_m = (float)(0.5 - mt);

@@ -130,3 +130,25 @@ def test_fast_chain_disqualified_tables_take_the_exact_chain(proc):
     got = _gpu_u8(proc, xyz, stock, **OFF)
     assert proc.fast_chain_stats()[1] == -1.0
     assert np.array_equal(got, _oracle_u8(xyz, stock, **OFF))
+
+
+def test_fast_chain_zero_density_toe(proc):
+    """A curve whose toe is exactly 0 puts dark pixels ON the lower face of the 3-D LUT lattice, where the fast
+    chain's roundings can land a hair below 0 (cell -1 of the guarded table): still bit-exact, still the fast path."""
+
+    class ZeroToe(SyntheticStock):
+        def get_density_curve(self, push_pull=0.0, color_masking=None):
+            c = super().get_density_curve(push_pull, color_masking)
+            c[1:] -= c[1:].min(axis=1, keepdims=True)        # every layer starts at exactly 0
+            c[1:, :40] = 0.0                                   # ... and stays there for a while
+            return c
+
+    stock = ZeroToe(name="zero toe")
+    rng = np.random.default_rng(8)
+    xyz = small_frame(300, 400, seed=13)
+    xyz[:100] *= np.float32(1e-5)                              # deep shadows: below the first curve sample
+    xyz[100:120] = 0.0
+    xyz[120:140] = rng.random((20, 400, 3), dtype=np.float32) * np.float32(1e-4)
+    got = _gpu_u8(proc, xyz, stock, **OFF)
+    assert proc.fast_chain_stats()[1] > 0                      # the tables qualify for the fast chain
+    assert np.array_equal(got, _oracle_u8(xyz, stock, **OFF))
