@@ -674,7 +674,9 @@ class B200Processor:
 
             # a synchronous call has no neighbouring frames to overlap with: stream the frame in and the result out
             # in bands around the first and last kernel instead (r2f_render_banded)
-            self._pipe = PipelinedRenderer(self, depth=3, bands=4)
+            import os
+
+            self._pipe = PipelinedRenderer(self, depth=3, bands=int(os.environ.get("R2F_CALL_BANDS", "4")))
         return self._pipe
 
     def resize_device(self, x_dev, size, out=None, stream=None):
