@@ -88,7 +88,9 @@ class PipelinedRenderer:
                 host = torch.empty(arr.shape, dtype=tdtype, pin_memory=True)
                 host.numpy()[...] = arr
             self._slot_buffers(slot, arr.shape, tdtype, out_shape, (h, w))
-            nb = self.bands if (pre is None and canvas is None and post is None and readback and h >= 256) else 1
+            nb = 1
+            if pre is None and canvas is None and post is None and readback:
+                nb = max(1, min(self.bands, h // 256))    # bands of at least 256 rows
             rows = [int(_cabi.lib.r2f_band_row(h, nb, i)) for i in range(nb + 1)]
             if nb > 1 and len(slot.get("in_ev", ())) != nb:
                 slot["in_ev"] = [torch.cuda.Event() for _ in range(nb)]
