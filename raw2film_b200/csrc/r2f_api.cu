@@ -72,6 +72,11 @@ struct KernelSet {
     bool fft_ok = false;
     int fft_chan[2] = {0, 1};
     float fft_alpha[2] = {1.f, 1.f}, fft_beta[2] = {0.f, 0.f};
+    // a THIRD filtered layer on the same base (black-and-white stocks filter all three layers alike,
+    // effects.py:248-250): a second transform pair over (layer, layer) finishes it
+    bool fft_third = false;
+    int fft_chan3 = 2;
+    float fft_alpha3 = 1.f, fft_beta3 = 0.f;
     DevBuf base;            // k x k base kernel, row-major, device
     uint64_t base_hash = 0;  // FNV-1a of the base kernel's bytes and size (keys the spectrum cache)
 };
@@ -387,6 +392,7 @@ int upload_kernel(r2f_ctx *ctx, KernelSet &ks, const float *kernel, int k, int c
     ks.set = true;
     ks.base_hash = 0;
     ks.fft_ok = false;
+    ks.fft_third = false;
     // y-symmetric layout: rows dy = 0..r, (w, w) pairs, centre row halved (exact: power-of-two scaling)
     ks.sym_ok = false;
     for (int c = 0; c < 3; ++c) ks.sym[c] = nullptr;
@@ -422,7 +428,7 @@ int upload_kernel(r2f_ctx *ctx, KernelSet &ks, const float *kernel, int k, int c
         int conv[3], nconv = 0;
         for (int c = 0; c < 3; ++c)
             if (mode[c]) conv[nconv++] = c;
-        if (nconv == 2) {
+        if (nconv >= 2) {
             const int c0 = conv[0], c1 = conv[1], mid = k / 2;
             auto at = [&](int i, int j, int c) { return (double)kernel[((size_t)i * k + j) * 3 + c]; };
             bool even = true;
@@ -472,6 +478,26 @@ int upload_kernel(r2f_ctx *ctx, KernelSet &ks, const float *kernel, int k, int c
                     ks.fft_beta[0] = (float)(at(mid, mid, c0) - bc);
                     ks.fft_alpha[1] = (float)alpha;
                     ks.fft_beta[1] = (float)(at(mid, mid, c1) - alpha * bc);
+                    if (nconv == 3) {  // the third layer must be a multiple of the same base as well
+                        const int c2 = conv[2];
+                        double n3 = 0.0;
+                        for (int i = 0; i < k; ++i)
+                            for (int j = 0; j < k; ++j)
+                                if (i != mid || j != mid) n3 += at(i, j, c2) * at(i, j, c0);
+                        const double alpha3 = n3 / den;
+                        double resid3 = 0.0;
+                        for (int i = 0; i < k; ++i)
+                            for (int j = 0; j < k; ++j)
+                                if (i != mid || j != mid) resid3 += std::fabs(at(i, j, c2) - alpha3 * at(i, j, c0));
+                        if (resid3 <= 1e-6) {
+                            ks.fft_third = true;
+                            ks.fft_chan3 = c2;
+                            ks.fft_alpha3 = (float)alpha3;
+                            ks.fft_beta3 = (float)(at(mid, mid, c2) - alpha3 * bc);
+                        } else {
+                            ks.fft_ok = false;
+                        }
+                    }
                 }
             }
         }
@@ -893,7 +919,9 @@ int render_body(r2f_ctx *c, const void *in, int in_format, float in_gain, int H,
         fa.curve = cv;
         fa.eps = c->t->eps;
         // the row-inverse kernel's fused log10 + curve epilogue knows uniform tables only
-        const bool fuse_density = tap_stage != R2F_TAP_HALATION && cv.xp == nullptr;
+        const bool third = c->t->hal.fft_third;  // three filtered layers: a second pass finishes the last one
+        const bool fuse_final = tap_stage != R2F_TAP_HALATION && cv.xp == nullptr;
+        const bool fuse_density = fuse_final && !third;
         {
             ProfScope ps_(c, st, R2F_PROF_FFT_ROWS_FWD);
             for (int b = 0; b < nb; ++b) {  // the row transforms of a band start as soon as its rows have arrived
@@ -910,12 +938,30 @@ int render_body(r2f_ctx *c, const void *in, int in_format, float in_gain, int H,
             ProfScope ps_(c, st, R2F_PROF_FFT_ROWS_FWD + stage - 1);
             CU(launch_fft_conv(fa, 1 + fmt, fuse_density, st, stage));
         }
+        if (third) {
+            // P[1] now holds the two filtered layers and the third one untouched: transform (layer3 + i layer3), mix
+            // it in place, pass the finished layers through, and apply the density epilogue to all three
+            FftConvArgs fb = fa;
+            fb.src_xyz = nullptr;
+            fb.src_planar = P[1].base;
+            fb.exp_planar = nullptr;
+            fb.dst_planar = P[1].base;
+            fb.chan[0] = fb.chan[1] = c->t->hal.fft_chan3;
+            fb.alpha[0] = fb.alpha[1] = c->t->hal.fft_alpha3;
+            fb.beta[0] = fb.beta[1] = c->t->hal.fft_beta3;
+            for (int stage = 1; stage <= 3; ++stage) {
+                ProfScope ps_(c, st, R2F_PROF_FFT_ROWS_FWD + stage - 1);
+                CU(launch_fft_conv(fb, 0, fuse_final, st, stage));
+            }
+            c->launches += 3;
+        }
+        const bool fuse_done = third ? fuse_final : fuse_density;
         c->launches += 2;  // + the one counted below
         if (tap_stage == R2F_TAP_HALATION) {
             c->launches += 1;
             return export_tap(P[1]);
         }
-        if (!fuse_density) {  // separate density pass (generic kernel, np.interp lookup): P[1] -> P[0] -> P[1]
+        if (!fuse_done) {  // separate density pass (generic kernel, np.interp lookup): P[1] -> P[0] -> P[1]
             ConvArgs a = identity_args(P[1].base, P[0].base, ps, H, W);
             a.epi = EPI_DENSITY_FAST;
             a.curve = cv;
@@ -1517,7 +1563,8 @@ int r2f_convolve2d(r2f_ctx *c, const float *in_dev, float *out_dev, int H, int W
     const size_t npix = (size_t)H * W;
     cudaError_t e = launch_interleaved_to_planar(in_dev, 3, 3, a, npix, c->num_sms, st);
     FftGeometry geo;
-    const bool use_fft = want_fft(c, ks, H, W, geo) && workspace_bytes >= ps * 9 * sizeof(float);
+    // (three filtered layers need the render path's second pass: the stage entry point keeps them on the direct kernel)
+    const bool use_fft = want_fft(c, ks, H, W, geo) && !ks.fft_third && workspace_bytes >= ps * 9 * sizeof(float);
     if (c->conv_path == 2 && !use_fft) {
         retire(c, ks.buf);
         retire(c, ks.base);

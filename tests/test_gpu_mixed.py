@@ -272,3 +272,35 @@ def test_banded_streaming_call_equals_plain_render(proc, st):
     want16 = proc.render_device(torch.from_numpy(u16).cuda(), stock, 6.0, 0.4, input_gain=32.0, **st).cpu().numpy()
     got16 = proc.process_preloaded(proc.extract_image_data_cpu(u16, input_gain=32.0, **st), stock, 6.0, 0.4, **st)
     assert np.array_equal(got16, want16)
+
+
+def test_black_and_white_stock_halation_through_fft(proc):
+    """B/W stocks filter all three layers with the same kernel (effects.py:248-250): the FFT path runs a second
+    transform pair for the third layer.  Taps vs the oracle, FFT vs forced direct correlation, uint8 <= 1 LSB."""
+    import torch
+
+    stock = SyntheticStock(density_measure="bw")
+    xyz = small_frame(400, 560, seed=19)
+    st = dict(frame_width=14.0, frame_height=10.0, grain=0, sharpness=True, halation_green_factor=0.4)   # 40 px/mm: 11x11
+    stages = {}
+    want = oracle_render(fo, xyz, stock, 6.0, 0.4, st, stages=stages)
+    x = torch.from_numpy(xyz).cuda()
+    proc.set_conv_path("fft")
+    try:
+        hal_fft = proc.render_tap(x, "halation", stock, 6.0, 0.4, **st).cpu().numpy()
+        dens_fft = proc.render_tap(x, "density", stock, 6.0, 0.4, **st).cpu().numpy()
+        got = proc.process(xyz, stock, 6.0, 0.4, **st)
+    finally:
+        proc.set_conv_path("direct")
+    try:
+        hal_dir = proc.render_tap(x, "halation", stock, 6.0, 0.4, **st).cpu().numpy()
+    finally:
+        proc.set_conv_path("auto")
+    assert proc.halation_kernel.shape[0] >= 9
+    assert not np.array_equal(stages["halation"][..., 2], stages["exposure"][..., 2])     # the blue layer is filtered
+    scale = float(stages["halation"].max())
+    assert np.abs(hal_fft - stages["halation"]).max() <= 1e-5 * scale
+    assert np.abs(hal_fft - hal_dir).max() <= 1e-5 * scale
+    assert np.abs(dens_fft - stages["density"]).max() <= 1e-4
+    diff = np.abs(got.astype(np.int16) - want.astype(np.int16))
+    assert diff.max() <= 1 and np.mean(diff != 0) < 2e-3
