@@ -16,9 +16,11 @@ struct Lut2D {
     const float *tab;    // (n, n, 3) lut[x_idx][y_idx], packed (the FFT row kernels park this 48 KB copy)
     const float4 *tab4;  // same vertices padded to float4: one 128-bit read per vertex
     int n;
-    __host__ __device__ Lut2D() : tab(nullptr), tab4(nullptr), n(0) {}
-    __host__ __device__ Lut2D(const float *t, int n_) : tab(t), tab4(nullptr), n(n_) {}
-    __host__ __device__ Lut2D(const float *t, const float4 *t4, int n_) : tab(t), tab4(t4), n(n_) {}
+    int pitch4;          // vertices per row of tab4 (n in global memory; n + 1 for the shared-memory copy of the fast
+                         // pointwise kernel, so that cells in neighbouring rows fall into different banks)
+    __host__ __device__ Lut2D() : tab(nullptr), tab4(nullptr), n(0), pitch4(0) {}
+    __host__ __device__ Lut2D(const float *t, int n_) : tab(t), tab4(nullptr), n(n_), pitch4(n_) {}
+    __host__ __device__ Lut2D(const float *t, const float4 *t4, int n_) : tab(t), tab4(t4), n(n_), pitch4(n_) {}
 };
 
 struct Curve1D {
@@ -161,10 +163,11 @@ __device__ __forceinline__ void lut2d_eval(const Lut2D &L, float X, float Y, flo
     const float wc = lower ? 1.0f - fs : fs - 1.0f;
     float a0, a1, a2, b0, b1, b2, c0, c1, c2;
     if (VEC4) {
-        const float4 *base = L.tab4 + (ri * n + gi);
-        const float4 *pa = base + n;                     // lut[ri+1][gi]
-        const float4 *pb = base + 1;                     // lut[ri][gi+1]
-        const float4 *pc = base + (lower ? 0 : n + 1);   // lut[ri][gi] or lut[ri+1][gi+1]
+        const int pitch = L.pitch4;
+        const float4 *base = L.tab4 + (ri * pitch + gi);
+        const float4 *pa = base + pitch;                     // lut[ri+1][gi]
+        const float4 *pb = base + 1;                         // lut[ri][gi+1]
+        const float4 *pc = base + (lower ? 0 : pitch + 1);   // lut[ri][gi] or lut[ri+1][gi+1]
         float4 va, vb, vc;
         if (SMEM) {
             va = lds_f32x4((unsigned)__cvta_generic_to_shared(pa));

@@ -54,9 +54,14 @@ __device__ __forceinline__ float4 noise_quad(uint32_t qx, uint32_t y, uint32_t c
     return make_float4(p.x, p.y, q.x, q.y);
 }
 
-__device__ __forceinline__ float noise_at(int x, int y, int ch, uint32_t k0, uint32_t k1) {
-    const float4 q = noise_quad((uint32_t)x >> 2, (uint32_t)y, (uint32_t)ch, k0, k1);
-    const int l = x & 3;
+// The field at pixel (x, y, ch): lane (x + shift) & 3 of quad (x + shift) >> 2.  `shift` = (grain kernel radius) & 3
+// puts the quad grid on the column grid of the fused kernels' noise tiles (tile column 0 is frame column
+// 64 * bx - radius), so that a tile row is filled with aligned 128-bit stores; every kernel that touches the field
+// of a render uses the same shift.
+__device__ __forceinline__ float noise_at(int x, int y, int ch, uint32_t k0, uint32_t k1, int shift) {
+    const uint32_t xs = (uint32_t)(x + shift);
+    const float4 q = noise_quad(xs >> 2, (uint32_t)y, (uint32_t)ch, k0, k1);
+    const int l = xs & 3;
     return l == 0 ? q.x : l == 1 ? q.y : l == 2 ? q.z : q.w;
 }
 

@@ -1044,6 +1044,7 @@ int render_body(r2f_ctx *c, const void *in, int in_format, float in_gain, int H,
         ga.k = c->t->grain.k;
         ga.kp = c->t->grain.kp;
         ga.bw = nch == 1;
+        ga.noise_shift = (c->t->grain.k / 2) & 3;
         ga.seed_lo = (uint32_t)c->t->seed;
         ga.seed_hi = (uint32_t)(c->t->seed >> 32);
         ga.gcurve = gcurve_of(c);
@@ -1077,7 +1078,7 @@ int render_body(r2f_ctx *c, const void *in, int in_format, float in_gain, int H,
             CU(launch_interleaved_to_planar(noise, nch, nch, P[2], npix, c->num_sms, st));
         } else {
             ProfScope ps_(c, st, R2F_PROF_NOISE);
-            CU(launch_noise(P[2], nch, H, W, c->t->seed, c->num_sms, st));
+            CU(launch_noise(P[2], nch, H, W, c->t->seed, (c->t->grain.k / 2) & 3, c->num_sms, st));
         }
         ConvArgs a = conv_args(c->t->grain, P[2].base, P[1 - cur].base, ps, H, W);
         for (int ch = 0; ch < 3; ++ch) a.in_plane[ch] = nch == 1 ? 0 : ch;
@@ -1611,7 +1612,7 @@ int r2f_generate_noise(r2f_ctx *c, float *out_dev, int H, int W, int channels, u
     const size_t ps = plane_stride_for(H, W), npix = (size_t)H * W;
     CU(c->h_noise.ensure(ps * 3 * sizeof(float)));
     Planes p{static_cast<float *>(c->h_noise.p), ps};
-    CU(launch_noise(p, channels, H, W, seed, c->num_sms, st));
+    CU(launch_noise(p, channels, H, W, seed, 0, c->num_sms, st));
     if (channels == 3) {
         CU(launch_planar_to_interleaved(p, out_dev, npix, c->num_sms, st));
     } else {

@@ -59,7 +59,10 @@ k_grain_finish_sym(const __grid_constant__ GrainFinishArgs a) {
     const int nch = a.bw ? 1 : 3;
     const int xs = tx0 - C::R;                                      // global x of tile column 0
     const bool interior = xs >= 0 && xs + C::COLS <= W;             // no horizontal reflection needed
-    const int q0 = xs >> 2, nq = ((xs + C::COLS - 1) >> 2) - q0 + 1;  // aligned noise quads covering a tile row
+    // quads of the shifted noise grid (noise.cuh): tile column 0 starts a quad, NQT of them cover a tile row
+    constexpr int NQT = (C::COLS + 3) / 4;
+    static_assert(4 * NQT <= C::PITCH, "a tile row of whole quads must fit the pitch");
+    const int q0 = (xs + a.noise_shift) >> 2;
     const int gx0 = tx0 + C::OW * warp;                             // first of the thread's 8 columns
     const bool vec_ok = (W & 3) == 0 && gx0 + C::OW <= W;           // whole 16-byte density loads
 
@@ -69,25 +72,18 @@ k_grain_finish_sym(const __grid_constant__ GrainFinishArgs a) {
         if (c < nch) {
             __syncthreads();  // the previous channel's window reads are done
             if (GEN) {
-                if (interior) {  // one Philox call per aligned quad of four samples
-                    // idx / nq by a reciprocal multiply (nq is CTA-uniform, idx < 2^16): exact, and ~20
-                    // instructions cheaper per quad than the generic division
-                    const unsigned magic = 0xffffffffu / (unsigned)nq + 1u;
-                    for (int idx = threadIdx.x; idx < C::ROWS * nq; idx += C::NT) {
-                        const int ty = (int)__umulhi((unsigned)idx, magic), tq = idx - ty * nq;
+                if (interior) {  // one Philox call and one aligned 128-bit store per quad of four samples
+                    for (int idx = threadIdx.x; idx < C::ROWS * NQT; idx += C::NT) {
+                        const int ty = idx / NQT, tq = idx - ty * NQT;  // compile-time divisor
                         const int gy = reflect101(ty0 - C::R + ty, H);
                         const float4 v = noise_quad((uint32_t)(q0 + tq), gy, c, a.seed_lo, a.seed_hi);
-                        const float vals[4] = {v.x, v.y, v.z, v.w};
-                        const int tx = 4 * (q0 + tq) - xs;
-#pragma unroll
-                        for (int l = 0; l < 4; ++l)
-                            if (tx + l >= 0 && tx + l < C::COLS) tile[ty * C::PITCH + tx + l] = vals[l];
+                        *reinterpret_cast<float4 *>(tile + ty * C::PITCH + 4 * tq) = v;
                     }
                 } else {
                     for (int idx = threadIdx.x; idx < C::ROWS * C::COLS; idx += C::NT) {
                         const int ty = idx / C::COLS, tx = idx - ty * C::COLS;
                         tile[ty * C::PITCH + tx] = noise_at(reflect101(xs + tx, W), reflect101(ty0 - C::R + ty, H), c,
-                                                            a.seed_lo, a.seed_hi);
+                                                            a.seed_lo, a.seed_hi, a.noise_shift);
                     }
                 }
             } else {

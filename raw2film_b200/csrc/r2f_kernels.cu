@@ -130,12 +130,18 @@ k_pointwise_fast(const void *__restrict__ in, float gain, uint8_t *__restrict__ 
     extern __shared__ __align__(16) float smem[];
     // shared memory: float4-padded 2-D LUT | scaled curve segments | per-warp queues
     {
-        const int n2f = l2.n * l2.n * 4, n1f = F.N * 3 * 2;
+        // row pitch n + 1 vertices: without the pad, cells in neighbouring rows are n * 16 bytes = a multiple of 128
+        // apart, i.e. in the same banks, and 40 % of the shared-memory wavefronts were conflicts (ncu r02_f)
+        const int n = l2.n, n2f = n * (n + 1) * 4, n1f = F.N * 3 * 2;
         const float *src2 = reinterpret_cast<const float *>(l2.tab4), *src1 = reinterpret_cast<const float *>(F.fseg);
-        for (int i = threadIdx.x; i < n2f / 4; i += NT) cp_async_16(smem + 4 * i, src2 + 4 * i);
+        for (int i = threadIdx.x; i < n * n; i += NT) {
+            const int r = i / n, col = i - r * n;
+            cp_async_16(smem + 4 * (r * (n + 1) + col), src2 + 4 * i);
+        }
         for (int i = threadIdx.x; i < n1f / 4; i += NT) cp_async_16(smem + n2f + 4 * i, src1 + 4 * i);
         for (int i = (n1f / 4) * 4 + threadIdx.x; i < n1f; i += NT) smem[n2f + i] = src1[i];
         l2.tab4 = reinterpret_cast<const float4 *>(smem);
+        l2.pitch4 = n + 1;
         F.fseg = reinterpret_cast<const float2 *>(smem + n2f);
         cp_async_wait_all();
         __syncthreads();
@@ -143,8 +149,8 @@ k_pointwise_fast(const void *__restrict__ in, float gain, uint8_t *__restrict__ 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     FastChainS S;
     S.lut2d = (unsigned)__cvta_generic_to_shared(smem);
-    S.row16 = (unsigned)l2.n * 16u;
-    S.n2 = l2.n;
+    S.row16 = (unsigned)(l2.n + 1) * 16u;
+    S.n2 = l2.n + 1;  // row pitch in vertices
     S.n2m1 = (float)(l2.n - 1);
     S.hi2 = (float)(l2.n - 2);
     S.eps = eps;
@@ -153,12 +159,12 @@ k_pointwise_fast(const void *__restrict__ in, float gain, uint8_t *__restrict__ 
     S.pscale = F.pscale;
     S.half_m = 0.5f - F.margin;
     for (int ch = 0; ch < 3; ++ch)
-        S.seg_w[ch] = S.lut2d + (unsigned)(l2.n * l2.n * 16) + (unsigned)(ch * F.N) * 8u - (kMagicBits << 3);
+        S.seg_w[ch] = S.lut2d + (unsigned)(l2.n * (l2.n + 1) * 16) + (unsigned)(ch * F.N) * 8u - (kMagicBits << 3);
     S.lut = F.lut255;
     S.n3 = F.n3;
     S.o111 = F.n3 * F.n3 + F.n3 + 1;
     S.neg_k = 0u - kMagicBits * (unsigned)S.o111;
-    unsigned *wq = reinterpret_cast<unsigned *>(smem + l2.n * l2.n * 4 + ((F.N * 3 * 2 + 3) & ~3)) + warp * kPwQueue;
+    unsigned *wq = reinterpret_cast<unsigned *>(smem + l2.n * (l2.n + 1) * 4 + ((F.N * 3 * 2 + 3) & ~3)) + warp * kPwQueue;
     int wq_count = 0;       // warp-uniform
     unsigned deferred = 0;  // lane 0 counts for the statistics
     const size_t nquad = npix / 4;
@@ -217,7 +223,7 @@ k_pointwise_fast(const void *__restrict__ in, float gain, uint8_t *__restrict__ 
 }
 
 size_t pointwise_fast_smem(const Lut2D &l2, const FastChain &F) {
-    return ((size_t)l2.n * l2.n * 4 + (((size_t)F.N * 3 * 2 + 3) & ~(size_t)3)) * sizeof(float) +
+    return ((size_t)l2.n * (l2.n + 1) * 4 + (((size_t)F.N * 3 * 2 + 3) & ~(size_t)3)) * sizeof(float) +
            (size_t)(1024 / 32) * kPwQueue * sizeof(unsigned);
 }
 
@@ -927,8 +933,8 @@ cudaError_t launch_interleaved_to_planar(const float *in, int cin, int nch, Plan
 // (reference GPU path: PCG-3D hash + Box-Muller, shaders/noise.wgsl:14-62; streams differ by design)
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kThreads)
-k_noise(float *__restrict__ out, size_t plane_stride, int nch, int H, int W, uint32_t k0, uint32_t k1) {
-    const int qw = (W + 3) >> 2;
+k_noise(float *__restrict__ out, size_t plane_stride, int nch, int H, int W, uint32_t k0, uint32_t k1, int shift) {
+    const int qw = (W + shift + 3) >> 2;  // quads of the shifted grid that touch columns 0 .. W-1
     const size_t per_ch = (size_t)H * qw, total = per_ch * nch;
     const size_t stride = (size_t)gridDim.x * kThreads;
     for (size_t t = (size_t)blockIdx.x * kThreads + threadIdx.x; t < total; t += stride) {
@@ -936,18 +942,20 @@ k_noise(float *__restrict__ out, size_t plane_stride, int nch, int H, int W, uin
         const size_t rem = t - (size_t)ch * per_ch;
         const int y = (int)(rem / qw), qx = (int)(rem - (size_t)y * qw);
         const float4 v = noise_quad(qx, y, ch, k0, k1);
-        float *row = out + (size_t)ch * plane_stride + (size_t)y * W + 4 * qx;
+        float *row = out + (size_t)ch * plane_stride + (size_t)y * W;
         const float vals[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-        for (int l = 0; l < 4; ++l)
-            if (4 * qx + l < W) row[l] = vals[l];
+        for (int l = 0; l < 4; ++l) {
+            const int x = 4 * qx + l - shift;
+            if (x >= 0 && x < W) row[x] = vals[l];
+        }
     }
 }
 
-cudaError_t launch_noise(Planes out, int nch, int H, int W, uint64_t seed, int num_sms, cudaStream_t st) {
-    const size_t items = (size_t)H * ((W + 3) / 4) * nch;
+cudaError_t launch_noise(Planes out, int nch, int H, int W, uint64_t seed, int shift, int num_sms, cudaStream_t st) {
+    const size_t items = (size_t)H * ((W + shift + 3) / 4) * nch;
     k_noise<<<grid_for(items, num_sms, 8), kThreads, 0, st>>>(out.base, out.plane_stride, nch, H, W, (uint32_t)seed,
-                                                             (uint32_t)(seed >> 32));
+                                                             (uint32_t)(seed >> 32), shift);
     return cudaGetLastError();
 }
 
@@ -980,7 +988,7 @@ k_grain_finish(GrainFinishArgs a) {
     const int nch = a.bw ? 1 : 3;
     const int xs = tx0 - rad;                                  // global x of tile column 0
     const bool interior = xs >= 0 && xs + cols <= W;           // no horizontal reflection needed
-    const int q0 = xs >> 2, nq = ((xs + cols - 1) >> 2) - q0 + 1;  // aligned noise quads covering the tile row
+    const int q0 = (xs + a.noise_shift) >> 2, nq = (cols + 3) >> 2;  // quads of the shifted grid covering the tile row
 #pragma unroll 1
     for (int c = 0; c < 3; ++c) {
         // issue this channel's 16 density loads first: their latency hides behind the noise generation
@@ -995,22 +1003,22 @@ k_grain_finish(GrainFinishArgs a) {
         if (c < nch) {
             __syncthreads();  // previous channel's window reads are done
             if (GEN) {
-                if (interior) {  // one Philox call per aligned quad of four samples
+                if (interior) {  // one Philox call per quad of four samples (quads start on tile columns 0, 4, ...)
                     for (int idx = threadIdx.x; idx < rows * nq; idx += 256) {
                         const int ty = idx / nq, tq = idx - ty * nq;
                         const int gy = reflect101(ty0 - rad + ty, H);
                         const float4 v = noise_quad((uint32_t)(q0 + tq), gy, c, a.seed_lo, a.seed_hi);
                         const float vals[4] = {v.x, v.y, v.z, v.w};
-                        const int tx = 4 * (q0 + tq) - xs;
+                        const int tx = 4 * tq;
 #pragma unroll
                         for (int l = 0; l < 4; ++l)
-                            if (tx + l >= 0 && tx + l < cols) tile[ty * cols + tx + l] = vals[l];
+                            if (tx + l < cols) tile[ty * cols + tx + l] = vals[l];
                     }
                 } else {
                     for (int idx = threadIdx.x; idx < rows * cols; idx += 256) {
                         const int ty = idx / cols, tx = idx - ty * cols;
                         tile[idx] = noise_at(reflect101(tx0 - rad + tx, W), reflect101(ty0 - rad + ty, H), c, a.seed_lo,
-                                             a.seed_hi);
+                                             a.seed_hi, a.noise_shift);
                     }
                 }
             } else {

@@ -100,7 +100,8 @@ cudaError_t launch_planar_to_interleaved(Planes in, float *out, size_t npix, int
 cudaError_t launch_interleaved_to_planar(const float *in, int cin, int nch, Planes out, size_t npix, int num_sms,
                                          cudaStream_t st);
 // white N(0,1) noise, Philox4x32-10 + Box-Muller, planar
-cudaError_t launch_noise(Planes out, int nch, int H, int W, uint64_t seed, int num_sms, cudaStream_t st);
+// `shift`: column shift of the field's quad grid, (grain kernel radius) & 3 inside a render (noise.cuh)
+cudaError_t launch_noise(Planes out, int nch, int H, int W, uint64_t seed, int shift, int num_sms, cudaStream_t st);
 // fused grain + burn apply + tetrahedral LUT + quantise (normal render path)
 struct GrainFinishArgs {
     const float *dens;   // planar density (after MTF)
@@ -119,6 +120,7 @@ struct GrainFinishArgs {
     BurnArgs burn;
     uint8_t *out_u8;
     int tile_y0, tile_rows;  // first tile row and tile-row count of this launch (0, 0 = all): banded output
+    int noise_shift;         // (k / 2) & 3: column shift of the noise field's quad grid (noise.cuh)
 };
 cudaError_t launch_grain_finish(const GrainFinishArgs &a, cudaStream_t st);
 // same contract for y-symmetric grain kernels without burn (r2f_grain_sym.cu): row-pair sums + packed FMA
