@@ -116,68 +116,80 @@ k_resize_area_int_u8(const uint8_t *__restrict__ src, int cin, int sw, uint8_t *
     }
 }
 
-__global__ void __launch_bounds__(kRsThreads)
-k_resize_lanczos4_u8(const uint8_t *__restrict__ src, int cin, int sw, int sh, uint8_t *__restrict__ dst, int dw,
-                     int dh, LanczosTabDev xt, LanczosTabDev yt) {
-    const size_t total = (size_t)dw * dh;
-    for (size_t p = (size_t)blockIdx.x * kRsThreads + threadIdx.x; p < total; p += (size_t)gridDim.x * kRsThreads) {
-        const int dy = (int)(p / dw), dx = (int)(p - (size_t)dy * dw);
-        const int sx = xt.ofs[dx], sy = yt.ofs[dy];
-        int xi[8], ia[8];
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            xi[k] = min(max(sx + k - 3, 0), sw - 1) * cin;
-            ia[k] = xt.icoef[dx * 8 + k];
-        }
-        int acc[3] = {0, 0, 0};
-#pragma unroll 1
-        for (int j = 0; j < 8; ++j) {
-            const uint8_t *row = src + (size_t)min(max(sy + j - 3, 0), sh - 1) * sw * cin;
-            const int ib = yt.icoef[dy * 8 + j];
-            int h[3] = {0, 0, 0};
-#pragma unroll
-            for (int k = 0; k < 8; ++k)
-#pragma unroll
-                for (int c = 0; c < 3; ++c) h[c] += (int)__ldg(row + xi[k] + c) * ia[k];
-#pragma unroll
-            for (int c = 0; c < 3; ++c) acc[c] += h[c] * ib;
-        }
-#pragma unroll
-        for (int c = 0; c < 3; ++c) dst[p * 3 + c] = (uint8_t)min(max((acc[c] + (1 << 21)) >> 22, 0), 255);
-    }
-}
+// One thread per column and strip of VS vertically adjacent destination pixels: when enlarging, neighbouring
+// destination rows share most of their eight source rows, so the horizontal 8-tap sums of a source row are formed
+// once and fed to every destination row of the strip that uses it (2.5x fewer loads than one pixel per thread at
+// 1.5x enlargement).  Each destination pixel still accumulates its rows in tap order j = 0..7, so the float32
+// result is the same as the pixel-per-thread form; the uint8 form is integer arithmetic.
+constexpr int kLzStrip = 4;
 
+template <typename T>
+struct LzAcc;
+template <>
+struct LzAcc<uint8_t> {
+    typedef int acc_t;
+    static __device__ __forceinline__ int coef(const LanczosTabDev &t, int i) { return t.icoef[i]; }
+    static __device__ __forceinline__ int load(const uint8_t *p) { return (int)__ldg(p); }
+    static __device__ __forceinline__ uint8_t store(int v) { return (uint8_t)min(max((v + (1 << 21)) >> 22, 0), 255); }
+};
+template <>
+struct LzAcc<float> {
+    typedef float acc_t;
+    static __device__ __forceinline__ float coef(const LanczosTabDev &t, int i) { return t.coef[i]; }
+    static __device__ __forceinline__ float load(const float *p) { return __ldg(p); }
+    static __device__ __forceinline__ float store(float v) { return v; }
+};
+
+template <typename T>
 __global__ void __launch_bounds__(kRsThreads)
-k_resize_lanczos4_f32(const float *__restrict__ src, int cin, int sw, int sh, float *__restrict__ dst, int dw, int dh,
-                      LanczosTabDev xt, LanczosTabDev yt) {
-    const size_t total = (size_t)dw * dh;
+k_resize_lanczos4(const T *__restrict__ src, int cin, int sw, int sh, T *__restrict__ dst, int dw, int dh,
+                  LanczosTabDev xt, LanczosTabDev yt) {
+    typedef typename LzAcc<T>::acc_t A;
+    const int nstrips = (dh + kLzStrip - 1) / kLzStrip;
+    const size_t total = (size_t)dw * nstrips;
     for (size_t p = (size_t)blockIdx.x * kRsThreads + threadIdx.x; p < total; p += (size_t)gridDim.x * kRsThreads) {
-        const int dy = (int)(p / dw), dx = (int)(p - (size_t)dy * dw);
-        const int sx = xt.ofs[dx], sy = yt.ofs[dy];
+        const int strip = (int)(p / dw), dx = (int)(p - (size_t)strip * dw);
+        const int dy0 = strip * kLzStrip, ny = min(kLzStrip, dh - dy0);
+        const int sx = xt.ofs[dx];
         int xi[8];
-        float fa[8];
+        A ca[8];
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
             xi[k] = min(max(sx + k - 3, 0), sw - 1) * cin;
-            fa[k] = xt.coef[dx * 8 + k];
+            ca[k] = LzAcc<T>::coef(xt, dx * 8 + k);
         }
-        float acc[3] = {0.f, 0.f, 0.f};
-#pragma unroll 1
-        for (int j = 0; j < 8; ++j) {
-            const float *row = src + (size_t)min(max(sy + j - 3, 0), sh - 1) * sw * cin;
-            const float fb = yt.coef[dy * 8 + j];
-            float h[3];
+        int sy[kLzStrip];
+        A acc[kLzStrip][3];
 #pragma unroll
-            for (int c = 0; c < 3; ++c) h[c] = __ldg(row + xi[0] + c) * fa[0];
+        for (int o = 0; o < kLzStrip; ++o) {
+            sy[o] = yt.ofs[min(dy0 + o, dh - 1)] - 3;  // first (unclamped) source row of destination row dy0 + o
+            acc[o][0] = acc[o][1] = acc[o][2] = (A)0;
+        }
+        const int r_first = sy[0], r_last = sy[ny - 1] + 7;  // yt.ofs is non-decreasing
+        for (int rr = r_first; rr <= r_last; ++rr) {
+            const T *row = src + (size_t)min(max(rr, 0), sh - 1) * sw * cin;
+            A h[3];
+#pragma unroll
+            for (int c = 0; c < 3; ++c) h[c] = LzAcc<T>::load(row + xi[0] + c) * ca[0];
 #pragma unroll
             for (int k = 1; k < 8; ++k)
 #pragma unroll
-                for (int c = 0; c < 3; ++c) h[c] = h[c] + __ldg(row + xi[k] + c) * fa[k];
+                for (int c = 0; c < 3; ++c) h[c] = h[c] + LzAcc<T>::load(row + xi[k] + c) * ca[k];
 #pragma unroll
-            for (int c = 0; c < 3; ++c) acc[c] = j == 0 ? h[c] * fb : acc[c] + h[c] * fb;
+            for (int o = 0; o < kLzStrip; ++o) {
+                const int j = rr - sy[o];
+                if (o < ny && j >= 0 && j < 8) {
+                    const A cb = LzAcc<T>::coef(yt, (dy0 + o) * 8 + j);
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) acc[o][c] = j == 0 ? h[c] * cb : acc[o][c] + h[c] * cb;
+                }
+            }
         }
 #pragma unroll
-        for (int c = 0; c < 3; ++c) dst[p * 3 + c] = acc[c];
+        for (int o = 0; o < kLzStrip; ++o)
+            if (o < ny)
+#pragma unroll
+                for (int c = 0; c < 3; ++c) dst[((size_t)(dy0 + o) * dw + dx) * 3 + c] = LzAcc<T>::store(acc[o][c]);
     }
 }
 
@@ -290,13 +302,13 @@ cudaError_t launch_resize_area_int(const void *src, bool u8, int cin, int sh, in
 
 cudaError_t launch_resize_lanczos4(const void *src, bool u8, int cin, int sh, int sw, void *dst, int dh, int dw,
                                    const LanczosTabDev &xt, const LanczosTabDev &yt, int num_sms, cudaStream_t st) {
-    const int grid = grid_for((size_t)dw * dh, num_sms);
+    const int grid = grid_for((size_t)dw * ((dh + kLzStrip - 1) / kLzStrip), num_sms);
     if (u8)
-        k_resize_lanczos4_u8<<<grid, kRsThreads, 0, st>>>(static_cast<const uint8_t *>(src), cin, sw, sh,
-                                                          static_cast<uint8_t *>(dst), dw, dh, xt, yt);
+        k_resize_lanczos4<uint8_t><<<grid, kRsThreads, 0, st>>>(static_cast<const uint8_t *>(src), cin, sw, sh,
+                                                                 static_cast<uint8_t *>(dst), dw, dh, xt, yt);
     else
-        k_resize_lanczos4_f32<<<grid, kRsThreads, 0, st>>>(static_cast<const float *>(src), cin, sw, sh,
-                                                           static_cast<float *>(dst), dw, dh, xt, yt);
+        k_resize_lanczos4<float><<<grid, kRsThreads, 0, st>>>(static_cast<const float *>(src), cin, sw, sh,
+                                                               static_cast<float *>(dst), dw, dh, xt, yt);
     return cudaGetLastError();
 }
 
