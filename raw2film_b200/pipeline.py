@@ -229,7 +229,11 @@ class PreviewGraph:
     def replay(self):
         if self.proc.table_version != self._version:
             raise RuntimeError("tables changed since this graph was captured: capture a new PreviewGraph")
-        with self._torch.cuda.stream(self._stream):
+        torch = self._torch
+        caller = torch.cuda.current_stream(self.proc.device)
+        self._stream.wait_stream(caller)              # the caller's writes to `frame` come first ...
+        with torch.cuda.stream(self._stream):
             self.graph.replay()
         _cabi.check(_cabi.lib.r2f_stream_mark(self.proc._ctx, self._stream.cuda_stream))
+        caller.wait_stream(self._stream)              # ... and its reads of `out` after the replay (no host sync)
         return self.out

@@ -361,6 +361,7 @@ class B200Processor:
         x = frame if torch.is_tensor(frame) else torch.from_numpy(np.ascontiguousarray(frame))
         if x.dtype not in (torch.float32, torch.uint16) or x.ndim != 3 or x.shape[2] not in (3, 4):
             raise ValueError("frame must be (H, W, 3|4) float32 or uint16")
+        self.stream.wait_stream(torch.cuda.current_stream(self.device))   # a device frame may still be in the making
         with torch.cuda.stream(self.stream):
             x = x.to(self.device, non_blocking=True).contiguous()
             mean = ctypes.c_double(0.0)
@@ -680,7 +681,7 @@ class B200Processor:
             self._pipe = PipelinedRenderer(self, depth=3, bands=int(os.environ.get("R2F_CALL_BANDS", "8")))
         return self._pipe
 
-    def resize_device(self, x_dev, size, out=None, stream=None):
+    def resize_device(self, x_dev, size, out=None, stream=None, sync_caller=None):
         """cv2.resize on the device the way `resolution_scaling` (reference utils.py:226-244) picks the filter:
         INTER_AREA when `size` = (rows, cols) is smaller than the image, INTER_LANCZOS4 when larger.  `x_dev`: float32
         (H, W, 3|4) or uint8 (H, W, 3) CUDA tensor; returns (rows, cols, 3) of the same dtype."""
@@ -694,13 +695,20 @@ class B200Processor:
             raise ValueError("resize_device keeps the aspect ratio: both sides shrink or both grow")
         if out is None or tuple(out.shape) != (rows, cols, 3) or out.dtype != x_dev.dtype:
             out = torch.empty((rows, cols, 3), dtype=x_dev.dtype, device=self.device)
+        if sync_caller is None:                       # a caller that names the stream orders the work itself
+            sync_caller = stream is None
         stream = self.stream if stream is None else stream
+        caller = torch.cuda.current_stream(self.device)
+        if sync_caller:
+            stream.wait_stream(caller)
         _cabi.check(_cabi.lib.r2f_resize(
             self._ctx, x_dev.data_ptr(), _cabi.PIX_U8 if x_dev.dtype == torch.uint8 else _cabi.PIX_F32, h, w, ch,
             out.data_ptr(), rows, cols, _cabi.INTER_AREA if shrink else _cabi.INTER_LANCZOS4, stream.cuda_stream))
+        if sync_caller:
+            caller.wait_stream(stream)
         return out
 
-    def present(self, image_dev, dst, canvas_colour=(255, 255, 255), stream=None):
+    def present(self, image_dev, dst, canvas_colour=(255, 255, 255), stream=None, sync_caller=None):
         """Blit a rendered uint8 (H, W, 3) CUDA tensor into `dst`, a uint8 (dst_h, dst_w, 4) CUDA tensor standing for
         the preview widget's texture: scaled to fit, letterboxed, canvas area filled (the reference's last GPU
         pass, shaders/copy_to_int.wgsl; geometry from the processor's pipeline / output / canvas resolutions like
@@ -712,10 +720,17 @@ class B200Processor:
             raise ValueError("dst must be a contiguous uint8 (h, w, 4) CUDA tensor")
         t = np.asarray(hostops.present_geometry((w, h), (dw, dh), self.pipeline_resolution, self.output_resolution,
                                                 self.canvas_resolution), dtype=F32)
+        if sync_caller is None:
+            sync_caller = stream is None
         stream = self.stream if stream is None else stream
+        caller = torch.cuda.current_stream(self.device)
+        if sync_caller:
+            stream.wait_stream(caller)
         r, g, b = (int(v) for v in canvas_colour)
         _cabi.check(_cabi.lib.r2f_present(self._ctx, image_dev.data_ptr(), h, w, dst.data_ptr(), dh, dw,
                                           _cabi.f32_ptr(t), r, g, b, stream.cuda_stream))
+        if sync_caller:
+            caller.wait_stream(stream)
         return dst
 
     def pinned_frame(self, h: int, w: int, channels: int = 3, dtype=np.float32) -> np.ndarray:
