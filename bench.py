@@ -420,7 +420,24 @@ def main():
         lat = np.sort(np.asarray(lat))
         latency["from_24mp"] = {"p50_ms": float(lat[len(lat) // 2]), "p99_ms": float(lat[int(len(lat) * 0.99)]),
                                 "what": "device INTER_AREA 6000x4000 -> 1620x1080 + pointwise render, per call"}
-        del big, small
+        del small
+        # (iii) the reference's own preview call (gui.py:2197-2224): process(src, resolution=widget size) on a 24 MP
+        # frame whose image parameters have not changed, so the frame stays on the device and only the shrink, the
+        # render and the 6 MB read-back happen per call
+        src24 = natural_frame(4000, 6000, 77, out=proc.pinned_frame(4000, 6000))
+        pv = dict(settings, resolution=(H, W), max_scale=None, cache=True, own_result=False)
+        proc.process(src24, stock, GRAIN_SIZE, GRAIN_SIGMA, **pv)
+        lat = []
+        for i in range(200):
+            t0 = time.perf_counter()
+            proc.process(src24, stock, GRAIN_SIZE, GRAIN_SIGMA, **pv)
+            lat.append((time.perf_counter() - t0) * 1e3)
+        lat = np.sort(np.asarray(lat))
+        latency["process_call_24mp_source"] = {
+            "p50_ms": float(lat[len(lat) // 2]), "p99_ms": float(lat[int(len(lat) * 0.99)]),
+            "what": "B200Processor.process(frame, resolution=(1080, 1920)) with the 24 MP frame cached on the device: "
+                    "INTER_AREA shrink + render + read-back of the 1620x1080 result, host array returned"}
+        del big
 
     # --- timed, end to end through the public API (pinned host in, host out) ---------------------
     # (a) the reference's entry point for preloaded frames, one synchronous call per frame
