@@ -1625,8 +1625,8 @@ int r2f_generate_noise(r2f_ctx *c, float *out_dev, int H, int W, int channels, u
 int r2f_chroma_nr(r2f_ctx *c, const float *in_dev, int in_channels, float *out_dev, int H, int W, const float *taps,
                   int ntaps, void *workspace_dev, size_t workspace_bytes, void *stream) {
     if (!c || !in_dev || !out_dev || !taps || H < 1 || W < 1 || ntaps < 1 || (ntaps & 1) == 0 ||
-        (in_channels != 3 && in_channels != 4))
-        return fail(R2F_ERR_INVALID, "r2f_chroma_nr: bad arguments");
+        (in_channels != 3 && in_channels != 4) || ntaps > 49)
+        return fail(R2F_ERR_INVALID, "r2f_chroma_nr: bad arguments (odd tap count up to 49)");
     DeviceGuard guard(c->device);
     const size_t ps = plane_stride_for(H, W);
     if (!workspace_dev || workspace_bytes < ps * 6 * sizeof(float))
@@ -1636,7 +1636,7 @@ int r2f_chroma_nr(r2f_ctx *c, const float *in_dev, int in_channels, float *out_d
     CU(cudaMemcpyAsync(c->cnr_taps.p, taps, (size_t)ntaps * sizeof(float), cudaMemcpyHostToDevice, st));
     CU(launch_chroma_nr(in_dev, in_channels, out_dev, H, W, static_cast<const float *>(c->cnr_taps.p), ntaps,
                         static_cast<float *>(workspace_dev), ps, c->num_sms, st));
-    c->launches += 3;
+    c->launches += 2;
     return R2F_OK;
 }
 

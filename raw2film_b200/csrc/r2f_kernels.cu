@@ -679,56 +679,78 @@ k_interleaved_to_planar(const float *__restrict__ in, int cin, int nch, float *_
 
 // ------------------------------------------------------------------------------------------
 // chroma noise reduction (reference effects.py:421-561; SURVEY 8f-3, runs BEFORE the render path)
-//   k_cnr_to_xyY : XYZ -> planar (x, y, Y)                      effects.py:497-519
-//   k_cnr_blur   : edge-clamped 1-D Gaussian on the x and y planes; float32 products accumulated
-//                  in binary64 in tap order, like the numba loops   effects.py:438-482
-//   k_cnr_finish : vertical pass + xyY -> XYZ                    effects.py:463-482, 522-544
+//   k_cnr_rows : XYZ -> (x, y, Y) (effects.py:497-519) and the horizontal pass of the edge-clamped 1-D Gaussian
+//                on x and y (effects.py:438-460), fused: a CTA turns a row segment plus its tap halo into
+//                chromaticities in shared memory and blurs from there; Y goes to its plane
+//   k_cnr_cols : vertical pass (effects.py:463-482) from a shared-memory tile of the row-blurred planes, then
+//                xyY -> XYZ (effects.py:522-544)
+// float32 products accumulated in binary64 in tap order, one rounding per pass, like the numba loops.
+// (the first version was three per-pixel kernels with per-tap global loads: 0.83 ms at 24 MP, size 3.)
 // ------------------------------------------------------------------------------------------
+constexpr int kCnrSeg = 512;      // outputs per CTA of the row kernel (two per thread)
+constexpr int kCnrMaxHalf = 24;   // chroma_nr <= 20 in the reference GUI (slider 0..10, doubled on export)
+constexpr int kCnrTileW = 64, kCnrTileH = 32;
+
 __global__ void __launch_bounds__(kThreads)
-k_cnr_to_xyY(const float *__restrict__ in, int cin, float *__restrict__ out, size_t ps, size_t npix) {
-    const size_t stride = (size_t)gridDim.x * kThreads;
-    for (size_t p = (size_t)blockIdx.x * kThreads + threadIdx.x; p < npix; p += stride) {
-        const float X = in[p * cin], Y = in[p * cin + 1], Z = in[p * cin + 2];
+k_cnr_rows(const float *__restrict__ in, int cin, float *__restrict__ tmp, float *__restrict__ yplane, size_t ps, int H,
+           int W, const float *__restrict__ taps, int half) {
+    __shared__ float sx[kCnrSeg + 2 * kCnrMaxHalf], sy[kCnrSeg + 2 * kCnrMaxHalf];
+    __shared__ float st[2 * kCnrMaxHalf + 1];
+    const int y = blockIdx.y, x0 = blockIdx.x * kCnrSeg;
+    const int n = min(kCnrSeg, W - x0), span = n + 2 * half;
+    for (int i = threadIdx.x; i <= 2 * half; i += kThreads) st[i] = taps[i];
+    const float *row = in + (size_t)y * W * cin;
+    for (int i = threadIdx.x; i < span; i += kThreads) {
+        const int gx = min(max(x0 - half + i, 0), W - 1);  // edge clamp of the blur = chromaticity of the clamped pixel
+        const float X = row[(size_t)gx * cin], Y = row[(size_t)gx * cin + 1], Z = row[(size_t)gx * cin + 2];
         const float denom = (X + Y) + Z;
         const bool ok = denom > 1e-8f;
-        out[p] = ok ? __fdiv_rn(X, denom) : 0.0f;
-        out[ps + p] = ok ? __fdiv_rn(Y, denom) : 0.0f;
-        out[2 * ps + p] = Y;
+        sx[i] = ok ? __fdiv_rn(X, denom) : 0.0f;
+        sy[i] = ok ? __fdiv_rn(Y, denom) : 0.0f;
+        if (i >= half && i < half + n) yplane[(size_t)y * W + x0 + i - half] = Y;
     }
-}
-
-__device__ __forceinline__ float cnr_tap_sum(const float *__restrict__ plane, int y, int x, int H, int W,
-                                             const float *__restrict__ taps, int half, bool vertical) {
-    double acc = 0.0;
-    for (int i = -half; i <= half; ++i) {
-        const int yy = vertical ? min(max(y + i, 0), H - 1) : y;
-        const int xx = vertical ? x : min(max(x + i, 0), W - 1);
-        acc += (double)(plane[(size_t)yy * W + xx] * taps[i + half]);  // float32 product, binary64 sum
-    }
-    return (float)acc;
-}
-
-__global__ void __launch_bounds__(kThreads)
-k_cnr_blur_h(const float *__restrict__ in, float *__restrict__ out, size_t ps, int H, int W,
-             const float *__restrict__ taps, int half) {
-    const size_t npix = (size_t)H * W, stride = (size_t)gridDim.x * kThreads;
-    for (size_t p = (size_t)blockIdx.x * kThreads + threadIdx.x; p < 2 * npix; p += stride) {
-        const int c = (int)(p / npix);
-        const size_t q = p - (size_t)c * npix;
-        const int y = (int)(q / W), x = (int)(q - (size_t)y * W);
-        out[c * ps + q] = cnr_tap_sum(in + c * ps, y, x, H, W, taps, half, false);
+    __syncthreads();
+    for (int o = threadIdx.x; o < n; o += kThreads) {
+        double ax = 0.0, ay = 0.0;
+        for (int t = 0; t <= 2 * half; ++t) {
+            const float w = st[t];
+            ax += (double)(sx[o + t] * w);  // float32 product, binary64 sum
+            ay += (double)(sy[o + t] * w);
+        }
+        const size_t idx = (size_t)y * W + x0 + o;
+        tmp[idx] = (float)ax;
+        tmp[ps + idx] = (float)ay;
     }
 }
 
 __global__ void __launch_bounds__(kThreads)
-k_cnr_finish(const float *__restrict__ blurred_h, const float *__restrict__ xyY, float *__restrict__ out, size_t ps,
-             int H, int W, const float *__restrict__ taps, int half) {
-    const size_t npix = (size_t)H * W, stride = (size_t)gridDim.x * kThreads;
-    for (size_t p = (size_t)blockIdx.x * kThreads + threadIdx.x; p < npix; p += stride) {
-        const int y = (int)(p / W), x = (int)(p - (size_t)y * W);
-        const float cx = cnr_tap_sum(blurred_h, y, x, H, W, taps, half, true);
-        const float cy = cnr_tap_sum(blurred_h + ps, y, x, H, W, taps, half, true);
-        const float Y = xyY[2 * ps + p];
+k_cnr_cols(const float *__restrict__ tmp, const float *__restrict__ yplane, float *__restrict__ out, size_t ps, int H,
+           int W, const float *__restrict__ taps, int half) {
+    extern __shared__ __align__(16) float tile[];  // [2][kCnrTileH + 2*half][kCnrTileW]
+    __shared__ float st[2 * kCnrMaxHalf + 1];
+    const int x0 = blockIdx.x * kCnrTileW, y0 = blockIdx.y * kCnrTileH;
+    const int rows = kCnrTileH + 2 * half;
+    for (int i = threadIdx.x; i <= 2 * half; i += kThreads) st[i] = taps[i];
+    for (int i = threadIdx.x; i < 2 * rows * kCnrTileW; i += kThreads) {
+        const int c = i / (rows * kCnrTileW), r = (i / kCnrTileW) % rows, col = i % kCnrTileW;
+        const int gy = min(max(y0 - half + r, 0), H - 1), gx = min(x0 + col, W - 1);
+        tile[i] = tmp[c * ps + (size_t)gy * W + gx];
+    }
+    __syncthreads();
+    const float *tx = tile, *ty = tile + rows * kCnrTileW;
+    for (int i = threadIdx.x; i < kCnrTileH * kCnrTileW; i += kThreads) {
+        const int r = i / kCnrTileW, col = i % kCnrTileW;
+        const int gy = y0 + r, gx = x0 + col;
+        if (gy >= H || gx >= W) continue;
+        double ax = 0.0, ay = 0.0;
+        for (int t = 0; t <= 2 * half; ++t) {
+            const float w = st[t];
+            ax += (double)(tx[(r + t) * kCnrTileW + col] * w);
+            ay += (double)(ty[(r + t) * kCnrTileW + col] * w);
+        }
+        const float cx = (float)ax, cy = (float)ay;
+        const size_t p = (size_t)gy * W + gx;
+        const float Y = yplane[p];
         float X = 0.0f, Yo = 0.0f, Z = 0.0f;
         if (cy > 1e-8f) {
             const float inv = __fdiv_rn(Y, cy);
@@ -744,11 +766,16 @@ k_cnr_finish(const float *__restrict__ blurred_h, const float *__restrict__ xyY,
 
 cudaError_t launch_chroma_nr(const float *in, int cin, float *out, int H, int W, const float *taps_dev, int ntaps,
                              float *ws /* 6 planes */, size_t ps, int num_sms, cudaStream_t st) {
-    const size_t npix = (size_t)H * W;
-    float *xyY = ws, *tmp = ws + 3 * ps;
-    k_cnr_to_xyY<<<grid_for(npix, num_sms, 8), kThreads, 0, st>>>(in, cin, xyY, ps, npix);
-    k_cnr_blur_h<<<grid_for(2 * npix, num_sms, 8), kThreads, 0, st>>>(xyY, tmp, ps, H, W, taps_dev, ntaps / 2);
-    k_cnr_finish<<<grid_for(npix, num_sms, 8), kThreads, 0, st>>>(tmp, xyY, out, ps, H, W, taps_dev, ntaps / 2);
+    (void)num_sms;
+    const int half = ntaps / 2;
+    if (half > kCnrMaxHalf) return cudaErrorInvalidValue;
+    float *tmp = ws, *yplane = ws + 2 * ps;
+    k_cnr_rows<<<dim3((W + kCnrSeg - 1) / kCnrSeg, H), kThreads, 0, st>>>(in, cin, tmp, yplane, ps, H, W, taps_dev, half);
+    const size_t smem = (size_t)2 * (kCnrTileH + 2 * half) * kCnrTileW * sizeof(float);
+    cudaError_t e = cudaFuncSetAttribute(k_cnr_cols, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    k_cnr_cols<<<dim3((W + kCnrTileW - 1) / kCnrTileW, (H + kCnrTileH - 1) / kCnrTileH), kThreads, smem, st>>>(
+        tmp, yplane, out, ps, H, W, taps_dev, half);
     return cudaGetLastError();
 }
 
