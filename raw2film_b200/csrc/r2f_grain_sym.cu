@@ -66,6 +66,34 @@ k_grain_finish_sym(const __grid_constant__ GrainFinishArgs a) {
     const int gx0 = tx0 + C::OW * warp;                             // first of the thread's 8 columns
     const bool vec_ok = (W & 3) == 0 && gx0 + C::OW <= W;           // whole 16-byte density loads
 
+    // The densities of all three layers are requested up front as asynchronous global -> shared copies (LDGSTS, no
+    // register, nothing waits) into the thread's own slots of `priv`; the grain apply overwrites them in place with the
+    // grained densities.  Slot layout [channel][chunk j = 2*h + half][thread] of float4: 128-bit accesses, consecutive
+    // threads in consecutive 16-byte slots.  (With the loads next to their use, 15 % of the kernel's stall samples were
+    // the HBM latency of this read.)
+    float4 *priv4 = reinterpret_cast<float4 *>(priv);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        const float *dplane = a.dens + c * ps;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int gy = ty0 + lane + 32 * h;
+            float4 *slot = priv4 + (c * 4 + 2 * h) * C::NT + threadIdx.x;
+            if (gy < H && vec_ok) {
+                const float *p = dplane + (size_t)gy * W + gx0;
+                cp_async_16(reinterpret_cast<float *>(slot), p);
+                cp_async_16(reinterpret_cast<float *>(slot + C::NT), p + 4);
+            } else {
+                float d[C::OW];
+#pragma unroll
+                for (int o = 0; o < C::OW; ++o)
+                    d[o] = (gy < H && gx0 + o < W) ? __ldcs(dplane + (size_t)gy * W + gx0 + o) : 0.0f;
+                slot[0] = make_float4(d[0], d[1], d[2], d[3]);
+                slot[C::NT] = make_float4(d[4], d[5], d[6], d[7]);
+            }
+        }
+    }
+
     float2 g[C::OW];
 #pragma unroll 1
     for (int c = 0; c < 3; ++c) {
@@ -97,28 +125,22 @@ k_grain_finish_sym(const __grid_constant__ GrainFinishArgs a) {
             sym_correlate<K, C::OW, C::PITCH, C::WROW>(ctr0, ctr1, wsm, g);
         }
         // grain apply on channel c (black-and-white grain reuses the single field)
-        const float *dplane = a.dens + c * ps;
+        if (c == 0) cp_async_wait_all();  // the thread's own copies: no barrier needed
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            const int gy = ty0 + lane + 32 * h;
-            float d[C::OW];
-            if (gy < H && vec_ok) {
-                const float4 *p = reinterpret_cast<const float4 *>(dplane + (size_t)gy * W + gx0);
-                const float4 u = __ldcs(p), v = __ldcs(p + 1);
-                d[0] = u.x; d[1] = u.y; d[2] = u.z; d[3] = u.w; d[4] = v.x; d[5] = v.y; d[6] = v.z; d[7] = v.w;
-            } else {
+        for (int j = 0; j < 4; ++j) {  // chunk j: tile row lane + 32 * (j / 2), columns 4 * (j % 2) .. + 3
+            float4 *slot = priv4 + (c * 4 + j) * C::NT + threadIdx.x;
+            const float4 dq = *slot;
+            const float d[4] = {dq.x, dq.y, dq.z, dq.w};
+            float val[4];
 #pragma unroll
-                for (int o = 0; o < C::OW; ++o)
-                    d[o] = (gy < H && gx0 + o < W) ? __ldcs(dplane + (size_t)gy * W + gx0 + o) : 0.0f;
+            for (int i = 0; i < 4; ++i) {
+                const int o = 4 * (j & 1) + i;
+                const float gn = j < 2 ? g[o].x : g[o].y;
+                const float amp = FASTC ? fast_curve_eval(a.gfast, c, d[i]) : curve_eval(a.gcurve, c, d[i]);
+                const float v = d[i] + gn * amp;
+                val[i] = v > 0.0f ? v : 0.0f;
             }
-#pragma unroll
-            for (int o = 0; o < C::OW; ++o) {
-                const float gn = h == 0 ? g[o].x : g[o].y;
-                const float amp = FASTC ? fast_curve_eval(a.gfast, c, d[o]) : curve_eval(a.gcurve, c, d[o]);
-                float val = d[o] + gn * amp;
-                val = val > 0.0f ? val : 0.0f;
-                priv[((c * 2 + h) * C::OW + o) * C::NT + threadIdx.x] = val;
-            }
+            *slot = make_float4(val[0], val[1], val[2], val[3]);
         }
     }
     __syncthreads();  // all noise-tile reads done: its storage becomes the output staging area
@@ -126,12 +148,28 @@ k_grain_finish_sym(const __grid_constant__ GrainFinishArgs a) {
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
         uint32_t px[C::OW];  // 0x00BBGGRR per pixel
+        unsigned undecided = 0;
 #pragma unroll
-        for (int o = 0; o < C::OW; ++o) {
-            const float d0 = priv[((0 * 2 + h) * C::OW + o) * C::NT + threadIdx.x];
-            const float d1 = priv[((1 * 2 + h) * C::OW + o) * C::NT + threadIdx.x];
-            const float d2 = priv[((2 * 2 + h) * C::OW + o) * C::NT + threadIdx.x];
-            px[o] = tetra_u8<true>(a.ft, a.l3, d0, d1, d2);  // the grain stage clipped: densities are >= 0
+        for (int half = 0; half < 2; ++half) {
+            const int j = 2 * h + half;
+            const float4 q0d = priv4[(0 * 4 + j) * C::NT + threadIdx.x];
+            const float4 q1d = priv4[(1 * 4 + j) * C::NT + threadIdx.x];
+            const float4 q2d = priv4[(2 * 4 + j) * C::NT + threadIdx.x];
+            const float d0[4] = {q0d.x, q0d.y, q0d.z, q0d.w}, d1[4] = {q1d.x, q1d.y, q1d.z, q1d.w};
+            const float d2[4] = {q2d.x, q2d.y, q2d.z, q2d.w};
+            // the grain stage clipped: densities are >= 0.  Branch-free, so the gathers of the pixels overlap
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+                if (!tetra_u8_try<true>(a.ft, d0[i], d1[i], d2[i], px[4 * half + i])) undecided |= 1u << (4 * half + i);
+        }
+        if (undecided) {  // rare: the exact binary64 interpolation decides (unrolled: px[] stays in registers)
+#pragma unroll
+            for (int o = 0; o < C::OW; ++o)
+                if (undecided >> o & 1u) {
+                    const int slot = (2 * h + (o >> 2)) * C::NT + threadIdx.x, i = o & 3;
+                    px[o] = tetra_exact_u8(a.l3, priv[(0 * 4 * C::NT + slot) * 4 + i], priv[(1 * 4 * C::NT + slot) * 4 + i],
+                                           priv[(2 * 4 * C::NT + slot) * 4 + i]);
+                }
         }
         // 8 pixels = 24 bytes = 6 packed words
         uint32_t *sp = reinterpret_cast<uint32_t *>(stage + (lane + 32 * h) * C::SPITCH + 3 * C::OW * warp);

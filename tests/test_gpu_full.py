@@ -282,6 +282,23 @@ def test_chroma_nr_bit_exact_vs_reference_golden(proc, size):
     assert got.dtype == np.float32 and np.array_equal(got, g[f"ref_out{size}"])
 
 
+@pytest.mark.parametrize("shape,size", [((90, 1100), 20), ((70, 513), 2), ((33, 65), 10), ((1, 1), 3), ((3, 700), 7)])
+def test_chroma_nr_tile_seams_vs_oracle(proc, shape, size):
+    """Frames that cross the 512-pixel row segments and the 64x32 column tiles of k_cnr_rows / k_cnr_cols, up to
+    the largest filter the reference GUI can ask for (slider 10, doubled on full-size export: effects.py:547-561),
+    with zero and near-zero denominators sprinkled in."""
+    rng = np.random.default_rng(size)
+    xyz = rng.random(shape + (3,), dtype=np.float32)
+    xyz[rng.random(shape) < 0.02] = 0.0
+    xyz[rng.random(shape) < 0.02] *= np.float32(1e-9)
+    assert np.array_equal(proc.chroma_nr_filter(xyz, size), fo.chroma_nr_filter(xyz, size))
+
+
+def test_chroma_nr_rejects_oversized_filter(proc):
+    with pytest.raises(Exception, match="tap"):
+        proc.chroma_nr_filter(np.ones((8, 8, 3), np.float32), 30)
+
+
 def test_process_with_chroma_nr_matches_oracle(proc):
     stock = SyntheticStock(n3=17)
     xyz = small_frame(100, 150, seed=41)
