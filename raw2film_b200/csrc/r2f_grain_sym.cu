@@ -38,7 +38,11 @@ struct GrainCfg {
     static constexpr int TILE_BYTES = ROWS * PITCH * 4 > T * SPITCH ? ROWS * PITCH * 4 : T * SPITCH;
     static constexpr int TILE_FLOATS = (TILE_BYTES + 15) / 16 * 4;
     static constexpr int W_FLOATS = (R + 1) * WROW * 2;
-    static constexpr int PRIV_FLOATS = 3 * 2 * OW * NT;  // grained densities, thread-private slots
+    static constexpr int DP = T + 4;                     // density tile row pitch (floats): 17 16-byte chunks, odd, so
+                                                         // the 128-bit accesses of a warp (one tile row per lane) are
+                                                         // bank-conflict free
+    static constexpr int PRIV_FLOATS = 3 * T * DP;       // the three layers' densities, overwritten in place by the
+                                                         // grained densities
     static constexpr int SMEM_BYTES = (TILE_FLOATS + W_FLOATS + PRIV_FLOATS) * 4;
 };
 
@@ -66,30 +70,35 @@ k_grain_finish_sym(const __grid_constant__ GrainFinishArgs a) {
     const int gx0 = tx0 + C::OW * warp;                             // first of the thread's 8 columns
     const bool vec_ok = (W & 3) == 0 && gx0 + C::OW <= W;           // whole 16-byte density loads
 
-    // The densities of all three layers are requested up front as asynchronous global -> shared copies (LDGSTS, no
-    // register, nothing waits) into the thread's own slots of `priv`; the grain apply overwrites them in place with the
-    // grained densities.  Slot layout [channel][chunk j = 2*h + half][thread] of float4: 128-bit accesses, consecutive
-    // threads in consecutive 16-byte slots.  (With the loads next to their use, 15 % of the kernel's stall samples were
-    // the HBM latency of this read.)
-    float4 *priv4 = reinterpret_cast<float4 *>(priv);
+    // The densities of all three layers are requested up front as asynchronous global -> shared copies (LDGSTS: no
+    // register, nothing waits) and complete behind the first noise field; the grain apply overwrites a thread's own
+    // values in place with the grained densities.  Full tiles are copied row-wise (a warp moves two 256-byte tile rows
+    // per instruction, 4 L1 wavefronts; with the thread mapping of the correlation -- one tile row per lane -- every
+    // load touched 32 lines, and the density read was 47 % of the kernel's global tag requests and 15 % of its stall
+    // samples).  Tiles that cross the frame edge or an unaligned frame use per-thread loads into the same slots.
+    const bool full_tile = (W & 3) == 0 && (ps & 3) == 0 && tx0 + C::T <= W && ty0 + C::T <= H &&
+                           (reinterpret_cast<uintptr_t>(a.dens) & 15) == 0;
+    if (full_tile) {
 #pragma unroll
-    for (int c = 0; c < 3; ++c) {
-        const float *dplane = a.dens + c * ps;
+        for (int c = 0; c < 3; ++c) {
+            const float *dplane = a.dens + c * ps + (size_t)ty0 * W + tx0;
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            const int gy = ty0 + lane + 32 * h;
-            float4 *slot = priv4 + (c * 4 + 2 * h) * C::NT + threadIdx.x;
-            if (gy < H && vec_ok) {
-                const float *p = dplane + (size_t)gy * W + gx0;
-                cp_async_16(reinterpret_cast<float *>(slot), p);
-                cp_async_16(reinterpret_cast<float *>(slot + C::NT), p + 4);
-            } else {
-                float d[C::OW];
+            for (int it = 0; it < C::T * (C::T / 4) / C::NT; ++it) {
+                const int idx = threadIdx.x + it * C::NT, row = idx / (C::T / 4), ch = idx % (C::T / 4);
+                cp_async_16(priv + (c * C::T + row) * C::DP + 4 * ch, dplane + (size_t)row * W + 4 * ch);
+            }
+        }
+    } else {
+#pragma unroll 1
+        for (int c = 0; c < 3; ++c) {
+            const float *dplane = a.dens + c * ps;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int gy = ty0 + lane + 32 * h;
+                float *slot = priv + (c * C::T + lane + 32 * h) * C::DP + C::OW * warp;
 #pragma unroll
                 for (int o = 0; o < C::OW; ++o)
-                    d[o] = (gy < H && gx0 + o < W) ? __ldcs(dplane + (size_t)gy * W + gx0 + o) : 0.0f;
-                slot[0] = make_float4(d[0], d[1], d[2], d[3]);
-                slot[C::NT] = make_float4(d[4], d[5], d[6], d[7]);
+                    slot[o] = (gy < H && gx0 + o < W) ? __ldcs(dplane + (size_t)gy * W + gx0 + o) : 0.0f;
             }
         }
     }
@@ -117,6 +126,7 @@ k_grain_finish_sym(const __grid_constant__ GrainFinishArgs a) {
             } else {
                 fill_tile(tile, a.noise + (size_t)c * ps, C::ROWS, C::COLS, ty0 - C::R, xs, H, W, C::NT, C::PITCH);
             }
+            if (c == 0) cp_async_wait_all();  // the density copies: visible to everyone after the barrier
             __syncthreads();
 #pragma unroll
             for (int o = 0; o < C::OW; ++o) g[o] = make_float2(0.f, 0.f);
@@ -125,10 +135,9 @@ k_grain_finish_sym(const __grid_constant__ GrainFinishArgs a) {
             sym_correlate<K, C::OW, C::PITCH, C::WROW>(ctr0, ctr1, wsm, g);
         }
         // grain apply on channel c (black-and-white grain reuses the single field)
-        if (c == 0) cp_async_wait_all();  // the thread's own copies: no barrier needed
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {  // chunk j: tile row lane + 32 * (j / 2), columns 4 * (j % 2) .. + 3
-            float4 *slot = priv4 + (c * 4 + j) * C::NT + threadIdx.x;
+        for (int j = 0; j < 4; ++j) {  // chunk j: tile row lane + 32 * (j / 2), columns 4 * (j % 2) .. + 3 of the thread's 8
+            float4 *slot = reinterpret_cast<float4 *>(priv + (c * C::T + lane + 32 * (j >> 1)) * C::DP + C::OW * warp) + (j & 1);
             const float4 dq = *slot;
             const float d[4] = {dq.x, dq.y, dq.z, dq.w};
             float val[4];
@@ -151,10 +160,10 @@ k_grain_finish_sym(const __grid_constant__ GrainFinishArgs a) {
         unsigned undecided = 0;
 #pragma unroll
         for (int half = 0; half < 2; ++half) {
-            const int j = 2 * h + half;
-            const float4 q0d = priv4[(0 * 4 + j) * C::NT + threadIdx.x];
-            const float4 q1d = priv4[(1 * 4 + j) * C::NT + threadIdx.x];
-            const float4 q2d = priv4[(2 * 4 + j) * C::NT + threadIdx.x];
+            const float *slot = priv + (lane + 32 * h) * C::DP + C::OW * warp + 4 * half;
+            const float4 q0d = *reinterpret_cast<const float4 *>(slot);
+            const float4 q1d = *reinterpret_cast<const float4 *>(slot + C::T * C::DP);
+            const float4 q2d = *reinterpret_cast<const float4 *>(slot + 2 * C::T * C::DP);
             const float d0[4] = {q0d.x, q0d.y, q0d.z, q0d.w}, d1[4] = {q1d.x, q1d.y, q1d.z, q1d.w};
             const float d2[4] = {q2d.x, q2d.y, q2d.z, q2d.w};
             // the grain stage clipped: densities are >= 0.  Branch-free, so the gathers of the pixels overlap
@@ -166,9 +175,8 @@ k_grain_finish_sym(const __grid_constant__ GrainFinishArgs a) {
 #pragma unroll
             for (int o = 0; o < C::OW; ++o)
                 if (undecided >> o & 1u) {
-                    const int slot = (2 * h + (o >> 2)) * C::NT + threadIdx.x, i = o & 3;
-                    px[o] = tetra_exact_u8(a.l3, priv[(0 * 4 * C::NT + slot) * 4 + i], priv[(1 * 4 * C::NT + slot) * 4 + i],
-                                           priv[(2 * 4 * C::NT + slot) * 4 + i]);
+                    const float *slot = priv + (lane + 32 * h) * C::DP + C::OW * warp + o;
+                    px[o] = tetra_exact_u8(a.l3, slot[0], slot[C::T * C::DP], slot[2 * C::T * C::DP]);
                 }
         }
         // 8 pixels = 24 bytes = 6 packed words
