@@ -394,6 +394,9 @@ __device__ __forceinline__ Group row_group() {
 
 // The 2-D input LUT (48 KB at n = 64) is gathered nine times per pixel; with ~200 KB of line buffers
 // the L1 has no room for it, so each group parks a copy in its idle ping-pong buffer when it fits.
+// WAIT = false: the copies are only queued; the caller completes them with stage_lut2d_finish() (after it has
+// issued its first frame loads, so the two round trips overlap).
+template <bool WAIT = true>
 __device__ __forceinline__ Lut2D stage_lut2d(const Lut2D &L, float2 *idle, int capacity_float2, const Group &g) {
     const int nfloat = L.n * L.n * 3;
     if (nfloat > 2 * capacity_float2) return L;
@@ -403,9 +406,15 @@ __device__ __forceinline__ Lut2D stage_lut2d(const Lut2D &L, float2 *idle, int c
     const int nq = (reinterpret_cast<uintptr_t>(L.tab) & 15) == 0 ? nfloat / 4 : 0;
     for (int i = g.tid; i < nq; i += g.size) cp_async_16(dst + 4 * i, L.tab + 4 * i);
     for (int i = 4 * nq + g.tid; i < nfloat; i += g.size) dst[i] = __ldg(L.tab + i);
+    if (WAIT) {
+        cp_async_wait_all();
+        group_sync(g);
+    }
+    return Lut2D(dst, L.n);
+}
+__device__ __forceinline__ void stage_lut2d_finish(const Group &g) {
     cp_async_wait_all();
     group_sync(g);
-    return Lut2D(dst, L.n);
 }
 
 // Interleaved frame row y -> 2-D input LUT -> (chan0 + i chan1) into `line` (offset r, swizzled) and, when asked, the
@@ -416,14 +425,19 @@ __device__ __forceinline__ void load_row_xyz(const FftConvArgs &a, const Lut2D &
     const int W = a.W, r = a.r;
     if ((W & 3) == 0) {  // row starts on a pixel-quad boundary: 128-bit frame loads
         const size_t q0 = (size_t)y * W / 4;
-        constexpr int U = 2;  // quads in flight per thread: the frame loads of a batch are issued together
-        for (int base = g.tid; base < W / 4; base += U * g.size) {
-            float px[U][4][3];
+        constexpr int U = 3;  // quads in flight per thread (a 6000-pixel row is one batch of a 512-thread group)
+        float px[U][4][3];
+        auto request = [&](int base) {
 #pragma unroll
             for (int u = 0; u < U; ++u) {
                 const int qx = base + u * g.size;
                 if (qx < W / 4) load_quad<FMT>(a.src_xyz, q0 + qx, a.gain, px[u]);
             }
+        };
+        int base = g.tid;
+        request(base);
+        if (LUT_SMEM) stage_lut2d_finish(g);  // the table copy and the first frame loads were in flight together
+        while (base < W / 4) {
 #pragma unroll
             for (int u = 0; u < U; ++u) {
                 const int qx = base + u * g.size;
@@ -443,8 +457,11 @@ __device__ __forceinline__ void load_row_xyz(const FftConvArgs &a, const Lut2D &
                     }
                 }
             }
+            base += U * g.size;
+            if (base < W / 4) request(base);
         }
     } else {
+        if (LUT_SMEM) stage_lut2d_finish(g);
         for (int x = g.tid; x < W; x += g.size) {
             float X, Y, Z, e0, e1, e2;
             load_px<FMT>(a.src_xyz, (size_t)y * W + x, a.gain, X, Y, Z);
@@ -484,7 +501,7 @@ k_fft_rows_fwd(const __grid_constant__ FftConvArgs a) {
                                           a.src_planar[(size_t)a.chan[1] * a.plane_stride + idx]);
             }
         } else {
-            const Lut2D l2 = stage_lut2d(a.lut2d, bufB, n, g);
+            const Lut2D l2 = stage_lut2d<false>(a.lut2d, bufB, n, g);   // completed inside load_row_xyz
             if (l2.tab != a.lut2d.tab) load_row_xyz<FMT, true>(a, l2, bufA, y, g);   // parked in shared memory
             else load_row_xyz<FMT, false>(a, l2, bufA, y, g);
         }
@@ -591,40 +608,48 @@ k_fft_cols(const __grid_constant__ FftConvArgs a) {
     }
 }
 
-// In-place variant (compile-time plans only): four 256-thread groups, one column each, n float2 per column.
+// In-place variant (compile-time plans only): one 256-thread group per column, n float2 per column.
 // IPLAN 1: n = 4096 (8 8 8 8), IPLAN 2: n = 6912 (3 3 3 4 8 8: the line's radices reversed); a.khat rows are
 // permuted by the line's perm[].
-template <int IPLAN>
-__global__ void __launch_bounds__(1024, 1)
+// NCOL columns per CTA: 4 = a whole 32-byte block row per thread, one 1024-thread CTA per SM; 2 = half a block
+// (16 bytes per row) in a 512-thread CTA, two (n = 4096: 64 KB each) per SM.  With one CTA per SM nothing overlaps
+// its load and store phases (a quarter of the kernel's stall samples at 24 MP); two independent half-block CTAs
+// overlap them with each other's transforms.  The two halves of a 32-byte sector are requested by neighbouring
+// CTAs within microseconds of each other, so DRAM still moves every sector once (L2 merges them).
+template <int IPLAN, int NCOL>
+__global__ void __launch_bounds__(256 * NCOL, 4 / NCOL)
 k_fft_cols_ip(const __grid_constant__ FftConvArgs a) {
     extern __shared__ __align__(16) float2 fsm[];
     constexpr int n = IPLAN == 1 ? 4096 : 6912;
-    constexpr int GS = 256;
+    constexpr int GS = 256, NT = 256 * NCOL;
     const int H = a.H, r = a.r;
-    const int b = blockIdx.x;
-    float2 *blk = a.S + (size_t)b * H * 4;
+    const int b = NCOL == 4 ? blockIdx.x : blockIdx.x >> 1;
+    const int c0 = NCOL == 4 ? 0 : 2 * (blockIdx.x & 1);   // first column of the block this CTA transforms
+    float2 *blk = a.S + (size_t)b * H * 4 + c0;
     {
         constexpr int U = 4;
-        for (int y0 = threadIdx.x; y0 < H; y0 += U * blockDim.x) {
+        for (int y0 = threadIdx.x; y0 < H; y0 += U * NT) {
             float4 lo[U], hi[U];
 #pragma unroll
             for (int u = 0; u < U; ++u) {
-                const int y = y0 + u * blockDim.x;
+                const int y = y0 + u * NT;
                 if (y < H) {
                     const float2 *sp = blk + (size_t)y * 4;
                     lo[u] = ldg_stream4(reinterpret_cast<const float4 *>(sp));
-                    hi[u] = ldg_stream4(reinterpret_cast<const float4 *>(sp + 2));
+                    if (NCOL == 4) hi[u] = ldg_stream4(reinterpret_cast<const float4 *>(sp + 2));
                 }
             }
 #pragma unroll
             for (int u = 0; u < U; ++u) {
-                const int y = y0 + u * blockDim.x;
+                const int y = y0 + u * NT;
                 if (y < H) {
                     const int e = sw(r + y);
                     fsm[e] = make_float2(lo[u].x, lo[u].y);
                     fsm[n + e] = make_float2(lo[u].z, lo[u].w);
-                    fsm[2 * n + e] = make_float2(hi[u].x, hi[u].y);
-                    fsm[3 * n + e] = make_float2(hi[u].z, hi[u].w);
+                    if (NCOL == 4) {
+                        fsm[2 * n + e] = make_float2(hi[u].x, hi[u].y);
+                        fsm[3 * n + e] = make_float2(hi[u].z, hi[u].w);
+                    }
                 }
             }
         }
@@ -635,18 +660,21 @@ k_fft_cols_ip(const __grid_constant__ FftConvArgs a) {
     float2 *home = fsm + (size_t)gi * n;
     pad_line(home, H, r, n, g);
     group_sync(g);
-    const int vcol = b * 4 + gi, vm = vcol <= a.row.n - vcol ? vcol : a.row.n - vcol;  // khat[v] == khat[Wp - v]
+    const int vcol = b * 4 + c0 + gi, vm = vcol <= a.row.n - vcol ? vcol : a.row.n - vcol;  // khat[v] == khat[Wp - v]
     const float *kh = a.khat + (size_t)vm * n;
     if constexpr (IPLAN == 1) ip_conv<4096, 4096, GS, 0, 8, 8, 8, 8>(home, a.col.tw_ip, kh, g);
     else ip_conv<6912, 6912, GS, 0, 3, 3, 3, 4, 8, 8>(home, a.col.tw_ip, kh, g);
     __syncthreads();
     // keep the swapped form: k_fft_rows_inv consumes swap(x) directly
-    for (int y = threadIdx.x; y < H; y += blockDim.x) {
+    for (int y = threadIdx.x; y < H; y += NT) {
         float2 *dp = blk + (size_t)y * 4;
         const int e = sw(r + y);
-        const float2 c0 = fsm[e], c1 = fsm[n + e], c2 = fsm[2 * n + e], c3 = fsm[3 * n + e];
-        *reinterpret_cast<float4 *>(dp) = make_float4(c0.x, c0.y, c1.x, c1.y);
-        *reinterpret_cast<float4 *>(dp + 2) = make_float4(c2.x, c2.y, c3.x, c3.y);
+        const float2 v0 = fsm[e], v1 = fsm[n + e];
+        *reinterpret_cast<float4 *>(dp) = make_float4(v0.x, v0.y, v1.x, v1.y);
+        if (NCOL == 4) {
+            const float2 v2 = fsm[2 * n + e], v3 = fsm[3 * n + e];
+            *reinterpret_cast<float4 *>(dp + 2) = make_float4(v2.x, v2.y, v3.x, v3.y);
+        }
     }
 }
 
@@ -676,6 +704,16 @@ k_fft_rows_inv(const __grid_constant__ FftConvArgs a) {
             }
         }
     }
+    if (SRC == 0) {  // the epilogue's exposure rows: ask L2 for them now, one request per 128-byte line
+        for (int row = 0; row < nrows; ++row) {
+            const size_t off = (size_t)(y0 + row) * W;
+            for (int i = threadIdx.x; i < 3 * ((W + 31) / 32); i += blockDim.x) {
+                const int c = i / ((W + 31) / 32), seg = i - c * ((W + 31) / 32);
+                const float *p = a.src_planar + (size_t)c * a.plane_stride + off + min(32 * seg, W - 1);
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+            }
+        }
+    }
     cp_async_wait_all();
     __syncthreads();
     if (half >= nrows) return;
@@ -700,27 +738,36 @@ k_fft_rows_inv(const __grid_constant__ FftConvArgs a) {
             for (int c = 0; c < 3; ++c) out[c] = density_eval_fast(a.curve, c, out[c], a.eps);
         }
     };
-    if ((W & 3) == 0) {
+    if ((W & 3) == 0 && SRC == 0) {
+        // planar hand-off (the exposure planes of this row were prefetched into L2 while the transform ran)
         const size_t q0 = (size_t)y * W / 4;
         for (int qx = g.tid; qx < W / 4; qx += g.size) {
             float px[4][3], res[3][4];
-            if (SRC != 0) {
-                load_quad<FMT>(a.src_xyz, q0 + qx, a.gain, px);
-            } else {
 #pragma unroll
-                for (int c = 0; c < 3; ++c) {
-                    const float4 v = __ldcs(reinterpret_cast<const float4 *>(a.src_planar + c * ps) + q0 + qx);
-                    px[0][c] = v.x; px[1][c] = v.y; px[2][c] = v.z; px[3][c] = v.w;
-                }
+            for (int c = 0; c < 3; ++c) {
+                const float4 v = __ldcs(reinterpret_cast<const float4 *>(a.src_planar + c * ps) + q0 + qx);
+                px[0][c] = v.x; px[1][c] = v.y; px[2][c] = v.z; px[3][c] = v.w;
             }
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
+                float out[3];
+                finish_px(px[i], buf[sw(r + 4 * qx + i)], out);
+                res[0][i] = out[0]; res[1][i] = out[1]; res[2][i] = out[2];
+            }
+#pragma unroll
+            for (int c = 0; c < 3; ++c)
+                reinterpret_cast<float4 *>(a.dst_planar + c * ps)[q0 + qx] =
+                    make_float4(res[c][0], res[c][1], res[c][2], res[c][3]);
+        }
+    } else if ((W & 3) == 0) {
+        const size_t q0 = (size_t)y * W / 4;
+        for (int qx = g.tid; qx < W / 4; qx += g.size) {
+            float px[4][3], res[3][4];
+            load_quad<FMT>(a.src_xyz, q0 + qx, a.gain, px);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
                 float src[3], out[3];
-                if (SRC != 0) {
-                    lut2d_eval(l2, px[i][0], px[i][1], px[i][2], src[0], src[1], src[2]);
-                } else {
-                    src[0] = px[i][0]; src[1] = px[i][1]; src[2] = px[i][2];
-                }
+                lut2d_eval(l2, px[i][0], px[i][1], px[i][2], src[0], src[1], src[2]);
                 finish_px(src, buf[sw(r + 4 * qx + i)], out);
                 res[0][i] = out[0]; res[1][i] = out[1]; res[2][i] = out[2];
             }
@@ -1035,12 +1082,20 @@ cudaError_t launch_fft_conv(const FftConvArgs &a, int src_mode, bool density, cu
     }
     if ((stage == 0 || stage == 2) && a.col_inplace) {
         const size_t ips = fft_cols_inplace_smem(a.col.n);
-        if (a.col.n == 4096) {
-            if ((e = set_smem(k_fft_cols_ip<1>, ips)) != cudaSuccess) return e;
-            k_fft_cols_ip<1><<<col_ctas, 1024, ips, st>>>(a);
+        static const char *ncol_env = getenv("R2F_FFT_COLS_PER_CTA");  // tuning knob: "4" forces whole-block CTAs
+        const bool split = 2 * (ips / 2 + 1024) <= 227 * 1024 && !(ncol_env && ncol_env[0] == '4');
+        if (a.col.n == 4096 && split) {
+            if ((e = set_smem(k_fft_cols_ip<1, 2>, ips / 2)) != cudaSuccess) return e;
+            k_fft_cols_ip<1, 2><<<2 * col_ctas, 512, ips / 2, st>>>(a);
+        } else if (a.col.n == 4096) {
+            if ((e = set_smem(k_fft_cols_ip<1, 4>, ips)) != cudaSuccess) return e;
+            k_fft_cols_ip<1, 4><<<col_ctas, 1024, ips, st>>>(a);
+        } else if (split) {
+            if ((e = set_smem(k_fft_cols_ip<2, 2>, ips / 2)) != cudaSuccess) return e;
+            k_fft_cols_ip<2, 2><<<2 * col_ctas, 512, ips / 2, st>>>(a);
         } else {
-            if ((e = set_smem(k_fft_cols_ip<2>, ips)) != cudaSuccess) return e;
-            k_fft_cols_ip<2><<<col_ctas, 1024, ips, st>>>(a);
+            if ((e = set_smem(k_fft_cols_ip<2, 4>, ips)) != cudaSuccess) return e;
+            k_fft_cols_ip<2, 4><<<col_ctas, 1024, ips, st>>>(a);
         }
         if ((e = cudaGetLastError()) != cudaSuccess) return e;
     } else if (stage == 0 || stage == 2) {
