@@ -502,6 +502,15 @@ k_fft_rows_fwd(const __grid_constant__ FftConvArgs a) {
             }
         } else {
             const Lut2D l2 = stage_lut2d<false>(a.lut2d, bufB, n, g);   // completed inside load_row_xyz
+            {   // ask L2 for the frame row that the CTA taking this one's place will read (two CTAs per SM resident)
+                constexpr int BPP = FMT == kFmtF32x3 ? 12 : (FMT == kFmtF32x4 ? 16 : (FMT == kFmtU16x3 ? 6 : 8));
+                const int ya = y + ROWS * a.rows_ahead;
+                if (a.rows_ahead > 0 && ya < yend) {
+                    const char *rowp = static_cast<const char *>(a.src_xyz) + (size_t)ya * W * BPP;
+                    for (int off = g.tid * 128; off < W * BPP; off += g.size * 128)
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(rowp + off));
+                }
+            }
             if (l2.tab != a.lut2d.tab) load_row_xyz<FMT, true>(a, l2, bufA, y, g);   // parked in shared memory
             else load_row_xyz<FMT, false>(a, l2, bufA, y, g);
         }
