@@ -88,14 +88,14 @@ __device__ __forceinline__ void tma_load_3d(float *smem_dst, const CUtensorMap *
 
 template <int K, int OW>
 __global__ void __launch_bounds__((64 / OW) * 32, OW == 8 ? 3 : 4)
-k_conv2d_sym(ConvArgs a, const __grid_constant__ CUtensorMap tmap, int use_tma) {
+k_conv2d_sym(ConvArgs a, const __grid_constant__ CUtensorMap tmap, int use_tma, int shift) {
     using C = SymCfg<K, OW>;
     extern __shared__ __align__(128) float smem[];
     __shared__ __align__(8) uint64_t tma_bar;
     float *tile = smem;
     float *wsm = smem + C::TILE_FLOATS;
     const int c = blockIdx.z;
-    const int tx0 = blockIdx.x * C::TW - C::SHIFT, ty0 = blockIdx.y * C::TH;
+    const int tx0 = blockIdx.x * C::TW - shift, ty0 = blockIdx.y * C::TH;
     const int H = a.H, W = a.W;
     const float *__restrict__ src = a.in + (size_t)a.in_plane[c] * a.plane_stride;
     float *__restrict__ dst = a.out + (size_t)c * a.plane_stride;
@@ -130,12 +130,12 @@ k_conv2d_sym(ConvArgs a, const __grid_constant__ CUtensorMap tmap, int use_tma) 
         sym_correlate<K, C::OW, C::PITCH, C::WROW>(ctr0, ctr1, wsm, acc);
         __syncthreads();  // everyone is done reading the input tile: reuse it as the output stage
     }
-    // 128-bit write-out when the tile's columns start on a 16-byte boundary of the destination rows (SHIFT == 0, i.e.
-    // kernel radii that are multiples of 4 -- the 17 x 17 MTF of a 24 MP frame) and the tile lies inside the frame
+    // 128-bit write-out when the tile's columns start on a 16-byte boundary of the destination rows (shift == 0: TMA
+    // staging, or a kernel radius that is a multiple of 4) and the tile lies inside the frame
     // horizontally: 4 + 4 staging stores and 8 x (LDS.128, STG.128) per thread instead of 32 + 32 x (LDS.32, STG.32);
     // the scalar write-out was a fifth of the kernel's stall samples.
     const bool conv = a.mode[c] != 0;
-    const bool vec_out = C::SHIFT == 0 && (W & 3) == 0 && (a.plane_stride & 3) == 0 && tx0 + C::TW <= W &&
+    const bool vec_out = shift == 0 && (W & 3) == 0 && (a.plane_stride & 3) == 0 && tx0 + C::TW <= W &&
                          (reinterpret_cast<uintptr_t>(a.out) & 15) == 0 && (reinterpret_cast<uintptr_t>(a.in) & 15) == 0;
     auto epilogue = [&](float val) {
         if (a.epi == EPI_DENSITY) val = density_eval(a.curve, c, val, a.eps);
@@ -230,8 +230,11 @@ cudaError_t launch_sym(const ConvArgs &a, cudaStream_t st) {
     if (e != cudaSuccess) return e;
     CUtensorMap map{};
     const int use_tma = make_plane_map(a, C::PITCH, C::ROWS, &map) ? 1 : 0;
-    dim3 grid((a.W + C::SHIFT + C::TW - 1) / C::TW, (a.H + C::TH - 1) / C::TH, 3);
-    kfn<<<grid, C::NT, C::SMEM_BYTES, st>>>(a, map, use_tma);
+    // the tiles start SHIFT columns left of a 64-column boundary so that the input tile's left edge is 16-byte aligned
+    // (cp.async and TMA both need that: a TMA box starting at an unaligned column faults as an illegal instruction)
+    const int shift = C::SHIFT;
+    dim3 grid((a.W + shift + C::TW - 1) / C::TW, (a.H + C::TH - 1) / C::TH, 3);
+    kfn<<<grid, C::NT, C::SMEM_BYTES, st>>>(a, map, use_tma, shift);
     return cudaGetLastError();
 }
 
