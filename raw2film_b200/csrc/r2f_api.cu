@@ -594,6 +594,7 @@ int fft_prepare(r2f_ctx *c, const KernelSet &ks, int H, int W, const FftGeometry
     a.nc = g.nc;
     a.col_groups = g.groups;
     a.col_inplace = g.inplace ? 1 : 0;
+    a.cols_prefetch = (size_t)g.Hp * g.Wp * 2 > ((size_t)64 << 20) ? 1 : 0;  // half the spectrum is stored (mirror rows)
     {
         static const char *ra = getenv("R2F_FFT_ROWS_AHEAD");  // tuning knob; default: the CTAs resident on the device
         a.rows_ahead = ra ? atoi(ra) : c->num_sms;  // measured at 24 MP: off 0.308, 148 0.302, 296 0.304 ms

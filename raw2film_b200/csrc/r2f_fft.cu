@@ -658,6 +658,22 @@ k_fft_cols_ip(const __grid_constant__ FftConvArgs a) {
     const int b = NCOL == 4 ? blockIdx.x : blockIdx.x >> 1;
     const int c0 = NCOL == 4 ? 0 : 2 * (blockIdx.x & 1);   // first column of the block this CTA transforms
     float2 *blk = a.S + (size_t)b * H * 4 + c0;
+    if (a.cols_prefetch) {
+        // L2 prefetches, one per 128-byte line: this CTA's rows of the kernel spectrum (read in the middle of the
+        // transform) and the block of the CTA that will take this one's place (a.rows_ahead CTAs ahead in launch
+        // order).  Pays when the kernel spectrum does not stay in L2 between frames: 61 MP 0.870 -> 0.829 ms, but
+        // 24 MP (50 MB of spectrum, L2-resident) 0.210 -> 0.214 ms, so r2f_api.cu sets the flag by size.
+        const int gi0 = (int)threadIdx.x / 256;
+        const int vc = b * 4 + c0 + gi0, vmm = vc <= a.row.n - vc ? vc : a.row.n - vc;
+        const float *khp = a.khat + (size_t)vmm * n;
+        for (int i = ((int)threadIdx.x % 256) * 32; i < n; i += 256 * 32) asm volatile("prefetch.global.L2 [%0];" ::"l"(khp + i));
+        const int ahead = (int)blockIdx.x + a.rows_ahead * (NCOL == 4 ? 1 : 2);
+        if (a.rows_ahead > 0 && ahead < (int)gridDim.x && (NCOL == 4 || (blockIdx.x & 1) == 0)) {
+            const char *nb = reinterpret_cast<const char *>(a.S + (size_t)(NCOL == 4 ? ahead : ahead >> 1) * H * 4);
+            for (int off = (int)threadIdx.x * 128; off < H * 32; off += NT * 128)
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(nb + off));
+        }
+    }
     {
         constexpr int U = 4;
         for (int y0 = threadIdx.x; y0 < H; y0 += U * NT) {

@@ -44,6 +44,7 @@ struct FftConvArgs {
     int nc;             // columns per CTA / per block of S (2..4, divides Wp)
     int col_groups;     // thread groups per column CTA (1 or 2)
     int rows_ahead;     // k_fft_rows_fwd prefetches the frame row of CTA blockIdx + rows_ahead into L2 (0: off)
+    int cols_prefetch;  // column kernel: L2-prefetch its kernel-spectrum rows and the next CTA's block
     int col_inplace;    // 1: in-place column kernel (one 256-thread group per column, khat permuted by col perm)
     float2 *S;          // spectrum scratch, (Wp / nc) x H x nc complex
     const float *khat;  // [Wp][Hp] real kernel spectrum, 1/(Hp*Wp) folded in
