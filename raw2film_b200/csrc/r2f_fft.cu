@@ -448,7 +448,7 @@ __device__ __forceinline__ void load_row_xyz(const FftConvArgs &a, const Lut2D &
     const int W = a.W, r = a.r;
     if ((W & 3) == 0) {  // row starts on a pixel-quad boundary: 128-bit frame loads
         const size_t q0 = (size_t)y * W / 4;
-        constexpr int U = 3;  // quads in flight per thread (a 6000-pixel row is one batch of a 512-thread group)
+        constexpr int U = 2;  // quads in flight per thread (three fit a 6000-pixel row in one batch but spill)
         float px[U][4][3];
         auto request = [&](int base) {
 #pragma unroll
@@ -512,7 +512,7 @@ k_fft_rows_fwd(const __grid_constant__ FftConvArgs a) {
     const int half = ROWS == 2 ? (int)(threadIdx.x >> 9) : 0;
     const int y0 = a.row0 + blockIdx.x * ROWS;                              // a.row0 is a multiple of ROWS
     const int yend = a.row_count > 0 ? min(H, a.row0 + a.row_count) : H;
-    const int nrows = min(ROWS, yend - y0);
+    const int nrows = ROWS == 1 ? 1 : min(ROWS, yend - y0);   // the grid has exactly ceil(rows / ROWS) CTAs
     float2 *bufA = fsm + (size_t)half * 2 * n, *bufB = bufA + n;
     const int y = y0 + half;
     if (half < nrows) {
@@ -737,7 +737,7 @@ k_fft_rows_inv(const __grid_constant__ FftConvArgs a) {
     const Group g = row_group<ROWS>();
     const int half = ROWS == 2 ? (int)(threadIdx.x >> 9) : 0;
     const int y0 = blockIdx.x * ROWS;
-    const int nrows = min(ROWS, H - y0);
+    const int nrows = ROWS == 1 ? 1 : min(ROWS, H - y0);   // the grid has exactly ceil(H / ROWS) CTAs
     // S holds swap(column-inverse); one more forward FFT along the row completes swap(IFFT2)
     const int nblk = n / NC;
     for (int b = threadIdx.x; b < nblk; b += blockDim.x) {
