@@ -356,6 +356,7 @@ def main():
     if rank == 0:
         sampler.start()
     _cabi.check(_cabi.lib.r2f_profile_enable(proc._ctx, 1))
+    proc.fast_chain_stats()          # reset the deferred-pixel counter: the share below is of the timed steps only
     launches0 = proc.launch_count
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
@@ -377,7 +378,7 @@ def main():
             deferred, margin = proc.fast_chain_stats()
             print(json.dumps({"ms_per_step": ms_total / args.steps, "kernel_only": True, "config": args.config,
                               "kernels_ms": ks, "fast_chain": {"margin": margin, "deferred_share": deferred / (
-                                  (args.steps + args.warmup) * H * W)}}))
+                                  args.steps * H * W)}}))
         proc.close()
         return
 
