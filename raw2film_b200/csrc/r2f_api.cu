@@ -65,6 +65,9 @@ struct KernelSet {
     // y-symmetric packed layout for k_conv2d_sym (r2f_conv_sym.cu); sym_ok when every filtered layer is
     // mirror-symmetric in y and the size is supported
     DevBuf symbuf;
+    std::vector<float> sym_host;   // same contents: kernels that take the weights as a launch parameter copy from here
+    size_t sym_per = 0;            // floats per layer
+    int sym_channels = 0;
     const float *sym[3] = {nullptr, nullptr, nullptr};
     bool sym_ok = false;
     // FFT eligibility (r2f_fft.cu): exactly two filtered layers that share one even-symmetric base
@@ -421,6 +424,9 @@ int upload_kernel(r2f_ctx *ctx, KernelSet &ks, const float *kernel, int k, int c
             if (rc != R2F_OK) return rc;
             for (int c = 0; c < 3; ++c)
                 ks.sym[c] = static_cast<const float *>(ks.symbuf.p) + sper * (channels == 3 ? c : 0);
+            ks.sym_host = sh;
+            ks.sym_per = sper;
+            ks.sym_channels = channels;
             ks.sym_ok = true;
         }
     }
@@ -645,6 +651,7 @@ ConvArgs conv_args(const KernelSet &ks, const float *in, float *out, size_t ps, 
     for (int c = 0; c < 3; ++c) {
         a.kern[c] = ks.chan[c];
         a.ksym[c] = ks.sym_ok ? ks.sym[c] : nullptr;
+        a.ksym_host[c] = ks.sym_ok ? ks.sym_host.data() + ks.sym_per * (ks.sym_channels == 3 ? c : 0) : nullptr;
         a.mode[c] = ks.mode[c];
         a.in_plane[c] = c;
     }
@@ -674,6 +681,7 @@ ConvArgs identity_args(const float *in, float *out, size_t ps, int H, int W) {
     for (int c = 0; c < 3; ++c) {
         a.kern[c] = nullptr;
         a.ksym[c] = nullptr;
+        a.ksym_host[c] = nullptr;
         a.mode[c] = 0;
         a.in_plane[c] = c;
     }

@@ -24,6 +24,7 @@
 // Reference semantics kept: correlation (not convolution), centre anchor, BORDER_REFLECT_101
 // (cv.filter2D as called from effects.py:146-156).
 #include <cstdlib>
+#include <cstring>
 
 #include <cuda.h>
 #include <cuda_runtime.h>
@@ -53,7 +54,13 @@ struct SymCfg {
     static constexpr int OPITCH = TW + 1;              // output staging pitch (odd: conflict-free), scalar write-out
     static constexpr int OP4 = TW + 4;                 // ... for the 128-bit write-out: 17 16-byte chunks per row (odd)
     static constexpr int TILE_FLOATS = ROWS * PITCH > TH * OP4 ? ROWS * PITCH : TH * OP4;
-    static constexpr int SMEM_BYTES = (TILE_FLOATS + (R + 1) * WROW * 2) * 4;
+    static constexpr int SMEM_BYTES = TILE_FLOATS * 4;
+};
+
+// the three layers' weights as a kernel parameter (3.9 KB at k = 17, 13.5 KB at k = 33; the limit is 32 KB)
+template <int K>
+struct SymWeights {
+    float2 w[3][(K / 2 + 1) * ((K + 1) / 2 * 2)];
 };
 
 // ---- TMA / mbarrier primitives (PTX ISA 8.x, sm_90+) ---------------------------------------------
@@ -88,12 +95,12 @@ __device__ __forceinline__ void tma_load_3d(float *smem_dst, const CUtensorMap *
 
 template <int K, int OW>
 __global__ void __launch_bounds__((64 / OW) * 32, OW == 8 ? 3 : 4)
-k_conv2d_sym(ConvArgs a, const __grid_constant__ CUtensorMap tmap, int use_tma, int shift) {
+k_conv2d_sym(ConvArgs a, const __grid_constant__ CUtensorMap tmap, int use_tma, int shift,
+             const __grid_constant__ SymWeights<K> wts) {
     using C = SymCfg<K, OW>;
     extern __shared__ __align__(128) float smem[];
     __shared__ __align__(8) uint64_t tma_bar;
     float *tile = smem;
-    float *wsm = smem + C::TILE_FLOATS;
     const int c = blockIdx.z;
     const int tx0 = blockIdx.x * C::TW - shift, ty0 = blockIdx.y * C::TH;
     const int H = a.H, W = a.W;
@@ -118,8 +125,6 @@ k_conv2d_sym(ConvArgs a, const __grid_constant__ CUtensorMap tmap, int use_tma, 
         } else {
             fill_tile_async<C::ROWS, C::COLS, C::PITCH, C::NT>(tile, src, gy0, gx0, H, W);
         }
-        const float *__restrict__ wg = a.ksym[c];
-        for (int idx = threadIdx.x; idx < (C::R + 1) * C::WROW * 2; idx += C::NT) wsm[idx] = __ldg(wg + idx);
         if (tma) mbar_wait(&tma_bar, 0);
         else cp_async_wait_all();
         __syncthreads();
@@ -127,7 +132,7 @@ k_conv2d_sym(ConvArgs a, const __grid_constant__ CUtensorMap tmap, int use_tma, 
         // rows lane and lane+32 of the tile; window starts at tile column OW*warp
         const float *ctr0 = tile + (lane + C::R) * C::PITCH + C::OW * warp;
         const float *ctr1 = ctr0 + 32 * C::PITCH;
-        sym_correlate<K, C::OW, C::PITCH, C::WROW>(ctr0, ctr1, wsm, acc);
+        sym_correlate<K, C::OW, C::PITCH, C::WROW, true>(ctr0, ctr1, reinterpret_cast<const float *>(wts.w[c]), acc);
         __syncthreads();  // everyone is done reading the input tile: reuse it as the output stage
     }
     // 128-bit write-out when the tile's columns start on a 16-byte boundary of the destination rows (shift == 0: TMA
@@ -234,7 +239,11 @@ cudaError_t launch_sym(const ConvArgs &a, cudaStream_t st) {
     // (cp.async and TMA both need that: a TMA box starting at an unaligned column faults as an illegal instruction)
     const int shift = C::SHIFT;
     dim3 grid((a.W + shift + C::TW - 1) / C::TW, (a.H + C::TH - 1) / C::TH, 3);
-    kfn<<<grid, C::NT, C::SMEM_BYTES, st>>>(a, map, use_tma, shift);
+    SymWeights<K> wts;
+    for (int c = 0; c < 3; ++c)
+        if (a.mode[c] != 0) memcpy(wts.w[c], a.ksym_host[c], sizeof(wts.w[c]));
+        else memset(wts.w[c], 0, sizeof(wts.w[c]));
+    kfn<<<grid, C::NT, C::SMEM_BYTES, st>>>(a, map, use_tma, shift, wts);
     return cudaGetLastError();
 }
 

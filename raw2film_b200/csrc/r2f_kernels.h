@@ -34,6 +34,7 @@ struct ConvArgs {
     // y-symmetric layout for k_conv2d_sym, or nullptr: ksym[c][(dy * wrow + j) * 2 + {0,1}] = K[r+dy][j][c]
     // (duplicated pair), row dy = 0 halved, wrow = conv_sym_wrow(k)
     const float *ksym[3];
+    const float *ksym_host[3];  // the same layout in host memory (kernel-parameter copy for the uniform-weight form)
     int mode[3];      // 0 = identity (exact centre delta), 1 = correlate
     int in_plane[3];  // source plane feeding output channel c
     int epi;

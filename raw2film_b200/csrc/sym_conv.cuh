@@ -12,7 +12,11 @@
 
 namespace r2f {
 
-template <int K, int OW, int PITCH, int WROW>
+// UNIFORM: `wsm` points at (w, w) pairs in the kernel's parameter space (a __grid_constant__ struct) instead of
+// shared memory.  The weight index is warp-uniform, so the pairs arrive through the uniform datapath (LDCU.64 into a
+// uniform register that FFMA2 takes directly as an operand): no weight LDS.128 (9 of the 41 shared-memory loads per
+// kernel row at k = 17), no vector registers for weights.
+template <int K, int OW, int PITCH, int WROW, bool UNIFORM = false>
 __device__ __forceinline__ void sym_correlate(const float *__restrict__ ctr0, const float *__restrict__ ctr1,
                                               const float *__restrict__ wsm, float2 (&acc)[OW]) {
     constexpr int R = K / 2;
@@ -32,17 +36,27 @@ __device__ __forceinline__ void sym_correlate(const float *__restrict__ ctr0, co
             P[4 * q + 2] = make_float2(x.z + y.z, z.z + w.z);
             P[4 * q + 3] = make_float2(x.w + y.w, z.w + w.w);
         }
-        const float4 *wr = reinterpret_cast<const float4 *>(wsm + dy * WROW * 2);
+        if (UNIFORM) {
+            const float2 *wr = reinterpret_cast<const float2 *>(wsm) + dy * WROW;
 #pragma unroll
-        for (int j = 0; j < K; j += 2) {
-            const float4 w4 = wr[j >> 1];
-            const float2 wa = make_float2(w4.x, w4.y);
+            for (int j = 0; j < K; ++j) {
+                const float2 wa = wr[j];
 #pragma unroll
-            for (int o = 0; o < OW; ++o) acc[o] = __ffma2_rn(wa, P[o + j], acc[o]);
-            if (j + 1 < K) {
-                const float2 wb = make_float2(w4.z, w4.w);
+                for (int o = 0; o < OW; ++o) acc[o] = __ffma2_rn(wa, P[o + j], acc[o]);
+            }
+        } else {
+            const float4 *wr = reinterpret_cast<const float4 *>(wsm + dy * WROW * 2);
 #pragma unroll
-                for (int o = 0; o < OW; ++o) acc[o] = __ffma2_rn(wb, P[o + j + 1], acc[o]);
+            for (int j = 0; j < K; j += 2) {
+                const float4 w4 = wr[j >> 1];
+                const float2 wa = make_float2(w4.x, w4.y);
+#pragma unroll
+                for (int o = 0; o < OW; ++o) acc[o] = __ffma2_rn(wa, P[o + j], acc[o]);
+                if (j + 1 < K) {
+                    const float2 wb = make_float2(w4.z, w4.w);
+#pragma unroll
+                    for (int o = 0; o < OW; ++o) acc[o] = __ffma2_rn(wb, P[o + j + 1], acc[o]);
+                }
             }
         }
     }
