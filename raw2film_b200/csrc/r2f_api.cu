@@ -1054,6 +1054,8 @@ int render_body(r2f_ctx *c, const void *in, int in_format, float in_gain, int H,
         ga.W = W;
         ga.gk = c->t->grain.chan[0];
         ga.gk_sym = c->t->grain.sym_ok ? c->t->grain.sym[0] : nullptr;
+        if (ga.gk_sym && c->t->grain.sym_per * sizeof(float) <= sizeof(ga.gkw))
+            memcpy(ga.gkw, c->t->grain.sym_host.data(), c->t->grain.sym_per * sizeof(float));
         ga.k = c->t->grain.k;
         ga.kp = c->t->grain.kp;
         ga.bw = nch == 1;

@@ -94,7 +94,7 @@ __device__ __forceinline__ void tma_load_3d(float *smem_dst, const CUtensorMap *
 }
 
 template <int K, int OW>
-__global__ void __launch_bounds__((64 / OW) * 32, OW == 8 ? 3 : 4)
+__global__ void __launch_bounds__((64 / OW) * 32, OW == 8 ? 3 : 6)
 k_conv2d_sym(ConvArgs a, const __grid_constant__ CUtensorMap tmap, int use_tma, int shift,
              const __grid_constant__ SymWeights<K> wts) {
     using C = SymCfg<K, OW>;

@@ -37,13 +37,12 @@ struct GrainCfg {
                                         // warp hit different banks when they store their packed words
     static constexpr int TILE_BYTES = ROWS * PITCH * 4 > T * SPITCH ? ROWS * PITCH * 4 : T * SPITCH;
     static constexpr int TILE_FLOATS = (TILE_BYTES + 15) / 16 * 4;
-    static constexpr int W_FLOATS = (R + 1) * WROW * 2;
     static constexpr int DP = T + 4;                     // density tile row pitch (floats): 17 16-byte chunks, odd, so
                                                          // the 128-bit accesses of a warp (one tile row per lane) are
                                                          // bank-conflict free
     static constexpr int PRIV_FLOATS = 3 * T * DP;       // the three layers' densities, overwritten in place by the
                                                          // grained densities
-    static constexpr int SMEM_BYTES = (TILE_FLOATS + W_FLOATS + PRIV_FLOATS) * 4;
+    static constexpr int SMEM_BYTES = (TILE_FLOATS + PRIV_FLOATS) * 4;
 };
 
 template <int K, int OW, bool GEN, bool FASTC>
@@ -52,13 +51,11 @@ k_grain_finish_sym(const __grid_constant__ GrainFinishArgs a) {
     using C = GrainCfg<K, OW>;
     extern __shared__ __align__(16) float smem[];
     float *tile = smem;
-    float *wsm = smem + C::TILE_FLOATS;
-    float *priv = wsm + C::W_FLOATS;
+    float *priv = smem + C::TILE_FLOATS;
     const int H = a.H, W = a.W;
     const int tx0 = blockIdx.x * C::T, ty0 = (blockIdx.y + a.tile_y0) * C::T;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const size_t ps = a.plane_stride;
-    for (int idx = threadIdx.x; idx < C::W_FLOATS; idx += C::NT) wsm[idx] = __ldg(a.gk_sym + idx);
 
     const int nch = a.bw ? 1 : 3;
     const int xs = tx0 - C::R;                                      // global x of tile column 0
@@ -132,7 +129,7 @@ k_grain_finish_sym(const __grid_constant__ GrainFinishArgs a) {
             for (int o = 0; o < C::OW; ++o) g[o] = make_float2(0.f, 0.f);
             const float *ctr0 = tile + (lane + C::R) * C::PITCH + C::OW * warp;
             const float *ctr1 = ctr0 + 32 * C::PITCH;
-            sym_correlate<K, C::OW, C::PITCH, C::WROW>(ctr0, ctr1, wsm, g);
+            sym_correlate<K, C::OW, C::PITCH, C::WROW, true>(ctr0, ctr1, reinterpret_cast<const float *>(a.gkw), g);
         }
         // grain apply on channel c (black-and-white grain reuses the single field)
 #pragma unroll

@@ -104,6 +104,7 @@ cudaError_t launch_interleaved_to_planar(const float *in, int cin, int nch, Plan
 // `shift`: column shift of the field's quad grid, (grain kernel radius) & 3 inside a render (noise.cuh)
 cudaError_t launch_noise(Planes out, int nch, int H, int W, uint64_t seed, int shift, int num_sms, cudaStream_t st);
 // fused grain + burn apply + tetrahedral LUT + quantise (normal render path)
+constexpr int kGrainSymMaxK = 21;
 struct GrainFinishArgs {
     const float *dens;   // planar density (after MTF)
     const float *noise;  // planar injected white noise, or nullptr: regenerate from the seed per tile
@@ -111,6 +112,7 @@ struct GrainFinishArgs {
     int H, W;
     const float *gk;     // grain kernel, transposed + padded: gk[j * kp + i]
     const float *gk_sym; // y-symmetric packed layout (ConvArgs::ksym) or nullptr
+    float2 gkw[(kGrainSymMaxK / 2 + 1) * ((kGrainSymMaxK + 1) / 2 * 2)];  // the same (w, w) pairs as a launch parameter
     int k, kp;
     int bw;              // one noise field for all three layers
     uint32_t seed_lo, seed_hi;
@@ -125,7 +127,6 @@ struct GrainFinishArgs {
 };
 cudaError_t launch_grain_finish(const GrainFinishArgs &a, cudaStream_t st);
 // same contract for y-symmetric grain kernels without burn (r2f_grain_sym.cu): row-pair sums + packed FMA
-constexpr int kGrainSymMaxK = 21;
 bool grain_finish_sym_supported(int k);
 cudaError_t launch_grain_finish_sym(const GrainFinishArgs &a, cudaStream_t st);
 // highlight-burn low-res mask: area down-sample of the green plane, max(x - d_ref, 0), 13-tap Gaussian (sigma 3)
