@@ -661,11 +661,14 @@ ConvArgs conv_args(const KernelSet &ks, const float *in, float *out, size_t ps, 
 }
 
 // direct correlation: the y-symmetric packed-FMA kernel when the kernel set allows it, else the generic one
-cudaError_t conv_dispatch(const r2f_ctx *c, const ConvArgs &a, cudaStream_t st) {
+bool conv_takes_sym(const r2f_ctx *c, const ConvArgs &a) {
     const bool any_conv = a.mode[0] || a.mode[1] || a.mode[2];
     const bool nonuniform = a.epi != EPI_NONE && a.curve.xp != nullptr;  // only the generic kernel runs np.interp
-    if (c->conv_sym && any_conv && a.ksym[0] && a.ksym[1] && a.ksym[2] && a.epi != EPI_GRAIN && !nonuniform)
-        return launch_conv2d_sym(a, st);
+    return c->conv_sym && any_conv && a.ksym[0] && a.ksym[1] && a.ksym[2] && a.epi != EPI_GRAIN && !nonuniform;
+}
+cudaError_t conv_dispatch(const r2f_ctx *c, const ConvArgs &a, cudaStream_t st) {
+    if (conv_takes_sym(c, a)) return launch_conv2d_sym(a, st);
+    if (a.tile_rows > 0) return cudaErrorInvalidValue;  // only the symmetric kernel renders a band of tile rows
     return launch_conv2d(a, st);
 }
 
@@ -1023,11 +1026,23 @@ int render_body(r2f_ctx *c, const void *in, int in_format, float in_gain, int H,
     int cur = 1;
     if (tap_stage == R2F_TAP_DENSITY) return export_tap(P[cur]);
 
-    // a6: MTF
+    // a6: MTF.  A banded call whose tail is MTF -> fused grain + finish runs the two kernels band by band (both are
+    // tile-local; the MTF reads its halo rows from the complete density planes), so that the first rows of the result
+    // can leave the device one band of MTF + grain after the density is complete, not a whole-frame MTF later.
+    const bool fused_grain = tap_stage == 0 && (flags & R2F_GRAIN) && !(flags & R2F_BURN) &&
+                             (size_t)(64 + c->t->grain.k - 1) * (64 + c->t->grain.k - 1) * 4 +
+                                     (size_t)c->t->grain.k * c->t->grain.kp * 4 + 16384 <= 200 * 1024;
+    ConvArgs mtf_band{};
+    bool band_mtf = false;
     if (flags & R2F_MTF) {
         ConvArgs a = conv_args(c->t->mtf, P[cur].base, P[1 - cur].base, ps, H, W);
-        ProfScope ps_(c, st, R2F_PROF_MTF);
-        CU(conv_dispatch(c, a, st));
+        if (nb > 1 && fused_grain && conv_takes_sym(c, a)) {
+            mtf_band = a;
+            band_mtf = true;
+        } else {
+            ProfScope ps_(c, st, R2F_PROF_MTF);
+            CU(conv_dispatch(c, a, st));
+        }
         c->launches += 1;
         cur = 1 - cur;
     }
@@ -1035,9 +1050,7 @@ int render_body(r2f_ctx *c, const void *in, int in_format, float in_gain, int H,
 
     // a7 + a8 + a9 + a10 fused (normal render): noise regenerated per tile, nothing but the density
     // read and the uint8 write touches HBM.  Taps keep the staged kernels below.
-    if (tap_stage == 0 && (flags & R2F_GRAIN) && !(flags & R2F_BURN) &&
-        (size_t)(64 + c->t->grain.k - 1) * (64 + c->t->grain.k - 1) * 4 + (size_t)c->t->grain.k * c->t->grain.kp * 4 + 16384 <=
-            200 * 1024) {
+    if (fused_grain) {
         const int nch = (flags & R2F_GRAIN_BW) ? 1 : 3;
         GrainFinishArgs ga{};
         ga.dens = P[cur].base;
@@ -1076,6 +1089,11 @@ int render_body(r2f_ctx *c, const void *in, int in_format, float in_gain, int H,
             if (r1 <= r0) continue;
             ga.tile_y0 = nb > 1 ? r0 / 64 : 0;
             ga.tile_rows = nb > 1 ? (r1 - r0 + 63) / 64 : 0;
+            if (band_mtf) {
+                mtf_band.tile_y0 = ga.tile_y0;
+                mtf_band.tile_rows = ga.tile_rows;
+                CU(launch_conv2d_sym(mtf_band, st));
+            }
             if (gsym) CU(launch_grain_finish_sym(ga, st));
             else CU(launch_grain_finish(ga, st));
             CU(done_out(b + 1));

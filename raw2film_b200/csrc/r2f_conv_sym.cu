@@ -102,7 +102,7 @@ k_conv2d_sym(ConvArgs a, const __grid_constant__ CUtensorMap tmap, int use_tma, 
     __shared__ __align__(8) uint64_t tma_bar;
     float *tile = smem;
     const int c = blockIdx.z;
-    const int tx0 = blockIdx.x * C::TW - shift, ty0 = blockIdx.y * C::TH;
+    const int tx0 = blockIdx.x * C::TW - shift, ty0 = ((int)blockIdx.y + a.tile_y0) * C::TH;
     const int H = a.H, W = a.W;
     const float *__restrict__ src = a.in + (size_t)a.in_plane[c] * a.plane_stride;
     float *__restrict__ dst = a.out + (size_t)c * a.plane_stride;
@@ -238,7 +238,7 @@ cudaError_t launch_sym(const ConvArgs &a, cudaStream_t st) {
     // the tiles start SHIFT columns left of a 64-column boundary so that the input tile's left edge is 16-byte aligned
     // (cp.async and TMA both need that: a TMA box starting at an unaligned column faults as an illegal instruction)
     const int shift = C::SHIFT;
-    dim3 grid((a.W + shift + C::TW - 1) / C::TW, (a.H + C::TH - 1) / C::TH, 3);
+    dim3 grid((a.W + shift + C::TW - 1) / C::TW, a.tile_rows > 0 ? a.tile_rows : (a.H + C::TH - 1) / C::TH, 3);
     SymWeights<K> wts;
     for (int c = 0; c < 3; ++c)
         if (a.mode[c] != 0) memcpy(wts.w[c], a.ksym_host[c], sizeof(wts.w[c]));

@@ -40,6 +40,7 @@ struct ConvArgs {
     int epi;
     Curve1D curve;  // H-D curve (EPI_DENSITY) or grain amplitude curve (EPI_GRAIN)
     float eps;
+    int tile_y0, tile_rows;  // k_conv2d_sym only: rows of 64-row tiles to compute (tile_rows == 0: the whole frame)
 };
 
 struct BurnArgs {

@@ -45,6 +45,22 @@ class PipelinedRenderer:
         self._last_slot = None
         self.h2d_bytes = 0
         self.d2h_bytes = 0
+        import os
+
+        self._timed = bool(os.environ.get("R2F_TIMELINE"))   # tools/micro/e2e_timeline.py: events that carry times
+
+    def timeline(self, ticket: int):
+        """R2F_TIMELINE=1 only: milliseconds after the start of the frame's upload at which each upload band had
+        arrived, the render had finished each output band, the whole render and the whole read-back were done."""
+        slot = self._slots[ticket % self.depth]
+        slot["d2h"].synchronize()
+        t0 = slot["t0"]
+        out = {"h2d_done": t0.elapsed_time(slot["h2d"]), "render_done": t0.elapsed_time(slot["done"]),
+               "d2h_done": t0.elapsed_time(slot["d2h"])}
+        if slot.get("in_ev"):
+            out["in_bands"] = [t0.elapsed_time(e) for e in slot["in_ev"]]
+            out["out_bands"] = [t0.elapsed_time(e) for e in slot["out_ev"]]
+        return out
 
     def _slot_buffers(self, slot, shape_in, tdtype, out_shape, render_hw):
         torch = self._torch
@@ -58,8 +74,8 @@ class PipelinedRenderer:
             slot["host_out"] = torch.empty(tuple(out_shape), dtype=torch.uint8, pin_memory=True)
             slot["canvas_dev"] = None
         if "h2d" not in slot:
-            for k in ("h2d", "done", "d2h"):
-                slot[k] = torch.cuda.Event()
+            for k in ("h2d", "done", "d2h", "t0"):
+                slot[k] = torch.cuda.Event(enable_timing=self._timed)
 
     def submit(self, cpu_payload, negative_film, grain_size, grain_sigma, upload: bool = True, readback: bool = True,
                **settings) -> int:
@@ -93,13 +109,14 @@ class PipelinedRenderer:
                 nb = max(1, min(self.bands, h // 256))    # bands of at least 256 rows
             rows = [int(_cabi.lib.r2f_band_row(h, nb, i)) for i in range(nb + 1)]
             if nb > 1 and len(slot.get("in_ev", ())) != nb:
-                slot["in_ev"] = [torch.cuda.Event() for _ in range(nb)]
-                slot["out_ev"] = [torch.cuda.Event() for _ in range(nb)]
+                slot["in_ev"] = [torch.cuda.Event(enable_timing=self._timed) for _ in range(nb)]
+                slot["out_ev"] = [torch.cuda.Event(enable_timing=self._timed) for _ in range(nb)]
                 for e in slot["in_ev"] + slot["out_ev"]:
                     e.record(self.s_in)               # creates the underlying cudaEvent_t
             with torch.cuda.stream(self.s_in):
                 if slot.get("last_read") is not None:
                     self.s_in.wait_event(slot["last_read"])   # the last render that read this dev_in has finished
+                slot["t0"].record(self.s_in)
                 if nb > 1:
                     for i in range(nb):
                         slot["dev_in"][rows[i]:rows[i + 1]].copy_(host[rows[i]:rows[i + 1]], non_blocking=True)

@@ -674,8 +674,10 @@ class B200Processor:
             from .pipeline import PipelinedRenderer
 
             # a synchronous call has no neighbouring frames to overlap with: stream the frame in and the result out
-            # in bands around the first and last kernel instead (r2f_render_banded); measured at 24 MP full emulation:
-            # 8.34 / 8.13 / 7.78 / 7.73 ms per call with 1 / 2 / 4 / 8 bands (A/B knob R2F_CALL_BANDS)
+            # in bands around the first and the last two kernels instead (r2f_render_banded; MTF and grain run band by
+            # band).  Measured at 24 MP full emulation (tools/micro/e2e_timeline.py): 8.09 / 7.33 / 7.30 / 7.49 ms per
+            # call with 1 / 4 / 8 / 16 bands (A/B knob R2F_CALL_BANDS); of the 7.30 ms, 5.26 are the 288 MB upload and
+            # 1.3 the 72 MB read-back, which starts 0.64 ms after the upload ends.
             import os
 
             self._pipe = PipelinedRenderer(self, depth=3, bands=int(os.environ.get("R2F_CALL_BANDS", "8")))
