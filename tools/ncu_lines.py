@@ -40,7 +40,12 @@ def main():
     page = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--kernel-name", "regex:" + kregex],
                           capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(page)))
-    hdr, data = rows[1], [r for r in rows[2:] if len(r) >= len(rows[1])]
+    hdr, data = rows[1], []
+    for r in rows[2:]:          # ncu prints the table once per view: keep the first copy
+        if r and r[0] == "Kernel Name":
+            break
+        if len(r) >= len(hdr):
+            data.append(r)
     ix = {n: i for i, n in enumerate(hdr)}
     sl = sass_lines(cubin, mangled)
     if len(sl) != len(data):

@@ -1,6 +1,7 @@
 #!/usr/bin/env python
 """SASS evidence for profiles/: per hot kernel of libr2f_b200.so, the mnemonic counts that show what the code
 is (UTMALDG = TMA bulk tensor load, FFMA2 / FADD2 / FMUL2 = packed float32x2, LDGSTS = cp.async, SYNCS = mbarrier,
+LDCU = uniform-datapath constant load (the correlation weights: FFMA2 takes the uniform register as an operand),
 MUFU, no UTC*MMA / LDTM: no tensor-core contraction on this path) and a short excerpt of the hottest loop.
 
     python tools/sass_excerpt.py > profiles/r02_sass.md        (needs cuobjdump; runs on the build machine)
@@ -18,13 +19,13 @@ LIB = os.path.join(ROOT, "raw2film_b200", "libr2f_b200.so")
 KERNELS = [  # (substring of the mangled name, title, regex of a mnemonic that marks the hot loop)
     ("k_pointwise_fastILi0ELi1024ELb1E", "k_pointwise_fast<F32x3, 1024 threads, packed pairs>", r"FADD2"),
     ("k_conv2d_symILi17ELi16E", "k_conv2d_sym<17, 16> (MTF)", r"FFMA2"),
-    ("k_grain_finish_symILi7ELb1ELb1E", "k_grain_finish_sym<7, GEN, FASTCURVE>", r"FFMA2"),
+    ("k_grain_finish_symILi7ELi8ELb1ELb1E", "k_grain_finish_sym<7, 8, GEN, FASTCURVE>", r"FFMA2"),
     ("k_fft_rows_fwdILi1ELi1ELi1E", "k_fft_rows_fwd<SRC=F32x3, ROWS=1, PLAN=1>", r"LDGSTS"),
-    ("k_fft_cols_ipILi1E", "k_fft_cols_ip<1> (n = 4096)", r"FFMA"),
+    ("k_fft_cols_ipILi1ELi2E", "k_fft_cols_ip<1, 2> (n = 4096, two columns per CTA)", r"FFMA"),
     ("k_fft_rows_invILi0ELi1ELi1ELi1E", "k_fft_rows_inv<0, 1, 1, 1>", r"MUFU"),
     ("k_resize_areaIfE", "k_resize_area<float>", r"FMUL"),
 ]
-WATCH = ["UTMALDG", "UTMAPF", "SYNCS", "LDGSTS", "FFMA2", "FADD2", "FMUL2", "FFMA", "FADD", "FMUL", "DFMA", "MUFU",
+WATCH = ["UTMALDG", "UTMAPF", "SYNCS", "LDGSTS", "LDCU", "CCTL", "FFMA2", "FADD2", "FMUL2", "FFMA", "FADD", "FMUL", "DFMA", "MUFU",
          "F2I", "I2FP", "FRND", "LDS", "LDG", "STG", "STS", "BAR", "UTCHMMA", "UTCQMMA", "LDTM", "HMMA"]
 
 
