@@ -1665,10 +1665,8 @@ int r2f_chroma_nr(r2f_ctx *c, const float *in_dev, int in_channels, float *out_d
     if (!workspace_dev || workspace_bytes < ps * 6 * sizeof(float))
         return fail(R2F_ERR_NOMEM, "workspace too small (see r2f_workspace_bytes)");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    CU(c->cnr_taps.ensure((size_t)ntaps * sizeof(float)));
-    CU(cudaMemcpyAsync(c->cnr_taps.p, taps, (size_t)ntaps * sizeof(float), cudaMemcpyHostToDevice, st));
-    CU(launch_chroma_nr(in_dev, in_channels, out_dev, H, W, static_cast<const float *>(c->cnr_taps.p), ntaps,
-                        static_cast<float *>(workspace_dev), ps, c->num_sms, st));
+    CU(launch_chroma_nr(in_dev, in_channels, out_dev, H, W, taps, ntaps, static_cast<float *>(workspace_dev), ps,
+                        c->num_sms, st));   // the taps travel as a kernel parameter
     c->launches += 2;
     return R2F_OK;
 }

@@ -690,15 +690,18 @@ k_interleaved_to_planar(const float *__restrict__ in, int cin, int nch, float *_
 constexpr int kCnrSeg = 512;      // outputs per CTA of the row kernel (two per thread)
 constexpr int kCnrMaxHalf = 24;   // chroma_nr <= 20 in the reference GUI (slider 0..10, doubled on export)
 constexpr int kCnrTileW = 64, kCnrTileH = 32;
+// the Gaussian taps travel as a kernel parameter: the tap index is warp-uniform, so they reach the multiplier through
+// the uniform datapath instead of a shared-memory broadcast per tap
+struct CnrTaps {
+    float w[2 * kCnrMaxHalf + 1];
+};
 
 __global__ void __launch_bounds__(kThreads)
 k_cnr_rows(const float *__restrict__ in, int cin, float *__restrict__ tmp, float *__restrict__ yplane, size_t ps, int H,
-           int W, const float *__restrict__ taps, int half) {
+           int W, const __grid_constant__ CnrTaps taps, int half) {
     __shared__ float sx[kCnrSeg + 2 * kCnrMaxHalf], sy[kCnrSeg + 2 * kCnrMaxHalf];
-    __shared__ float st[2 * kCnrMaxHalf + 1];
     const int y = blockIdx.y, x0 = blockIdx.x * kCnrSeg;
     const int n = min(kCnrSeg, W - x0), span = n + 2 * half;
-    for (int i = threadIdx.x; i <= 2 * half; i += kThreads) st[i] = taps[i];
     const float *row = in + (size_t)y * W * cin;
     for (int i = threadIdx.x; i < span; i += kThreads) {
         const int gx = min(max(x0 - half + i, 0), W - 1);  // edge clamp of the blur = chromaticity of the clamped pixel
@@ -713,7 +716,7 @@ k_cnr_rows(const float *__restrict__ in, int cin, float *__restrict__ tmp, float
     for (int o = threadIdx.x; o < n; o += kThreads) {
         double ax = 0.0, ay = 0.0;
         for (int t = 0; t <= 2 * half; ++t) {
-            const float w = st[t];
+            const float w = taps.w[t];
             ax += (double)(sx[o + t] * w);  // float32 product, binary64 sum
             ay += (double)(sy[o + t] * w);
         }
@@ -725,12 +728,10 @@ k_cnr_rows(const float *__restrict__ in, int cin, float *__restrict__ tmp, float
 
 __global__ void __launch_bounds__(kThreads)
 k_cnr_cols(const float *__restrict__ tmp, const float *__restrict__ yplane, float *__restrict__ out, size_t ps, int H,
-           int W, const float *__restrict__ taps, int half) {
+           int W, const __grid_constant__ CnrTaps taps, int half) {
     extern __shared__ __align__(16) float tile[];  // [2][kCnrTileH + 2*half][kCnrTileW]
-    __shared__ float st[2 * kCnrMaxHalf + 1];
     const int x0 = blockIdx.x * kCnrTileW, y0 = blockIdx.y * kCnrTileH;
     const int rows = kCnrTileH + 2 * half;
-    for (int i = threadIdx.x; i <= 2 * half; i += kThreads) st[i] = taps[i];
     for (int i = threadIdx.x; i < 2 * rows * kCnrTileW; i += kThreads) {
         const int c = i / (rows * kCnrTileW), r = (i / kCnrTileW) % rows, col = i % kCnrTileW;
         const int gy = min(max(y0 - half + r, 0), H - 1), gx = min(x0 + col, W - 1);
@@ -744,7 +745,7 @@ k_cnr_cols(const float *__restrict__ tmp, const float *__restrict__ yplane, floa
         if (gy >= H || gx >= W) continue;
         double ax = 0.0, ay = 0.0;
         for (int t = 0; t <= 2 * half; ++t) {
-            const float w = st[t];
+            const float w = taps.w[t];
             ax += (double)(tx[(r + t) * kCnrTileW + col] * w);
             ay += (double)(ty[(r + t) * kCnrTileW + col] * w);
         }
@@ -764,11 +765,13 @@ k_cnr_cols(const float *__restrict__ tmp, const float *__restrict__ yplane, floa
     }
 }
 
-cudaError_t launch_chroma_nr(const float *in, int cin, float *out, int H, int W, const float *taps_dev, int ntaps,
-                             float *ws /* 6 planes */, size_t ps, int num_sms, cudaStream_t st) {
+cudaError_t launch_chroma_nr(const float *in, int cin, float *out, int H, int W, const float *taps_host, int ntaps,
+                             float *ws /* 3 planes */, size_t ps, int num_sms, cudaStream_t st) {
     (void)num_sms;
     const int half = ntaps / 2;
     if (half > kCnrMaxHalf) return cudaErrorInvalidValue;
+    CnrTaps taps_dev{};
+    for (int i = 0; i < ntaps; ++i) taps_dev.w[i] = taps_host[i];
     float *tmp = ws, *yplane = ws + 2 * ps;
     k_cnr_rows<<<dim3((W + kCnrSeg - 1) / kCnrSeg, H), kThreads, 0, st>>>(in, cin, tmp, yplane, ps, H, W, taps_dev, half);
     const size_t smem = (size_t)2 * (kCnrTileH + 2 * half) * kCnrTileW * sizeof(float);

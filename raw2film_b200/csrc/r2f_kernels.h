@@ -75,7 +75,7 @@ cudaError_t launch_conv2d_sym(const ConvArgs &a, cudaStream_t st);
 cudaError_t launch_finish(Planes in, size_t npix, int H, int W, const Lut3D &l3, const BurnArgs &burn, uint8_t *out_u8,
                           float *out_f32, int f32_stage_rgb, int num_sms, cudaStream_t st);
 // chroma NR pre-stage (reference effects.py:421-561): needs 6 float planes of scratch
-cudaError_t launch_chroma_nr(const float *in, int cin, float *out, int H, int W, const float *taps_dev, int ntaps,
+cudaError_t launch_chroma_nr(const float *in, int cin, float *out, int H, int W, const float *taps_host, int ntaps,
                              float *ws, size_t ps, int num_sms, cudaStream_t st);
 // 3 x 256 histogram counts of a uint8 H x W x 3 image (reference utils.py:158-169)
 cudaError_t launch_histogram(const uint8_t *img, size_t npix, unsigned int *counts_dev, int num_sms, cudaStream_t st);
