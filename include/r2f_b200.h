@@ -110,8 +110,10 @@ int r2f_set_grain(r2f_ctx *ctx, const float *curve, int N, const float *kernel, 
  * 2 = force FFT (render fails if the kernel or frame is not eligible). */
 #define R2F_OPT_CONV_PATH 1
 #define R2F_OPT_CONV_SYM 2
-/* R2F_OPT_FUSE_MTF: 1 (default) = the MTF correlation is fused into the grain/finish kernel when the kernels
- * allow it, 0 = separate launches (A/B and parity tests).
+/* R2F_OPT_FUSE_MTF: 1 (default) = in a banded call (r2f_render_banded) the MTF correlation is issued band by band
+ * together with the grain + finish kernel, so the first rows of the result are final one band of MTF + grain after
+ * the density planes are complete; 0 = one whole-frame MTF launch before the banded grain kernel (A/B; same bytes).
+ * (A single kernel doing both was measured not to pay: both are compute-bound and want different thread shapes.)
  * R2F_OPT_FAST_CHAIN: 1 (default) = per-pixel chains evaluate a guarded float32 fast path and defer the pixels
  * whose uint8 result it cannot prove to the exact path; 0 = exact path for every pixel. */
 #define R2F_OPT_FUSE_MTF 3

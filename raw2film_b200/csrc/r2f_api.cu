@@ -199,7 +199,7 @@ struct r2f_ctx {
     DevBuf khat_scratch;
     int conv_path = 0;  // R2F_OPT_CONV_PATH: 0 auto, 1 direct, 2 fft
     int conv_sym = 1;   // R2F_OPT_CONV_SYM: 1 = y-symmetric kernels take the packed-FMA kernel
-    int fuse_mtf = 1;   // R2F_OPT_FUSE_MTF: 1 = MTF fused into the grain/finish kernel when supported
+    int fuse_mtf = 1;   // R2F_OPT_FUSE_MTF: 1 = banded calls issue the MTF band by band with the grain kernel
     int fast_chain = 1; // R2F_OPT_FAST_CHAIN: 1 = guarded float32 fast path of the pointwise chain
 
     // per-kernel profiling (r2f_profile_*)
@@ -1036,7 +1036,7 @@ int render_body(r2f_ctx *c, const void *in, int in_format, float in_gain, int H,
     bool band_mtf = false;
     if (flags & R2F_MTF) {
         ConvArgs a = conv_args(c->t->mtf, P[cur].base, P[1 - cur].base, ps, H, W);
-        if (nb > 1 && fused_grain && conv_takes_sym(c, a)) {
+        if (nb > 1 && c->fuse_mtf && fused_grain && conv_takes_sym(c, a)) {
             mtf_band = a;
             band_mtf = true;
         } else {

@@ -173,7 +173,8 @@ class B200Processor:
         _cabi.check(_cabi.lib.r2f_set_option(self._ctx, _cabi.OPT_FAST_CHAIN, 1 if enabled else 0))
 
     def set_fuse_mtf(self, enabled: bool = True) -> None:
-        """MTF fused into the grain / finish kernel (default) or run as its own correlation pass."""
+        """Banded calls (`process_preloaded`): issue the MTF correlation band by band together with the grain kernel
+        (default) or as one whole-frame launch before it.  Same bytes either way; A/B switch."""
         _cabi.check(_cabi.lib.r2f_set_option(self._ctx, _cabi.OPT_FUSE_MTF, 1 if enabled else 0))
 
     def fast_chain_stats(self):

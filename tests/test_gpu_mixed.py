@@ -274,6 +274,21 @@ def test_banded_streaming_call_equals_plain_render(proc, st):
     assert np.array_equal(got16, want16)
 
 
+def test_banded_mtf_switch_gives_the_same_bytes(proc):
+    """R2F_OPT_FUSE_MTF: the MTF issued band by band with the grain kernel or as one whole-frame launch."""
+    stock = SyntheticStock()
+    st = dict(halation=True, sharpness=True, grain=2, halation_green_factor=0.3)
+    xyz = natural_frame(1100, 1500, 23)
+    payload = proc.extract_image_data_cpu(xyz, **st)
+    a = np.array(proc.process_preloaded(payload, stock, 6.0, 0.4, **st))
+    proc.set_fuse_mtf(False)
+    try:
+        b = np.array(proc.process_preloaded(payload, stock, 6.0, 0.4, **st))
+    finally:
+        proc.set_fuse_mtf(True)
+    assert np.array_equal(a, b)
+
+
 def test_black_and_white_stock_halation_through_fft(proc):
     """B/W stocks filter all three layers with the same kernel (effects.py:248-250): the FFT path runs a second
     transform pair for the third layer.  Taps vs the oracle, FFT vs forced direct correlation, uint8 <= 1 LSB."""
