@@ -277,7 +277,7 @@ def test_banded_streaming_call_equals_plain_render(proc, st):
 def test_banded_mtf_switch_gives_the_same_bytes(proc):
     """R2F_OPT_FUSE_MTF: the MTF issued band by band with the grain kernel or as one whole-frame launch."""
     stock = SyntheticStock()
-    st = dict(halation=True, sharpness=True, grain=2, halation_green_factor=0.3)
+    st = dict(halation=True, sharpness=True, grain=2, halation_green_factor=0.3, grain_seed=1234)
     xyz = natural_frame(1100, 1500, 23)
     payload = proc.extract_image_data_cpu(xyz, **st)
     a = np.array(proc.process_preloaded(payload, stock, 6.0, 0.4, **st))
