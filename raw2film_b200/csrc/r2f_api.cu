@@ -518,7 +518,7 @@ FftLineDev *fft_line_for(r2f_ctx *c, int n);
 
 struct FftGeometry {
     int Hp = 0, Wp = 0, nc = 0, groups = 0;
-    bool inplace = false;  // in-place column kernel: four columns per CTA, one thread group each
+    bool inplace = false;  // in-place column kernel: one 256-thread group per column, two (or four) columns per CTA
     bool ok = false;
 };
 

@@ -308,8 +308,8 @@ __device__ __forceinline__ float2 *fft_run(float2 *a, float2 *b, const FftLine &
 // In-place passes for the column kernel: forward decimation-in-frequency (natural order in, mixed-radix digit-
 // reversed order out), product with the (equally permuted) kernel spectrum, inverse as a forward decimation-in-
 // time transform of the re/im-swapped data (digit-reversed in, natural out).  No ping-pong partner: a column
-// needs n float2 of shared memory instead of 2n, so all four columns of a block are transformed concurrently by
-// four 256-thread groups.  The innermost radix of the forward transform, the product and the innermost radix of
+// needs n float2 of shared memory instead of 2n, so every column of a CTA is transformed concurrently by its own
+// 256-thread group (two columns per CTA and two CTAs per SM by default, see k_fft_cols_ip).  The innermost radix of the forward transform, the product and the innermost radix of
 // the inverse touch the same R contiguous elements and are fused in registers (ip_mid).
 // ------------------------------------------------------------------------------------------
 template <int R, int N, int B, int GS, bool DIT>
