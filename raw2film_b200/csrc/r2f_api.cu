@@ -595,6 +595,8 @@ int fft_prepare(r2f_ctx *c, const KernelSet &ks, int H, int W, const FftGeometry
     a.H = H;
     a.W = W;
     a.r = ks.k / 2;
+    a.row_off = (4 - a.r % 4) % 4;
+    if (W + 2 * a.r + a.row_off > g.Wp) a.row_off = 0;   // no slack in the padded length: unshifted, 8-byte accesses
     a.row = row->line();
     a.col = col->line();
     a.nc = g.nc;

@@ -399,12 +399,14 @@ __device__ __forceinline__ void ip_conv(float2 *__restrict__ x, const float2 *__
 
 // reflect-101 fill of the r-wide borders of a padded line whose interior [r, r+len) is loaded,
 // and zero fill of the tail [len+2r, n).
-__device__ __forceinline__ void pad_line(float2 *buf, int len, int r, int n, const Group &g) {
+// `off`: the padded line starts `off` elements into the buffer (row kernels, FftConvArgs::row_off); [0, off) is zeroed.
+__device__ __forceinline__ void pad_line(float2 *buf, int len, int r, int n, const Group &g, int off = 0) {
     for (int p = g.tid; p < r; p += g.size) {
-        buf[sw(p)] = buf[sw(r + reflect101(p - r, len))];
-        buf[sw(r + len + p)] = buf[sw(r + reflect101(len + p, len))];
+        buf[sw(off + p)] = buf[sw(off + r + reflect101(p - r, len))];
+        buf[sw(off + r + len + p)] = buf[sw(off + r + reflect101(len + p, len))];
     }
-    for (int p = len + 2 * r + g.tid; p < n; p += g.size) buf[sw(p)] = make_float2(0.f, 0.f);
+    for (int p = off + len + 2 * r + g.tid; p < n; p += g.size) buf[sw(p)] = make_float2(0.f, 0.f);
+    if (g.tid < off) buf[sw(g.tid)] = make_float2(0.f, 0.f);
 }
 
 // Row kernels: ROWS image rows per CTA, one thread group per row (ROWS == 2: two 512-thread groups
@@ -445,7 +447,9 @@ __device__ __forceinline__ void stage_lut2d_finish(const Group &g) {
 template <int FMT, bool LUT_SMEM>
 __device__ __forceinline__ void load_row_xyz(const FftConvArgs &a, const Lut2D &l2, float2 *__restrict__ line, int y,
                                              const Group &g) {
-    const int W = a.W, r = a.r;
+    const int W = a.W, r = a.r + a.row_off;   // offset of pixel 0 in the line buffer
+    const bool quad_aligned = (r & 3) == 0;   // a quad's four values: two aligned 16-byte stores (2 x 6 shared-memory
+                                              // wavefronts per warp instead of 4 x 6 for four 8-byte stores)
     if ((W & 3) == 0) {  // row starts on a pixel-quad boundary: 128-bit frame loads
         const size_t q0 = (size_t)y * W / 4;
         constexpr int U = 2;  // quads in flight per thread (three fit a 6000-pixel row in one batch but spill)
@@ -466,11 +470,19 @@ __device__ __forceinline__ void load_row_xyz(const FftConvArgs &a, const Lut2D &
                 const int qx = base + u * g.size;
                 if (qx < W / 4) {
                     float e[3][4];
+                    float2 z[4];
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
                         lut2d_eval<LUT_SMEM>(l2, px[u][i][0], px[u][i][1], px[u][i][2], e[0][i], e[1][i], e[2][i]);
-                        line[sw(r + 4 * qx + i)] = make_float2(pick3(a.chan[0], e[0][i], e[1][i], e[2][i]),
-                                                           pick3(a.chan[1], e[0][i], e[1][i], e[2][i]));
+                        z[i] = make_float2(pick3(a.chan[0], e[0][i], e[1][i], e[2][i]),
+                                           pick3(a.chan[1], e[0][i], e[1][i], e[2][i]));
+                    }
+                    if (quad_aligned) {  // sw() permutes aligned pairs as a unit
+                        *reinterpret_cast<float4 *>(line + sw(r + 4 * qx)) = make_float4(z[0].x, z[0].y, z[1].x, z[1].y);
+                        *reinterpret_cast<float4 *>(line + sw(r + 4 * qx + 2)) = make_float4(z[2].x, z[2].y, z[3].x, z[3].y);
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) line[sw(r + 4 * qx + i)] = z[i];
                     }
                     if (a.exp_planar != nullptr) {
 #pragma unroll
@@ -520,7 +532,7 @@ k_fft_rows_fwd(const __grid_constant__ FftConvArgs a) {
         if (SRC == 0) {
             for (int x = g.tid; x < W; x += g.size) {
                 const size_t idx = (size_t)y * W + x;
-                bufA[sw(r + x)] = make_float2(a.src_planar[(size_t)a.chan[0] * a.plane_stride + idx],
+                bufA[sw(r + a.row_off + x)] = make_float2(a.src_planar[(size_t)a.chan[0] * a.plane_stride + idx],
                                           a.src_planar[(size_t)a.chan[1] * a.plane_stride + idx]);
             }
         } else {
@@ -538,7 +550,7 @@ k_fft_rows_fwd(const __grid_constant__ FftConvArgs a) {
             else load_row_xyz<FMT, false>(a, l2, bufA, y, g);
         }
         group_sync(g);
-        pad_line(bufA, W, r, n, g);
+        pad_line(bufA, W, r, n, g, a.row_off);
         group_sync(g);
         fft_run<PLAN>(bufA, bufB, a.row, g);
     }
@@ -733,7 +745,7 @@ template <int SRC, int DENSITY, int ROWS, int PLAN>
 __global__ void __launch_bounds__(1024, 1)
 k_fft_rows_inv(const __grid_constant__ FftConvArgs a) {
     extern __shared__ __align__(16) float2 fsm[];
-    const int W = a.W, H = a.H, r = a.r, n = a.row.n, NC = a.nc;
+    const int W = a.W, H = a.H, r = a.r + a.row_off, n = a.row.n, NC = a.nc;   // r: offset of pixel 0 in the line
     const Group g = row_group<ROWS>();
     const int half = ROWS == 2 ? (int)(threadIdx.x >> 9) : 0;
     const int y0 = blockIdx.x * ROWS;
@@ -796,10 +808,20 @@ k_fft_rows_inv(const __grid_constant__ FftConvArgs a) {
                 const float4 v = __ldcs(reinterpret_cast<const float4 *>(a.src_planar + c * ps) + q0 + qx);
                 px[0][c] = v.x; px[1][c] = v.y; px[2][c] = v.z; px[3][c] = v.w;
             }
+            float2 z[4];
+            if ((r & 3) == 0) {  // two aligned 16-byte reads instead of four 8-byte ones (sw() keeps aligned pairs together)
+                const float4 z01 = *reinterpret_cast<const float4 *>(buf + sw(r + 4 * qx));
+                const float4 z23 = *reinterpret_cast<const float4 *>(buf + sw(r + 4 * qx + 2));
+                z[0] = make_float2(z01.x, z01.y); z[1] = make_float2(z01.z, z01.w);
+                z[2] = make_float2(z23.x, z23.y); z[3] = make_float2(z23.z, z23.w);
+            } else {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) z[i] = buf[sw(r + 4 * qx + i)];
+            }
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
                 float out[3];
-                finish_px(px[i], buf[sw(r + 4 * qx + i)], out);
+                finish_px(px[i], z[i], out);
                 res[0][i] = out[0]; res[1][i] = out[1]; res[2][i] = out[2];
             }
 #pragma unroll

@@ -43,6 +43,9 @@ struct FftConvArgs {
     FftLine row, col;   // lengths Wp (>= W + 2r, multiple of kFftColsPerBlock) and Hp (>= H + 2r)
     int nc;             // columns per CTA / per block of S (2..4, divides Wp)
     int col_groups;     // thread groups per column CTA (1 or 2)
+    int row_off;        // row kernels: the padded row starts row_off elements into the line buffer (0..3), chosen so that
+                        // r + row_off is a multiple of 4 and a pixel quad's four values are two aligned 16-byte accesses;
+                        // a circular shift of the line shifts the filtered row by the same amount
     int rows_ahead;     // k_fft_rows_fwd prefetches the frame row of CTA blockIdx + rows_ahead into L2 (0: off)
     int cols_prefetch;  // column kernel: L2-prefetch its kernel-spectrum rows and the next CTA's block
     int col_inplace;    // 1: in-place column kernel (one 256-thread group per column, khat permuted by col perm)
