@@ -152,6 +152,28 @@ k_grain_finish_sym(const __grid_constant__ GrainFinishArgs a) {
         }
     }
     __syncthreads();  // all noise-tile reads done: its storage becomes the output staging area
+    if (a.dens_out != nullptr) {  // grain stage only: the grained density tile leaves as planar float32 rows
+#pragma unroll 1
+        for (int c = 0; c < 3; ++c) {
+            float *oplane = a.dens_out + c * ps;
+            for (int idx = threadIdx.x; idx < C::T * (C::T / 4); idx += C::NT) {
+                const int row = idx / (C::T / 4), ch = idx % (C::T / 4);
+                const int gy = ty0 + row, gx = tx0 + 4 * ch;
+                if (gy >= H || gx >= W) continue;
+                const float4 v = *reinterpret_cast<const float4 *>(priv + (c * C::T + row) * C::DP + 4 * ch);
+                float *dp = oplane + (size_t)gy * W + gx;
+                if (full_tile && (reinterpret_cast<uintptr_t>(a.dens_out) & 15) == 0) {
+                    *reinterpret_cast<float4 *>(dp) = v;
+                } else {
+                    dp[0] = v.x;
+                    if (gx + 1 < W) dp[1] = v.y;
+                    if (gx + 2 < W) dp[2] = v.z;
+                    if (gx + 3 < W) dp[3] = v.w;
+                }
+            }
+        }
+        return;
+    }
     uint8_t *stage = reinterpret_cast<uint8_t *>(tile);
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
@@ -237,7 +259,7 @@ cudaError_t launch_gs(const GrainFinishArgs &a, cudaStream_t st) {
 bool grain_finish_sym_supported(int k) { return k >= 3 && k <= kGrainSymMaxK && (k & 1); }
 
 cudaError_t launch_grain_finish_sym(const GrainFinishArgs &a, cudaStream_t st) {
-    if (a.gk_sym == nullptr || a.burn.map != nullptr) return cudaErrorInvalidValue;
+    if (a.gk_sym == nullptr || a.burn.map != nullptr) return cudaErrorInvalidValue;   // burn: dens_out + launch_finish
     switch (a.k) {
 #define R2F_GS(KK) case KK: return launch_gs<KK>(a, st);
         R2F_GS(3) R2F_GS(5) R2F_GS(7) R2F_GS(9) R2F_GS(11) R2F_GS(13) R2F_GS(15) R2F_GS(17) R2F_GS(19) R2F_GS(21)

@@ -593,7 +593,7 @@ __device__ __forceinline__ float burn_sample(const BurnArgs &b, int y, int x) {
 template <bool F32_OUT>
 __global__ void __launch_bounds__(kThreads)
 k_finish(const float *__restrict__ in, size_t plane_stride, size_t npix, int W, Lut3D l3, BurnArgs burn,
-         uint8_t *__restrict__ out_u8, float *__restrict__ out_f32, int f32_stage_rgb) {
+         uint8_t *__restrict__ out_u8, float *__restrict__ out_f32, int f32_stage_rgb, FastTetra ft) {
     const size_t nquad = (npix + 3) / 4;
     const size_t stride = (size_t)gridDim.x * kThreads;
     for (size_t q = (size_t)blockIdx.x * kThreads + threadIdx.x; q < nquad; q += stride) {
@@ -620,7 +620,10 @@ k_finish(const float *__restrict__ in, size_t plane_stride, size_t npix, int W, 
             } else if (F32_OUT) {
                 tetra_eval(l3, d0, d1, d2, f[3 * p], f[3 * p + 1], f[3 * p + 2]);
             } else {
-                tetra_quant_u8(l3, d0, d1, d2, b[3 * p], b[3 * p + 1], b[3 * p + 2]);
+                // conversion-free guarded float32 tail (fast_chain.cuh) with the exact path for undecided pixels and
+                // for negative / NaN densities
+                const uint32_t px = tetra_u8<false>(ft, l3, d0, d1, d2);
+                b[3 * p] = px & 255u; b[3 * p + 1] = (px >> 8) & 255u; b[3 * p + 2] = px >> 16;
             }
         }
         if (q * 4 + 4 <= npix) {
@@ -645,14 +648,14 @@ k_finish(const float *__restrict__ in, size_t plane_stride, size_t npix, int W, 
 }
 
 cudaError_t launch_finish(Planes in, size_t npix, int H, int W, const Lut3D &l3, const BurnArgs &burn, uint8_t *out_u8,
-                          float *out_f32, int f32_stage_rgb, int num_sms, cudaStream_t st) {
+                          float *out_f32, int f32_stage_rgb, int num_sms, cudaStream_t st, const FastTetra &ft) {
     (void)H;
     const int grid = grid_for((npix + 3) / 4, num_sms, 8);
     if (out_f32 != nullptr)
         k_finish<true><<<grid, kThreads, 0, st>>>(in.base, in.plane_stride, npix, W, l3, burn, nullptr, out_f32,
-                                                 f32_stage_rgb);
+                                                 f32_stage_rgb, ft);
     else
-        k_finish<false><<<grid, kThreads, 0, st>>>(in.base, in.plane_stride, npix, W, l3, burn, out_u8, nullptr, 1);
+        k_finish<false><<<grid, kThreads, 0, st>>>(in.base, in.plane_stride, npix, W, l3, burn, out_u8, nullptr, 1, ft);
     return cudaGetLastError();
 }
 

@@ -72,8 +72,10 @@ bool conv_sym_supported(int k);
 cudaError_t launch_conv2d_sym(const ConvArgs &a, cudaStream_t st);
 // planar density -> [burn] -> tetrahedral LUT -> u8 interleaved, or float32 interleaved (taps)
 
+// `ft`: guarded float32 tetrahedral tail for the uint8 output (ft.ok == 0: the exact path for every pixel)
 cudaError_t launch_finish(Planes in, size_t npix, int H, int W, const Lut3D &l3, const BurnArgs &burn, uint8_t *out_u8,
-                          float *out_f32, int f32_stage_rgb, int num_sms, cudaStream_t st);
+                          float *out_f32, int f32_stage_rgb, int num_sms, cudaStream_t st,
+                          const FastTetra &ft = FastTetra{});
 // chroma NR pre-stage (reference effects.py:421-561): needs 6 float planes of scratch
 cudaError_t launch_chroma_nr(const float *in, int cin, float *out, int H, int W, const float *taps_host, int ntaps,
                              float *ws, size_t ps, int num_sms, cudaStream_t st);
@@ -123,11 +125,14 @@ struct GrainFinishArgs {
     FastTetra ft;        // guarded float32 tetrahedral LUT + quantise (ok == 0: exact path only)
     BurnArgs burn;
     uint8_t *out_u8;
+    float *dens_out;         // k_grain_finish_sym only: not null = stop after the grain stage and write the grained
+                             // density planes here (may alias `dens`; the burn mask needs the whole grained frame)
     int tile_y0, tile_rows;  // first tile row and tile-row count of this launch (0, 0 = all): banded output
     int noise_shift;         // (k / 2) & 3: column shift of the noise field's quad grid (noise.cuh)
 };
 cudaError_t launch_grain_finish(const GrainFinishArgs &a, cudaStream_t st);
-// same contract for y-symmetric grain kernels without burn (r2f_grain_sym.cu): row-pair sums + packed FMA
+// same contract for y-symmetric grain kernels (r2f_grain_sym.cu): row-pair sums + packed FMA; no burn apply (with
+// burn, run it with dens_out and finish with launch_finish)
 bool grain_finish_sym_supported(int k);
 cudaError_t launch_grain_finish_sym(const GrainFinishArgs &a, cudaStream_t st);
 // highlight-burn low-res mask: area down-sample of the green plane, max(x - d_ref, 0), 13-tap Gaussian (sigma 3)
