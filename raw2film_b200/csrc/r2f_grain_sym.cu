@@ -72,9 +72,11 @@ k_grain_finish_sym(const __grid_constant__ GrainFinishArgs a) {
     // values in place with the grained densities.  Full tiles are copied row-wise (a warp moves two 256-byte tile rows
     // per instruction, 4 L1 wavefronts; with the thread mapping of the correlation -- one tile row per lane -- every
     // load touched 32 lines, and the density read was 47 % of the kernel's global tag requests and 15 % of its stall
-    // samples).  Tiles that cross the frame edge or an unaligned frame use per-thread loads into the same slots.
-    const bool full_tile = (W & 3) == 0 && (ps & 3) == 0 && tx0 + C::T <= W && ty0 + C::T <= H &&
-                           (reinterpret_cast<uintptr_t>(a.dens) & 15) == 0;
+    // samples).  Frames whose rows are not 16-byte aligned use per-thread loads into the same slots.
+    // (tiles that cross the bottom or right edge still copy row-wise and zero what lies outside the frame -- with W a
+    // multiple of 4 a 16-byte chunk is inside or outside as a whole: on a small frame the kernel lasts as long as its
+    // slowest CTA, and the per-thread path made the last tile row three times slower)
+    const bool full_tile = (W & 3) == 0 && (ps & 3) == 0 && (reinterpret_cast<uintptr_t>(a.dens) & 15) == 0;
     if (full_tile) {
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
@@ -82,7 +84,9 @@ k_grain_finish_sym(const __grid_constant__ GrainFinishArgs a) {
 #pragma unroll
             for (int it = 0; it < C::T * (C::T / 4) / C::NT; ++it) {
                 const int idx = threadIdx.x + it * C::NT, row = idx / (C::T / 4), ch = idx % (C::T / 4);
-                cp_async_16(priv + (c * C::T + row) * C::DP + 4 * ch, dplane + (size_t)row * W + 4 * ch);
+                float *dst = priv + (c * C::T + row) * C::DP + 4 * ch;
+                if (ty0 + row < H && tx0 + 4 * ch < W) cp_async_16(dst, dplane + (size_t)row * W + 4 * ch);
+                else *reinterpret_cast<float4 *>(dst) = make_float4(0.f, 0.f, 0.f, 0.f);
             }
         }
     } else {

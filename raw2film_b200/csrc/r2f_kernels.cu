@@ -442,7 +442,7 @@ __device__ __forceinline__ void conv_tail(float (&acc)[16], float (&v)[16], cons
 // become LDS with immediate offsets (no per-step pointer arithmetic); PITCH == 0: pitch = TW + k - 1.
 template <int TW, int TH, bool W_SMEM, int PITCH>
 __global__ void __launch_bounds__((TW / 32) * (TH / 16) * 32)
-k_conv2d(ConvArgs a) {
+k_conv2d(const __grid_constant__ ConvArgs a) {
     constexpr int NWX = TW / 32;
     constexpr int NT = (TW / 32) * (TH / 16) * 32;
     extern __shared__ __align__(16) float smem[];
@@ -592,8 +592,9 @@ __device__ __forceinline__ float burn_sample(const BurnArgs &b, int y, int x) {
 
 template <bool F32_OUT>
 __global__ void __launch_bounds__(kThreads)
-k_finish(const float *__restrict__ in, size_t plane_stride, size_t npix, int W, Lut3D l3, BurnArgs burn,
-         uint8_t *__restrict__ out_u8, float *__restrict__ out_f32, int f32_stage_rgb, FastTetra ft) {
+k_finish(const float *__restrict__ in, size_t plane_stride, size_t npix, int W, const __grid_constant__ Lut3D l3,
+         const __grid_constant__ BurnArgs burn, uint8_t *__restrict__ out_u8, float *__restrict__ out_f32,
+         int f32_stage_rgb, const __grid_constant__ FastTetra ft) {
     const size_t nquad = (npix + 3) / 4;
     const size_t stride = (size_t)gridDim.x * kThreads;
     for (size_t q = (size_t)blockIdx.x * kThreads + threadIdx.x; q < nquad; q += stride) {
@@ -1003,7 +1004,7 @@ constexpr int kGfTile = 64;
 
 template <bool GEN>
 __global__ void __launch_bounds__(256, 2)
-k_grain_finish(GrainFinishArgs a) {
+k_grain_finish(const __grid_constant__ GrainFinishArgs a) {
     extern __shared__ __align__(16) float smem[];
     const int H = a.H, W = a.W, k = a.k, kp = a.kp, rad = k / 2;
     const int cols = kGfTile + k - 1, rows = kGfTile + k - 1;
