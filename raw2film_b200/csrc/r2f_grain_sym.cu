@@ -64,15 +64,13 @@ k_grain_finish_sym(const __grid_constant__ GrainFinishArgs a) {
     constexpr int NQT = (C::COLS + 3) / 4;
     static_assert(4 * NQT <= C::PITCH, "a tile row of whole quads must fit the pitch");
     const int q0 = (xs + a.noise_shift) >> 2;
-    const int gx0 = tx0 + C::OW * warp;                             // first of the thread's 8 columns
-    const bool vec_ok = (W & 3) == 0 && gx0 + C::OW <= W;           // whole 16-byte density loads
 
     // The densities of all three layers are requested up front as asynchronous global -> shared copies (LDGSTS: no
     // register, nothing waits) and complete behind the first noise field; the grain apply overwrites a thread's own
     // values in place with the grained densities.  Full tiles are copied row-wise (a warp moves two 256-byte tile rows
     // per instruction, 4 L1 wavefronts; with the thread mapping of the correlation -- one tile row per lane -- every
     // load touched 32 lines, and the density read was 47 % of the kernel's global tag requests and 15 % of its stall
-    // samples).  Frames whose rows are not 16-byte aligned use per-thread loads into the same slots.
+    // samples).  Frames whose rows are not 16-byte aligned copy the same rows four bytes at a time.
     // (tiles that cross the bottom or right edge still copy row-wise and zero what lies outside the frame -- with W a
     // multiple of 4 a 16-byte chunk is inside or outside as a whole: on a small frame the kernel lasts as long as its
     // slowest CTA, and the per-thread path made the last tile row three times slower)
@@ -89,17 +87,16 @@ k_grain_finish_sym(const __grid_constant__ GrainFinishArgs a) {
                 else *reinterpret_cast<float4 *>(dst) = make_float4(0.f, 0.f, 0.f, 0.f);
             }
         }
-    } else {
+    } else {  // rows that are not 16-byte aligned: the same row-wise copies, four bytes at a time
 #pragma unroll 1
         for (int c = 0; c < 3; ++c) {
             const float *dplane = a.dens + c * ps;
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                const int gy = ty0 + lane + 32 * h;
-                float *slot = priv + (c * C::T + lane + 32 * h) * C::DP + C::OW * warp;
-#pragma unroll
-                for (int o = 0; o < C::OW; ++o)
-                    slot[o] = (gy < H && gx0 + o < W) ? __ldcs(dplane + (size_t)gy * W + gx0 + o) : 0.0f;
+            for (int idx = threadIdx.x; idx < C::T * C::T; idx += C::NT) {
+                const int row = idx / C::T, col = idx % C::T;
+                const int gy = ty0 + row, gx = tx0 + col;
+                float *dst = priv + (c * C::T + row) * C::DP + col;
+                if (gy < H && gx < W) cp_async_4(dst, dplane + (size_t)gy * W + gx);
+                else *dst = 0.0f;
             }
         }
     }
@@ -225,9 +222,24 @@ k_grain_finish_sym(const __grid_constant__ GrainFinishArgs a) {
             __stcs(reinterpret_cast<uint4 *>(a.out_u8 + ((size_t)(ty0 + r) * W + tx0) * 3) + s16, v);
         }
     } else {
-        for (int idx = threadIdx.x; idx < th * row_bytes; idx += C::NT) {
-            const int r = idx / row_bytes, bcol = idx - r * row_bytes;
-            a.out_u8[((size_t)(ty0 + r) * W + tx0) * 3 + bcol] = stage[r * C::SPITCH + bcol];
+        // rows whose byte address is not 16-byte aligned (widths that are not multiples of 16/3 pixels, edge tiles): a
+        // warp writes one tile row as aligned 32-bit words funnel-shifted out of the staged bytes, plus at most three
+        // leading and three trailing single bytes (byte-wise stores of the whole row cost 0.1 ms per 24 MP frame)
+        const uint32_t *stage32 = reinterpret_cast<const uint32_t *>(stage);
+        for (int r = warp; r < th; r += C::NT / 32) {
+            uint8_t *gbase = a.out_u8 + ((size_t)(ty0 + r) * W + tx0) * 3;
+            const uint8_t *sbase = stage + r * C::SPITCH;           // SPITCH is a multiple of 4
+            const int mis = (int)(reinterpret_cast<uintptr_t>(gbase) & 3);
+            const int lead = mis ? min(4 - mis, row_bytes) : 0;
+            if (lane < lead) gbase[lane] = sbase[lane];
+            const int nwords = (row_bytes - lead) >> 2;
+            for (int k = lane; k < nwords; k += 32) {
+                const int sb = lead + 4 * k, wi = (r * C::SPITCH + sb) >> 2;
+                const uint32_t v = __funnelshift_r(stage32[wi], stage32[wi + 1], 8 * (sb & 3));   // bytes sb .. sb + 3
+                *reinterpret_cast<uint32_t *>(gbase + sb) = v;
+            }
+            const int tail0 = lead + 4 * nwords;
+            if (lane < row_bytes - tail0) gbase[tail0 + lane] = sbase[tail0 + lane];
         }
     }
 }
