@@ -40,20 +40,22 @@ __device__ __forceinline__ void cp_async_16(float *smem_dst, const float *gsrc) 
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
+// `gpitch`: row pitch of the source plane in floats (0: W).
 template <int ROWS, int COLS, int PITCH, int NT>
 __device__ __forceinline__ void fill_tile_async(float *__restrict__ tile, const float *__restrict__ src, int gy0,
-                                                int gx0, int H, int W) {
+                                                int gx0, int H, int W, int gpitch = 0) {
+    if (gpitch == 0) gpitch = W;
     const bool inside_x = gx0 >= 0 && gx0 + COLS <= W;
-    if (COLS % 4 == 0 && inside_x && ((gx0 | W) & 3) == 0 && (reinterpret_cast<uintptr_t>(src) & 15) == 0) {
+    if (COLS % 4 == 0 && inside_x && ((gx0 | gpitch) & 3) == 0 && (reinterpret_cast<uintptr_t>(src) & 15) == 0) {
         constexpr int QPR = COLS / 4;
         for (int idx = threadIdx.x; idx < ROWS * QPR; idx += NT) {
             const int ty = idx / QPR, q = idx - ty * QPR;
-            cp_async_16(tile + ty * PITCH + 4 * q, src + (size_t)reflect101(gy0 + ty, H) * W + gx0 + 4 * q);
+            cp_async_16(tile + ty * PITCH + 4 * q, src + (size_t)reflect101(gy0 + ty, H) * gpitch + gx0 + 4 * q);
         }
     } else {
         const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
         for (int ty = warp; ty < ROWS; ty += NT / 32) {
-            const float *row = src + (size_t)reflect101(gy0 + ty, H) * W;
+            const float *row = src + (size_t)reflect101(gy0 + ty, H) * gpitch;
             float *dst = tile + ty * PITCH;
             if (inside_x) {
                 for (int tx = lane; tx < COLS; tx += 32) cp_async_4(dst + tx, row + gx0 + tx);

@@ -929,6 +929,22 @@ int render_body(r2f_ctx *c, const void *in, int in_format, float in_gain, int H,
     const bool hal_fft = (flags & R2F_HALATION) && want_fft(c, c->t->hal, H, W, geo);
     if (c->conv_path == 2 && (flags & R2F_HALATION) && !hal_fft)
         return fail(R2F_ERR_INVALID, "FFT path forced (R2F_OPT_CONV_PATH=2) but this kernel/frame is not eligible");
+    // Odd frame widths: when the density planes go straight from k_fft_rows_inv through the symmetric MTF kernel into
+    // the fused symmetric grain kernel (the default full emulation), their rows are padded to a multiple of 4 floats so
+    // that TMA, the 16-byte copies and the 128-bit write-out keep working (plane_stride_for reserves the room).
+    int plane_pitch = W;
+    if ((W & 3) != 0 && hal_fft && tap_stage == 0 && !c->t->hal.fft_third && cv.xp == nullptr &&
+        (flags & R2F_GRAIN) && !(flags & R2F_BURN) && c->conv_sym && c->t->grain.sym_ok &&
+        grain_finish_sym_supported(c->t->grain.k) && gcurve_of(c).xp == nullptr &&
+        (size_t)(64 + c->t->grain.k - 1) * (64 + c->t->grain.k - 1) * 4 + (size_t)c->t->grain.k * c->t->grain.kp * 4 + 16384 <=
+            200 * 1024) {
+        bool mtf_ok = true;
+        if (flags & R2F_MTF) {
+            ConvArgs probe = conv_args(c->t->mtf, P[1].base, P[0].base, ps, H, W);
+            mtf_ok = conv_takes_sym(c, probe);
+        }
+        if (mtf_ok) plane_pitch = padded_pitch(W);
+    }
     if (hal_fft && tap_stage != R2F_TAP_EXPOSURE) {
         // XYZ -> 2-D LUT is fused into the row transforms; the exposure image is never materialised
         FftConvArgs fa{};
@@ -947,6 +963,7 @@ int render_body(r2f_ctx *c, const void *in, int in_format, float in_gain, int H,
         const bool third = c->t->hal.fft_third;  // three filtered layers: a second pass finishes the last one
         const bool fuse_final = tap_stage != R2F_TAP_HALATION && cv.xp == nullptr;
         const bool fuse_density = fuse_final && !third;
+        fa.dst_pitch = (fuse_density && plane_pitch != W) ? plane_pitch : 0;
         {
             ProfScope ps_(c, st, R2F_PROF_FFT_ROWS_FWD);
             for (int b = 0; b < nb; ++b) {  // the row transforms of a band start as soon as its rows have arrived
@@ -1045,6 +1062,7 @@ int render_body(r2f_ctx *c, const void *in, int in_format, float in_gain, int H,
     bool band_mtf = false;
     if (flags & R2F_MTF) {
         ConvArgs a = conv_args(c->t->mtf, P[cur].base, P[1 - cur].base, ps, H, W);
+        a.pitch = plane_pitch != W ? plane_pitch : 0;
         if (nb > 1 && c->fuse_mtf && fused_grain && conv_takes_sym(c, a)) {
             mtf_band = a;
             band_mtf = true;
@@ -1098,6 +1116,7 @@ int render_body(r2f_ctx *c, const void *in, int in_format, float in_gain, int H,
         GrainFinishArgs ga{};
         const int grc = grain_args(ga, nch);
         if (grc != R2F_OK) return grc;
+        ga.dens_pitch = plane_pitch != W ? plane_pitch : 0;
         ProfScope ps_(c, st, R2F_PROF_GRAIN);
         const bool gsym = c->conv_sym && ga.gk_sym && grain_finish_sym_supported(ga.k) && ga.gcurve.xp == nullptr;
         for (int b = 0; b < nb; ++b) {  // the result of a band can leave while the next one is computed

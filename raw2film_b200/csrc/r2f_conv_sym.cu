@@ -104,6 +104,7 @@ k_conv2d_sym(ConvArgs a, const __grid_constant__ CUtensorMap tmap, int use_tma, 
     const int c = blockIdx.z;
     const int tx0 = blockIdx.x * C::TW - shift, ty0 = ((int)blockIdx.y + a.tile_y0) * C::TH;
     const int H = a.H, W = a.W;
+    const int gp = a.pitch > 0 ? a.pitch : W;   // row pitch of the planes (padded for odd widths)
     const float *__restrict__ src = a.in + (size_t)a.in_plane[c] * a.plane_stride;
     float *__restrict__ dst = a.out + (size_t)c * a.plane_stride;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -123,7 +124,7 @@ k_conv2d_sym(ConvArgs a, const __grid_constant__ CUtensorMap tmap, int use_tma, 
                 tma_load_3d(tile, &tmap, gx0, gy0, a.in_plane[c], &tma_bar);
             }
         } else {
-            fill_tile_async<C::ROWS, C::COLS, C::PITCH, C::NT>(tile, src, gy0, gx0, H, W);
+            fill_tile_async<C::ROWS, C::COLS, C::PITCH, C::NT>(tile, src, gy0, gx0, H, W, gp);
         }
         if (tma) mbar_wait(&tma_bar, 0);
         else cp_async_wait_all();
@@ -140,7 +141,7 @@ k_conv2d_sym(ConvArgs a, const __grid_constant__ CUtensorMap tmap, int use_tma, 
     // horizontally: 4 + 4 staging stores and 8 x (LDS.128, STG.128) per thread instead of 32 + 32 x (LDS.32, STG.32);
     // the scalar write-out was a fifth of the kernel's stall samples.
     const bool conv = a.mode[c] != 0;
-    const bool vec_out = shift == 0 && (W & 3) == 0 && (a.plane_stride & 3) == 0 && tx0 + C::TW <= W &&
+    const bool vec_out = shift == 0 && (gp & 3) == 0 && (a.plane_stride & 3) == 0 && tx0 + C::TW <= W &&
                          (reinterpret_cast<uintptr_t>(a.out) & 15) == 0 && (reinterpret_cast<uintptr_t>(a.in) & 15) == 0;
     auto epilogue = [&](float val) {
         if (a.epi == EPI_DENSITY) val = density_eval(a.curve, c, val, a.eps);
@@ -163,7 +164,7 @@ k_conv2d_sym(ConvArgs a, const __grid_constant__ CUtensorMap tmap, int use_tma, 
             const int rr = idx / (C::TW / 4), c4 = idx % (C::TW / 4);
             const int gy = ty0 + rr;
             if (gy >= H) break;
-            const size_t gi = (size_t)gy * W + tx0 + 4 * c4;
+            const size_t gi = (size_t)gy * gp + tx0 + 4 * c4;
             float4 v = conv ? *reinterpret_cast<const float4 *>(tile + rr * C::OP4 + 4 * c4)
                             : __ldg(reinterpret_cast<const float4 *>(src + gi));
             v.x = epilogue(v.x); v.y = epilogue(v.y); v.z = epilogue(v.z); v.w = epilogue(v.w);
@@ -188,7 +189,7 @@ k_conv2d_sym(ConvArgs a, const __grid_constant__ CUtensorMap tmap, int use_tma, 
         for (int rr = rsub; rr < C::TH; rr += C::NT / 64) {
             const int gy = ty0 + rr;
             if (gy >= H) break;
-            const size_t idx = (size_t)gy * W + gx;
+            const size_t idx = (size_t)gy * gp + gx;
             dst[idx] = epilogue(conv ? tile[rr * C::OPITCH + col] : __ldg(src + idx));
         }
     }
@@ -215,10 +216,11 @@ EncodeTiledFn encode_tiled_fn() {
 bool make_plane_map(const ConvArgs &a, int box_w, int box_h, CUtensorMap *map) {
     if (getenv("R2F_NO_TMA")) return false;
     EncodeTiledFn enc = encode_tiled_fn();
-    if (!enc || (a.W & 3) != 0 || (reinterpret_cast<uintptr_t>(a.in) & 15) != 0 || box_w > 256 || box_h > 256)
+    const int gp = a.pitch > 0 ? a.pitch : a.W;
+    if (!enc || (gp & 3) != 0 || (reinterpret_cast<uintptr_t>(a.in) & 15) != 0 || box_w > 256 || box_h > 256)
         return false;
     const cuuint64_t dims[3] = {(cuuint64_t)a.W, (cuuint64_t)a.H, 3};
-    const cuuint64_t strides[2] = {(cuuint64_t)a.W * 4, (cuuint64_t)a.plane_stride * 4};
+    const cuuint64_t strides[2] = {(cuuint64_t)gp * 4, (cuuint64_t)a.plane_stride * 4};
     const cuuint32_t box[3] = {(cuuint32_t)box_w, (cuuint32_t)box_h, 1};
     const cuuint32_t estr[3] = {1, 1, 1};
     return enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float *>(a.in), dims, strides, box, estr,

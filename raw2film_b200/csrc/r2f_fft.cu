@@ -859,8 +859,9 @@ k_fft_rows_inv(const __grid_constant__ FftConvArgs a) {
                 lut2d_eval(l2, X, Y, Z, src[0], src[1], src[2]);
             }
             finish_px(src, buf[sw(r + x)], out);
+            const size_t oidx = a.dst_pitch > 0 ? (size_t)y * a.dst_pitch + x : idx;
 #pragma unroll
-            for (int c = 0; c < 3; ++c) a.dst_planar[c * ps + idx] = out[c];
+            for (int c = 0; c < 3; ++c) a.dst_planar[c * ps + oidx] = out[c];
         }
     }
 }

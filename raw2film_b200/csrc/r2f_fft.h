@@ -46,6 +46,7 @@ struct FftConvArgs {
     int row_off;        // row kernels: the padded row starts row_off elements into the line buffer (0..3), chosen so that
                         // r + row_off is a multiple of 4 and a pixel quad's four values are two aligned 16-byte accesses;
                         // a circular shift of the line shifts the filtered row by the same amount
+    int dst_pitch;      // k_fft_rows_inv: row pitch of dst_planar (0: W)
     int rows_ahead;     // k_fft_rows_fwd prefetches the frame row of CTA blockIdx + rows_ahead into L2 (0: off)
     int cols_prefetch;  // column kernel: L2-prefetch its kernel-spectrum rows and the next CTA's block
     int col_inplace;    // 1: in-place column kernel (one 256-thread group per column, khat permuted by col perm)

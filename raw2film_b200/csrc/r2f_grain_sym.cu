@@ -74,16 +74,19 @@ k_grain_finish_sym(const __grid_constant__ GrainFinishArgs a) {
     // (tiles that cross the bottom or right edge still copy row-wise and zero what lies outside the frame -- with W a
     // multiple of 4 a 16-byte chunk is inside or outside as a whole: on a small frame the kernel lasts as long as its
     // slowest CTA, and the per-thread path made the last tile row three times slower)
-    const bool full_tile = (W & 3) == 0 && (ps & 3) == 0 && (reinterpret_cast<uintptr_t>(a.dens) & 15) == 0;
+    const int dp = a.dens_pitch > 0 ? a.dens_pitch : W;   // row pitch of the density planes (padded for odd widths)
+    const bool full_tile = (dp & 3) == 0 && (ps & 3) == 0 && (reinterpret_cast<uintptr_t>(a.dens) & 15) == 0;
     if (full_tile) {
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
-            const float *dplane = a.dens + c * ps + (size_t)ty0 * W + tx0;
+            const float *dplane = a.dens + c * ps + (size_t)ty0 * dp + tx0;
 #pragma unroll
             for (int it = 0; it < C::T * (C::T / 4) / C::NT; ++it) {
                 const int idx = threadIdx.x + it * C::NT, row = idx / (C::T / 4), ch = idx % (C::T / 4);
                 float *dst = priv + (c * C::T + row) * C::DP + 4 * ch;
-                if (ty0 + row < H && tx0 + 4 * ch < W) cp_async_16(dst, dplane + (size_t)row * W + 4 * ch);
+                // a chunk lies inside the padded row as a whole; the (up to three) pad columns of an odd-width frame
+                // hold unspecified values, which only feed outputs that are never written
+                if (ty0 + row < H && tx0 + 4 * ch < W) cp_async_16(dst, dplane + (size_t)row * dp + 4 * ch);
                 else *reinterpret_cast<float4 *>(dst) = make_float4(0.f, 0.f, 0.f, 0.f);
             }
         }
@@ -95,7 +98,7 @@ k_grain_finish_sym(const __grid_constant__ GrainFinishArgs a) {
                 const int row = idx / C::T, col = idx % C::T;
                 const int gy = ty0 + row, gx = tx0 + col;
                 float *dst = priv + (c * C::T + row) * C::DP + col;
-                if (gy < H && gx < W) cp_async_4(dst, dplane + (size_t)gy * W + gx);
+                if (gy < H && gx < W) cp_async_4(dst, dplane + (size_t)gy * dp + gx);
                 else *dst = 0.0f;
             }
         }
@@ -162,14 +165,14 @@ k_grain_finish_sym(const __grid_constant__ GrainFinishArgs a) {
                 const int gy = ty0 + row, gx = tx0 + 4 * ch;
                 if (gy >= H || gx >= W) continue;
                 const float4 v = *reinterpret_cast<const float4 *>(priv + (c * C::T + row) * C::DP + 4 * ch);
-                float *dp = oplane + (size_t)gy * W + gx;
-                if (full_tile && (reinterpret_cast<uintptr_t>(a.dens_out) & 15) == 0) {
-                    *reinterpret_cast<float4 *>(dp) = v;
+                float *op = oplane + (size_t)gy * W + gx;
+                if ((W & 3) == 0 && (ps & 3) == 0 && (reinterpret_cast<uintptr_t>(a.dens_out) & 15) == 0) {
+                    *reinterpret_cast<float4 *>(op) = v;
                 } else {
-                    dp[0] = v.x;
-                    if (gx + 1 < W) dp[1] = v.y;
-                    if (gx + 2 < W) dp[2] = v.z;
-                    if (gx + 3 < W) dp[3] = v.w;
+                    op[0] = v.x;
+                    if (gx + 1 < W) op[1] = v.y;
+                    if (gx + 2 < W) op[2] = v.z;
+                    if (gx + 3 < W) op[3] = v.w;
                 }
             }
         }

@@ -10,14 +10,18 @@
 
 namespace r2f {
 
-// Planar float32 working image: plane c lives at base + c * plane_stride, row pitch = W.
+// Planar float32 working image: plane c lives at base + c * plane_stride, row pitch = W -- except the density planes
+// between k_fft_rows_inv, k_conv2d_sym and k_grain_finish_sym of a frame whose width is not a multiple of 4, whose rows
+// are padded to a multiple of 4 floats (ConvArgs::pitch, GrainFinishArgs::dens_pitch, FftConvArgs::dst_pitch) so that
+// the 16-byte paths and the TMA tensor map survive odd widths.
 struct Planes {
     float *base;
     size_t plane_stride;  // floats, multiple of 64
 };
 
+inline int padded_pitch(int W) { return (W + 3) & ~3; }
 inline size_t plane_stride_for(int H, int W) {
-    size_t n = (size_t)H * (size_t)W;
+    size_t n = (size_t)H * (size_t)padded_pitch(W);
     return (n + 63) / 64 * 64;
 }
 
@@ -41,6 +45,7 @@ struct ConvArgs {
     Curve1D curve;  // H-D curve (EPI_DENSITY) or grain amplitude curve (EPI_GRAIN)
     float eps;
     int tile_y0, tile_rows;  // k_conv2d_sym only: rows of 64-row tiles to compute (tile_rows == 0: the whole frame)
+    int pitch;               // k_conv2d_sym only: row pitch of the source and destination planes (0: W)
 };
 
 struct BurnArgs {
@@ -125,6 +130,7 @@ struct GrainFinishArgs {
     FastTetra ft;        // guarded float32 tetrahedral LUT + quantise (ok == 0: exact path only)
     BurnArgs burn;
     uint8_t *out_u8;
+    int dens_pitch;          // k_grain_finish_sym only: row pitch of `dens` (0: W); dens_out and noise keep W
     float *dens_out;         // k_grain_finish_sym only: not null = stop after the grain stage and write the grained
                              // density planes here (may alias `dens`; the burn mask needs the whole grained frame)
     int tile_y0, tile_rows;  // first tile row and tile-row count of this launch (0, 0 = all): banded output

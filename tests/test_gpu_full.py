@@ -38,6 +38,37 @@ def test_process_full_emulation_injected_noise(proc, grain_mode):
     assert mx <= 1 and rate < 2e-3, (mx, rate)
 
 
+@pytest.mark.parametrize("shape", [(241, 363), (250, 361), (239, 358), (130, 1027)])
+def test_full_emulation_odd_widths_injected_noise(proc, shape):
+    """Widths that are not multiples of 4: the density planes between the row-inverse FFT kernel, the MTF kernel and
+    the grain kernel use a padded row pitch (TMA / 16-byte paths); the bytes must still be the oracle's (<= 1 LSB),
+    and the same as through the generic kernels, whose planes are unpadded."""
+    stock = SyntheticStock(n3=17)
+    xyz = small_frame(*shape, seed=shape[1])
+    noise = fo.white_noise(xyz.shape, False, seed=9)
+    st = dict(frame_width=3.0, frame_height=3.0 * shape[0] / shape[1], grain=2, halation_green_factor=0.3)
+    want = oracle_render(fo, xyz, stock, 6.0, 0.4, st, noise=noise)
+    got = proc.process(xyz, stock, 6.0, 0.4, grain_noise=noise, **st)
+    mx, rate = _lsb_report(got, want)
+    assert mx <= 1 and rate < 2e-3, (mx, rate)
+    proc.set_conv_sym(False)
+    try:
+        generic = proc.process(xyz, stock, 6.0, 0.4, grain_noise=noise, **st)
+    finally:
+        proc.set_conv_sym(True)
+    mx, rate = _lsb_report(got, generic)
+    assert mx <= 1 and rate < 2e-3, (mx, rate)
+    # regenerated noise (no injection): the same field through both kernel families
+    a = proc.process(xyz, stock, 6.0, 0.4, grain_seed=77, **st)
+    proc.set_conv_sym(False)
+    try:
+        b = proc.process(xyz, stock, 6.0, 0.4, grain_seed=77, **st)
+    finally:
+        proc.set_conv_sym(True)
+    mx, rate = _lsb_report(a, b)
+    assert mx <= 1 and rate < 2e-3, (mx, rate)
+
+
 def test_process_pointwise_config_bit_exact(proc):
     """Config C1 through the public API: stages off -> bit-exact uint8."""
     stock = SyntheticStock()
