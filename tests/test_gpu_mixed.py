@@ -274,6 +274,18 @@ def test_banded_streaming_call_equals_plain_render(proc, st):
     assert np.array_equal(got16, want16)
 
 
+def test_banded_call_at_an_odd_width_equals_plain_render(proc):
+    """Odd width (padded plane pitch between rows_inv, MTF and grain) through the banded synchronous call."""
+    import torch
+
+    stock = SyntheticStock()
+    st = dict(halation=True, sharpness=True, grain=2, halation_green_factor=0.3, grain_seed=4321)
+    xyz = natural_frame(1100, 1501, 29)
+    want = proc.render_device(torch.from_numpy(xyz).cuda(), stock, 6.0, 0.4, **st).cpu().numpy()
+    got = proc.process_preloaded(proc.extract_image_data_cpu(xyz, **st), stock, 6.0, 0.4, **st)
+    assert proc._own_pipeline().bands >= 4 and np.array_equal(got, want)
+
+
 def test_banded_mtf_switch_gives_the_same_bytes(proc):
     """R2F_OPT_FUSE_MTF: the MTF issued band by band with the grain kernel or as one whole-frame launch."""
     stock = SyntheticStock()
